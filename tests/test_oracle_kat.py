@@ -1,0 +1,193 @@
+"""Known-answer and cross-restatement tests that pin the oracle; CPU only."""
+import itertools
+
+import numpy as np
+import torch
+
+from oracle import np_oracle as O
+from oracle import torch_ref as R
+
+
+def _rand_nade(N=7, D=9, H=5, seed=0, dtype=np.float64):
+    rng = np.random.default_rng(seed)
+    x = (rng.random((N, D)) < 0.3).astype(dtype)
+    return (x, rng.standard_normal((N, H)).astype(dtype), rng.standard_normal((N, D)).astype(dtype),
+            rng.standard_normal((D, H)).astype(dtype) * 0.5, rng.standard_normal((D, H)).astype(dtype) * 0.5)
+
+
+def test_nade_loop_equals_triangular():
+    args = _rand_nade()
+    nll1, p1 = O.nade_log_prob(*args)
+    nll2, p2 = O.nade_log_prob_triangular(*args)
+    np.testing.assert_allclose(nll1, nll2, rtol=1e-13)
+    np.testing.assert_allclose(p1, p2, rtol=1e-13)
+
+
+def test_nade_zero_weights_closed_form():
+    x, be, bd, we, wd = _rand_nade()
+    nll, p = O.nade_log_prob(x, be, bd, we * 0, wd * 0)
+    ps = 1 / (1 + np.exp(-bd))
+    np.testing.assert_allclose(p, ps, rtol=1e-14)
+    ref = -(x * np.log(1e-6 + ps) + (1 - x) * np.log(1e-6 + 1 - ps)).sum(1)
+    np.testing.assert_allclose(nll, ref, rtol=1e-13)
+
+
+def test_nade_normalises_up_to_safe_log_eps():
+    D, H = 6, 4
+    rng = np.random.default_rng(1)
+    we, wd = rng.standard_normal((D, H)), rng.standard_normal((D, H))
+    be, bd = rng.standard_normal((1, H)), rng.standard_normal((1, D))
+    vs = np.array(list(itertools.product([0., 1.], repeat=D)))
+    nll, _ = O.nade_log_prob(vs, np.repeat(be, len(vs), 0), np.repeat(bd, len(vs), 0), we, wd)
+    total = np.exp(-nll).sum()
+    assert abs(total - 1.0) < 5 * D * 1e-6 and total > 1.0
+
+
+def test_nade_sample_consistent_with_log_prob():
+    x, be, bd, we, wd = _rand_nade(N=16)
+    u = np.random.default_rng(2).random(x.shape)
+    v, nll_s = O.nade_sample(be, bd, we, wd, u)
+    nll, p = O.nade_log_prob(v, be, bd, we, wd)
+    np.testing.assert_allclose(nll, nll_s, rtol=1e-13)
+    assert np.array_equal(v, (u < p).astype(v.dtype))
+    v2, _ = O.nade_sample(be, bd, we, wd, u)
+    assert np.array_equal(v, v2)                      # pure function of the uniforms
+    vt, _ = O.nade_sample(be, bd, we, wd, None)        # temperature=None -> threshold
+    _, pt = O.nade_log_prob(vt, be, bd, we, wd)
+    assert np.array_equal(vt, (pt >= .5).astype(vt.dtype))
+
+
+def test_torch_fp32_matches_numpy_fp64_nade():
+    args = _rand_nade(N=32, D=84, H=64)
+    nll64, p64 = O.nade_log_prob(*args)
+    t = [torch.tensor(a, dtype=torch.float32) for a in args]
+    nll32, p32 = R.nade_log_prob(*t)
+    np.testing.assert_allclose(nll32.numpy(), nll64, rtol=1e-5)
+    np.testing.assert_allclose(p32.numpy(), p64, atol=2e-6)
+
+
+def test_lstm_cell_matches_torch_lstm_after_gate_permutation():
+    rng = np.random.default_rng(3)
+    B, I, Rr, T = 4, 6, 5, 7
+    kernel = rng.standard_normal((I + Rr, 4 * Rr)) * 0.3
+    bias = rng.standard_normal(4 * Rr) * 0.1
+    xs = rng.standard_normal((B, T, I))
+    outs, st = O.rnn_scan(xs, [(kernel, bias)])
+    lstm = torch.nn.LSTM(I, Rr, batch_first=True).double()
+    # TF order i,j,f,o -> torch order i,f,g(j),o
+    perm = np.concatenate([np.arange(0, Rr), np.arange(2 * Rr, 3 * Rr), np.arange(Rr, 2 * Rr), np.arange(3 * Rr, 4 * Rr)])
+    with torch.no_grad():
+        lstm.weight_ih_l0.copy_(torch.tensor(kernel[:I, perm].T))
+        lstm.weight_hh_l0.copy_(torch.tensor(kernel[I:, perm].T))
+        lstm.bias_ih_l0.copy_(torch.tensor(bias[perm]))
+        lstm.bias_hh_l0.zero_()
+        y, (hn, cn) = lstm(torch.tensor(xs))
+    np.testing.assert_allclose(outs, y.numpy(), atol=1e-12)
+    np.testing.assert_allclose(st[0][0], cn[0].numpy(), atol=1e-12)
+
+
+def test_dropout_tf_semantics():
+    x = np.ones((2, 4), np.float32)
+    u = np.array([[0.0, 0.099, 0.1, 0.5], [0.9, 0.95, 0.1000001, 0.0999]], np.float32)
+    y = O.dropout(x, 0.9, u)
+    keep = np.floor(np.float32(0.9) + u)
+    np.testing.assert_array_equal(y, x / np.float32(0.9) * keep)
+    assert y[0, 0] == 0 and y[0, 3] > 1.1
+
+
+def test_rbm_free_energy_vs_bruteforce():
+    rng = np.random.default_rng(4)
+    D, H = 5, 6
+    W, bh, bv = rng.standard_normal((D, H)), rng.standard_normal((1, H)), rng.standard_normal((1, D))
+    v = (rng.random((3, D)) < 0.5).astype(np.float64)
+    hs = np.array(list(itertools.product([0., 1.], repeat=H)))
+    E = -(v @ W @ hs.T) - (hs @ bh.T).T - (v @ bv.T)          # [3, 2^H]
+    F_bf = -np.log(np.exp(-E).sum(1))
+    np.testing.assert_allclose(O.rbm_free_energy(v, W, bh, bv), F_bf, rtol=1e-12)
+
+
+def test_rbm_free_energy_cost_equals_broadcast_mean():
+    rng = np.random.default_rng(5)
+    D, H, N = 5, 6, 4
+    W, bh, bv = rng.standard_normal((D, H)), rng.standard_normal((1, H)), rng.standard_normal((1, D))
+    v = (rng.random((N, D)) < 0.5).astype(np.float64)
+    vs = (rng.random((N, D)) < 0.5).astype(np.float64)
+
+    def F_ref(vv):  # literal common/rbm.py:258 with its [N]-[N,1] -> [N,N] broadcast
+        return -np.log(1 + np.exp(vv @ W + bh)).sum(1) - vv @ bv.T
+    lit = (F_ref(v) - F_ref(vs)).mean()
+    np.testing.assert_allclose(O.rbm_free_energy_cost_mean(v, vs, W, bh, bv), lit, rtol=1e-12)
+
+
+def test_gibbs_pure_function_and_k0():
+    rng = np.random.default_rng(6)
+    D, H, N, k = 8, 7, 5, 3
+    W, bh, bv = rng.standard_normal((D, H)), rng.standard_normal((N, H)), rng.standard_normal((N, D))
+    v = (rng.random((N, D)) < 0.5).astype(np.float64)
+    uh, uv = rng.random((k, N, H)), rng.random((k, N, D))
+    a = O.rbm_gibbs(v, W, bh, bv, k, uh, uv)
+    b = O.rbm_gibbs(v, W, bh, bv, k, uh, uv)
+    assert np.array_equal(a[1], b[1]) and set(np.unique(a[1])) <= {0., 1.}
+    p0, v0 = O.rbm_gibbs(v, W, bh, bv, 0, uh, uv)
+    assert np.array_equal(p0, v) and np.array_equal(v0, v)
+
+
+def test_tf_adam_first_step_closed_form_and_clip():
+    p, g = np.array([1.0, -2.0]), np.array([0.5, -0.25])
+    p1, m1, v1 = O.tf_adam_step(p, g, np.zeros(2), np.zeros(2), 1)
+    lr_t = 0.01 * np.sqrt(1 - 0.999) / (1 - 0.9)
+    np.testing.assert_allclose(p1, p - lr_t * (0.1 * g) / (np.sqrt(0.001 * g * g) + 1e-4), rtol=1e-14)
+    for scale, expect in ((1.0, 1.0), (10.0, None)):
+        gs = [np.array([3.0, 4.0]) * scale]
+        c, gn = O.clip_by_global_norm(gs, 5.0)
+        assert np.isclose(gn, 5 * scale)
+        assert np.isclose(np.linalg.norm(c[0]), 5.0)
+    c, gn = O.clip_by_global_norm([np.array([0.3, 0.4])], 5.0)
+    np.testing.assert_allclose(c[0], [0.3, 0.4])
+
+
+def test_composer_torch_matches_numpy_and_fd_gradient():
+    B, T, D, M, H = 2, 3, 5, 2, 4
+    x = O.synthetic_pianoroll(B, T, D, M, density=0.3)
+    p = O.init_composer_params(D, M, H, (6, 4), seed=7)
+    out = O.composer_forward(x.astype(np.float64), O.cast_params(p, np.float64))
+    tp = R.to_torch(p, torch.float64, requires_grad=True)
+    loss, nll = R.composer_loss(torch.tensor(x, dtype=torch.float64), tp)
+    np.testing.assert_allclose(float(loss), out['loss'], rtol=1e-12)
+    np.testing.assert_allclose(nll.detach().numpy(), out['nll'], rtol=1e-12)
+    leaves = R.flat_params(tp)
+    grads = torch.autograd.grad(loss, leaves)
+    # finite differences on a few entries of each leaf
+    rng = np.random.default_rng(0)
+    for leaf, g in zip(leaves, grads):
+        flat = leaf.detach().view(-1)
+        for idx in rng.choice(flat.numel(), size=min(3, flat.numel()), replace=False):
+            old = float(flat[idx])
+            with torch.no_grad():
+                flat[idx] = old + 1e-6
+                lp = float(R.composer_loss(torch.tensor(x, dtype=torch.float64), tp)[0])
+                flat[idx] = old - 1e-6
+                lm = float(R.composer_loss(torch.tensor(x, dtype=torch.float64), tp)[0])
+                flat[idx] = old
+            fd = (lp - lm) / 2e-6
+            assert abs(fd - float(g.view(-1)[idx])) <= 1e-6 + 1e-5 * abs(fd)
+
+
+def test_flatten_row_order_is_batch_major():
+    x = O.synthetic_pianoroll(3, 4, 2, 2, density=0.5)
+    inp, tgt = O.composer_inputs_targets(x)
+    assert inp.shape == (3, 4, 4) and np.all(inp[:, 0] == 0)
+    np.testing.assert_array_equal(inp[:, 1:], tgt[:, :-1])
+    # feature index = d*M + m (multinn_composer.py:74-78)
+    assert tgt[1, 2, 1 * 2 + 0] == x[1, 2, 1, 0]
+    assert tgt.reshape(12, 4)[1 * 4 + 2, 3] == x[1, 2, 1, 1]
+
+
+def test_composer_generate_shapes_and_determinism():
+    B, Ti, D, M, H, S = 2, 3, 5, 2, 4, 4
+    x = O.synthetic_pianoroll(B, Ti, D, M, density=0.3).astype(np.float64)
+    p = O.cast_params(O.init_composer_params(D, M, H, (6, 4), seed=7), np.float64)
+    u = np.random.default_rng(1).random((S, M, B, D))
+    a = O.composer_generate(x, p, S, u)
+    b = O.composer_generate(x, p, S, u)
+    assert a.shape == (B, S, D, M) and np.array_equal(a, b) and set(np.unique(a)) <= {0., 1.}
