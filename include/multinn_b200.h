@@ -1,0 +1,113 @@
+/* libmultinn_sm100.so -- C ABI of the B200-native MultINN hot path.
+ *
+ * The reference (ilya16/MultINN) has no FFI: its boundary is the Python module interface
+ * (Encoder / Generator / RnnEstimator / NADE / RBM classes) over TF 1.13.1 library ops. Each entry
+ * point below replaces the TF ops behind one reference call site (cited as file:line relative to
+ * /root/reference/multinn/). The host-side mirror of the Python interface lives in multinn_b200/.
+ *
+ * Conventions: every function returns 0 on success, a negative MNN_ERR_* code for argument errors,
+ * or a positive cudaError_t; mnn_last_error_string() describes the last failure of the calling
+ * thread. All pointers are DEVICE pointers owned by the caller (workspace included); fp32,
+ * row-major; `ld*` are row strides in elements; the last argument is the CUDA stream. No function
+ * allocates, synchronises or throws. Sequence tensors are time-major: row n' = t * B + b.
+ */
+#ifndef MULTINN_B200_H_
+#define MULTINN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* mnn_stream_t;
+
+#define MNN_OK 0
+#define MNN_ERR_ARG (-1)
+#define MNN_ERR_UNSUPPORTED (-2)
+#define MNN_ERR_WORKSPACE (-3)
+
+int mnn_version(void);
+const char* mnn_last_error_string(void);
+
+/* K0 -- input staging. core/multi_encoder_nn.py:66-87 (_build_inputs zero-pad + unstack, _build_targets),
+ * multinn_composer.py:73-87 (stack axis=3, reshape, [:, :-1] / [:, 1:] shift), multinn_jamming.py:60-68.
+ * x[B,T,D,M] -> xin[(T+1),B,D*M] (slot 0 zero; feature d*M+m), xtr[M,(T+1),B,D] (optional),
+ * bits[M,T*B,4] target bit masks. Any of xin/xtr/bits may be NULL. D <= 128. */
+int mnn_pack_pianoroll(const float* x, float* xin, float* xtr, uint32_t* bits, int B, int T, int D, int M,
+                       mnn_stream_t stream);
+/* Bit masks of an already flattened binary matrix v[N,D] (element (n,d) at v[n*ld + d*dim_stride]). */
+int mnn_pack_rows(const float* v, long long ld, int dim_stride, uint32_t* bits, int N, int D, mnn_stream_t stream);
+
+/* fp32 GEMM: C = alpha*op(A)*op(B) + beta*C (+ bias[n]). tf.matmul / tf.layers.Dense at common/rnn.py:124
+ * (LSTMBlockCell xh.W), generators/rnn_nade.py:54-57,212 (Dense output_layer), generators/rnn_rbm.py:252-253
+ * (Wuh, Wuv), common/rbm.py:351,370, common/dnn.py:56-60. transA=0: A is [M,K]; 1: A is stored [K,M]. */
+int mnn_gemm_f32(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+                 long long ldc, const float* bias, float alpha, float beta, int M, int N, int K, mnn_stream_t stream);
+
+/* K2 -- LSTM temporal unit. common/rnn.py:104-145 (CudnnCompatibleLSTMCell, gate blocks i,j,f,o, forget_bias 0;
+ * DropoutWrapper output_keep_prob; MultiRNNCell), driven like dynamic_decode at generators/rnn_nade.py:204-218.
+ * One cell step: gates[B,4R] in = pre-activations, out = activations; out = h/keep*floor(keep+u). */
+int mnn_lstm_cell_fwd(float* gates, const float* c_prev, float* c, float* h, float* out, float* dscale,
+                      const float* u, float keep, unsigned long long seed, unsigned long long offset, int B, int R,
+                      mnn_stream_t stream);
+/* Whole sequence, one layer. gates[T,B,4R] in = x.Wx + b for every step, out = gate activations (saved for
+ * backward); wh[R,4R] = kernel rows I..I+R-1; hbuf/cbuf[(T+1),B,R] slot 0 = initial state, slot t+1 = state
+ * after step t; out[T,B,R] = dropped-out h (NULL to skip); dscale[T,B,R] required when keep < 1;
+ * u[T,B,R] uniforms or NULL (Philox(seed)). */
+int mnn_lstm_seq_fwd(float* gates, const float* wh, float* hbuf, float* cbuf, float* out, float* dscale,
+                     const float* u, float keep, unsigned long long seed, int T, int B, int R, mnn_stream_t stream);
+/* BPTT of the same: gates in = activations, out = d(pre-activations) [T,B,4R]; dout[T,B,R] = grad wrt the
+ * dropped-out outputs; dh_work/dc_work[B,R] scratch. Weight/input grads are then GEMMs over all rows. */
+int mnn_lstm_seq_bwd(float* gates, const float* wh, const float* cbuf, const float* dout, const float* dscale,
+                     float* dh_work, float* dc_work, int T, int B, int R, mnn_stream_t stream);
+/* out[c] (+)= sum_r A[r,c] (bias gradients). */
+int mnn_colsum(const float* A, long long ld, int rows, int cols, float* out, int accumulate, mnn_stream_t stream);
+
+/* K4 -- NADE / MultiNADE teacher-forced log-likelihood. common/nade.py:155-229 (log_prob), :310-329
+ * (_cond_prob), utils/auxiliary.py:9-11 (safe_log), generators/rnn_multinade.py:231-290 (bias split, per-track
+ * loop). fc[N,ld] is the Dense output read in place: b_enc of track m at column enc_col0 + m*H, b_dec at
+ * dec_col0 + m*D. w_enc/w_dec[M,D,H]. Outputs nll[M,N] (positive), cond_p[M,N,D] (optional). When dfc != NULL
+ * (training) the d b_dec columns of dfc[N,ld] receive gscale * dNLL/dl. */
+int mnn_nade_logprob_fwd(const uint32_t* bits, const float* fc, long long ld, int enc_col0, int dec_col0,
+                         const float* w_enc, const float* w_dec, float* nll, float* cond_p, float* dfc, float gscale,
+                         int N, int M, int D, int H, mnn_stream_t stream);
+/* K5 -- its backward (what tf.gradients builds through nade.py:199-226). Needs the d b_dec columns written by
+ * the forward; writes the d b_enc columns of dfc and ACCUMULATES into dw_enc/dw_dec[M,D,H]. */
+int mnn_nade_logprob_bwd(const uint32_t* bits, const float* fc, long long ld, int enc_col0, int dec_col0,
+                         const float* w_enc, const float* w_dec, float* dfc, float* dw_enc, float* dw_dec, int N,
+                         int M, int D, int H, mnn_stream_t stream);
+/* K6 -- NADE ancestral sampling, common/nade.py:231-308 (+ tfp Bernoulli(logits).sample(), :283-287;
+ * rnn_multinade.py:292-317 stacks tracks with axis=2). u[M,N,D] uniforms; u == NULL and use_philox == 0 means
+ * temperature=None (p >= .5). out[row*out_ld + i*out_dim_stride + m*out_track_stride] in {0,1}. */
+int mnn_nade_sample(const float* fc, long long ld, int enc_col0, int dec_col0, const float* w_enc,
+                    const float* w_dec, const float* u, int use_philox, unsigned long long seed,
+                    unsigned long long offset, float* out, long long out_ld, int out_dim_stride, int out_track_stride,
+                    float* nll, int N, int M, int D, int H, mnn_stream_t stream);
+
+/* K7 -- RBM half-steps: p = sigmoid(pre + bias), s = float(u < p). common/rbm.py:337-387, used by forward
+ * (:148-167), reconstruct (:169-190), the Gibbs chain (:192-231), DBN (common/dbn.py:136-180) and the sigmoid
+ * Dense feedback module (common/dnn.py:97-116). ld_bias == 0 broadcasts one bias row. */
+int mnn_bias_sigmoid_sample(const float* pre, long long ld_pre, const float* bias, long long ld_bias, const float* u,
+                            long long ld_u, int use_philox, unsigned long long seed, unsigned long long offset,
+                            float* p, long long ld_p, float* s, long long ld_s, int N, int C, mnn_stream_t stream);
+/* F(v)[n] = -sum_j softplus(pre[n,j] + bh[j]) - v[n].bv, common/rbm.py:256-258 (pre = v.W). */
+int mnn_rbm_free_energy(const float* pre, long long ld_pre, const float* bh, long long ld_bh, const float* v,
+                        long long ld_v, const float* bv, long long ld_bv, float* F, int N, int H, int D,
+                        mnn_stream_t stream);
+
+/* K9 -- reductions and the optimiser. utils/training.py:151-177 (clip_by_global_norm(5.)), train.py:61-64
+ * (AdamOptimizer(lr, epsilon=1e-4) / GradientDescentOptimizer), metrics/statistical.py:34 (reduce_mean). */
+size_t mnn_reduce_workspace_bytes(void);
+int mnn_sum(const float* x, size_t n, void* ws, float* out, float scale, int accumulate, mnn_stream_t stream);
+int mnn_sqnorm(const float* x, size_t n, void* ws, float* out, mnn_stream_t stream);
+int mnn_clip_adam(float* p, const float* g, float* m, float* v, size_t n, const float* sqnorm, float grad_scale,
+                  float clip_norm, float lr, float beta1, float beta2, float eps, int step, mnn_stream_t stream);
+int mnn_clip_sgd(float* p, const float* g, size_t n, const float* sqnorm, float grad_scale, float clip_norm,
+                 float lr, mnn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MULTINN_B200_H_ */

@@ -1,0 +1,70 @@
+// Shared device helpers for libmultinn_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MNN_OK 0
+#define MNN_ERR_ARG (-1)          // bad argument (null pointer, non-positive size)
+#define MNN_ERR_UNSUPPORTED (-2)  // shape outside what the sm_100a kernels are instantiated for
+#define MNN_ERR_WORKSPACE (-3)
+
+void mnn_set_error(const char* msg);
+int mnn_check_launch(const char* what);
+
+#define MNN_REQUIRE(cond, code, msg) \
+  do {                               \
+    if (!(cond)) {                   \
+      mnn_set_error(msg);            \
+      return (code);                 \
+    }                                \
+  } while (0)
+
+namespace mnn {
+
+constexpr float kSafeLogEps = 1e-6f;  // reference utils/auxiliary.py:11
+
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  // ex2.approx + rcp.approx: ~2 ulp, 2 MUFU ops.
+  return __fdividef(1.0f, 1.0f + __expf(-x));
+}
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float tanh_acc(float x) {
+  // tanh via exp: accurate to ~2 ulp over the LSTM's range; tanhf would also do.
+  return tanhf(x);
+}
+
+// Packed fp32x2 FMA (Blackwell FFMA2): d = a*b + c on both halves.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ua, ub, uc, ud;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(uc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(ud) : "l"(ua), "l"(ub), "l"(uc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(ud));
+  return d;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Philox4x32-10 counter-based RNG (Salmon et al. 2011). One call -> 4 x 32 random bits.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+// 24-bit uniform in [0,1): exactly representable in fp32, strict-< comparisons behave like TF's.
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+}  // namespace mnn
