@@ -1,0 +1,288 @@
+"""bench.py -- train time-steps/sec of Composer LSTM-MultiNADE on synthetic piano-rolls (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference ...                     (CPU restatement of the reference's TF1 graph)
+
+A "step" is one full training step (fwd + bwd + allreduce + clip + Adam) over the global batch [B,T,84,5];
+strong scaling: the global batch is fixed and sharded over ranks. Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    'C5': dict(B=2048, T=256, name='composer-lstm-multinade [2048,256,84,5] (BASELINE configs[4])'),
+    'C2': dict(B=256, T=128, name='composer-lstm-multinade [256,128,84,5] (BASELINE configs[1])'),
+}
+D, M, H, RNN = 84, 5, 256, (512, 256)
+# algorithmic forward flops per time-step (one (b,t) row, all 5 tracks); fwd+bwd = 3x
+DENSE_FLOPS_FWD = 6_260_736
+NADE_FLOPS_FWD = 9_139_200
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], tf_burst=d['bf16_tflops'], tf_sust=d.get('bf16_tflops_sustained', d['bf16_tflops']),
+                    src='measured')
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src='fallback')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_port_run(B, T, steps, warmup, threads=None):
+    """The reference's training step restated op for op on torch-CPU (oracle/torch_ref.py): unrolled 84-iteration
+    NADE loop per track, per-step LSTM loop, autograd, clip 5, TF-Adam. Returns (time-steps/s, cores, loss)."""
+    import torch
+    from oracle import np_oracle as O
+    from oracle import torch_ref as R
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    params = R.to_torch(O.init_composer_params(D, M, H, RNN, seed=23), torch.float32, requires_grad=True)
+    opt = R.TFAdam(R.flat_params(params), lr=0.01)
+    x = torch.from_numpy(O.synthetic_pianoroll(B, T, D, M, seed=23))
+    rng = np.random.default_rng(0)
+    times, loss = [], None
+    for it in range(warmup + steps):
+        u = [torch.from_numpy(rng.random((T, B, r), dtype=np.float32)) for r in RNN]
+        t0 = time.perf_counter()
+        loss, _ = R.composer_train_step(x, params, opt, keep=0.9, u_drop=u)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return B * T / float(np.mean(times)), cores, loss, float(np.mean(times))
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    sB, sT = args.cpu_batch, wl['T']
+    v, cores, loss, sec = cpu_port_run(sB, sT, max(1, args.steps), min(args.warmup, 1))
+    sample = (f'[{sB},{sT},84,5] slice of the workload per step ({sec:.2f} s/step), torch-CPU fp32 op-for-op '
+              f'restatement of the TF1 graph (TF 1.13.1 not installable), keep_prob 0.9')
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'train time-steps/sec (Composer LSTM-MultiNADE)', 'value': v,
+        'unit': 'time-steps/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'config': {'workload': wl['name'], 'global_batch': wl['B'], 'time_steps': wl['T']},
+        'cpu_baseline': {'value': v, 'unit': 'time-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': 'time-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0, 'final_loss': loss}))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from multinn_b200 import _lib
+    from multinn_b200.multinn import MultINN, default_config, default_params
+    from oracle import np_oracle as O   # synthetic data generator + cpu_baseline leg only
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    wl = WORKLOADS[args.workload]
+    B, T = wl['B'], wl['T']
+    assert B % world == 0
+    Bl = B // world
+    model = MultINN(default_config(), default_params(mode='composer', keep_prob=0.9), 'composer')
+    step = model.train_generators('adam', 0.01)
+
+    # synthetic Bernoulli(0.05) piano-rolls, two alternating host batches in pinned memory
+    rng = np.random.default_rng(23 + rank)
+    hosts = [torch.from_numpy((rng.random((Bl, T, D, M)) < 0.05).astype(np.float32)).pin_memory() for _ in range(2)]
+    xdev = [h.cuda(non_blocking=True) for h in hosts]
+    xbuf = torch.empty_like(xdev[0])
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / n
+
+    losses = []
+    resident = lambda i: losses.append(step(xdev[i & 1]))
+
+    def e2e_step(i):
+        xbuf.copy_(hosts[i & 1], non_blocking=True)      # H2D of this step's inputs from pinned memory
+        l = step(xbuf)
+        losses.append(float(l))                          # D2H read of the step's loss
+
+    for i in range(args.warmup):
+        resident(i)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    n0 = _lib.lib.mnn_launch_count()
+    ms = timed(resident, args.steps)
+    launches = (_lib.lib.mnn_launch_count() - n0)
+    clk = clocks.stop() if rank == 0 else None
+    final_loss = float(losses[-1])
+    e2e_step(0)
+    ms_e2e = timed(e2e_step, args.steps)
+
+    # ---- per-phase device times of one more step (CUDA events on the launching stream) -> roofline
+    phases = profile_phases(model, xdev[0], args)
+
+    if rank == 0:
+        pk = peaks()
+        tps = B * T / (ms * 1e-3)
+        n_rows = Bl * T
+        dense_tf = 3 * DENSE_FLOPS_FWD * n_rows / (phases['dense_ms'] * 1e-3) / 1e12 if phases['dense_ms'] else 0.0
+        out = {
+            'metric': 'train time-steps/sec (Composer LSTM-MultiNADE)', 'value': tps, 'unit': 'time-steps/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': wl['name'], 'global_batch': B, 'time_steps': T, 'per_gpu_batch': Bl,
+                       'keep_prob': 0.9, 'parallelism': f'dp{world}',
+                       'l2_policy': 'per-step working set (~20 GB of activations at C5) exceeds the 126 MB L2'},
+            'e2e': {'value': B * T / (ms_e2e * 1e-3), 'unit': 'time-steps/s', 'ms_per_step': ms_e2e,
+                    'h2d_bytes_per_step': hosts[0].numel() * 4, 'd2h_bytes_per_step': 4},
+            'gpu_launches': int(launches),
+            'clocks': clk,
+            'roofline': {'bound': 'tensor', 'kernel': 'LSTM/Dense GEMMs (mnn_gemm_*), fwd+bwd',
+                         'achieved': dense_tf, 'peak': pk['tf_sust'], 'unit': 'TFLOP/s',
+                         'frac': dense_tf / pk['tf_sust'], 'traffic': None, 'peak_source': pk['src'],
+                         'phases_ms': phases},
+            'final_loss': final_loss,
+        }
+        if world == 1 and not args.no_cpu:
+            v, cores, _, sec = cpu_port_run(args.cpu_batch, T, 1, 1)
+            out['cpu_baseline'] = {'value': v, 'unit': 'time-steps/s', 'cores': cores, 'kind': 'port',
+                                   'sample': f'[{args.cpu_batch},{T},84,5] slice, 1 warm-up + 1 timed step '
+                                             f'({sec:.2f} s), torch-CPU fp32 restatement of the TF1 graph'}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def profile_phases(model, x, args):
+    """Device time of each phase of one training step, CUDA events on the current stream (max of 2 runs dropped,
+    mean of the rest). 'dense_ms' = every GEMM-shaped phase (input projections, recurrences, Dense, weight grads)."""
+    import torch
+    from multinn_b200 import ops
+    core = model._model
+    gen = core.generators[0]
+    marks = []
+
+    def wrap(name, fn):
+        def f(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            marks.append((name, e0, e1))
+            return r
+        return f
+
+    names = {'gemm': 'gemm', 'lstm_seq_fwd': 'recur_fwd', 'lstm_seq_bwd': 'recur_bwd', 'nade_logprob_fwd': 'nade_fwd',
+             'nade_logprob_bwd': 'nade_bwd', 'pack_pianoroll': 'pack', 'clip_adam': 'optim', 'sqnorm_into': 'optim',
+             'colsum': 'colsum', 'sum_into': 'loss_sum'}
+    saved = {k: getattr(ops, k) for k in names}
+    step = core.train_generators('adam', 0.01)
+    try:
+        for k, v in names.items():
+            setattr(ops, k, wrap(v, saved[k]))
+        step(x)
+        torch.cuda.synchronize()
+        marks.clear()
+        step(x)
+        torch.cuda.synchronize()
+    finally:
+        for k, v in saved.items():
+            setattr(ops, k, v)
+    acc = {}
+    for name, e0, e1 in marks:
+        acc[name] = acc.get(name, 0.0) + e0.elapsed_time(e1)
+    acc = {k + '_ms': round(v, 3) for k, v in acc.items()}
+    acc['dense_ms'] = round(acc.get('gemm_ms', 0) + acc.get('recur_fwd_ms', 0) + acc.get('recur_bwd_ms', 0), 3)
+    return acc
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='C5', choices=sorted(WORKLOADS))
+    ap.add_argument('--cpu-batch', type=int, default=64, help='batch rows of the bounded CPU sample')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -30,6 +30,8 @@ typedef struct CUstream_st* mnn_stream_t;
 
 int mnn_version(void);
 const char* mnn_last_error_string(void);
+/* Number of CUDA kernels this library has launched in the calling process (bench.py gpu_launches). */
+unsigned long long mnn_launch_count(void);
 
 /* K0 -- input staging. core/multi_encoder_nn.py:66-87 (_build_inputs zero-pad + unstack, _build_targets),
  * multinn_composer.py:73-87 (stack axis=3, reshape, [:, :-1] / [:, 1:] shift), multinn_jamming.py:60-68.

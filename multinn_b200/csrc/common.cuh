@@ -9,7 +9,7 @@
 #define MNN_ERR_WORKSPACE (-3)
 
 void mnn_set_error(const char* msg);
-int mnn_check_launch(const char* what);
+int mnn_check_launch(const char* what, int kernels = 1);  // also counts kernel launches
 
 #define MNN_REQUIRE(cond, code, msg) \
   do {                               \

@@ -174,5 +174,5 @@ extern "C" int mnn_gemm_f32(const float* A, long long lda, int transA, const flo
     }
   }
   gemm_f32_kernel<<<grid, GT, 0, stream>>>(g);
-  return mnn_check_launch("gemm_f32");
+  return mnn_check_launch("gemm_f32", (splits > 1 && beta != 1.f) ? 2 : 1);
 }

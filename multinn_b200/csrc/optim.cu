@@ -86,7 +86,7 @@ static int reduce_impl(const float* x, size_t n, void* ws, float* out, float sca
   if (sq) reduce_stage1<true><<<nb, kRedThreads, 0, stream>>>(x, n, partial);
   else reduce_stage1<false><<<nb, kRedThreads, 0, stream>>>(x, n, partial);
   reduce_stage2<<<1, 256, 0, stream>>>(partial, nb, out, scale, accumulate);
-  return mnn_check_launch("reduce");
+  return mnn_check_launch("reduce", 2);
 }
 
 extern "C" int mnn_sum(const float* x, size_t n, void* ws, float* out, float scale, int accumulate,

@@ -1,5 +1,6 @@
 // Library-level plumbing: version, last-error string, launch checks. No global mutable state
 // beyond the thread-local error message.
+#include <atomic>
 #include <stdio.h>
 #include <string.h>
 
@@ -13,7 +14,10 @@ void mnn_set_error(const char* msg) {
   g_err[sizeof(g_err) - 1] = 0;
 }
 
-int mnn_check_launch(const char* what) {
+static std::atomic<unsigned long long> g_launches{0};
+
+int mnn_check_launch(const char* what, int kernels) {
+  g_launches.fetch_add((unsigned long long)kernels, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
@@ -23,4 +27,5 @@ int mnn_check_launch(const char* what) {
 }
 
 extern "C" int mnn_version(void) { return 100; }
+extern "C" unsigned long long mnn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" const char* mnn_last_error_string(void) { return g_err; }

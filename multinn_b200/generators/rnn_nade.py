@@ -1,0 +1,163 @@
+"""RNN-NADE generator (mirrors reference models/generators/rnn_nade.py:21-326) generalised over M tracks so that
+RnnMultiNADE (rnn_multinade.py) is the same code path with M > 1.
+
+Pipeline per sequence batch (time-major, rows n' = t*B + b):
+  LSTM stack -> Dense `fc[N, M*(H+D)]` (rnn_nade.py:54-57, :212) -> column split [M*H | M*D]
+  (rnn_nade.py:234-251, rnn_multinade.py:231-256; the NADE kernels read the columns in place) ->
+  teacher-forced NADE NLL per track (common/nade.py:155-229).
+Training = fwd + analytic backward of the same graph tf.gradients would differentiate (generator.py:176-205).
+"""
+import torch
+
+from .. import ops
+from ..common.nade import NADE, NADEBank
+from ..params import glorot_uniform, zeros
+from .rnn_estimator import RnnEstimator, RnnEstimatorStateTuple
+
+
+class RnnNade(RnnEstimator):
+    def __init__(self, num_dims, num_hidden, num_hidden_rnn, keep_prob=1.0, internal_bias=False, name='rnn-nade',
+                 track_name='all', arena=None, num_inputs=None, num_tracks=1):
+        if internal_bias:
+            raise NotImplementedError('internal_bias=True is not used by any MultINN mode for NADE generators')
+        self._num_tracks = num_tracks
+        super().__init__(arena, num_inputs if num_inputs is not None else num_dims * num_tracks, num_dims,
+                         num_hidden, num_hidden_rnn, keep_prob, internal_bias, name, track_name)
+        self._ws = {}
+        self._saved = None
+
+    # -------------------------------------------------------------- construction
+    def _init_estimator(self):
+        M, D, H = self._num_tracks, self._num_dims, self._num_hidden[-1]
+        r_top = self._num_hidden_rnn[-1]
+        units = M * (D + H)
+        self._fc_kernel = self._arena.add(f'{self.name}/dense/kernel', (r_top, units), glorot_uniform(r_top, units))
+        self._fc_bias = self._arena.add(f'{self.name}/dense/bias', (units,), zeros())
+        self._bank = NADEBank(self._arena, M, D, H, name=f'{self.name}/nade')
+        self._nades = [NADE(D, H, bank=self._bank, track=m, name=f'{self.name}/nade{m}') for m in range(M)]
+
+    num_tracks = property(lambda s: s._num_tracks)
+    num_outputs = property(lambda s: s._num_tracks * s._num_dims)
+    enc_col0 = 0
+    dec_col0 = property(lambda s: s._num_tracks * s._num_hidden[-1])
+
+    @property
+    def trainable_params(self):
+        return self._rnn.trainable_params + [self._fc_kernel, self._fc_bias] + self._bank.trainable_params
+
+    def zero_state(self, batch_size, device='cuda'):
+        """generator.py zero_state; rnn_multinade.py:223-229 (quirk Q6 implemented as intended)."""
+        M, D, H = self._num_tracks, self._num_dims, self._num_hidden[-1]
+        fc = torch.zeros(batch_size, M * (H + D), device=device)
+        return self._state_from_fc(fc, self._rnn.zero_state(batch_size, device))
+
+    # -------------------------------------------------------------- state helpers
+    def _state_from_fc(self, fc, rnn_state):
+        """_build_biases: track m's b_enc = cols [m*H,(m+1)*H), b_dec = cols [M*H + m*D, ...)."""
+        M, D, H = self._num_tracks, self._num_dims, self._num_hidden[-1]
+        be = [fc[:, m * H:(m + 1) * H] for m in range(M)]
+        bd = [fc[:, M * H + m * D:M * H + (m + 1) * D] for m in range(M)]
+        st = RnnEstimatorStateTuple(be if M > 1 else be[0], bd if M > 1 else bd[0], rnn_state)
+        self._last_fc = fc
+        return st
+
+    def _fc_of(self, state):
+        be0 = state.b_enc[0] if isinstance(state.b_enc, (list, tuple)) else state.b_enc
+        # b_enc of track 0 starts at column 0 of the Dense buffer it is a view of
+        M, D, H = self._num_tracks, self._num_dims, self._num_hidden[-1]
+        return be0.as_strided((be0.shape[0], M * (H + D)), (be0.stride(0), 1))
+
+    def _workspace(self, N, device, training):
+        key = (N, training)
+        ws = self._ws.get(key)
+        if ws is None:
+            M, D, H = self._num_tracks, self._num_dims, self._num_hidden[-1]
+            U = M * (H + D)
+            ws = dict(fc=torch.empty(N, U, device=device), nll=torch.empty(M, N, device=device),
+                      loss=torch.zeros(1, device=device))
+            if training:
+                ws['dfc'] = torch.empty(N, U, device=device)
+                ws['dout'] = torch.empty(N, self._num_hidden_rnn[-1], device=device)
+            self._ws = {key: ws}
+        return ws
+
+    def _get_state(self, inputs, lengths=None, initial_state=None, last_outputs=False, keep=1.0, u_drop=None,
+                   seed=0, training=False):
+        """rnn_nade.py:173-232. inputs[T,B,I] time-major (or [B,I] = one step). Full lengths only."""
+        if lengths is not None:
+            raise NotImplementedError('variable `lengths` (padded flatten) is a next-row item; pass None')
+        if inputs.dim() == 2:
+            inputs = inputs.unsqueeze(0)
+        T, B, _ = inputs.shape
+        rnn_init = None if initial_state is None else initial_state.rnn_state
+        outs, rnn_state = self._rnn.forward_sequence(inputs.contiguous(), keep=keep, u=u_drop, seed=seed,
+                                                     initial_state=rnn_init)
+        if last_outputs:
+            fc = torch.empty(B, self._fc_kernel.shape[1], device=inputs.device)
+            ops.gemm(outs[T - 1], self._fc_kernel.data, fc, bias=self._fc_bias.data)
+            rnn_state = [type(s)(s[0].clone(), s[1].clone()) for s in rnn_state]
+        else:
+            ws = self._workspace(T * B, inputs.device, training)
+            fc = ws['fc']
+            ops.gemm(outs.reshape(T * B, -1), self._fc_kernel.data, fc, bias=self._fc_bias.data)
+        self._outs = outs
+        return self._state_from_fc(fc, rnn_state)
+
+    # -------------------------------------------------------------- teacher-forced likelihood
+    def log_prob(self, inputs, bits, keep=1.0, u_drop=None, seed=0, cond_probs=False):
+        """rnn_nade.py:279-302 / rnn_multinade.py:258-290. inputs[T,B,I], bits[M,T*B,4] target masks.
+        Returns (nll[M,N'] positive, cond_p[M,N',D] or None); rows n' = t*B + b."""
+        T, B, _ = inputs.shape
+        self._get_state(inputs, keep=keep, u_drop=u_drop, seed=seed)
+        ws = self._ws[(T * B, False)]
+        cp = None
+        if cond_probs:
+            cp = torch.empty(self._num_tracks, T * B, self._num_dims, device=inputs.device)
+        ops.nade_logprob_fwd(bits, ws['fc'], self.enc_col0, self.dec_col0, self._bank.w_enc.data,
+                             self._bank.w_dec.data, ws['nll'], cond_p=cp)
+        return ws['nll'], cp
+
+    def forward_backward(self, inputs, bits, keep=None, u_drop=None, seed=0, loss_scale=1.0, need_dx=False):
+        """One training pass: loss = loss_scale * mean_m mean_n NLL (statistical.py:34; rnn_multinade.py:200-203)
+        and its gradient wrt every trainable parameter (written into the arena's grad buffer; NADE weight grads
+        are ACCUMULATED, so the caller zeroes the grad buffer once per step). Returns (loss[1], nll[M,N'], dx)."""
+        keep = self._keep_prob if keep is None else keep
+        T, B, _ = inputs.shape
+        N, M = T * B, self._num_tracks
+        self._get_state(inputs, keep=keep, u_drop=u_drop, seed=seed, training=True)
+        ws = self._ws[(N, True)]
+        gscale = loss_scale / (N * M)
+        ops.nade_logprob_fwd(bits, ws['fc'], self.enc_col0, self.dec_col0, self._bank.w_enc.data,
+                             self._bank.w_dec.data, ws['nll'], dfc=ws['dfc'], gscale=gscale)
+        ops.sum_into(ws['nll'], ws['loss'], scale=gscale)
+        ops.nade_logprob_bwd(bits, ws['fc'], self.enc_col0, self.dec_col0, self._bank.w_enc.data,
+                             self._bank.w_dec.data, ws['dfc'], self._bank.w_enc.grad, self._bank.w_dec.grad)
+        outs = self._outs.reshape(N, -1)
+        ops.gemm(outs, ws['dfc'], self._fc_kernel.grad, transA=True)
+        ops.colsum(ws['dfc'], self._fc_bias.grad)
+        ops.gemm(ws['dfc'], self._fc_kernel.data, ws['dout'], transB=True)
+        dx = self._rnn.backward_sequence(ws['dout'].view(T, B, -1), need_dx=need_dx)
+        return ws['loss'], ws['nll'], dx
+
+    # -------------------------------------------------------------- generation
+    def single_step(self, inputs, initial_state):
+        """rnn_nade.py:253-277: one RNN step + Dense -> new biases."""
+        out, rnn_state = self._rnn.step(inputs, initial_state.rnn_state)
+        fc = torch.empty(inputs.shape[0], self._fc_kernel.shape[1], device=inputs.device)
+        ops.gemm(out, self._fc_kernel.data, fc, bias=self._fc_bias.data)
+        return self._state_from_fc(fc, rnn_state)
+
+    def sample_single(self, inputs, state, u=None, seed=0, offset=0, out=None, temperature=1.0):
+        """rnn_nade.py:304-318 / rnn_multinade.py:292-317: NADE.sample(temperature=1.) per track, tracks stacked
+        with axis=2 then flattened: feature index d*M + m. u[M,B,D] uniforms or None (Philox). `inputs` unused."""
+        fc = self._fc_of(state)
+        B = fc.shape[0]
+        M, D = self._num_tracks, self._num_dims
+        if out is None:
+            out = torch.empty(B, M * D, device=fc.device)
+        nll = torch.empty(M, B, device=fc.device)
+        sampling = temperature is not None
+        ops.nade_sample(fc, self.enc_col0, self.dec_col0, self._bank.w_enc.data, self._bank.w_dec.data, out,
+                        out.stride(0), M, 1, u=u.contiguous() if (sampling and u is not None) else None,
+                        use_philox=sampling and u is None, seed=seed, offset=offset, nll=nll)
+        return out, nll

@@ -1,0 +1,65 @@
+"""Composer MultINN (mirrors reference models/multinn/multinn_composer.py:17-199): per-track encoders, ONE
+generator with a shared temporal unit and per-track NADEs (RnnMultiNADE) over the stacked encodings."""
+import torch
+
+from ..generators.rnn_multinade import RnnMultiNADE
+from .core import MultINNCore
+
+
+class MultINNComposer(MultINNCore):
+    def __init__(self, config, params, name='MultINN-composer', **kw):
+        super().__init__(config, params, name=name, **kw)
+        self._mode = 'composer'
+
+    def _init_encoders(self, encoder_class):
+        nh = self._params['encoder']['num_hidden']
+        encs = [encoder_class(num_dims=self.num_dims, num_hidden=nh, track_name=t, arena=self._enc_arena,
+                              name=f'encoder/{t}') for t in self.tracks]
+        self._num_dims_generator = encs[0].num_outputs
+        return encs
+
+    def _init_generators(self, generator_class):
+        if self.generator_type == 'RBM':
+            raise NotImplementedError("MultiRNNRBM is not implemented yet :(")     # multinn_composer.py:44-45
+        g = self._params['generator']
+        self._generator = RnnMultiNADE(num_dims=self._num_dims_generator, num_hidden=g['num_hidden'],
+                                       num_hidden_rnn=g['num_hidden_rnn'], tracks=self.tracks,
+                                       keep_prob=self.keep_prob, arena=self._arena, name='generator')
+        return [self._generator]
+
+    def _require_pass(self):
+        if self.encoder_type != 'Pass':
+            raise NotImplementedError('Composer with DBN encoders: use feedback/joint modes or Pass encoders')
+
+    def _forward_backward(self, x, keep, u_drop, seed):
+        self._require_pass()
+        B, T, D, M = x.shape
+        st = self._stage_inputs(x, stacked=True, bits=True)
+        # inputs = slots 0..T-1 ([0, x_0..x_{T-2}]), targets = slots 1..T (multinn_composer.py:82-86)
+        loss, nll, _ = self._generator.forward_backward(st['xin'][:T], st['bits'], keep=keep, u_drop=u_drop, seed=seed)
+        self._last_nll = (nll, T, B)
+        return loss
+
+    def evaluate(self, x, lengths=None, cond_probs=False):
+        """is_train=False forward: per-row NLL[N,M] (rows n = b*T + t), `batch/loss` = mean over tracks of the
+        per-track means (metrics/statistical.py:34, rnn_multinade.py:200-203)."""
+        self._require_pass()
+        x = self._check_x(x, lengths)
+        B, T, D, M = x.shape
+        st = self._stage_inputs(x, stacked=True, bits=True)
+        nll, cp = self._generator.log_prob(st['xin'][:T], st['bits'], cond_probs=cond_probs)
+        out = {'nll': self.rows_to_reference_order(nll, T, B)}
+        out['batch/loss'] = out['log_likelihood'] = out['nll'].mean(0).mean()
+        if cp is not None:
+            out['cond_probs'] = cp.view(M, T, B, D).permute(2, 1, 3, 0).reshape(B * T, D, M)
+        self._metrics.update(out)
+        return out
+
+    def generate(self, x, num_steps, u=None, seed=0):
+        """multinn_composer.py:114-151. x[B,Ti,D,M] intro -> samples[B,num_steps,D,M]; u[num_steps,M,B,D]."""
+        self._require_pass()
+        x = self._check_x(x, None)
+        B, T, D, M = x.shape
+        st = self._stage_inputs(x, stacked=True)
+        samples = self._generator.generate(st['xin'], num_steps, u=u, seed=seed)     # whole padded intro
+        return samples.view(B, num_steps, D, M)

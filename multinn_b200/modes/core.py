@@ -1,0 +1,186 @@
+"""MultINN core (mirrors reference models/multinn/core/{multinn_interface,multinn_core,multi_encoder_nn}.py).
+
+The reference builds one TF graph around placeholders x[B,T,D,M], lengths[B], is_train and runs it with
+sess.run; here the same pipeline (inputs -> encoders -> generators -> metrics, multinn_core.py:178-244) is a
+set of eager methods on device tensors:
+  train_generators(optimizer, lr) -> step(x, ...) -> loss      (one sess.run of train.py:186-189)
+  evaluate(x) -> {'batch/loss', 'log_likelihood', 'nll'}       (is_train=False forward)
+  generate(x_intro, num_steps) / sampler(num_beats)            (multinn_core.py:324-341)
+Inputs are staged once per call by the K0 kernel (zero-pad, unstack/stack, shift, target bit masks).
+"""
+import abc
+
+import torch
+
+from .. import ops
+from ..common.model import Model
+from ..encoders.pass_encoder import PassEncoder
+from ..params import ParamArena
+from ..training import AdamOptimizer, GradientApplier, GradientDescentOptimizer
+
+
+class MultINNCore(Model, abc.ABC):
+    def __init__(self, config, params, name='MultINN', device='cuda', seed=23):
+        super().__init__(name=name)
+        self._mode = 'core'
+        self._config, self._params = config, params
+        self._device = torch.device(device)
+        self._encoder_type = params['encoder']['type']
+        self._generator_type = params['generator']['type']
+        if self._encoder_type == 'Pass':
+            encoder_class = PassEncoder
+        elif self._encoder_type in ('RBM', 'DBN'):
+            from ..encoders.dbn_encoder import DBNEncoder
+            encoder_class = DBNEncoder
+        else:
+            raise ValueError('Incorrect encoder type, supported types are `Pass`, `RBM`, and `DBN`')
+        if self._generator_type == 'RBM':
+            from ..generators.rnn_rbm import RnnRBM
+            generator_class = RnnRBM
+        elif self._generator_type == 'NADE':
+            from ..generators.rnn_nade import RnnNade
+            generator_class = RnnNade
+        else:
+            raise ValueError('Incorrect generator type, supported types are `RBM`, and `NADE`')
+        pr = config['data']['pitch_range']
+        self._num_dims = (pr['highest'] - pr['lowest']) * config['training']['num_pixels']   # multinn_core.py:57-58
+        self._tracks = list(config['data']['instruments'])
+        self._feedback_module = False
+        self._keep_prob = params['keep_prob']
+        self._tune_encoder = params['tune_encoder']
+        self._placeholders = {'x': None, 'lengths': None, 'is_train': None}
+        self._enc_arena = ParamArena()      # encoders are trained separately (train_encoders.py) and frozen here
+        self._arena = ParamArena()          # generators (+ feedback module): one flat bucket
+        self._encoders = self._init_encoders(encoder_class)
+        self._generators = self._init_generators(generator_class)
+        self._enc_arena.finalize(self._device, seed=seed + 1)
+        self._arena.finalize(self._device, seed=seed)
+        self._applier = None
+        self._stage = {}
+
+    # ------------------------------------------------------------------ properties (multinn_interface.py)
+    mode = property(lambda s: s._mode)
+    num_dims = property(lambda s: s._num_dims)
+    tracks = property(lambda s: s._tracks)
+    num_tracks = property(lambda s: len(s._tracks))
+    encoder_type = property(lambda s: s._encoder_type)
+    generator_type = property(lambda s: s._generator_type)
+    encoders = property(lambda s: s._encoders)
+    generators = property(lambda s: s._generators)
+    feedback_module = property(lambda s: s._feedback_module)
+    keep_prob = property(lambda s: s._keep_prob)
+    tune_encoder = property(lambda s: s._tune_encoder)
+    placeholders = property(lambda s: s._placeholders)
+    arena = property(lambda s: s._arena)
+    encoder_arena = property(lambda s: s._enc_arena)
+
+    @property
+    def trainable_params(self):
+        return list(self._arena.params)
+
+    @abc.abstractmethod
+    def _init_encoders(self, encoder_class):
+        ...
+
+    @abc.abstractmethod
+    def _init_generators(self, generator_class):
+        ...
+
+    # ------------------------------------------------------------------ input staging (K0)
+    def _check_x(self, x, lengths):
+        if x.dim() != 4 or x.shape[2] != self.num_dims or x.shape[3] != self.num_tracks:
+            raise ValueError(f'x must be [batch, time, {self.num_dims}, {self.num_tracks}], got {tuple(x.shape)}')
+        if lengths is not None and int(lengths.min()) != x.shape[1]:
+            raise NotImplementedError('variable sequence lengths are not supported yet (all BASELINE configs '
+                                      'use full lengths)')
+        if not x.is_cuda:
+            raise ValueError('x must be a CUDA tensor: multinn_b200 has no CPU path')
+        return x.contiguous().float()
+
+    def _stage_inputs(self, x, stacked=False, per_track=False, bits=False):
+        """core/multi_encoder_nn.py:66-87: zero-pad one step in front of time + unstack tracks (+ Composer's
+        stack/reshape, multinn_composer.py:73-80). Returns time-major tensors (T+1 slots)."""
+        B, T, D, M = x.shape
+        key = (B, T)
+        st = self._stage.get(key)
+        if st is None:
+            st = self._stage = {key: {}}
+            st = st[key]
+        else:
+            pass
+        dev = x.device
+        if stacked and 'xin' not in st:
+            st['xin'] = torch.empty(T + 1, B, D * M, device=dev)
+        if per_track and 'xtr' not in st:
+            st['xtr'] = torch.empty(M, T + 1, B, D, device=dev)
+        if bits and 'bits' not in st:
+            st['bits'] = torch.empty(M, T * B, 4, dtype=torch.int32, device=dev)
+        ops.pack_pianoroll(x, st['xin'] if stacked else None, st['xtr'] if per_track else None,
+                           st['bits'] if bits else None)
+        return st
+
+    @staticmethod
+    def rows_to_reference_order(t, T, B):
+        """[..., T*B] time-major rows -> [B*T, ...] in the reference's flatten order n = b*T + t
+        (utils/sequences.py:22-24), moving the leading (track) axis last."""
+        M = t.shape[0]
+        return t.view(M, T, B).permute(2, 1, 0).reshape(B * T, M)
+
+    # ------------------------------------------------------------------ training
+    def _make_optimizer(self, optimizer, lr):
+        if isinstance(optimizer, str):
+            optimizer = AdamOptimizer(lr) if optimizer.lower() == 'adam' else GradientDescentOptimizer(lr)
+        return optimizer
+
+    def train_generators(self, optimizer='adam', lr=0.01, separate_losses=False):
+        """Returns `step(x, lengths=None, u_drop=None, seed=None) -> loss` (device scalar): one fwd + bwd +
+        allreduce + clip + apply, the unit train.py:186-189 runs per batch piece. Quirk Q7: always joint."""
+        opt = self._make_optimizer(optimizer, lr)
+        self._applier = GradientApplier(self._arena, opt, lr=lr)
+        counter = [0]
+
+        def step(x, lengths=None, u_drop=None, seed=None, keep=None):
+            x = self._check_x(x, lengths)
+            self._applier.zero_grad()
+            s = counter[0] if seed is None else seed
+            counter[0] += 1
+            loss = self._forward_backward(x, keep=self._keep_prob if keep is None else keep, u_drop=u_drop,
+                                          seed=s * 1000003)
+            self._applier.apply()
+            self._metrics['batch/loss'] = loss
+            return loss
+
+        return step
+
+    @abc.abstractmethod
+    def _forward_backward(self, x, keep, u_drop, seed):
+        ...
+
+    @abc.abstractmethod
+    def evaluate(self, x, lengths=None):
+        ...
+
+    @abc.abstractmethod
+    def generate(self, x, num_steps, u=None, seed=0):
+        ...
+
+    def sampler(self, num_beats):
+        """multinn_core.py:324-341: returns `sample(x_intro, u=None) -> [B,num_steps,D,M]`."""
+        dc = self._config['data']
+        pitch_span = dc['pitch_range']['highest'] - dc['pitch_range']['lowest']
+        num_steps = num_beats * dc['beat_resolution'] * pitch_span // self.num_dims
+        return lambda x, u=None, seed=0: self.generate(x, num_steps, u=u, seed=seed)
+
+    # ------------------------------------------------------------------ checkpoints (model.py:180-234: trainable vars only)
+    def state_dict(self):
+        return {'generators': self._arena.state_dict(), 'encoders': self._enc_arena.state_dict()}
+
+    def load_state_dict(self, sd):
+        self._arena.load_state_dict(sd.get('generators', {}))
+        self._enc_arena.load_state_dict(sd.get('encoders', {}))
+
+    def save(self, path):
+        torch.save(self.state_dict(), path)
+
+    def load(self, path):
+        self.load_state_dict(torch.load(path, map_location='cpu'))

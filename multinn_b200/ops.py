@@ -1,0 +1,152 @@
+"""Thin torch-tensor wrappers over the C ABI (include/multinn_b200.h). torch is plumbing only: device
+memory, the current CUDA stream and torch.distributed. Every op launches on torch's current stream.
+"""
+import torch
+
+from ._lib import check, lib
+
+GEMM_MODE = "f32"  # "f32": CUDA-core exact fp32 GEMM; "tc": tcgen05 3xTF32 GEMM (fp32-accurate)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ValueError("multinn_b200 ops need CUDA tensors (no CPU fallback)")
+    if t.dtype not in (torch.float32, torch.int32, torch.uint8, torch.float64):
+        raise ValueError(f"unsupported dtype {t.dtype}")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _rowstride(t):
+    assert t.dim() == 2 and t.stride(1) == 1, "need a row-major 2-D view"
+    return t.stride(0)
+
+
+def pack_pianoroll(x, xin=None, xtr=None, bits=None):
+    """x[B,T,D,M] -> xin[T+1,B,D*M], xtr[M,T+1,B,D], bits[M,T*B,4] (any subset)."""
+    B, T, D, M = x.shape
+    assert x.is_contiguous()
+    check(lib.mnn_pack_pianoroll(_ptr(x), _ptr(xin), _ptr(xtr), _ptr(bits), B, T, D, M, _stream()), "pack_pianoroll")
+
+
+def pack_rows(v, bits, D=None, dim_stride=1):
+    """bits[N,4] of a binary matrix view v[N, ...] (element (n,d) at v[n*ld + d*dim_stride])."""
+    N = v.shape[0]
+    ld = v.stride(0)
+    D = D if D is not None else v.shape[1]
+    check(lib.mnn_pack_rows(_ptr(v), ld, dim_stride, _ptr(bits), N, D, _stream()), "pack_rows")
+
+
+def gemm(A, B, C, transA=False, transB=False, bias=None, alpha=1.0, beta=0.0):
+    """C[M,N] = alpha * op(A) op(B) + beta * C (+ bias). A, B, C are row-major 2-D views (row stride free)."""
+    M, N = C.shape
+    K = A.shape[0] if transA else A.shape[1]
+    assert (A.shape[1] if transA else A.shape[0]) == M
+    assert (B.shape[1] if transB else B.shape[0]) == K and (B.shape[0] if transB else B.shape[1]) == N
+    check(lib.mnn_gemm_f32(_ptr(A), _rowstride(A), int(transA), _ptr(B), _rowstride(B), int(transB), _ptr(C),
+                           _rowstride(C), _ptr(bias), float(alpha), float(beta), M, N, K, _stream()), "gemm_f32")
+
+
+def colsum(A, out, accumulate=False):
+    rows, cols = A.shape
+    check(lib.mnn_colsum(_ptr(A), _rowstride(A), rows, cols, _ptr(out), int(accumulate), _stream()), "colsum")
+
+
+def lstm_cell_fwd(gates, c_prev, c, h, out=None, dscale=None, u=None, keep=1.0, seed=0, offset=0):
+    B, R4 = gates.shape
+    check(lib.mnn_lstm_cell_fwd(_ptr(gates), _ptr(c_prev), _ptr(c), _ptr(h), _ptr(out), _ptr(dscale), _ptr(u),
+                                float(keep), seed, offset, B, R4 // 4, _stream()), "lstm_cell_fwd")
+
+
+def lstm_seq_fwd(gates, wh, hbuf, cbuf, out=None, dscale=None, u=None, keep=1.0, seed=0):
+    T, B, R4 = gates.shape
+    assert gates.is_contiguous() and hbuf.is_contiguous() and cbuf.is_contiguous()
+    assert wh.stride(1) == 1 and wh.stride(0) == R4
+    check(lib.mnn_lstm_seq_fwd(_ptr(gates), _ptr(wh), _ptr(hbuf), _ptr(cbuf), _ptr(out), _ptr(dscale), _ptr(u),
+                               float(keep), seed, T, B, R4 // 4, _stream()), "lstm_seq_fwd")
+
+
+def lstm_seq_bwd(gates, wh, cbuf, dout, dscale, dh_work, dc_work):
+    T, B, R4 = gates.shape
+    check(lib.mnn_lstm_seq_bwd(_ptr(gates), _ptr(wh), _ptr(cbuf), _ptr(dout), _ptr(dscale), _ptr(dh_work),
+                               _ptr(dc_work), T, B, R4 // 4, _stream()), "lstm_seq_bwd")
+
+
+def nade_logprob_fwd(bits, fc, enc_col0, dec_col0, w_enc, w_dec, nll, cond_p=None, dfc=None, gscale=0.0):
+    M, D, H = w_enc.shape
+    N = fc.shape[0]
+    check(lib.mnn_nade_logprob_fwd(_ptr(bits), _ptr(fc), _rowstride(fc), enc_col0, dec_col0, _ptr(w_enc), _ptr(w_dec),
+                                   _ptr(nll), _ptr(cond_p), _ptr(dfc), float(gscale), N, M, D, H, _stream()),
+          "nade_logprob_fwd")
+
+
+def nade_logprob_bwd(bits, fc, enc_col0, dec_col0, w_enc, w_dec, dfc, dw_enc, dw_dec):
+    M, D, H = w_enc.shape
+    N = fc.shape[0]
+    check(lib.mnn_nade_logprob_bwd(_ptr(bits), _ptr(fc), _rowstride(fc), enc_col0, dec_col0, _ptr(w_enc), _ptr(w_dec),
+                                   _ptr(dfc), _ptr(dw_enc), _ptr(dw_dec), N, M, D, H, _stream()), "nade_logprob_bwd")
+
+
+def nade_sample(fc, enc_col0, dec_col0, w_enc, w_dec, out, out_ld, out_dim_stride, out_track_stride, u=None,
+                use_philox=False, seed=0, offset=0, nll=None):
+    M, D, H = w_enc.shape
+    N = fc.shape[0]
+    check(lib.mnn_nade_sample(_ptr(fc), _rowstride(fc), enc_col0, dec_col0, _ptr(w_enc), _ptr(w_dec), _ptr(u),
+                              int(use_philox), seed, offset, _ptr(out), out_ld, out_dim_stride, out_track_stride,
+                              _ptr(nll), N, M, D, H, _stream()), "nade_sample")
+
+
+def bias_sigmoid_sample(pre, bias=None, u=None, p=None, s=None, use_philox=False, seed=0, offset=0):
+    """p = sigmoid(pre + bias); s = float(u < p). bias is [C]/[1,C] (broadcast) or [N,C] (per row)."""
+    N, Cc = pre.shape
+    ld_bias = 0
+    if bias is not None and bias.dim() == 2 and bias.shape[0] == N and N > 1:
+        ld_bias = bias.stride(0)
+    check(lib.mnn_bias_sigmoid_sample(_ptr(pre), _rowstride(pre), _ptr(bias), ld_bias, _ptr(u),
+                                      _rowstride(u) if u is not None else 0, int(use_philox), seed, offset,
+                                      _ptr(p), _rowstride(p) if p is not None else 0, _ptr(s),
+                                      _rowstride(s) if s is not None else 0, N, Cc, _stream()), "bias_sigmoid_sample")
+
+
+def rbm_free_energy(pre, bh, v, bv, F):
+    N, H = pre.shape
+    D = v.shape[1]
+    ld_bh = bh.stride(0) if (bh.dim() == 2 and bh.shape[0] == N and N > 1) else 0
+    ld_bv = bv.stride(0) if (bv.dim() == 2 and bv.shape[0] == N and N > 1) else 0
+    check(lib.mnn_rbm_free_energy(_ptr(pre), _rowstride(pre), _ptr(bh), ld_bh, _ptr(v), _rowstride(v), _ptr(bv),
+                                  ld_bv, _ptr(F), N, H, D, _stream()), "rbm_free_energy")
+
+
+_ws = {}
+
+
+def _reduce_ws(device):
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    if key not in _ws:
+        _ws[key] = torch.empty(int(lib.mnn_reduce_workspace_bytes()), dtype=torch.uint8, device=device)
+    return _ws[key]
+
+
+def sum_into(x, out, scale=1.0, accumulate=False):
+    check(lib.mnn_sum(_ptr(x), x.numel(), _ptr(_reduce_ws(x.device)), _ptr(out), float(scale), int(accumulate),
+                      _stream()), "sum")
+
+
+def sqnorm_into(x, out):
+    check(lib.mnn_sqnorm(_ptr(x), x.numel(), _ptr(_reduce_ws(x.device)), _ptr(out), _stream()), "sqnorm")
+
+
+def clip_adam(p, g, m, v, sqnorm, step, lr, grad_scale=1.0, clip_norm=5.0, beta1=0.9, beta2=0.999, eps=1e-4):
+    check(lib.mnn_clip_adam(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(sqnorm), float(grad_scale),
+                            float(clip_norm), float(lr), float(beta1), float(beta2), float(eps), int(step), _stream()),
+          "clip_adam")
+
+
+def clip_sgd(p, g, sqnorm, lr, grad_scale=1.0, clip_norm=5.0):
+    check(lib.mnn_clip_sgd(_ptr(p), _ptr(g), p.numel(), _ptr(sqnorm), float(grad_scale), float(clip_norm), float(lr),
+                           _stream()), "clip_sgd")

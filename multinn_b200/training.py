@@ -1,0 +1,73 @@
+"""Optimiser step and data-parallel exchange (mirrors reference utils/training.py:151-177 compute_gradients and
+train.py:61-64): grads of `batch/loss` over the listed variables -> clip_by_global_norm(5.) -> TF-style Adam
+(epsilon on the uncorrected sqrt(v)) or SGD. Data parallel: ONE NCCL allreduce of the flat fp32 gradient
+buffer per step, before the clip (the clip must see the global-batch gradient)."""
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+class AdamOptimizer:
+    """tf.train.AdamOptimizer(learning_rate, epsilon=1e-4) as constructed at train.py:64."""
+
+    def __init__(self, learning_rate=0.01, beta1=0.9, beta2=0.999, epsilon=1e-4):
+        self.lr, self.beta1, self.beta2, self.epsilon = learning_rate, beta1, beta2, epsilon
+        self.kind = 'adam'
+
+
+class GradientDescentOptimizer:
+    """tf.train.GradientDescentOptimizer (train.py:61-62, --sgd)."""
+
+    def __init__(self, learning_rate=0.01):
+        self.lr = learning_rate
+        self.kind = 'sgd'
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+class GradientApplier:
+    """compute_gradients(): allreduce -> global norm -> clip -> apply, over one contiguous arena range."""
+
+    def __init__(self, arena, optimizer, lr=None, clip_norm=5.0, offset=0, length=None):
+        self.arena, self.opt = arena, optimizer
+        self.lr = optimizer.lr if lr is None else lr
+        self.clip_norm = clip_norm                      # hard-coded 5. in the reference (training.py:166, quirk Q13)
+        self.offset = offset
+        self.length = arena.size - offset if length is None else length
+        self.step_count = 0
+        self.sqnorm = torch.zeros(1, device=arena.flat.device)
+        if optimizer.kind == 'adam':
+            arena.ensure_slots()
+
+    def _rng(self, t):
+        return t[self.offset:self.offset + self.length]
+
+    def zero_grad(self):
+        self._rng(self.arena.grad).zero_()
+
+    def apply(self):
+        g = self._rng(self.arena.grad)
+        rank, ws = world()
+        grad_scale = 1.0
+        if ws > 1:
+            dist.all_reduce(g)                          # sum of per-rank mean-loss grads; averaged below
+            grad_scale = 1.0 / ws
+        ops.sqnorm_into(g, self.sqnorm)
+        self.step_count += 1
+        p = self._rng(self.arena.flat)
+        if self.opt.kind == 'adam':
+            ops.clip_adam(p, g, self._rng(self.arena.m), self._rng(self.arena.v), self.sqnorm, self.step_count,
+                          self.lr, grad_scale=grad_scale, clip_norm=self.clip_norm, beta1=self.opt.beta1,
+                          beta2=self.opt.beta2, eps=self.opt.epsilon)
+        else:
+            ops.clip_sgd(p, g, self.sqnorm, self.lr, grad_scale=grad_scale, clip_norm=self.clip_norm)
+
+    def grad_norm(self):
+        """Global gradient norm of the last step (after averaging over ranks)."""
+        _, ws = world()
+        return float(self.sqnorm.sqrt()) / ws

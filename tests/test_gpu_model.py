@@ -1,0 +1,196 @@
+"""GPU parity tests, model level: the Composer / Jamming modes through the public MultINN interface against
+the CPU oracle (same inputs, same weights, same uniforms). BASELINE: per-step NLL within 1e-4 relative (fp32),
+sampled piano-rolls bit-exact given the same uniform-noise tensors."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_oracle as O
+from oracle import torch_ref as R
+
+pytestmark = pytest.mark.gpu
+
+
+def make(mode, keep_prob=1.0, H=256, Rnn=(512, 256), **kw):
+    from multinn_b200.multinn import MultINN, default_config, default_params
+    return MultINN(default_config(), default_params(mode=mode, num_hidden=H, num_hidden_rnn=Rnn, keep_prob=keep_prob,
+                                                    **kw), mode)
+
+
+def load_rnn_nade(model, prefix, p, multi):
+    a = model.arena
+    for l, (k, b) in enumerate(p['lstm']):
+        a.load(f'{prefix}/rnn/cell_{l}/kernel', k)
+        a.load(f'{prefix}/rnn/cell_{l}/bias', b)
+    a.load(f'{prefix}/dense/kernel', p['dense'][0])
+    a.load(f'{prefix}/dense/bias', p['dense'][1])
+    nade = p['nade'] if multi else [p['nade']]
+    a.load(f'{prefix}/nade/w_enc', np.stack([n[0] for n in nade]))
+    a.load(f'{prefix}/nade/w_dec', np.stack([n[1] for n in nade]))
+
+
+def arena_to_params(model, prefix, L, multi):
+    sd = model.arena.state_dict()
+    lstm = [(sd[f'{prefix}/rnn/cell_{l}/kernel'].numpy(), sd[f'{prefix}/rnn/cell_{l}/bias'].numpy()) for l in range(L)]
+    we, wd = sd[f'{prefix}/nade/w_enc'].numpy(), sd[f'{prefix}/nade/w_dec'].numpy()
+    nade = [(we[m], wd[m]) for m in range(we.shape[0])]
+    return dict(lstm=lstm, dense=(sd[f'{prefix}/dense/kernel'].numpy(), sd[f'{prefix}/dense/bias'].numpy()),
+                nade=nade if multi else nade[0])
+
+
+def test_mode_and_type_errors():
+    from multinn_b200.multinn import MultINN, default_config, default_params
+    with pytest.raises(ValueError):
+        MultINN(default_config(), default_params(), 'orchestra')
+    with pytest.raises(ValueError):
+        MultINN(default_config(), default_params(encoder='CNN'), 'composer')
+    with pytest.raises(ValueError):
+        MultINN(default_config(), default_params(generator='GAN'), 'jamming')
+    with pytest.raises(NotImplementedError):
+        MultINN(default_config(), default_params(generator='RBM'), 'composer')
+
+
+@pytest.mark.parametrize("B,T", [(8, 16), (256, 128)])
+def test_composer_nll_parity(B, T):
+    """Config C2 = Composer [256,128,84,5]: per-row NLL vs the fp64 loop oracle, <= 1e-4 relative."""
+    model = make('composer')
+    p = O.init_composer_params(seed=23)
+    load_rnn_nade(model, 'generator', p, multi=True)
+    x = O.synthetic_pianoroll(B, T, seed=23)
+    out = model.evaluate(torch.from_numpy(x).cuda())
+    ref = O.composer_forward(x.astype(np.float64), O.cast_params(p, np.float64))
+    np.testing.assert_allclose(out['nll'].cpu().numpy(), ref['nll'], rtol=1e-4)
+    assert abs(float(out['batch/loss']) - ref['loss']) / ref['loss'] < 1e-5
+
+
+def test_composer_cond_probs_and_ragged_batch():
+    model = make('composer', H=128, Rnn=(64,))
+    x = O.synthetic_pianoroll(3, 5, seed=5, density=0.3)
+    out = model.evaluate(torch.from_numpy(x).cuda(), cond_probs=True)
+    p = arena_to_params(model, 'generator', 1, True)
+    ref = O.composer_forward(x.astype(np.float64), O.cast_params(p, np.float64))
+    np.testing.assert_allclose(out['nll'].cpu().numpy(), ref['nll'], rtol=1e-4)
+    cp = out['cond_probs'].cpu().numpy()                 # [N,D,M]
+    np.testing.assert_allclose(cp.transpose(2, 0, 1), ref['cond_p'], rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("keep", [1.0, 0.9])
+def test_composer_training_trajectory(keep):
+    """>= 8 optimiser steps: loss curve and final weights vs torch-autograd + TF-Adam oracle (fp64)."""
+    B, T, H, Rn = 6, 10, 128, (96, 64)
+    model = make('composer', keep_prob=keep, H=H, Rnn=Rn)
+    p32 = arena_to_params(model, 'generator', 2, True)
+    params = R.to_torch(p32, torch.float64, requires_grad=True)
+    leaves = R.flat_params(params)
+    opt = R.TFAdam(leaves, lr=0.01)
+    step = model.train_generators('adam', 0.01)
+    rng = np.random.default_rng(1)
+    for it in range(8):
+        x = O.synthetic_pianoroll(B, T, seed=100 + it, density=0.1)
+        u = [rng.random((T, B, r), dtype=np.float32) for r in Rn] if keep < 1 else None
+        ref_loss, _ = R.composer_train_step(torch.tensor(x, dtype=torch.float64), params, opt, keep,
+                                            None if u is None else [torch.tensor(a, dtype=torch.float64) for a in u])
+        loss = step(torch.from_numpy(x).cuda(), u_drop=None if u is None else [torch.from_numpy(a).cuda() for a in u])
+        assert abs(float(loss) - ref_loss) / ref_loss < 2e-4, (it, float(loss), ref_loss)
+    got = arena_to_params(model, 'generator', 2, True)
+    for a, b in zip(R.flat_params(R.to_torch(got, torch.float64)), leaves):
+        assert float((a - b.detach()).abs().max()) < 2e-3 * max(1e-2, float(b.detach().abs().max()))
+
+
+def test_composer_gradients_match_autograd():
+    B, T, H, Rn = 4, 7, 128, (64, 32)
+    model = make('composer', H=H, Rnn=Rn)
+    p32 = arena_to_params(model, 'generator', 2, True)
+    params = R.to_torch(p32, torch.float64, requires_grad=True)
+    x = O.synthetic_pianoroll(B, T, seed=3, density=0.15)
+    loss, _ = R.composer_loss(torch.tensor(x, dtype=torch.float64), params)
+    grads = torch.autograd.grad(loss, R.flat_params(params))
+    core = model._model
+    xd = core._check_x(torch.from_numpy(x).cuda(), None)
+    core.arena.grad.zero_()
+    l = core._forward_backward(xd, keep=1.0, u_drop=None, seed=0)
+    assert abs(float(l) - float(loss)) / float(loss) < 1e-5
+    named = core.arena.named()
+    names = ['generator/rnn/cell_0/kernel', 'generator/rnn/cell_0/bias', 'generator/rnn/cell_1/kernel',
+             'generator/rnn/cell_1/bias', 'generator/dense/kernel', 'generator/dense/bias']
+    for n, g in zip(names, grads[:6]):
+        got = named[n].grad.cpu().double()
+        assert float((got - g).norm() / g.norm()) < 1e-4, n
+    gwe = torch.stack([grads[6 + 2 * m] for m in range(5)])
+    gwd = torch.stack([grads[7 + 2 * m] for m in range(5)])
+    assert float((named['generator/nade/w_enc'].grad.cpu().double() - gwe).norm() / gwe.norm()) < 1e-4
+    assert float((named['generator/nade/w_dec'].grad.cpu().double() - gwd).norm() / gwd.norm()) < 1e-4
+
+
+def test_composer_generate_bit_exact():
+    """512-step style autoregressive sampling (shortened): identical uniforms -> identical piano-rolls."""
+    B, Ti, S = 5, 6, 12
+    model = make('composer', H=128, Rnn=(64, 32))
+    p = arena_to_params(model, 'generator', 2, True)
+    x = O.synthetic_pianoroll(B, Ti, seed=9, density=0.1)
+    u = np.random.default_rng(2).random((S, 5, B, 84), dtype=np.float32)
+    got = model.generate(torch.from_numpy(x).cuda(), S, u=torch.from_numpy(u).cuda()).cpu().numpy()
+    ref = O.composer_generate(x.astype(np.float64), O.cast_params(p, np.float64), S, u.astype(np.float64))
+    assert got.shape == (B, S, 84, 5)
+    np.testing.assert_array_equal(got, ref)
+    thr = model.generate(torch.from_numpy(x).cuda(), 3, u=None, seed=0)
+    assert set(np.unique(thr.cpu().numpy())) <= {0.0, 1.0}
+
+
+def test_jamming_parity_and_training():
+    """Config C1 = Jamming LSTM-NADE: NLL parity + joint clip/Adam over the union of the 5 generators."""
+    B, T, H, Rn = 4, 9, 128, (48, 32)
+    model = make('jamming', H=H, Rnn=Rn)
+    M = 5
+    plist = [arena_to_params(model, f'generator/{t}', 2, False) for t in model.tracks]
+    x = O.synthetic_pianoroll(B, T, seed=4, density=0.1)
+    out = model.evaluate(torch.from_numpy(x).cuda())
+    tp = [R.to_torch(p, torch.float64, requires_grad=True) for p in plist]
+    loss, nll = R.jamming_loss(torch.tensor(x, dtype=torch.float64), tp)
+    np.testing.assert_allclose(out['nll'].cpu().numpy(), nll.detach().numpy(), rtol=1e-4)
+    leaves = R.flat_params(tp)
+    opt = R.TFAdam(leaves, lr=0.01)
+    step = model.train_generators('adam', 0.01)
+    for it in range(4):
+        x = O.synthetic_pianoroll(B, T, seed=40 + it, density=0.1)
+        l, _ = R.jamming_loss(torch.tensor(x, dtype=torch.float64), tp)
+        opt.step(list(torch.autograd.grad(l, leaves)))
+        got = step(torch.from_numpy(x).cuda(), keep=1.0)
+        assert abs(float(got) - float(l)) / float(l) < 2e-4
+
+
+def test_jamming_generate_bit_exact():
+    B, Ti, S = 3, 4, 6
+    model = make('jamming', H=128, Rnn=(32,))
+    x = O.synthetic_pianoroll(B, Ti, seed=6, density=0.1)
+    u = np.random.default_rng(3).random((S, 5, B, 84), dtype=np.float32)
+    got = model.generate(torch.from_numpy(x).cuda(), S, u=torch.from_numpy(u).cuda()).cpu().numpy()
+    for m, t in enumerate(model.tracks):
+        p = O.cast_params(arena_to_params(model, f'generator/{t}', 1, False), np.float64)
+        pm = dict(lstm=p['lstm'], dense=p['dense'], nade=[p['nade']])
+        ref = O.composer_generate(x[..., m:m + 1].astype(np.float64), pm, S, u[:, m:m + 1].astype(np.float64))
+        np.testing.assert_array_equal(got[..., m], ref[..., 0])
+
+
+def test_sgd_step_and_sampler():
+    model = make('composer', H=128, Rnn=(32,))
+    step = model.train_generators('sgd', 0.05)
+    x = torch.from_numpy(O.synthetic_pianoroll(4, 6, seed=1)).cuda()
+    l0 = float(step(x, keep=1.0))
+    for _ in range(5):
+        l1 = float(step(x, keep=1.0))
+    assert l1 < l0
+    sample = model.sampler(1)                      # 1 beat * 12 * 84 // 84 = 12 steps
+    s = sample(x)
+    assert s.shape == (4, 12, 84, 5)
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    model = make('composer', H=128, Rnn=(32,))
+    x = torch.from_numpy(O.synthetic_pianoroll(2, 5, seed=1)).cuda()
+    a = model.evaluate(x)['nll'].clone()
+    model.save(str(tmp_path / 'ck.pt'))
+    other = make('composer', H=128, Rnn=(32,))
+    other.arena.flat.mul_(0.5)
+    other.load(str(tmp_path / 'ck.pt'))
+    assert torch.equal(other.evaluate(x)['nll'], a)
