@@ -48,6 +48,14 @@ int mnn_pack_rows(const float* v, long long ld, int dim_stride, uint32_t* bits, 
 int mnn_gemm_f32(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
                  long long ldc, const float* bias, float alpha, float beta, int M, int N, int K, mnn_stream_t stream);
 
+/* Same contract on the tcgen05 tensor cores with fp32 accuracy (3xTF32 error-compensated splitting, fp32 accumulation
+ * in TMEM); a_exact != 0 promises that A is exactly representable in tf32 (binary piano-roll rows), which drops one
+ * of the three products. Needs 16-byte aligned A/B and lda/ldb % 4 == 0 (TMA); mnn_gemm_tc_supported() tells. */
+int mnn_gemm_tc_supported(const float* A, long long lda, const float* B, long long ldb);
+int mnn_gemm_tc(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+                long long ldc, const float* bias, float alpha, float beta, int M, int N, int K, int a_exact,
+                mnn_stream_t stream);
+
 /* K2 -- LSTM temporal unit. common/rnn.py:104-145 (CudnnCompatibleLSTMCell, gate blocks i,j,f,o, forget_bias 0;
  * DropoutWrapper output_keep_prob; MultiRNNCell), driven like dynamic_decode at generators/rnn_nade.py:204-218.
  * One cell step: gates[B,4R] in = pre-activations, out = activations; out = h/keep*floor(keep+u). */

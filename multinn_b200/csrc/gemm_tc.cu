@@ -1,0 +1,492 @@
+// fp32-accurate GEMM on the 5th-gen tensor cores (tcgen05, kind::tf32) by error-compensated splitting ("3xTF32"):
+//   x = hi + lo, hi = the top 19 bits of the fp32 word (what kind::tf32 reads), lo = x - hi (exact in fp32)
+//   A.B ~= A_hi.B_hi + A_hi.B_lo + A_lo.B_hi      (lo.lo ~ 2^-22 dropped), fp32 accumulation in TMEM.
+// Replaces the tf.matmul / Dense / LSTMBlockCell matmuls of the reference (common/rnn.py:124,
+// generators/rnn_nade.py:54-57,212, generators/rnn_rbm.py:252-253, common/rbm.py:351,370) and the GEMMs
+// tf.gradients derives from them.
+//
+// Pipeline per CTA (persistent over output tiles, optional split-K), 384 threads:
+//   warp 0      TMA producer: raw fp32 tiles of A and B -> smem ring (SWIZZLE_128B), mbarrier complete_tx
+//   warps 8-11  converters: lo = x - trunc_tf32(x) for every element of the stage (same swizzled layout, so it is
+//               a flat elementwise pass), fence.proxy.async, arrive
+//   warp 1      MMA issuer: one thread, 2-3 tcgen05.mma per K=8 step into a double-buffered TMEM accumulator,
+//               tcgen05.commit frees the smem stage / publishes the accumulator
+//   warps 4-7   epilogue: tcgen05.ld 32x32b -> registers -> alpha*acc + bias + beta*C -> global (or red.add for split-K)
+// Operands may be K-major (row-major [rows,K]) or MN-major (row-major [K,rows]); all four combinations are
+// expressed through the UMMA instruction descriptor's a_major/b_major bits, so no transposed copies exist.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "multinn_b200.h"
+
+namespace mnn {
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 32;  // fp32 elements per k-block: one 128-byte swizzle row
+constexpr int kThreads = 384;
+constexpr int kConvThreads = 128;
+constexpr int kEpiThreads = 128;
+
+struct Params {
+  float* C;
+  const float* bias;
+  long long ldc;
+  float alpha, beta;
+  int M, N, K;
+  int tiles_m, tiles_n, splits, kb_total, kb_per_split;
+  int n_products;  // 3, or 2 when A is exactly representable in tf32 (binary piano-roll rows)
+  int atomic;      // split-K: red.global.add into C
+};
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor layout): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 4;   // 16 KB
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // raw + lo for both operands
+  static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024;  // + alignment slack
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+  using C_ = Cfg<BN>;
+  constexpr int STAGES = C_::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[3 * STAGES + 4];
+  __shared__ uint32_t tmem_base_s;
+
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const uint32_t bar_full = smem_u32(&bars[0]);              // [STAGES]
+  const uint32_t bar_conv = smem_u32(&bars[STAGES]);         // [STAGES]
+  const uint32_t bar_empty = smem_u32(&bars[2 * STAGES]);    // [STAGES]
+  const uint32_t bar_tfull = smem_u32(&bars[3 * STAGES]);    // [2]
+  const uint32_t bar_tempty = smem_u32(&bars[3 * STAGES + 2]);  // [2]
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_conv + 8 * s, kConvThreads);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, kEpiThreads);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"((uint32_t)C_::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int n_items = p.tiles_m * p.tiles_n * p.splits;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const int n_blk = w % p.tiles_n, m_blk = (w / p.tiles_n) % p.tiles_m, split = w / (p.tiles_n * p.tiles_m);
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int m0 = m_blk * BM, n0 = n_blk * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t full = bar_full + 8 * stage;
+          mbar_expect_tx(full, C_::A_BYTES + C_::B_BYTES);
+          const uint32_t a_dst = smem0 + stage * C_::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + 2 * C_::A_BYTES;
+          const int k0 = kb * BK;
+          if (!A_MN) {
+            tma_load_2d(a_dst, &map_a, full, k0, m0);                 // box {32 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 32; ++c) tma_load_2d(a_dst + c * (BK * 128), &map_a, full, m0 + 32 * c, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d(b_dst, &map_b, full, k0, n0);                 // box {32 k, BN rows}
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) tma_load_2d(b_dst + c * (BK * 128), &map_b, full, n0 + 32 * c, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13),
+      // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // K-major: 8-row groups 1024 B apart (SBO), LBO unused (=16 B like CUTLASS); k-step = +32 B inside the row.
+      // MN-major: 32-element column chunks BK*128 B apart (LBO), 8-k groups 1024 B apart (SBO); k-step = +1024 B.
+      const uint32_t a_lbo = A_MN ? BK * 128 : 16, b_lbo = B_MN ? BK * 128 : 16;
+      const uint32_t a_kstep = A_MN ? 1024 : 32, b_kstep = B_MN ? 1024 : 32;
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const int split = w / (p.tiles_n * p.tiles_m);
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          mbar_wait(bar_conv + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t a_raw = smem0 + stage * C_::STAGE_BYTES, a_lo = a_raw + C_::A_BYTES;
+          const uint32_t b_raw = a_raw + 2 * C_::A_BYTES, b_lo = b_raw + C_::B_BYTES;
+#pragma unroll
+          for (int j = 0; j < BK / 8; ++j) {
+            const uint64_t da = smem_desc(a_raw + j * a_kstep, a_lbo, 1024);
+            const uint64_t db = smem_desc(b_raw + j * b_kstep, b_lbo, 1024);
+            const uint64_t dbl = smem_desc(b_lo + j * b_kstep, b_lbo, 1024);
+            umma_tf32(tmem_d, da, dbl, idesc, (kb > kb0 || j > 0) ? 1u : 0u);   // small terms first
+            if (p.n_products == 3) {
+              const uint64_t dal = smem_desc(a_lo + j * a_kstep, a_lbo, 1024);
+              umma_tf32(tmem_d, dal, db, idesc, 1u);
+            }
+            umma_tf32(tmem_d, da, db, idesc, 1u);
+          }
+          umma_commit(bar_empty + 8 * stage);   // smem stage reusable once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar_tfull + 8 * acc);        // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ converters: lo = x - trunc_tf32(x)
+    const int t = threadIdx.x - 8 * 32;
+    int stage = 0;
+    uint32_t phase = 0;
+    const int a_vec = (p.n_products == 3) ? C_::A_BYTES / 16 : 0;
+    constexpr int b_vec = C_::B_BYTES / 16;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const int split = w / (p.tiles_n * p.tiles_m);
+      const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(bar_full + 8 * stage, phase);
+        uint8_t* base = smem_gen + (size_t)stage * C_::STAGE_BYTES;
+        const float4* a_raw = reinterpret_cast<const float4*>(base);
+        float4* a_lo = reinterpret_cast<float4*>(base + C_::A_BYTES);
+        const float4* b_raw = reinterpret_cast<const float4*>(base + 2 * C_::A_BYTES);
+        float4* b_lo = reinterpret_cast<float4*>(base + 2 * C_::A_BYTES + C_::B_BYTES);
+        auto split4 = [](float4 x) {
+          float4 r;
+          r.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+          r.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+          r.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+          r.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+          return r;
+        };
+#pragma unroll 4
+        for (int i = t; i < a_vec; i += kConvThreads) a_lo[i] = split4(a_raw[i]);
+#pragma unroll 4
+        for (int i = t; i < b_vec; i += kConvThreads) b_lo[i] = split4(b_raw[i]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
+        mbar_arrive(bar_conv + 8 * stage);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (warps 4..7 -> TMEM lane quadrants 0..3)
+    const int q = warp - 4;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const int n_blk = w % p.tiles_n, m_blk = (w / p.tiles_n) % p.tiles_m, split = w / (p.tiles_n * p.tiles_m);
+      const int row = m_blk * BM + q * 32 + lane;
+      const int n0 = n_blk * BN;
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const bool add_bias = p.bias != nullptr && (!p.atomic || split == 0);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;   // warp-uniform
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+        if (row < p.M) {
+          float* dst = p.C + (size_t)row * p.ldc + col0;
+          const bool full = col0 + 32 <= p.N;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float o = p.alpha * v[i];
+            if (add_bias && (full || col0 + i < p.N)) o += __ldg(p.bias + col0 + i);
+            v[i] = o;
+          }
+          if (p.atomic) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (full || col0 + i < p.N) atomicAdd(dst + i, v[i]);
+          } else if (full && vec_ok) {
+            float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              if (p.beta != 0.f) {
+                const float4 old = d4[i];
+                o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
+              }
+              d4[i] = o;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < p.N) dst[i] = (p.beta != 0.f) ? v[i] + p.beta * dst[i] : v[i];
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C_::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; long long ld; int inner, outer, box_outer;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && ld == o.ld && inner == o.inner && outer == o.outer && box_outer == o.box_outer;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h ^= (size_t)k.ld * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h ^= ((size_t)k.inner << 32 | (uint32_t)k.outer) * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
+    return h ^ (size_t)k.box_outer * 0x165667B19E3779F9ull;
+  }
+};
+
+// 2-D fp32 tensor map over a row-major matrix [outer][inner] with row stride ld; box {32, box_outer}, SWIZZLE_128B.
+static int make_map(const float* ptr, long long ld, int inner, int outer, int box_outer, CUtensorMap* out) {
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  static std::mutex mu;
+  const MapKey key{ptr, ld, inner, outer, box_outer};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return MNN_OK; }
+  }
+  EncodeTiledFn enc = get_encode();
+  MNN_REQUIRE(enc != nullptr, MNN_ERR_UNSUPPORTED, "gemm_tc: cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mnn_set_error("gemm_tc: cuTensorMapEncodeTiled failed");
+    return MNN_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, *out);
+  return MNN_OK;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, cudaStream_t stream) {
+  using C_ = Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_::SMEM);
+    attr_set = true;
+  }
+  const int items = p.tiles_m * p.tiles_n * p.splits;
+  const int grid = items < num_sms() ? items : num_sms();
+  gemm_tc_kernel<BN, A_MN, B_MN><<<grid, kThreads, C_::SMEM, stream>>>(ma, mb, p);
+  return mnn_check_launch("gemm_tc");
+}
+
+template <int BN>
+static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const Params& p,
+                          cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch<BN, false, false>(ma, mb, p, s);
+  if (!a_mn && b_mn) return launch<BN, false, true>(ma, mb, p, s);
+  if (a_mn && !b_mn) return launch<BN, true, false>(ma, mb, p, s);
+  return launch<BN, true, true>(ma, mb, p, s);
+}
+
+}  // namespace tc
+}  // namespace mnn
+
+using namespace mnn;
+
+extern "C" int mnn_gemm_tc_supported(const float* A, long long lda, const float* B, long long ldb) {
+  return ((lda & 3) == 0) && ((ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
+         ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+}
+
+extern "C" int mnn_gemm_tc(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+                           long long ldc, const float* bias, float alpha, float beta, int M, int N, int K, int a_exact,
+                           cudaStream_t stream) {
+  using namespace mnn::tc;
+  MNN_REQUIRE(A && B && C, MNN_ERR_ARG, "gemm_tc: null pointer");
+  MNN_REQUIRE(M > 0 && N > 0 && K > 0, MNN_ERR_ARG, "gemm_tc: non-positive size");
+  MNN_REQUIRE(mnn_gemm_tc_supported(A, lda, B, ldb), MNN_ERR_UNSUPPORTED,
+              "gemm_tc: TMA needs 16-byte aligned operand pointers and row strides that are multiples of 4 floats");
+  const bool a_mn = transA != 0;   // A stored [K,M]: M contiguous
+  const bool b_mn = transB == 0;   // B stored [K,N]: N contiguous
+  const int BN = N > 128 ? 256 : (N > 64 ? 128 : 64);
+
+  Params p{};
+  p.C = C; p.bias = bias; p.ldc = ldc; p.alpha = alpha; p.beta = beta; p.M = M; p.N = N; p.K = K;
+  p.tiles_m = (M + BM - 1) / BM;
+  p.tiles_n = (N + BN - 1) / BN;
+  p.kb_total = (K + BK - 1) / BK;
+  p.n_products = a_exact ? 2 : 3;
+  const int tiles = p.tiles_m * p.tiles_n;
+  int splits = 1;
+  if (tiles * 2 <= num_sms() && p.kb_total >= 32) {
+    splits = num_sms() / tiles;
+    const int maxs = p.kb_total / 8;
+    if (splits > maxs) splits = maxs;
+    if (splits < 1) splits = 1;
+  }
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.atomic = p.splits > 1;
+  if (p.atomic) {
+    // partial sums are red.add-ed into C: bring C to beta*C first (beta is 0 or 1 at every call site)
+    MNN_REQUIRE(beta == 0.f || beta == 1.f, MNN_ERR_UNSUPPORTED, "gemm_tc: split-K needs beta in {0,1}");
+    if (beta == 0.f) cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, stream);
+  }
+
+  CUtensorMap ma, mb;
+  int rc;
+  if (!a_mn) rc = make_map(A, lda, K, M, BM, &ma);     // [M rows][K]   box {32 k, 128 rows}
+  else rc = make_map(A, lda, M, K, BK, &ma);           // [K rows][M]   box {32 m, 32 k}
+  if (rc) return rc;
+  if (!b_mn) rc = make_map(B, ldb, K, N, BN, &mb);     // [N rows][K]   box {32 k, BN rows}
+  else rc = make_map(B, ldb, N, K, BK, &mb);           // [K rows][N]   box {32 n, 32 k}
+  if (rc) return rc;
+
+  if (BN == 256) return dispatch_major<256>(a_mn, b_mn, ma, mb, p, stream);
+  if (BN == 128) return dispatch_major<128>(a_mn, b_mn, ma, mb, p, stream);
+  return dispatch_major<64>(a_mn, b_mn, ma, mb, p, stream);
+}

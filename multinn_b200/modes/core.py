@@ -35,8 +35,7 @@ class MultINNCore(Model, abc.ABC):
         else:
             raise ValueError('Incorrect encoder type, supported types are `Pass`, `RBM`, and `DBN`')
         if self._generator_type == 'RBM':
-            from ..generators.rnn_rbm import RnnRBM
-            generator_class = RnnRBM
+            generator_class = 'RBM'          # resolved lazily by the modes that support it (joint, jamming, ...)
         elif self._generator_type == 'NADE':
             from ..generators.rnn_nade import RnnNade
             generator_class = RnnNade

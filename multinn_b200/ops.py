@@ -42,12 +42,20 @@ def pack_rows(v, bits, D=None, dim_stride=1):
     check(lib.mnn_pack_rows(_ptr(v), ld, dim_stride, _ptr(bits), N, D, _stream()), "pack_rows")
 
 
-def gemm(A, B, C, transA=False, transB=False, bias=None, alpha=1.0, beta=0.0):
-    """C[M,N] = alpha * op(A) op(B) + beta * C (+ bias). A, B, C are row-major 2-D views (row stride free)."""
+def gemm(A, B, C, transA=False, transB=False, bias=None, alpha=1.0, beta=0.0, a_exact=False, mode=None):
+    """C[M,N] = alpha * op(A) op(B) + beta * C (+ bias). A, B, C are row-major 2-D views (row stride free).
+    mode 'tc': tcgen05 3xTF32 (fp32-accurate) kernel; 'f32': CUDA-core fp32 kernel (also used when an operand is
+    not TMA-addressable). a_exact: A holds only tf32-exact values (binary inputs) -> 2 products instead of 3."""
     M, N = C.shape
     K = A.shape[0] if transA else A.shape[1]
     assert (A.shape[1] if transA else A.shape[0]) == M
     assert (B.shape[1] if transB else B.shape[0]) == K and (B.shape[0] if transB else B.shape[1]) == N
+    mode = mode or GEMM_MODE
+    if mode == 'tc' and lib.mnn_gemm_tc_supported(_ptr(A), _rowstride(A), _ptr(B), _rowstride(B)):
+        check(lib.mnn_gemm_tc(_ptr(A), _rowstride(A), int(transA), _ptr(B), _rowstride(B), int(transB), _ptr(C),
+                              _rowstride(C), _ptr(bias), float(alpha), float(beta), M, N, K, int(a_exact), _stream()),
+              "gemm_tc")
+        return
     check(lib.mnn_gemm_f32(_ptr(A), _rowstride(A), int(transA), _ptr(B), _rowstride(B), int(transB), _ptr(C),
                            _rowstride(C), _ptr(bias), float(alpha), float(beta), M, N, K, _stream()), "gemm_f32")
 

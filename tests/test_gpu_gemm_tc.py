@@ -1,0 +1,72 @@
+"""GPU: the tcgen05 3xTF32 GEMM against fp64 matmul for every operand-major combination, ragged shapes,
+split-K, bias/beta epilogues and the a_exact (binary A) 2-product mode. fp32-level accuracy is the contract."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(M, N, K, ta, tb, bias=False, beta=0.0, a_exact=False, seed=0, alpha=1.0):
+    from multinn_b200 import ops
+    rng = np.random.default_rng(seed + M + 3 * N + 7 * K)
+    if a_exact:
+        A = (rng.random((K, M) if ta else (M, K)) < 0.2).astype(np.float32)
+    else:
+        A = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
+    B = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+    bv = rng.standard_normal(N).astype(np.float32) if bias else None
+    C0 = rng.standard_normal((M, N)).astype(np.float32)
+    ref = alpha * ((A.T if ta else A).astype(np.float64) @ (B.T if tb else B).astype(np.float64))
+    if bias:
+        ref = ref + bv
+    ref = ref + beta * C0
+    C = torch.from_numpy(C0.copy()).cuda()
+    ops.gemm(torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), C, transA=bool(ta), transB=bool(tb),
+             bias=None if bv is None else torch.from_numpy(bv).cuda(), alpha=alpha, beta=beta, a_exact=a_exact, mode='tc')
+    torch.cuda.synchronize()
+    got = C.cpu().numpy().astype(np.float64)
+    scale = np.sqrt(K) if not a_exact else np.sqrt(0.2 * K)
+    return float(np.abs(got - ref).max() / scale)
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 1), (0, 0), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 256, 64), (256, 64, 96), (300, 200, 100), (77, 340, 420),
+                                   (1000, 1700, 256), (2048, 2048, 512)])
+def test_gemm_tc_majors(M, N, K, ta, tb):
+    err = _run(M, N, K, ta, tb)
+    assert err < 3e-6, err
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 1), (0, 0), (1, 0)])
+def test_gemm_tc_epilogues(ta, tb):
+    assert _run(200, 340, 256, ta, tb, bias=True) < 3e-6
+    assert _run(200, 340, 256, ta, tb, beta=1.0) < 3e-6
+    assert _run(130, 84, 64, ta, tb, bias=True, beta=1.0, alpha=0.5) < 3e-6
+
+
+def test_gemm_tc_split_k_weight_grad_shapes():
+    # dW = X^T dG with the time*batch rows as the reduction dimension (both operands MN-major)
+    assert _run(420, 2048, 16384, 1, 0) < 3e-6
+    assert _run(256, 1700, 8192, 1, 0, beta=1.0) < 3e-6
+    assert _run(512, 1024, 4096, 1, 0, bias=True) < 3e-6
+
+
+def test_gemm_tc_binary_a_two_products():
+    assert _run(512, 2048, 420, 0, 0, a_exact=True, bias=True) < 3e-6
+    assert _run(420, 512, 4096, 1, 0, a_exact=True) < 3e-6
+
+
+def test_gemm_tc_matches_f32_kernel_on_views():
+    from multinn_b200 import ops
+    rng = np.random.default_rng(1)
+    big = torch.from_numpy(rng.standard_normal((300, 932)).astype(np.float32)).cuda()
+    W = torch.from_numpy(rng.standard_normal((932, 2048)).astype(np.float32)).cuda()
+    C1 = torch.empty(300, 2048, device='cuda')
+    C2 = torch.empty(300, 2048, device='cuda')
+    ops.gemm(big[:, :420], W[:420], C1, mode='tc')
+    ops.gemm(big[:, :420], W[:420], C2, mode='f32')
+    assert float((C1 - C2).abs().max()) < 1e-4
+    ops.gemm(big[:, 420:], W[420:], C1, beta=1.0, mode='tc')
+    ops.gemm(big[:, 420:], W[420:], C2, beta=1.0, mode='f32')
+    assert float((C1 - C2).abs().max()) < 2e-4

@@ -203,13 +203,13 @@ def _lstm_case(T, B, I, R, seed):
     return x, kernel, bias
 
 
-@pytest.mark.parametrize("T,B,I,R,keep", [(9, 5, 84, 64, 1.0), (6, 33, 420, 512, 1.0), (7, 4, 30, 32, 0.8)])
-def test_lstm_sequence_fwd_bwd(T, B, I, R, keep):
+@pytest.mark.parametrize("T,B,I,Rn,keep", [(9, 5, 84, 64, 1.0), (6, 33, 420, 512, 1.0), (7, 4, 30, 32, 0.8)])
+def test_lstm_sequence_fwd_bwd(T, B, I, Rn, keep):
     ops = _ops()
-    x, kernel, bias = _lstm_case(T, B, I, R, seed=T * B)
+    x, kernel, bias = _lstm_case(T, B, I, Rn, seed=T * B)
     rng = np.random.default_rng(9)
-    u = rng.random((T, B, R), dtype=np.float32)
-    dout = rng.standard_normal((T, B, R)).astype(np.float32)
+    u = rng.random((T, B, Rn), dtype=np.float32)
+    dout = rng.standard_normal((T, B, Rn)).astype(np.float32)
     # oracle (fp64 autograd)
     xt = torch.tensor(x.transpose(1, 0, 2), dtype=torch.float64)          # [B,T,I]
     k_t = torch.tensor(kernel, dtype=torch.float64, requires_grad=True)
@@ -218,23 +218,23 @@ def test_lstm_sequence_fwd_bwd(T, B, I, R, keep):
     (outs * torch.tensor(dout.transpose(1, 0, 2), dtype=torch.float64)).sum().backward()
     # device
     xd, kd, bd = dev(x), dev(kernel), dev(bias)
-    gates = torch.empty(T, B, 4 * R, device='cuda')
-    ops.gemm(xd.view(T * B, I), kd[:I], gates.view(T * B, 4 * R), bias=bd)
-    hbuf = torch.zeros(T + 1, B, R, device='cuda')
-    cbuf = torch.zeros(T + 1, B, R, device='cuda')
-    out = torch.empty(T, B, R, device='cuda')
-    dscale = torch.empty(T, B, R, device='cuda')
+    gates = torch.empty(T, B, 4 * Rn, device='cuda')
+    ops.gemm(xd.view(T * B, I), kd[:I], gates.view(T * B, 4 * Rn), bias=bd)
+    hbuf = torch.zeros(T + 1, B, Rn, device='cuda')
+    cbuf = torch.zeros(T + 1, B, Rn, device='cuda')
+    out = torch.empty(T, B, Rn, device='cuda')
+    dscale = torch.empty(T, B, Rn, device='cuda')
     ops.lstm_seq_fwd(gates, kd[I:], hbuf, cbuf, out=out, dscale=dscale, u=dev(u), keep=keep)
     assert rel_err(out.cpu().numpy(), outs.detach().numpy().transpose(1, 0, 2)) < 1e-5
     assert rel_err(cbuf[T].cpu().numpy(), state[0][0].detach().numpy()) < 1e-5
-    dh_work = torch.empty(B, R, device='cuda')
-    dc_work = torch.empty(B, R, device='cuda')
+    dh_work = torch.empty(B, Rn, device='cuda')
+    dc_work = torch.empty(B, Rn, device='cuda')
     ops.lstm_seq_bwd(gates, kd[I:], cbuf, dev(dout), dscale if keep < 1 else None, dh_work, dc_work)
     dk = torch.empty_like(kd)
     db = torch.empty_like(bd)
-    dg = gates.view(T * B, 4 * R)
+    dg = gates.view(T * B, 4 * Rn)
     ops.gemm(xd.view(T * B, I), dg, dk[:I], transA=True)
-    ops.gemm(hbuf[:T].view(T * B, R), dg, dk[I:], transA=True)
+    ops.gemm(hbuf[:T].view(T * B, Rn), dg, dk[I:], transA=True)
     ops.colsum(dg, db)
     assert rel_err(dk.cpu().numpy(), k_t.grad.numpy()) < 2e-5
     assert rel_err(db.cpu().numpy(), b_t.grad.numpy()) < 2e-5
