@@ -72,8 +72,21 @@ int mnn_lstm_seq_fwd(float* gates, const float* wh, float* hbuf, float* cbuf, fl
  * dropped-out outputs; dh_work/dc_work[B,R] scratch. Weight/input grads are then GEMMs over all rows. */
 int mnn_lstm_seq_bwd(float* gates, const float* wh, const float* cbuf, const float* dout, const float* dscale,
                      float* dh_work, float* dc_work, int T, int B, int R, mnn_stream_t stream);
-/* out[c] (+)= sum_r A[r,c] (bias gradients). */
-int mnn_colsum(const float* A, long long ld, int rows, int cols, float* out, int accumulate, mnn_stream_t stream);
+/* The same two sequence passes on the tensor cores: per step one tcgen05 3xTF32 GEMM (h_{t-1}.Wh, resp. dG_{t+1}.Wh^T)
+ * with the LSTM cell (resp. its backward) fused into the epilogue; persistent != 0 runs all T steps in ONE cooperative
+ * launch (CTAs sharing a 128-row batch slab hand h_t / dG_t over through per-slab counters in `ws`). Needs R % 8 == 0.
+ * ws >= mnn_lstm_workspace_bytes(B, R); dc_work[B,R] scratch. Philox dropout differs in stream from the elementwise path. */
+size_t mnn_lstm_workspace_bytes(int B, int R);
+int mnn_lstm_tc_supported(int B, int R);
+int mnn_lstm_seq_fwd_tc(float* gates, const float* wh, float* hbuf, float* cbuf, float* out, float* dscale,
+                        const float* u, float keep, unsigned long long seed, int T, int B, int R, void* ws,
+                        int persistent, mnn_stream_t stream);
+int mnn_lstm_seq_bwd_tc(float* gates, const float* wh, const float* cbuf, const float* dout, const float* dscale,
+                        float* dc_work, int T, int B, int R, void* ws, int persistent, mnn_stream_t stream);
+/* out[c] (+)= sum_r A[r,c] (bias gradients); deterministic two-stage sum, ws >= mnn_colsum_workspace_bytes(cols). */
+size_t mnn_colsum_workspace_bytes(int cols);
+int mnn_colsum(const float* A, long long ld, int rows, int cols, float* out, int accumulate, void* ws,
+               mnn_stream_t stream);
 
 /* K4 -- NADE / MultiNADE teacher-forced log-likelihood. common/nade.py:155-229 (log_prob), :310-329
  * (_cond_prob), utils/auxiliary.py:9-11 (safe_log), generators/rnn_multinade.py:231-290 (bias split, per-track

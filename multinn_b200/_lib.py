@@ -39,7 +39,12 @@ SIGNATURES = {
     "mnn_lstm_cell_fwd": [_p, _p, _p, _p, _p, _p, _p, _f, _u64, _u64, _i, _i, _p],
     "mnn_lstm_seq_fwd": [_p, _p, _p, _p, _p, _p, _p, _f, _u64, _i, _i, _i, _p],
     "mnn_lstm_seq_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
-    "mnn_colsum": [_p, _ll, _i, _i, _p, _i, _p],
+    "mnn_lstm_workspace_bytes": [_i, _i],
+    "mnn_lstm_tc_supported": [_i, _i],
+    "mnn_lstm_seq_fwd_tc": [_p, _p, _p, _p, _p, _p, _p, _f, _u64, _i, _i, _i, _p, _i, _p],
+    "mnn_lstm_seq_bwd_tc": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _i, _p],
+    "mnn_colsum_workspace_bytes": [_i],
+    "mnn_colsum": [_p, _ll, _i, _i, _p, _i, _p, _p],
     "mnn_nade_logprob_fwd": [_p, _p, _ll, _i, _i, _p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _p],
     "mnn_nade_logprob_bwd": [_p, _p, _ll, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "mnn_nade_sample": [_p, _ll, _i, _i, _p, _p, _p, _i, _u64, _u64, _p, _ll, _i, _i, _p, _i, _i, _i, _i, _p],
@@ -51,7 +56,8 @@ SIGNATURES = {
     "mnn_clip_adam": [_p, _p, _p, _p, _sz, _p, _f, _f, _f, _f, _f, _f, _i, _p],
     "mnn_clip_sgd": [_p, _p, _sz, _p, _f, _f, _f, _p],
 }
-_RESTYPES = {"mnn_last_error_string": C.c_char_p, "mnn_launch_count": C.c_ulonglong, "mnn_reduce_workspace_bytes": C.c_size_t}
+_RESTYPES = {"mnn_last_error_string": C.c_char_p, "mnn_launch_count": C.c_ulonglong, "mnn_reduce_workspace_bytes": C.c_size_t,
+             "mnn_colsum_workspace_bytes": C.c_size_t, "mnn_lstm_workspace_bytes": C.c_size_t}
 
 for _name, _args in SIGNATURES.items():
     _fn = getattr(lib, _name, None)

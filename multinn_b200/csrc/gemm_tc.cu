@@ -9,8 +9,8 @@
 //   warp 0      TMA producer: raw fp32 tiles of A and B -> smem ring (SWIZZLE_128B), mbarrier complete_tx
 //   warps 8-11  converters: lo = x - trunc_tf32(x) for every element of the stage (same swizzled layout, so it is
 //               a flat elementwise pass), fence.proxy.async, arrive
-//   warp 1      MMA issuer: one thread, 2-3 tcgen05.mma per K=8 step into a double-buffered TMEM accumulator,
-//               tcgen05.commit frees the smem stage / publishes the accumulator
+//   warp 1      MMA issuer: one thread, 2-3 tcgen05.mma per K=8 step into double-buffered TMEM accumulators (main:
+//               hi.hi, aux: the cross terms), tcgen05.commit frees the smem stage / publishes the accumulators
 //   warps 4-7   epilogue: tcgen05.ld 32x32b -> registers -> alpha*acc + bias + beta*C -> global (or red.add for split-K)
 // Operands may be K-major (row-major [rows,K]) or MN-major (row-major [K,rows]); all four combinations are
 // expressed through the UMMA instruction descriptor's a_major/b_major bits, so no transposed copies exist.
@@ -19,14 +19,12 @@
 #include <mutex>
 #include <unordered_map>
 
-#include "common.cuh"
 #include "multinn_b200.h"
+#include "tc_common.cuh"
 
 namespace mnn {
 namespace tc {
 
-constexpr int BM = 128;
-constexpr int BK = 32;  // fp32 elements per k-block: one 128-byte swizzle row
 constexpr int kThreads = 384;
 constexpr int kConvThreads = 128;
 constexpr int kEpiThreads = 128;
@@ -42,78 +40,14 @@ struct Params {
   int atomic;      // split-K: red.global.add into C
 };
 
-// ------------------------------------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor layout): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
-// version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
-}
-
 template <int BN>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 4;   // 16 KB
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // raw + lo for both operands
-  static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int STAGES = (BN == 128 ? 3 : 4);
+  // two accumulators per tile (main: hi.hi, aux: hi.lo + lo.hi), double buffered across tiles
+  static constexpr int TMEM_COLS = 4 * BN;
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024;  // + alignment slack
 };
 
@@ -196,13 +130,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
-      // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13),
-      // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      // K-major: 8-row groups 1024 B apart (SBO), LBO unused (=16 B like CUTLASS); k-step = +32 B inside the row.
-      // MN-major: 32-element column chunks BK*128 B apart (LBO), 8-k groups 1024 B apart (SBO); k-step = +1024 B.
+      const uint32_t idesc = idesc_tf32(BN, A_MN, B_MN);
+      // K-major (SWIZZLE_128B): 8-row groups 1024 B apart (SBO), LBO unused (=16 B like CUTLASS); k-step = +32 B in the row.
+      // MN-major (SWIZZLE_128B_BASE32B): 32-element column chunks BK*128 B apart (LBO), 4-k-row atoms 512 B apart (SBO);
+      // one K=8 instruction spans two atoms, k-step = +1024 B.
       const uint32_t a_lbo = A_MN ? BK * 128 : 16, b_lbo = B_MN ? BK * 128 : 16;
+      const uint32_t a_sbo = A_MN ? 512 : 1024, b_sbo = B_MN ? 512 : 1024;
+      const uint32_t a_lay = A_MN ? 1 : 2, b_lay = B_MN ? 1 : 2;
       const uint32_t a_kstep = A_MN ? 1024 : 32, b_kstep = B_MN ? 1024 : 32;
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
@@ -211,7 +145,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
+        // main accumulator takes only the hi.hi products: the tensor core truncates its fp32 accumulator on every
+        // instruction, so the error of a chain grows with its length; the small cross terms go to their own chain
+        const uint32_t tmem_d = tmem_base + acc * 2 * BN, tmem_x = tmem_d + BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           mbar_wait(bar_conv + 8 * stage, phase);
@@ -220,15 +156,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t b_raw = a_raw + 2 * C_::A_BYTES, b_lo = b_raw + C_::B_BYTES;
 #pragma unroll
           for (int j = 0; j < BK / 8; ++j) {
-            const uint64_t da = smem_desc(a_raw + j * a_kstep, a_lbo, 1024);
-            const uint64_t db = smem_desc(b_raw + j * b_kstep, b_lbo, 1024);
-            const uint64_t dbl = smem_desc(b_lo + j * b_kstep, b_lbo, 1024);
-            umma_tf32(tmem_d, da, dbl, idesc, (kb > kb0 || j > 0) ? 1u : 0u);   // small terms first
+            const uint64_t da = smem_desc(a_raw + j * a_kstep, a_lbo, a_sbo, a_lay);
+            const uint64_t db = smem_desc(b_raw + j * b_kstep, b_lbo, b_sbo, b_lay);
+            const uint64_t dbl = smem_desc(b_lo + j * b_kstep, b_lbo, b_sbo, b_lay);
+            const uint32_t first = (kb > kb0 || j > 0) ? 1u : 0u;
+            umma_tf32(tmem_x, da, dbl, idesc, first);
             if (p.n_products == 3) {
-              const uint64_t dal = smem_desc(a_lo + j * a_kstep, a_lbo, 1024);
-              umma_tf32(tmem_d, dal, db, idesc, 1u);
+              const uint64_t dal = smem_desc(a_lo + j * a_kstep, a_lbo, a_sbo, a_lay);
+              umma_tf32(tmem_x, dal, db, idesc, 1u);
             }
-            umma_tf32(tmem_d, da, db, idesc, 1u);
+            umma_tf32(tmem_d, da, db, idesc, first);
           }
           umma_commit(bar_empty + 8 * stage);   // smem stage reusable once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -254,14 +191,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         float4* a_lo = reinterpret_cast<float4*>(base + C_::A_BYTES);
         const float4* b_raw = reinterpret_cast<const float4*>(base + 2 * C_::A_BYTES);
         float4* b_lo = reinterpret_cast<float4*>(base + 2 * C_::A_BYTES + C_::B_BYTES);
-        auto split4 = [](float4 x) {
-          float4 r;
-          r.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
-          r.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
-          r.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
-          r.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
-          return r;
-        };
+        auto split4 = [](float4 x) { return tf32_lo4(x); };
 #pragma unroll 4
         for (int i = t; i < a_vec; i += kConvThreads) a_lo[i] = split4(a_raw[i]);
 #pragma unroll 4
@@ -288,14 +218,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int c = 0; c < BN / 32; ++c) {
         const int col0 = n0 + c * 32;
         if (col0 >= p.N) break;   // warp-uniform
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+        float v[32], vx[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * BN + c * 32), v);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * BN + BN + c * 32), vx);
         if (row < p.M) {
           float* dst = p.C + (size_t)row * p.ldc + col0;
           const bool full = col0 + 32 <= p.N;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            float o = p.alpha * v[i];
+            float o = p.alpha * (v[i] + vx[i]);
             if (add_bias && (full || col0 + i < p.N)) o += __ldg(p.bias + col0 + i);
             v[i] = o;
           }
@@ -355,7 +286,7 @@ static EncodeTiledFn get_encode() {
 }
 
 struct MapKey {
-  const void* ptr; long long ld; int inner, outer, box_outer;
+  const void* ptr; long long ld; long long inner, outer; int box_outer;   // box_outer < 0 encodes the MN-major swizzle
   bool operator==(const MapKey& o) const {
     return ptr == o.ptr && ld == o.ld && inner == o.inner && outer == o.outer && box_outer == o.box_outer;
   }
@@ -364,16 +295,18 @@ struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.ptr);
     h ^= (size_t)k.ld * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
-    h ^= ((size_t)k.inner << 32 | (uint32_t)k.outer) * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
+    h ^= ((size_t)k.inner * 0x9E3779B1ull ^ (size_t)k.outer) * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
     return h ^ (size_t)k.box_outer * 0x165667B19E3779F9ull;
   }
 };
 
-// 2-D fp32 tensor map over a row-major matrix [outer][inner] with row stride ld; box {32, box_outer}, SWIZZLE_128B.
-static int make_map(const float* ptr, long long ld, int inner, int outer, int box_outer, CUtensorMap* out) {
+// 2-D fp32 tensor map over a row-major matrix [outer][inner] with row stride ld; box {32, box_outer}; SWIZZLE_128B for
+// K-major tiles, SWIZZLE_128B_ATOM_32B for MN-major tiles (matches UMMA SWIZZLE_128B_BASE32B).
+static int make_map(const float* ptr, long long ld, long long inner, long long outer, int box_outer, bool mn_major,
+                    CUtensorMap* out) {
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   static std::mutex mu;
-  const MapKey key{ptr, ld, inner, outer, box_outer};
+  const MapKey key{ptr, ld, inner, outer, mn_major ? -box_outer : box_outer};
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -386,7 +319,9 @@ static int make_map(const float* ptr, long long ld, int inner, int outer, int bo
   const cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
   const cuuint32_t estr[2] = {1u, 1u};
   const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     mnn_set_error("gemm_tc: cuTensorMapEncodeTiled failed");
@@ -437,6 +372,12 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUt
 
 using namespace mnn;
 
+int mnn_tc_make_map(const float* ptr, long long ld, long long inner, long long outer, int box_outer, bool mn_major,
+                    CUtensorMap* out) {
+  return mnn::tc::make_map(ptr, ld, inner, outer, box_outer, mn_major, out);
+}
+int mnn_tc_num_sms() { return mnn::tc::num_sms(); }
+
 extern "C" int mnn_gemm_tc_supported(const float* A, long long lda, const float* B, long long ldb) {
   return ((lda & 3) == 0) && ((ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
          ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
@@ -452,7 +393,7 @@ extern "C" int mnn_gemm_tc(const float* A, long long lda, int transA, const floa
               "gemm_tc: TMA needs 16-byte aligned operand pointers and row strides that are multiples of 4 floats");
   const bool a_mn = transA != 0;   // A stored [K,M]: M contiguous
   const bool b_mn = transB == 0;   // B stored [K,N]: N contiguous
-  const int BN = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  const int BN = N > 64 ? 128 : 64;
 
   Params p{};
   p.C = C; p.bias = bias; p.ldc = ldc; p.alpha = alpha; p.beta = beta; p.M = M; p.N = N; p.K = K;
@@ -479,14 +420,13 @@ extern "C" int mnn_gemm_tc(const float* A, long long lda, int transA, const floa
 
   CUtensorMap ma, mb;
   int rc;
-  if (!a_mn) rc = make_map(A, lda, K, M, BM, &ma);     // [M rows][K]   box {32 k, 128 rows}
-  else rc = make_map(A, lda, M, K, BK, &ma);           // [K rows][M]   box {32 m, 32 k}
+  if (!a_mn) rc = make_map(A, lda, K, M, BM, false, &ma);    // [M rows][K]   box {32 k, 128 rows}
+  else rc = make_map(A, lda, M, K, BK, true, &ma);           // [K rows][M]   box {32 m, 32 k}
   if (rc) return rc;
-  if (!b_mn) rc = make_map(B, ldb, K, N, BN, &mb);     // [N rows][K]   box {32 k, BN rows}
-  else rc = make_map(B, ldb, N, K, BK, &mb);           // [K rows][N]   box {32 n, 32 k}
+  if (!b_mn) rc = make_map(B, ldb, K, N, BN, false, &mb);    // [N rows][K]   box {32 k, BN rows}
+  else rc = make_map(B, ldb, N, K, BK, true, &mb);           // [K rows][N]   box {32 n, 32 k}
   if (rc) return rc;
 
-  if (BN == 256) return dispatch_major<256>(a_mn, b_mn, ma, mb, p, stream);
   if (BN == 128) return dispatch_major<128>(a_mn, b_mn, ma, mb, p, stream);
   return dispatch_major<64>(a_mn, b_mn, ma, mb, p, stream);
 }

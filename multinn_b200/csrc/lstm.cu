@@ -83,21 +83,41 @@ __global__ void lstm_cell_bwd_kernel(CellBwdArgs a) {
   a.dc[idx] = dc * gf;
 }
 
-// out[c] (+)= sum_r A[r][c]; one block per 32 columns, 8 row-lanes, deterministic.
-__global__ void colsum_kernel(const float* A, long long ld, int rows, int cols, float* out, int accumulate) {
+// out[c] (+)= sum_r A[r][c]. Two deterministic stages: grid (cols/32, RB) blocks each reduce a row range into
+// ws[rb][c]; a second pass adds the RB partials in a fixed order. HBM-bound: every element of A is read once.
+__global__ void colsum_partial_kernel(const float* __restrict__ A, long long ld, int rows, int cols, int rows_per_block,
+                                      float* __restrict__ ws) {
   __shared__ float red[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
-  float s = 0.f;
-  if (c < cols)
-    for (int r = threadIdx.y; r < rows; r += 8) s += A[(size_t)r * ld + c];
-  red[threadIdx.y][threadIdx.x] = s;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (c < cols) {
+    int r = r0 + threadIdx.y;
+    for (; r + 24 < r1; r += 32) {
+      s0 += __ldg(A + (size_t)r * ld + c);
+      s1 += __ldg(A + (size_t)(r + 8) * ld + c);
+      s2 += __ldg(A + (size_t)(r + 16) * ld + c);
+      s3 += __ldg(A + (size_t)(r + 24) * ld + c);
+    }
+    for (; r < r1; r += 8) s0 += __ldg(A + (size_t)r * ld + c);
+  }
+  red[threadIdx.y][threadIdx.x] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (threadIdx.y == 0 && c < cols) {
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    out[c] = accumulate ? out[c] + t : t;
+    ws[(size_t)blockIdx.y * cols + c] = t;
   }
+}
+
+__global__ void colsum_final_kernel(const float* __restrict__ ws, int rb, int cols, float* __restrict__ out,
+                                    int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float t = 0.f;
+  for (int i = 0; i < rb; ++i) t += ws[(size_t)i * cols + c];
+  out[c] = accumulate ? out[c] + t : t;
 }
 
 }  // namespace mnn
@@ -159,9 +179,18 @@ extern "C" int mnn_lstm_seq_bwd(float* gates, const float* wh, const float* cbuf
   return MNN_OK;
 }
 
-extern "C" int mnn_colsum(const float* A, long long ld, int rows, int cols, float* out, int accumulate,
+extern "C" size_t mnn_colsum_workspace_bytes(int cols) { return (size_t)64 * (size_t)cols * sizeof(float); }
+
+extern "C" int mnn_colsum(const float* A, long long ld, int rows, int cols, float* out, int accumulate, void* ws,
                           cudaStream_t stream) {
-  MNN_REQUIRE(A && out && rows > 0 && cols > 0, MNN_ERR_ARG, "colsum: bad argument");
-  colsum_kernel<<<(cols + 31) / 32, dim3(32, 8), 0, stream>>>(A, ld, rows, cols, out, accumulate);
-  return mnn_check_launch("colsum");
+  MNN_REQUIRE(A && out && ws && rows > 0 && cols > 0, MNN_ERR_ARG, "colsum: bad argument");
+  int rb = (rows + 255) / 256;
+  if (rb > 64) rb = 64;
+  int rpb = (rows + rb - 1) / rb;
+  rpb = (rpb + 7) / 8 * 8;
+  rb = (rows + rpb - 1) / rpb;
+  colsum_partial_kernel<<<dim3((cols + 31) / 32, rb), dim3(32, 8), 0, stream>>>(A, ld, rows, cols, rpb,
+                                                                              reinterpret_cast<float*>(ws));
+  colsum_final_kernel<<<(cols + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const float*>(ws), rb, cols, out, accumulate);
+  return mnn_check_launch("colsum", 2);
 }

@@ -5,7 +5,7 @@ import torch
 
 from ._lib import check, lib
 
-GEMM_MODE = "f32"  # "f32": CUDA-core exact fp32 GEMM; "tc": tcgen05 3xTF32 GEMM (fp32-accurate)
+GEMM_MODE = "tc"   # "tc": tcgen05 3xTF32 GEMM (fp32-accurate); "f32": CUDA-core fp32 GEMM (checker / unaligned operands)
 
 
 def _ptr(t):
@@ -60,9 +60,18 @@ def gemm(A, B, C, transA=False, transB=False, bias=None, alpha=1.0, beta=0.0, a_
                            _rowstride(C), _ptr(bias), float(alpha), float(beta), M, N, K, _stream()), "gemm_f32")
 
 
+_colsum_ws = {}
+
+
 def colsum(A, out, accumulate=False):
     rows, cols = A.shape
-    check(lib.mnn_colsum(_ptr(A), _rowstride(A), rows, cols, _ptr(out), int(accumulate), _stream()), "colsum")
+    key = (A.device.index, torch.cuda.current_stream().cuda_stream)
+    need = int(lib.mnn_colsum_workspace_bytes(cols))
+    ws = _colsum_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = _colsum_ws[key] = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=A.device)
+    check(lib.mnn_colsum(_ptr(A), _rowstride(A), rows, cols, _ptr(out), int(accumulate), _ptr(ws), _stream()),
+          "colsum")
 
 
 def lstm_cell_fwd(gates, c_prev, c, h, out=None, dscale=None, u=None, keep=1.0, seed=0, offset=0):
@@ -71,16 +80,43 @@ def lstm_cell_fwd(gates, c_prev, c, h, out=None, dscale=None, u=None, keep=1.0, 
                                 float(keep), seed, offset, B, R4 // 4, _stream()), "lstm_cell_fwd")
 
 
-def lstm_seq_fwd(gates, wh, hbuf, cbuf, out=None, dscale=None, u=None, keep=1.0, seed=0):
+LSTM_MODE = "tc"          # "tc": tcgen05 recurrence with fused cell; "simt": per-step fp32 GEMM + cell kernels
+LSTM_PERSISTENT = True    # one cooperative launch for all T steps (tc mode)
+_lstm_ws = {}
+
+
+def _lstm_workspace(B, R, device):
+    key = (device.index, torch.cuda.current_stream().cuda_stream, B, R)
+    ws = _lstm_ws.get(key)
+    if ws is None:
+        ws = _lstm_ws[key] = torch.empty(int(lib.mnn_lstm_workspace_bytes(B, R)), dtype=torch.uint8, device=device)
+    return ws
+
+
+def lstm_seq_fwd(gates, wh, hbuf, cbuf, out=None, dscale=None, u=None, keep=1.0, seed=0, mode=None, persistent=None):
     T, B, R4 = gates.shape
     assert gates.is_contiguous() and hbuf.is_contiguous() and cbuf.is_contiguous()
     assert wh.stride(1) == 1 and wh.stride(0) == R4
+    mode = mode or LSTM_MODE
+    if mode == "tc" and lib.mnn_lstm_tc_supported(B, R4 // 4):
+        pers = LSTM_PERSISTENT if persistent is None else persistent
+        check(lib.mnn_lstm_seq_fwd_tc(_ptr(gates), _ptr(wh), _ptr(hbuf), _ptr(cbuf), _ptr(out), _ptr(dscale), _ptr(u),
+                                      float(keep), seed, T, B, R4 // 4, _ptr(_lstm_workspace(B, R4 // 4, gates.device)),
+                                      int(pers), _stream()), "lstm_seq_fwd_tc")
+        return
     check(lib.mnn_lstm_seq_fwd(_ptr(gates), _ptr(wh), _ptr(hbuf), _ptr(cbuf), _ptr(out), _ptr(dscale), _ptr(u),
                                float(keep), seed, T, B, R4 // 4, _stream()), "lstm_seq_fwd")
 
 
-def lstm_seq_bwd(gates, wh, cbuf, dout, dscale, dh_work, dc_work):
+def lstm_seq_bwd(gates, wh, cbuf, dout, dscale, dh_work, dc_work, mode=None, persistent=None):
     T, B, R4 = gates.shape
+    mode = mode or LSTM_MODE
+    if mode == "tc" and lib.mnn_lstm_tc_supported(B, R4 // 4):
+        pers = LSTM_PERSISTENT if persistent is None else persistent
+        check(lib.mnn_lstm_seq_bwd_tc(_ptr(gates), _ptr(wh), _ptr(cbuf), _ptr(dout), _ptr(dscale), _ptr(dc_work), T, B,
+                                      R4 // 4, _ptr(_lstm_workspace(B, R4 // 4, gates.device)), int(pers), _stream()),
+              "lstm_seq_bwd_tc")
+        return
     check(lib.mnn_lstm_seq_bwd(_ptr(gates), _ptr(wh), _ptr(cbuf), _ptr(dout), _ptr(dscale), _ptr(dh_work),
                                _ptr(dc_work), T, B, R4 // 4, _stream()), "lstm_seq_bwd")
 

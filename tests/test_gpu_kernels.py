@@ -37,10 +37,10 @@ def test_gemm_f32(M, N, K, ta, tb):
     C0 = rng.standard_normal((M, N)).astype(np.float32)
     ref = (A.T if ta else A).astype(np.float64) @ (B.T if tb else B).astype(np.float64)
     C = dev(C0)
-    ops.gemm(dev(A), dev(B), C, transA=bool(ta), transB=bool(tb))
+    ops.gemm(dev(A), dev(B), C, transA=bool(ta), transB=bool(tb), mode='f32')
     assert rel_err(C.cpu().numpy(), ref) < 2e-6
     C = dev(C0)
-    ops.gemm(dev(A), dev(B), C, transA=bool(ta), transB=bool(tb), bias=dev(bias), alpha=0.5, beta=1.0)
+    ops.gemm(dev(A), dev(B), C, transA=bool(ta), transB=bool(tb), bias=dev(bias), alpha=0.5, beta=1.0, mode='f32')
     assert rel_err(C.cpu().numpy(), 0.5 * ref + C0 + bias) < 2e-6
 
 
@@ -51,7 +51,7 @@ def test_gemm_strided_views():
     A = big[:, 10:80]                      # row stride 300
     W = dev(rng.standard_normal((200, 64)).astype(np.float32))
     C = torch.zeros(100, 128, device='cuda')
-    ops.gemm(A, W[50:120], C[:, 32:96])
+    ops.gemm(A, W[50:120], C[:, 32:96], mode='f32')
     ref = A.double().cpu().numpy() @ W[50:120].double().cpu().numpy()
     assert rel_err(C[:, 32:96].cpu().numpy(), ref) < 2e-6
     assert float(C[:, :32].abs().max()) == 0 and float(C[:, 96:].abs().max()) == 0
@@ -203,8 +203,10 @@ def _lstm_case(T, B, I, R, seed):
     return x, kernel, bias
 
 
-@pytest.mark.parametrize("T,B,I,Rn,keep", [(9, 5, 84, 64, 1.0), (6, 33, 420, 512, 1.0), (7, 4, 30, 32, 0.8)])
-def test_lstm_sequence_fwd_bwd(T, B, I, Rn, keep):
+@pytest.mark.parametrize("mode,persistent", [("simt", False), ("tc", False), ("tc", True)])
+@pytest.mark.parametrize("T,B,I,Rn,keep", [(9, 5, 84, 64, 1.0), (6, 33, 420, 512, 1.0), (7, 4, 30, 32, 0.8),
+                                           (12, 300, 64, 256, 0.9), (5, 130, 20, 48, 1.0), (3, 1100, 16, 96, 1.0)])
+def test_lstm_sequence_fwd_bwd(T, B, I, Rn, keep, mode, persistent):
     ops = _ops()
     x, kernel, bias = _lstm_case(T, B, I, Rn, seed=T * B)
     rng = np.random.default_rng(9)
@@ -219,22 +221,24 @@ def test_lstm_sequence_fwd_bwd(T, B, I, Rn, keep):
     # device
     xd, kd, bd = dev(x), dev(kernel), dev(bias)
     gates = torch.empty(T, B, 4 * Rn, device='cuda')
-    ops.gemm(xd.view(T * B, I), kd[:I], gates.view(T * B, 4 * Rn), bias=bd)
+    ops.gemm(xd.view(T * B, I), kd[:I], gates.view(T * B, 4 * Rn), bias=bd, mode='f32')
     hbuf = torch.zeros(T + 1, B, Rn, device='cuda')
     cbuf = torch.zeros(T + 1, B, Rn, device='cuda')
     out = torch.empty(T, B, Rn, device='cuda')
     dscale = torch.empty(T, B, Rn, device='cuda')
-    ops.lstm_seq_fwd(gates, kd[I:], hbuf, cbuf, out=out, dscale=dscale, u=dev(u), keep=keep)
+    ops.lstm_seq_fwd(gates, kd[I:], hbuf, cbuf, out=out, dscale=dscale, u=dev(u), keep=keep, mode=mode,
+                     persistent=persistent)
     assert rel_err(out.cpu().numpy(), outs.detach().numpy().transpose(1, 0, 2)) < 1e-5
     assert rel_err(cbuf[T].cpu().numpy(), state[0][0].detach().numpy()) < 1e-5
     dh_work = torch.empty(B, Rn, device='cuda')
     dc_work = torch.empty(B, Rn, device='cuda')
-    ops.lstm_seq_bwd(gates, kd[I:], cbuf, dev(dout), dscale if keep < 1 else None, dh_work, dc_work)
+    ops.lstm_seq_bwd(gates, kd[I:], cbuf, dev(dout), dscale if keep < 1 else None, dh_work, dc_work, mode=mode,
+                     persistent=persistent)
     dk = torch.empty_like(kd)
     db = torch.empty_like(bd)
     dg = gates.view(T * B, 4 * Rn)
-    ops.gemm(xd.view(T * B, I), dg, dk[:I], transA=True)
-    ops.gemm(hbuf[:T].view(T * B, Rn), dg, dk[I:], transA=True)
+    ops.gemm(xd.view(T * B, I), dg, dk[:I], transA=True, mode='f32')
+    ops.gemm(hbuf[:T].view(T * B, Rn), dg, dk[I:], transA=True, mode='f32')
     ops.colsum(dg, db)
     assert rel_err(dk.cpu().numpy(), k_t.grad.numpy()) < 2e-5
     assert rel_err(db.cpu().numpy(), b_t.grad.numpy()) < 2e-5
