@@ -185,19 +185,31 @@ __global__ void __launch_bounds__(kFwdThreads, 1) nade_fwd_kernel(NadeArgs p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K5 backward. Thread k owns hidden unit k: its w_dec column and its dW_dec column accumulators live
-// in registers (the i loop is fully unrolled), its dW_enc column accumulators in shared memory, so no
-// reduction over k is ever needed. Walks i = D-1..0 and reverses the prefix (a -= w_enc[i-1]) at each
-// set target bit. Requires the forward kernel to have written dl into the d b_dec columns of dfc.
-constexpr int kBwdRows = 4;
+// K5 backward. Thread k owns hidden unit k: its w_dec column and its dW_dec column accumulators live in registers
+// (the i loop is fully unrolled), its dW_enc column accumulators in shared memory, so no reduction over k is ever
+// needed. Walks i = D-1..0 and reverses the prefix (a -= w_enc[i-1]) at each set target bit. Requires the forward
+// kernel to have written dl into the d b_dec columns of dfc.
+// Rows are staged in batches of kBwdRows through a cp.async double buffer (b_enc row, dl row, target mask), so the
+// global-load latency of batch b+1 hides behind the arithmetic of batch b; two rows are walked at a time to give
+// every thread two independent dependency chains.
+constexpr int kBwdRows = 8;
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src));
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src));
+}
 
 template <int H, int D>
 __global__ void __launch_bounds__(H, 1) nade_bwd_kernel(NadeArgs p) {
+  static_assert(D % 4 == 0, "D must be a multiple of 4");
   extern __shared__ __align__(16) float smem[];
-  float* wenc_s = smem;                       // [D][H]
-  float* acce_s = smem + (size_t)D * H;       // [D][H]
-  float* dl_s = acce_s + (size_t)D * H;       // [kBwdRows][D] (padded to 128)
-  uint32_t* mk_s = reinterpret_cast<uint32_t*>(dl_s + kBwdRows * 128);  // [kBwdRows][kNW]
+  float* wenc_s = smem;                            // [D][H]
+  float* acce_s = smem + (size_t)D * H;            // [D][H]
+  float* a_s = acce_s + (size_t)D * H;             // [2][kBwdRows][H]
+  float* dl_s = a_s + 2 * kBwdRows * H;            // [2][kBwdRows][D]
+  uint32_t* mk_s = reinterpret_cast<uint32_t*>(dl_s + 2 * kBwdRows * D);  // [2][kBwdRows][kNW]
 
   const int m = blockIdx.x % p.M;
   const int cta = blockIdx.x / p.M;
@@ -218,60 +230,141 @@ __global__ void __launch_bounds__(H, 1) nade_bwd_kernel(NadeArgs p) {
   const int enc_col = p.enc_col0 + m * H, dec_col = p.dec_col0 + m * D;
   const int nbatches = (p.N + kBwdRows - 1) / kBwdRows;
 
+  auto prefetch = [&](int batch, int buf) {
+    const int row0 = batch * kBwdRows;
+    float* ab = a_s + (size_t)buf * kBwdRows * H;
+    float* db = dl_s + (size_t)buf * kBwdRows * D;
+    uint32_t* mb = mk_s + buf * kBwdRows * kNW;
+    for (int c = k; c < kBwdRows * H / 4; c += H) {          // b_enc rows, 16 B chunks
+      const int r = c / (H / 4), off = (c % (H / 4)) * 4, row = row0 + r;
+      if (row < p.N) cp_async16(ab + r * H + off, p.fc + (size_t)row * p.ld + enc_col + off);
+      else *reinterpret_cast<float4*>(ab + r * H + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int c = k; c < kBwdRows * D; c += H) {              // dl rows
+      const int r = c / D, i = c - r * D, row = row0 + r;
+      if (row < p.N) cp_async4(db + c, p.dfc + (size_t)row * p.ld + dec_col + i);
+      else db[c] = 0.f;
+    }
+    if (k < kBwdRows) {
+      const int row = row0 + k;
+      if (row < p.N) cp_async16(mb + k * kNW, bits + (size_t)row * kNW);
+      else *reinterpret_cast<uint4*>(mb + k * kNW) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int buf = 0;
+  if (cta < nbatches) prefetch(cta, 0);
+  __syncthreads();   // weights staged
   for (int b = cta; b < nbatches; b += nctas) {
+    const int nb = b + nctas;
+    if (nb < nbatches) {
+      prefetch(nb, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
     const int row0 = b * kBwdRows;
-    __syncthreads();
-    for (int t = threadIdx.x; t < kBwdRows * 128; t += H) {
-      const int r = t >> 7, i = t & 127, row = row0 + r;
-      dl_s[t] = (row < p.N && i < D) ? p.dfc[(size_t)row * p.ld + dec_col + i] : 0.f;
-    }
-    if (threadIdx.x < kBwdRows * kNW) {
-      const int r = threadIdx.x / kNW, row = row0 + r;
-      mk_s[threadIdx.x] = row < p.N ? bits[(size_t)row * kNW + (threadIdx.x % kNW)] : 0u;
-    }
-    __syncthreads();
+    const float* ab = a_s + (size_t)buf * kBwdRows * H;
+    const float* db = dl_s + (size_t)buf * kBwdRows * D;
+    const uint32_t* mb = mk_s + buf * kBwdRows * kNW;
 #pragma unroll 1
-    for (int r = 0; r < kBwdRows; ++r) {
-      const int row = row0 + r;
-      if (row >= p.N) break;
-      uint32_t mk[kNW];
+    for (int r = 0; r < kBwdRows; r += 2) {
+      if (row0 + r >= p.N) break;
+      uint32_t mk0[kNW], mk1[kNW];
 #pragma unroll
-      for (int w = 0; w < kNW; ++w) mk[w] = mk_s[r * kNW + w];
-      float a = p.fc[(size_t)row * p.ld + enc_col + k];
+      for (int w = 0; w < kNW; ++w) { mk0[w] = mb[r * kNW + w]; mk1[w] = mb[(r + 1) * kNW + w]; }
+      float a0 = ab[r * H + k], a1 = ab[(r + 1) * H + k];
       // forward prefix over set bits j < D-1 (bit D-1 opens no segment that any dim reads)
 #pragma unroll
       for (int w = 0; w < kNW; ++w) {
-        uint32_t x = mk[w];
+        uint32_t x0 = mk0[w], x1 = mk1[w];
         if (w * 32 + 32 > D - 1) {
           const int keep = (D - 1) - w * 32;  // number of low bits to keep (may be <= 0)
-          x = keep <= 0 ? 0u : (keep >= 32 ? x : (x & ((1u << keep) - 1u)));
+          const uint32_t msk = keep <= 0 ? 0u : (keep >= 32 ? 0xffffffffu : ((1u << keep) - 1u));
+          x0 &= msk; x1 &= msk;
         }
-        while (x) {
-          const int j = __ffs(x) - 1;
-          x &= x - 1;
-          a += wenc_s[(w * 32 + j) * H + k];
-        }
+        while (x0) { const int j = __ffs(x0) - 1; x0 &= x0 - 1; a0 += wenc_s[(w * 32 + j) * H + k]; }
+        while (x1) { const int j = __ffs(x1) - 1; x1 &= x1 - 1; a1 += wenc_s[(w * 32 + j) * H + k]; }
       }
-      float h = sigmoid_fast(a), ga = 0.f, dh = 0.f;
-      const float* dl = dl_s + r * 128;
+      float h0 = sigmoid_fast(a0), h1 = sigmoid_fast(a1);
+      float ga0 = 0.f, ga1 = 0.f, dh0 = 0.f, dh1 = 0.f;
+      const float* dl0 = db + r * D;
+      const float* dl1 = db + (r + 1) * D;
+      // Segment boundaries (a set target bit j ends the segment that dims > j read) are rare, so the walk over dims is
+      // a jump-table entry into ONE unrolled run of FMAs (Duff's device): the hot code stays a few KB instead of one
+      // boundary block per dim, which overflowed the instruction cache (ncu: stall_no_instruction dominated).
+      uint32_t rm[kNW];   // boundaries still ahead: bit j set <=> stop after dim j + 1
 #pragma unroll
-      for (int i = D - 1; i >= 0; --i) {
-        const float d = dl[i];
-        dh = fmaf(d, wdec[i], dh);
-        accw[i] = fmaf(d, h, accw[i]);
-        if (i > 0) {
-          if (mk[(i - 1) >> 5] & (1u << ((i - 1) & 31))) {  // block-uniform
-            ga += dh * h * (1.f - h);
-            dh = 0.f;
-            acce_s[(i - 1) * H + k] += ga;
-            a -= wenc_s[(i - 1) * H + k];
-            h = sigmoid_fast(a);
-          }
+      for (int w = 0; w < kNW; ++w) {
+        rm[w] = mk0[w] | mk1[w];
+        if (w * 32 + 32 > D - 1) {
+          const int keep = (D - 1) - w * 32;
+          rm[w] &= keep <= 0 ? 0u : (keep >= 32 ? 0xffffffffu : ((1u << keep) - 1u));
         }
       }
-      ga += dh * h * (1.f - h);
-      p.dfc[(size_t)row * p.ld + enc_col + k] = ga;
+      int i = D - 1;
+#pragma unroll 1
+      for (;;) {
+        int s = 0;   // stop position: process dims i..s, then handle the boundary in front of dim s (if s > 0)
+#pragma unroll
+        for (int w = kNW - 1; w >= 0; --w)
+          if (s == 0 && rm[w]) {
+            const int bpos = 31 - __clz(rm[w]);
+            rm[w] &= ~(1u << bpos);
+            s = w * 32 + bpos + 1;
+          }
+        float4 q0 = *reinterpret_cast<const float4*>(dl0 + (i & ~3));
+        float4 q1 = *reinterpret_cast<const float4*>(dl1 + (i & ~3));
+#define MNN_BWD_STEP(I)                                                                                   \
+  case (I):                                                                                               \
+    if constexpr ((I) < D) {                                                                              \
+      if (((I) & 3) == 3) {                                                                               \
+        q0 = *reinterpret_cast<const float4*>(dl0 + ((I) & ~3));                                          \
+        q1 = *reinterpret_cast<const float4*>(dl1 + ((I) & ~3));                                          \
+      }                                                                                                   \
+      const float d0 = ((I) & 3) == 3 ? q0.w : (((I) & 3) == 2 ? q0.z : (((I) & 3) == 1 ? q0.y : q0.x));  \
+      const float d1 = ((I) & 3) == 3 ? q1.w : (((I) & 3) == 2 ? q1.z : (((I) & 3) == 1 ? q1.y : q1.x));  \
+      dh0 = fmaf(d0, wdec[(I) < D ? (I) : 0], dh0);                                                       \
+      dh1 = fmaf(d1, wdec[(I) < D ? (I) : 0], dh1);                                                       \
+      accw[(I) < D ? (I) : 0] = fmaf(d0, h0, fmaf(d1, h1, accw[(I) < D ? (I) : 0]));                      \
+      if ((I) == s) break;                                                                                \
     }
+#define MNN_BWD_STEP4(I) MNN_BWD_STEP((I) + 3) MNN_BWD_STEP((I) + 2) MNN_BWD_STEP((I) + 1) MNN_BWD_STEP(I)
+#define MNN_BWD_STEP16(I) MNN_BWD_STEP4((I) + 12) MNN_BWD_STEP4((I) + 8) MNN_BWD_STEP4((I) + 4) MNN_BWD_STEP4(I)
+        switch (i) {
+          MNN_BWD_STEP16(112) MNN_BWD_STEP16(96) MNN_BWD_STEP16(80) MNN_BWD_STEP16(64)
+          MNN_BWD_STEP16(48) MNN_BWD_STEP16(32) MNN_BWD_STEP16(16) MNN_BWD_STEP16(0)
+          default: break;
+        }
+#undef MNN_BWD_STEP16
+#undef MNN_BWD_STEP4
+#undef MNN_BWD_STEP
+        if (s == 0) break;
+        if (pick_word(mk0, (s - 1) >> 5) & (1u << ((s - 1) & 31))) {  // block-uniform
+          ga0 += dh0 * h0 * (1.f - h0);
+          dh0 = 0.f;
+          acce_s[(s - 1) * H + k] += ga0;
+          a0 -= wenc_s[(s - 1) * H + k];
+          h0 = sigmoid_fast(a0);
+        }
+        if (pick_word(mk1, (s - 1) >> 5) & (1u << ((s - 1) & 31))) {
+          ga1 += dh1 * h1 * (1.f - h1);
+          dh1 = 0.f;
+          acce_s[(s - 1) * H + k] += ga1;
+          a1 -= wenc_s[(s - 1) * H + k];
+          h1 = sigmoid_fast(a1);
+        }
+        i = s - 1;
+      }
+      ga0 += dh0 * h0 * (1.f - h0);
+      ga1 += dh1 * h1 * (1.f - h1);
+      p.dfc[(size_t)(row0 + r) * p.ld + enc_col + k] = ga0;
+      if (row0 + r + 1 < p.N) p.dfc[(size_t)(row0 + r + 1) * p.ld + enc_col + k] = ga1;
+    }
+    __syncthreads();   // everyone is done with `buf` before it is refilled two iterations from now
+    buf ^= 1;
   }
   float* gdd = p.dw_dec + (size_t)m * D * H;
   float* gde = p.dw_enc + (size_t)m * D * H;
@@ -437,7 +530,8 @@ extern "C" int mnn_nade_logprob_fwd(const uint32_t* bits, const float* fc, long 
 
 template <int H, int D>
 static int launch_bwd(const NadeArgs& a, cudaStream_t stream) {
-  const size_t smem = ((size_t)2 * D * H + kBwdRows * 128) * sizeof(float) + kBwdRows * kNW * sizeof(uint32_t);
+  const size_t smem = ((size_t)2 * D * H + 2 * kBwdRows * H + 2 * kBwdRows * D) * sizeof(float) +
+                      2 * kBwdRows * kNW * sizeof(uint32_t);
   cudaFuncSetAttribute(nade_bwd_kernel<H, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int grid = num_sms();
   const int need = a.M * ((a.N + kBwdRows - 1) / kBwdRows);
