@@ -115,6 +115,9 @@ int mnn_nade_sample(const float* fc, long long ld, int enc_col0, int dec_col0, c
 int mnn_bias_sigmoid_sample(const float* pre, long long ld_pre, const float* bias, long long ld_bias, const float* u,
                             long long ld_u, int use_philox, unsigned long long seed, unsigned long long offset,
                             float* p, long long ld_p, float* s, long long ld_s, int N, int C, mnn_stream_t stream);
+/* d(pre) = dy * y * (1 - y): backward of a sigmoid layer (Dense feedback module, common/dnn.py:56-60). */
+int mnn_sigmoid_bwd(const float* y, long long ld_y, const float* dy, long long ld_dy, float* dpre, long long ld_d, int N,
+                    int C, mnn_stream_t stream);
 /* F(v)[n] = -sum_j softplus(pre[n,j] + bh[j]) - v[n].bv, common/rbm.py:256-258 (pre = v.W). */
 int mnn_rbm_free_energy(const float* pre, long long ld_pre, const float* bh, long long ld_bh, const float* v,
                         long long ld_v, const float* bv, long long ld_bv, float* F, int N, int H, int D,
@@ -127,6 +130,8 @@ int mnn_sum(const float* x, size_t n, void* ws, float* out, float scale, int acc
 int mnn_sqnorm(const float* x, size_t n, void* ws, float* out, mnn_stream_t stream);
 int mnn_clip_adam(float* p, const float* g, float* m, float* v, size_t n, const float* sqnorm, float grad_scale,
                   float clip_norm, float lr, float beta1, float beta2, float eps, int step, mnn_stream_t stream);
+/* y += alpha * x (CD-k assign_add, common/rbm.py:322-330). */
+int mnn_axpy(float* y, const float* x, float alpha, size_t n, mnn_stream_t stream);
 int mnn_clip_sgd(float* p, const float* g, size_t n, const float* sqnorm, float grad_scale, float clip_norm,
                  float lr, mnn_stream_t stream);
 

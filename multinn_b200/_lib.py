@@ -49,11 +49,13 @@ SIGNATURES = {
     "mnn_nade_logprob_bwd": [_p, _p, _ll, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "mnn_nade_sample": [_p, _ll, _i, _i, _p, _p, _p, _i, _u64, _u64, _p, _ll, _i, _i, _p, _i, _i, _i, _i, _p],
     "mnn_bias_sigmoid_sample": [_p, _ll, _p, _ll, _p, _ll, _i, _u64, _u64, _p, _ll, _p, _ll, _i, _i, _p],
+    "mnn_sigmoid_bwd": [_p, _ll, _p, _ll, _p, _ll, _i, _i, _p],
     "mnn_rbm_free_energy": [_p, _ll, _p, _ll, _p, _ll, _p, _ll, _p, _i, _i, _i, _p],
     "mnn_reduce_workspace_bytes": [],
     "mnn_sum": [_p, _sz, _p, _p, _f, _i, _p],
     "mnn_sqnorm": [_p, _sz, _p, _p, _p],
     "mnn_clip_adam": [_p, _p, _p, _p, _sz, _p, _f, _f, _f, _f, _f, _f, _i, _p],
+    "mnn_axpy": [_p, _p, _f, _sz, _p],
     "mnn_clip_sgd": [_p, _p, _sz, _p, _f, _f, _f, _p],
 }
 _RESTYPES = {"mnn_last_error_string": C.c_char_p, "mnn_launch_count": C.c_ulonglong, "mnn_reduce_workspace_bytes": C.c_size_t,

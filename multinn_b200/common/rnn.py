@@ -29,13 +29,14 @@ class LSTMStateTuple(tuple):
 class RNN:
     """`RNN(num_units, keep_prob, name)`; `num_units` is the list of layer sizes (rnn.py:27-60)."""
 
-    def __init__(self, arena, num_inputs, num_units, keep_prob=1.0, name='rnn'):
+    def __init__(self, arena, num_inputs, num_units, keep_prob=1.0, name='rnn', binary_inputs=False):
         if isinstance(num_units, int):
             num_units = [num_units]
         self.name = name
         self._num_units = list(num_units)
         self._num_inputs = num_inputs
         self._keep_prob = keep_prob
+        self._binary_inputs = binary_inputs     # layer-0 inputs are exactly {0,1}: 2 tf32 products instead of 3
         self.kernels, self.biases = [], []
         i = num_inputs
         for l, r in enumerate(self._num_units):
@@ -102,7 +103,7 @@ class RNN:
             kern, bias = self.kernels[l].data, self.biases[l].data
             i_l = inp.shape[1]
             gates = w['gates'].view(T * B, 4 * r)
-            ops.gemm(inp, kern[:i_l], gates, bias=bias)            # hoisted input projection, all steps at once
+            ops.gemm(inp, kern[:i_l], gates, bias=bias, a_exact=(l == 0 and self._binary_inputs))   # hoisted input projection
             if initial_state is None:
                 w['hbuf'][0].zero_()
                 w['cbuf'][0].zero_()
@@ -135,7 +136,7 @@ class RNN:
             dg = w['gates'].view(T * B, 4 * r)                       # now d(pre-activations)
             inp = x.view(T * B, I) if l == 0 else \
                 (ws[l - 1]['out'] if dropout else ws[l - 1]['hbuf'][1:]).view(T * B, i_l)
-            ops.gemm(inp, dg, kern.grad[:i_l], transA=True)          # dWx = x^T dG
+            ops.gemm(inp, dg, kern.grad[:i_l], transA=True, a_exact=(l == 0 and self._binary_inputs))   # dWx = x^T dG
             ops.gemm(w['hbuf'][:T].view(T * B, r), dg, kern.grad[i_l:], transA=True)   # dWh = h_{t-1}^T dG
             ops.colsum(dg, self.biases[l].grad)
             if l > 0 or need_dx:

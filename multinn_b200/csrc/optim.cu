@@ -71,9 +71,23 @@ __global__ void clip_sgd_kernel(float* __restrict__ p, const float* __restrict__
     p[i] -= lr * g[i] * s;
 }
 
+__global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float alpha, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = fmaf(alpha, x[i], y[i]);
+}
+
 }  // namespace mnn
 
 using namespace mnn;
+
+// y += alpha * x  (CD-k assign_add of reference common/rbm.py:322-330; gradient accumulation)
+extern "C" int mnn_axpy(float* y, const float* x, float alpha, size_t n, cudaStream_t stream) {
+  MNN_REQUIRE(y && x && n > 0, MNN_ERR_ARG, "axpy: bad argument");
+  int nb = (int)((n + 255) / 256);
+  if (nb > 148 * 8) nb = 148 * 8;
+  axpy_kernel<<<nb, 256, 0, stream>>>(y, x, alpha, n);
+  return mnn_check_launch("axpy");
+}
 
 extern "C" size_t mnn_reduce_workspace_bytes(void) { return kRedBlocks * sizeof(double); }
 

@@ -57,9 +57,27 @@ __global__ void free_energy_kernel(const float* pre, long long ld_pre, const flo
   if (lane == 0) F[row] = -s - d;
 }
 
+// d(pre) = dy * y * (1 - y)  (backward of the sigmoid Dense feedback layers, common/dnn.py:56-60)
+__global__ void sigmoid_bwd_kernel(const float* __restrict__ y, long long ld_y, const float* __restrict__ dy, long long ld_dy,
+                                   float* __restrict__ dpre, long long ld_d, int N, int C) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)N * C) return;
+  const int r = (int)(idx / C), c = (int)(idx - (size_t)r * C);
+  const float yy = y[(size_t)r * ld_y + c];
+  dpre[(size_t)r * ld_d + c] = dy[(size_t)r * ld_dy + c] * yy * (1.f - yy);
+}
+
 }  // namespace mnn
 
 using namespace mnn;
+
+extern "C" int mnn_sigmoid_bwd(const float* y, long long ld_y, const float* dy, long long ld_dy, float* dpre,
+                               long long ld_d, int N, int C, cudaStream_t stream) {
+  MNN_REQUIRE(y && dy && dpre && N > 0 && C > 0, MNN_ERR_ARG, "sigmoid_bwd: bad argument");
+  const size_t n = (size_t)N * C;
+  sigmoid_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(y, ld_y, dy, ld_dy, dpre, ld_d, N, C);
+  return mnn_check_launch("sigmoid_bwd");
+}
 
 extern "C" int mnn_bias_sigmoid_sample(const float* pre, long long ld_pre, const float* bias, long long ld_bias,
                                        const float* u, long long ld_u, int use_philox, unsigned long long seed,

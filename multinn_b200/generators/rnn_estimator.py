@@ -19,11 +19,12 @@ class RnnEstimatorStateTuple(_Base):
 
 class RnnEstimator(Generator, abc.ABC):
     def __init__(self, arena, num_inputs, num_dims, num_hidden, num_hidden_rnn, keep_prob=1.0, internal_bias=False,
-                 name='rnn-estimator', track_name='all'):
+                 name='rnn-estimator', track_name='all', binary_inputs=False):
         super().__init__(num_dims, num_hidden, num_hidden_rnn, keep_prob, internal_bias, name, track_name)
         self._arena = arena
         self._num_inputs = num_inputs
-        self._rnn = RNN(arena, num_inputs, self._num_hidden_rnn, keep_prob=keep_prob, name=f'{name}/rnn')
+        self._rnn = RNN(arena, num_inputs, self._num_hidden_rnn, keep_prob=keep_prob, name=f'{name}/rnn',
+                        binary_inputs=binary_inputs)
         self._init_estimator()
 
     @abc.abstractmethod

@@ -22,7 +22,8 @@ class RnnNade(RnnEstimator):
             raise NotImplementedError('internal_bias=True is not used by any MultINN mode for NADE generators')
         self._num_tracks = num_tracks
         super().__init__(arena, num_inputs if num_inputs is not None else num_dims * num_tracks, num_dims,
-                         num_hidden, num_hidden_rnn, keep_prob, internal_bias, name, track_name)
+                         num_hidden, num_hidden_rnn, keep_prob, internal_bias, name, track_name,
+                         binary_inputs=num_inputs is None)   # own-track / stacked encodings are exactly {0,1}
         self._ws = {}
         self._saved = None
 

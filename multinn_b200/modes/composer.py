@@ -31,7 +31,7 @@ class MultINNComposer(MultINNCore):
         if self.encoder_type != 'Pass':
             raise NotImplementedError('Composer with DBN encoders: use feedback/joint modes or Pass encoders')
 
-    def _forward_backward(self, x, keep, u_drop, seed):
+    def _forward_backward(self, x, keep, u_drop, seed, **extra):
         self._require_pass()
         B, T, D, M = x.shape
         st = self._stage_inputs(x, stacked=True, bits=True)

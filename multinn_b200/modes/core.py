@@ -138,13 +138,13 @@ class MultINNCore(Model, abc.ABC):
         self._applier = GradientApplier(self._arena, opt, lr=lr)
         counter = [0]
 
-        def step(x, lengths=None, u_drop=None, seed=None, keep=None):
+        def step(x, lengths=None, u_drop=None, seed=None, keep=None, **extra):
             x = self._check_x(x, lengths)
             self._applier.zero_grad()
             s = counter[0] if seed is None else seed
             counter[0] += 1
             loss = self._forward_backward(x, keep=self._keep_prob if keep is None else keep, u_drop=u_drop,
-                                          seed=s * 1000003)
+                                          seed=s * 1000003, **extra)
             self._applier.apply()
             self._metrics['batch/loss'] = loss
             return loss
@@ -152,8 +152,8 @@ class MultINNCore(Model, abc.ABC):
         return step
 
     @abc.abstractmethod
-    def _forward_backward(self, x, keep, u_drop, seed):
-        ...
+    def _forward_backward(self, x, keep, u_drop, seed, **extra):
+        """One fwd+bwd over the batch; `extra` carries mode-specific uniform-noise tensors for parity runs."""
 
     @abc.abstractmethod
     def evaluate(self, x, lengths=None):

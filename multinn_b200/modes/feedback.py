@@ -1,0 +1,144 @@
+"""Feedback MultINN (mirrors reference models/multinn/multinn_feedback.py:17-218): per-track encoders and generators;
+every generator's input is [its own track's encoding ; feedback(stacked encodings of ALL tracks)] where the feedback
+module is a sigmoid Dense net (here) or an LSTM stack (feedback_rnn.py). Generators and feedback module are optimised
+jointly with one global-norm clip (multinn_jamming.py:235-243 via inheritance, quirk Q7)."""
+import torch
+
+from .. import ops
+from ..common.dnn import DNN
+from ..generators.rnn_nade import RnnNade
+from .core import MultINNCore
+
+
+class MultINNFeedback(MultINNCore):
+    def __init__(self, config, params, name='MultINN-feedback', **kw):
+        super().__init__(config, params, name=name, **kw)
+        self._mode = 'feedback'
+        self._feedback_module = True
+
+    # ------------------------------------------------------------------ construction
+    def _init_encoders(self, encoder_class):
+        nh = self._params['encoder']['num_hidden']
+        encs = [encoder_class(num_dims=self.num_dims, num_hidden=nh, track_name=t, arena=self._enc_arena,
+                              name=f'encoder/{t}') for t in self.tracks]
+        self._num_dims_generator = encs[0].num_outputs
+        return encs
+
+    def _feedback_units(self):
+        fb = self._params['generator']['feedback']
+        if fb is None:
+            raise ValueError('feedback modes need `generator.feedback`, e.g. [128, 128]')
+        return [fb] if isinstance(fb, int) else list(fb)
+
+    def _init_feedback(self):
+        """multinn_feedback.py:46-52."""
+        return DNN(self._arena, self._num_dims_generator * self.num_tracks, self._feedback_units(), name='feedback')
+
+    def _init_generators(self, generator_class):
+        if generator_class == 'RBM':
+            raise NotImplementedError('RnnRBM generators cannot take [encoding ; feedback] inputs (the Gibbs chain '
+                                      'starts from the input frame, generators/rnn_rbm.py:112)')
+        g = self._params['generator']
+        E, F = self._num_dims_generator, self._feedback_units()[-1]
+        gens = [RnnNade(num_dims=E, num_hidden=g['num_hidden'], num_hidden_rnn=g['num_hidden_rnn'],
+                        keep_prob=self.keep_prob, track_name=t, arena=self._arena, name=f'generator/{t}',
+                        num_inputs=E + F) for t in self.tracks]
+        self._feedback_layer = self._init_feedback()           # after the generators, like the variable order in TF
+        return gens
+
+    # ------------------------------------------------------------------ encodings
+    def _encode(self, x, u_enc=None, seed=0):
+        """Per-track encodings xe[M][(T+1),B,E] of the zero-padded inputs and their stack [(T+1),B,E*M] (feature
+        e*M + m, multinn_feedback.py:67-73), plus target bit masks [M,T*B,4] of xe[m][1:]."""
+        B, T, D, M = x.shape
+        if self.encoder_type == 'Pass':
+            st = self._stage_inputs(x, stacked=True, per_track=True, bits=True)
+            return [st['xtr'][m] for m in range(M)], st['xin'], st['bits']
+        st = self._stage_inputs(x, per_track=True)
+        xe = []
+        for m, enc in enumerate(self._encoders):
+            _, h = enc.encode(st['xtr'][m].view((T + 1) * B, D), u=None if u_enc is None else u_enc[m], seed=seed + 31 * m)
+            xe.append(h.view(T + 1, B, -1))
+        stack = torch.stack(xe, dim=3).reshape(T + 1, B, -1)
+        bits = torch.empty(M, T * B, 4, dtype=torch.int32, device=x.device)
+        for m in range(M):
+            ops.pack_rows(xe[m][1:].reshape(T * B, -1), bits[m])
+        return xe, stack, bits
+
+    def _apply_feedback(self, stack, keep=1.0, u_fb=None, seed=0, save=True):
+        """multinn_feedback.py:99-118: Dense feedback over every (padded) step. stack[(T+1),B,E*M] -> [(T+1),B,F]."""
+        T1, B, _ = stack.shape
+        return self._feedback_layer(stack.reshape(T1 * B, -1), save=save).view(T1, B, -1)
+
+    def _feedback_backward(self, dfb):
+        T1, B, F = dfb.shape
+        self._feedback_layer.backward(dfb.reshape(T1 * B, F))
+
+    # ------------------------------------------------------------------ train / eval
+    def _forward_backward(self, x, keep, u_drop, seed, u_enc=None, u_fb=None, **extra):
+        B, T, D, M = x.shape
+        xe, stack, bits = self._encode(x, u_enc, seed)
+        fb = self._apply_feedback(stack, keep=keep, u_fb=u_fb, seed=seed + 17)
+        E, F = self._num_dims_generator, fb.shape[2]
+        dfb = torch.zeros(T + 1, B, F, device=x.device)
+        total = torch.zeros(1, device=x.device)
+        for m, gen in enumerate(self._generators):
+            inp = torch.cat([xe[m][:T], fb[:T]], dim=2)                       # multinn_feedback.py:86-88
+            loss, nll, dx = gen.forward_backward(inp, bits[m:m + 1], keep=keep,
+                                                 u_drop=None if u_drop is None else u_drop[m],
+                                                 seed=seed + 104729 * m, loss_scale=1.0 / M, need_dx=True)
+            total += loss
+            dfb[:T] += dx[:, :, E:]
+        self._feedback_backward(dfb)
+        return total
+
+    def evaluate(self, x, lengths=None, u_enc=None, seed=0):
+        x = self._check_x(x, lengths)
+        B, T, D, M = x.shape
+        xe, stack, bits = self._encode(x, u_enc, seed)
+        fb = self._apply_feedback(stack, save=False)
+        nll = torch.empty(M, T * B, device=x.device)
+        for m, gen in enumerate(self._generators):
+            n, _ = gen.log_prob(torch.cat([xe[m][:T], fb[:T]], dim=2), bits[m:m + 1])
+            nll[m] = n[0]
+        out = {'nll': self.rows_to_reference_order(nll, T, B)}
+        out['batch/loss'] = out['log_likelihood'] = out['nll'].mean(0).mean()
+        self._metrics.update(out)
+        return out
+
+    # ------------------------------------------------------------------ generation (multinn_feedback.py:120-218)
+    def _feedback_step(self, samples_stack, state):
+        return self._feedback_layer(samples_stack, save=False), state
+
+    def _feedback_intro_state(self):
+        return None
+
+    def generate(self, x, num_steps, u=None, seed=0, u_enc=None, u_dec=None):
+        """x[B,Ti,D,M] -> [B,num_steps,D,M]; u[num_steps,M,B,E] uniforms for the NADE samplers."""
+        x = self._check_x(x, None)
+        B, T, D, M = x.shape
+        E = self._num_dims_generator
+        xe, stack, _ = self._encode(x, u_enc, seed)
+        fb = self._apply_feedback(stack, save=False)
+        fb_state = self._feedback_intro_state()
+        states = [gen.steps(torch.cat([xe[m], fb], dim=2)) for m, gen in enumerate(self._generators)]
+        samples_h = torch.empty(B, num_steps, E, M, device=x.device)
+        prev = None
+        for s in range(num_steps):
+            cur = torch.empty(B, E, M, device=x.device)
+            for m, gen in enumerate(self._generators):
+                tmp = torch.empty(B, E, device=x.device)
+                gen.sample_single(prev, states[m], u=None if u is None else u[s, m:m + 1], seed=seed + 104729 * m,
+                                  offset=s, out=tmp)
+                cur[:, :, m] = tmp
+            samples_h[:, s] = cur
+            x_fb, fb_state = self._feedback_step(cur.reshape(B, E * M), fb_state)
+            states = [gen.single_step(torch.cat([cur[:, :, m], x_fb], dim=1), states[m])
+                      for m, gen in enumerate(self._generators)]
+            prev = cur
+        music = torch.empty(B, num_steps, D, M, device=x.device)
+        for m, enc in enumerate(self._encoders):
+            _, v = enc.decode(samples_h[..., m].reshape(B * num_steps, E), u=None if u_dec is None else u_dec[m],
+                              seed=seed + 977 * m) if enc.stochastic else enc.decode(samples_h[..., m].reshape(B * num_steps, E))
+            music[..., m] = v.view(B, num_steps, D)
+        return music

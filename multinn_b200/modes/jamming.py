@@ -28,7 +28,7 @@ class MultINNJamming(MultINNCore):
         if self.encoder_type != 'Pass':
             raise NotImplementedError('Jamming with DBN encoders is not wired yet')
 
-    def _forward_backward(self, x, keep, u_drop, seed):
+    def _forward_backward(self, x, keep, u_drop, seed, **extra):
         self._require_pass()
         B, T, D, M = x.shape
         st = self._stage_inputs(x, per_track=True, bits=True)

@@ -157,6 +157,12 @@ def bias_sigmoid_sample(pre, bias=None, u=None, p=None, s=None, use_philox=False
                                       _rowstride(s) if s is not None else 0, N, Cc, _stream()), "bias_sigmoid_sample")
 
 
+def sigmoid_bwd(y, dy, dpre):
+    N, Cc = y.shape
+    check(lib.mnn_sigmoid_bwd(_ptr(y), _rowstride(y), _ptr(dy), _rowstride(dy), _ptr(dpre), _rowstride(dpre), N, Cc,
+                              _stream()), "sigmoid_bwd")
+
+
 def rbm_free_energy(pre, bh, v, bv, F):
     N, H = pre.shape
     D = v.shape[1]
@@ -189,6 +195,12 @@ def clip_adam(p, g, m, v, sqnorm, step, lr, grad_scale=1.0, clip_norm=5.0, beta1
     check(lib.mnn_clip_adam(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(sqnorm), float(grad_scale),
                             float(clip_norm), float(lr), float(beta1), float(beta2), float(eps), int(step), _stream()),
           "clip_adam")
+
+
+def axpy(y, x, alpha):
+    """y += alpha * x (contiguous tensors of equal size)."""
+    assert y.is_contiguous() and x.is_contiguous() and y.numel() == x.numel()
+    check(lib.mnn_axpy(_ptr(y), _ptr(x), float(alpha), y.numel(), _stream()), "axpy")
 
 
 def clip_sgd(p, g, sqnorm, lr, grad_scale=1.0, clip_norm=5.0):

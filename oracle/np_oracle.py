@@ -412,3 +412,59 @@ def cast_params(p, dtype):
     if isinstance(p, (list, tuple)):
         return type(p)(cast_params(v, dtype) for v in p)
     return p.astype(dtype)
+
+
+# ----------------------------------------------------------------------------- feedback modes (numpy)
+def dnn_forward(x, layers):
+    """common/dnn.py:97-116."""
+    for K, b in layers:
+        x = sigmoid(x @ K + b)
+    return x
+
+
+def init_dnn(rng, in_dim, units):
+    layers = []
+    i = in_dim
+    for u in units:
+        layers.append((_glorot(rng, i, u), np.zeros((u,), np.float32)))
+        i = u
+    return layers
+
+
+def feedback_generate(xe, gen_params, fb_params, kind, num_steps, u):
+    """multinn_feedback.py:120-218 on given per-track intro encodings xe[m][B,Ti+1,E] (zero-padded).
+    u[S,M,B,E] uniforms. Returns sampled encodings [B,S,E,M] (before encoder.decode)."""
+    M = len(xe)
+    B, T1, E = xe[0].shape
+    stack = np.stack(xe, axis=3).reshape(B, T1, E * M)
+    if kind == 'dense':
+        fb = dnn_forward(stack.reshape(B * T1, -1), fb_params).reshape(B, T1, -1)
+        fb_state = None
+    else:
+        fb, fb_state = rnn_scan(stack, fb_params)
+    states, fcs = [], []
+    for m in range(M):
+        p = gen_params[m]
+        outs, st = rnn_scan(np.concatenate([xe[m], fb], axis=2), p['lstm'])
+        states.append(st)
+        fcs.append(dense(outs[:, -1], *p['dense']))
+    H = gen_params[0]['nade'][0].shape[1]
+    out = np.zeros((B, num_steps, E, M), xe[0].dtype)
+    for s in range(num_steps):
+        cur = []
+        for m in range(M):
+            p = gen_params[m]
+            v, _ = nade_sample(fcs[m][:, :H], fcs[m][:, H:H + E], *p['nade'], u=u[s, m])
+            cur.append(v)
+        samples = np.stack(cur, axis=-1)                       # [B,E,M]
+        out[:, s] = samples
+        sstack = samples.reshape(B, E * M)
+        if kind == 'dense':
+            x_fb = dnn_forward(sstack, fb_params)
+        else:
+            x_fb, fb_state = multi_rnn_step(sstack, fb_state, fb_params)
+        for m in range(M):
+            p = gen_params[m]
+            o, states[m] = multi_rnn_step(np.concatenate([cur[m], x_fb], axis=1), states[m], p['lstm'])
+            fcs[m] = dense(o, *p['dense'])
+    return out

@@ -175,3 +175,43 @@ def composer_train_step(x, params, opt, keep=1.0, u_drop=None):
     grads = torch.autograd.grad(loss, leaves)
     gn = opt.step(list(grads))
     return float(loss), gn
+
+
+# ----------------------------------------------------------------------------- RBM / DBN / feedback (torch, autograd)
+def rbm_free_energy(v, W, bh, bv):
+    """common/rbm.py:256-258 per row (un-broadcast [N] vector, quirk Q4)."""
+    return -torch.nn.functional.softplus(v @ W + bh).sum(1) - (v * bv).sum(1)
+
+
+def rbm_free_energy_cost_mean(v, v_sample, W, bh, bv):
+    """common/rbm.py:233-263 + statistical.py:34 (mean over the [N,N] broadcast)."""
+    return rbm_free_energy(v, W, bh, bv).mean() - rbm_free_energy(v_sample, W, bh, bv).mean()
+
+
+def dnn_forward(x, layers):
+    """common/dnn.py:97-116: sigmoid Dense layers."""
+    for K, b in layers:
+        x = torch.sigmoid(x @ K + b)
+    return x
+
+
+def feedback_loss(xe, gen_params, fb_params, kind='dense', keep=1.0, u_drop=None, u_fb=None):
+    """multinn_feedback.py:54-97 / multinn_feedback_rnn.py:41-79 training graph on given per-track encodings.
+    xe: list of M tensors [B,T+1,E] (zero-padded, already encoded). gen_params: list of rnn-nade param dicts (LSTM input
+    = E + F). fb_params: dense -> [(K,b)..]; rnn -> [(kernel,bias)..]. Returns (loss, nll[N,M])."""
+    M = len(xe)
+    B, T1, E = xe[0].shape
+    T = T1 - 1
+    stack = torch.stack(xe, dim=3).reshape(B, T1, E * M)
+    if kind == 'dense':
+        fb = dnn_forward(stack.reshape(B * T1, -1), fb_params).reshape(B, T1, -1)
+    else:
+        fb, _ = rnn_scan(stack, fb_params, keep, u_fb)
+    losses, nlls = [], []
+    for m in range(M):
+        inp = torch.cat([xe[m], fb], dim=2)[:, :-1]
+        tgt = xe[m][:, 1:]
+        l, n = rnn_nade_loss(inp, tgt, gen_params[m], keep, None if u_drop is None else u_drop[m])
+        losses.append(l)
+        nlls.append(n)
+    return torch.stack(losses).mean(), torch.stack(nlls, 1)

@@ -1,0 +1,264 @@
+"""GPU parity: RBM / DBN primitives, the Joint (DBN + LSTM-RBM) mode and the Feedback / Feedback-RNN modes against the
+CPU oracle with the same weights and the same uniform-noise tensors."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_oracle as O
+from oracle import torch_ref as R
+
+pytestmark = pytest.mark.gpu
+f64 = np.float64
+
+
+def make(mode, **kw):
+    from multinn_b200.multinn import MultINN, default_config, default_params
+    kw.setdefault('keep_prob', 1.0)
+    return MultINN(default_config(), default_params(mode=mode, **kw), mode)
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+def sd_np(arena):
+    return {k: v.numpy() for k, v in arena.state_dict().items()}
+
+
+def rnn_nade_params(sd, prefix, L):
+    return dict(lstm=[(sd[f'{prefix}/rnn/cell_{l}/kernel'], sd[f'{prefix}/rnn/cell_{l}/bias']) for l in range(L)],
+                dense=(sd[f'{prefix}/dense/kernel'], sd[f'{prefix}/dense/bias']),
+                nade=(sd[f'{prefix}/nade/w_enc'][0], sd[f'{prefix}/nade/w_dec'][0]))
+
+
+def dbn_params(sd, prefix, L):
+    return [(sd[f'{prefix}/rbm_{i}/W'], sd[f'{prefix}/rbm_{i}/bh'], sd[f'{prefix}/rbm_{i}/bv']) for i in range(L)]
+
+
+# ----------------------------------------------------------------------------- RBM / DBN primitives
+def test_rbm_gibbs_free_energy_and_cd():
+    from multinn_b200.common.rbm import RBM
+    from multinn_b200.params import ParamArena
+    rng = np.random.default_rng(0)
+    N, D, H, k = 70, 84, 256, 3
+    arena = ParamArena()
+    rbm = RBM(D, H, k=k, arena=arena, name='rbm')
+    arena.finalize('cuda', seed=1)
+    arena.load('rbm/bh', rng.standard_normal((1, H)) * 0.2)
+    arena.load('rbm/bv', rng.standard_normal((1, D)) * 0.2)
+    W, bh, bv = (sd_np(arena)[n].astype(f64) for n in ('rbm/W', 'rbm/bh', 'rbm/bv'))
+    v = (rng.random((N, D)) < 0.3).astype(np.float32)
+    bh_t = (rng.standard_normal((N, H)) * 0.3).astype(np.float32)
+    bv_t = (rng.standard_normal((N, D)) * 0.3).astype(np.float32)
+    uh, uv = rng.random((k, N, H), dtype=np.float32), rng.random((k, N, D), dtype=np.float32)
+    p_v, vk = rbm.sample(cu(v), cu(bh_t), cu(bv_t), u=(cu(uh), cu(uv)))
+    rp, rv = O.rbm_gibbs(v.astype(f64), W, bh_t.astype(f64), bv_t.astype(f64), k, uh.astype(f64), uv.astype(f64))
+    np.testing.assert_array_equal(vk.cpu().numpy(), rv)
+    np.testing.assert_allclose(p_v.cpu().numpy(), rp, rtol=2e-5)
+    p0, v0 = rbm.sample(cu(v), k=0)
+    assert torch.equal(v0, cu(v))
+    cost, fe = rbm.free_energy_cost(cu(v), vk)
+    ref = O.rbm_free_energy_cost_mean(v.astype(f64), rv, W, bh, bv)
+    assert abs(float(cost) - ref) < 1e-4 * max(1.0, abs(ref))
+    assert abs(float(fe) - O.rbm_free_energy(v.astype(f64), W, bh, bv).mean()) < 1e-3
+    # gradient of the cost (internal biases) vs autograd
+    t = lambda a: torch.tensor(a, dtype=torch.float64, requires_grad=True)
+    Wt, bht, bvt = t(W), t(bh), t(bv)
+    R.rbm_free_energy_cost_mean(torch.tensor(v, dtype=torch.float64), torch.tensor(rv), Wt, bht, bvt).backward()
+    arena.grad.zero_()
+    rbm.free_energy_cost_backward(cu(v), vk)
+    for p, g in ((rbm.W, Wt.grad), (rbm.bh, bht.grad), (rbm.bv, bvt.grad)):
+        assert float((p.grad.cpu().double() - g).norm() / g.norm()) < 1e-4
+    # CD-k update
+    u = dict(uh=uh, uv=uv, uh0=rng.random((N, H), dtype=np.float32), uhk=rng.random((N, H), dtype=np.float32))
+    dW, dbv, dbh = O.rbm_cd_update(v.astype(f64), W, bh, bv, k, 0.05, uh.astype(f64), uv.astype(f64),
+                                   u['uh0'].astype(f64), u['uhk'].astype(f64))
+    rbm.train(cu(v), 0.05, u={k_: cu(a) for k_, a in u.items()})
+    new = sd_np(arena)
+    np.testing.assert_allclose(new['rbm/W'], W + dW, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(new['rbm/bv'], bv + dbv, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(new['rbm/bh'], bh + dbh, rtol=1e-4, atol=1e-6)
+
+
+def test_rbm_philox_half_step_statistics():
+    from multinn_b200.common.rbm import RBM
+    from multinn_b200.params import ParamArena
+    arena = ParamArena()
+    rbm = RBM(84, 256, arena=arena, name='rbm')
+    arena.finalize('cuda', seed=2)
+    v = torch.zeros(4096, 84, device='cuda')
+    p, h = rbm.forward(v)                      # zero input, zero bias -> p = 0.5
+    assert set(np.unique(h.cpu().numpy())) <= {0.0, 1.0}
+    assert abs(float(h.mean()) - 0.5) < 0.005
+    _, h2 = rbm.forward(v)
+    assert not torch.equal(h, h2)              # fresh noise on every call (quirk Q12)
+
+
+def test_dbn_encoder_encode_decode_and_layerwise_cd():
+    from multinn_b200.encoders.dbn_encoder import DBNEncoder
+    from multinn_b200.params import ParamArena
+    rng = np.random.default_rng(3)
+    arena = ParamArena()
+    enc = DBNEncoder(84, [168, 84], arena=arena, name='enc')
+    arena.finalize('cuda', seed=4)
+    rbms = [tuple(a.astype(f64) for a in r) for r in dbn_params(sd_np(arena), 'enc', 2)]
+    N = 50
+    x = (rng.random((N, 84)) < 0.2).astype(np.float32)
+    us = [rng.random((N, 168), dtype=np.float32), rng.random((N, 84), dtype=np.float32)]
+    p_h, h = enc.encode(cu(x), u=[cu(a) for a in us])
+    rp, rh = O.dbn_forward(x.astype(f64), rbms, [a.astype(f64) for a in us])
+    np.testing.assert_array_equal(h.cpu().numpy(), rh)
+    np.testing.assert_allclose(p_h.cpu().numpy(), rp, rtol=2e-5)
+    ud = [rng.random((N, 168), dtype=np.float32), rng.random((N, 84), dtype=np.float32)]
+    p_v, v = enc.decode(h, u=[cu(a) for a in ud])
+    rpv, rv = O.dbn_reconstruct(rh, rbms, [a.astype(f64) for a in ud])
+    np.testing.assert_array_equal(v.cpu().numpy(), rv)
+    # layer-1 CD-1 on the sampled layer-0 codes
+    k = 1
+    u = dict(lower=[cu(us[0])], cd={n: cu(a) for n, a in dict(
+        uh=rng.random((k, N, 84), dtype=np.float32), uv=rng.random((k, N, 168), dtype=np.float32),
+        uh0=rng.random((N, 84), dtype=np.float32), uhk=rng.random((N, 84), dtype=np.float32)).items()})
+    _, h0 = O.rbm_forward(x.astype(f64), rbms[0][0], rbms[0][1], us[0].astype(f64))
+    W1, bh1, bv1 = rbms[1]
+    c = {n: a.cpu().numpy().astype(f64) for n, a in u['cd'].items()}
+    dW, dbv, dbh = O.rbm_cd_update(h0, W1, bh1, bv1, k, 0.1, c['uh'], c['uv'], c['uh0'], c['uhk'])
+    enc.train(cu(x), 0.1, layer=1, u=u)
+    np.testing.assert_allclose(sd_np(arena)['enc/rbm_1/W'], W1 + dW, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(sd_np(arena)['enc/rbm_0/W'], rbms[0][0], rtol=0, atol=0)   # lower layer frozen
+
+
+# ----------------------------------------------------------------------------- Joint: DBN encoder + LSTM-RBM (config C3)
+def _joint_uniforms(rng, B, T, k, H=64):
+    N1, N = (T + 1) * B, T * B
+    return dict(u_enc=[rng.random((N1, 168), dtype=np.float32), rng.random((N1, 84), dtype=np.float32)],
+                u_gibbs=(rng.random((k, N, H), dtype=np.float32), rng.random((k, N, 84), dtype=np.float32)))
+
+
+def test_joint_dbn_rnn_rbm_parity_and_gradients():
+    B, T, H, Rn, k = 6, 7, 64, (48, 32), 10
+    model = make('joint', encoder='DBN', encoder_hidden=[168, 84], generator='RBM', num_hidden=H, num_hidden_rnn=Rn)
+    rng = np.random.default_rng(5)
+    core = model._model
+    core.arena.load('generator/rbm/bh', rng.standard_normal((1, H)) * 0.1)
+    core.arena.load('generator/rbm/bv', rng.standard_normal((1, 84)) * 0.1)
+    sd, esd = sd_np(core.arena), sd_np(core.encoder_arena)
+    x = O.synthetic_pianoroll(B, T, seed=8, density=0.1)
+    u = _joint_uniforms(rng, B, T, k, H)
+    out = model.evaluate(cu(x), u_enc=[cu(a) for a in u['u_enc']], u_gibbs=tuple(cu(a) for a in u['u_gibbs']))
+    # oracle (time-major row order n' = t*B + b to share the uniforms)
+    rbms = [tuple(a.astype(f64) for a in r) for r in dbn_params(esd, 'encoder/all', 2)]
+    inp, _ = O.composer_inputs_targets(x)
+    pad = np.concatenate([inp, x.reshape(B, T, -1)[:, -1:]], axis=1)             # [B,T+1,420]
+    flat_tm = pad.transpose(1, 0, 2).reshape((T + 1) * B, -1).astype(f64)
+    _, codes = O.dbn_forward(flat_tm, rbms, [a.astype(f64) for a in u['u_enc']])
+    np.testing.assert_array_equal(out['codes'].cpu().numpy().reshape((T + 1) * B, -1), codes)
+    codes_bm = codes.reshape(T + 1, B, -1).transpose(1, 0, 2)                    # [B,T+1,84]
+    p = dict(lstm=[(sd[f'generator/rnn/cell_{l}/kernel'].astype(f64), sd[f'generator/rnn/cell_{l}/bias'].astype(f64))
+                   for l in range(2)],
+             rbm=tuple(sd[f'generator/rbm/{n}'].astype(f64) for n in ('W', 'bh', 'bv')),
+             Wuh=sd['generator/Wuh'].astype(f64), Wuv=sd['generator/Wuv'].astype(f64))
+    to_bm = lambda a, C: a.reshape(a.shape[0], T, B, C).transpose(0, 2, 1, 3).reshape(a.shape[0], B * T, C)
+    ref = O.rnn_rbm_forward(codes_bm[:, :-1], codes_bm[:, 1:], p, k, to_bm(u['u_gibbs'][0].astype(f64), H),
+                            to_bm(u['u_gibbs'][1].astype(f64), 84))
+    got_sample = out['sample'].cpu().numpy().reshape(T, B, -1).transpose(1, 0, 2).reshape(B * T, -1)
+    np.testing.assert_array_equal(got_sample, ref['sample'])
+    assert abs(float(out['batch/loss']) - ref['loss'] / 5) < 1e-4 * max(1.0, abs(ref['loss']))
+    # training step: gradient reaches W, bh, bv only (quirk Q3); LSTM / Wuh / Wuv stay untouched
+    before = core.arena.state_dict()
+    step = model.train_generators('sgd', 0.1)
+    step(cu(x), u_enc=[cu(a) for a in u['u_enc']], u_gibbs=tuple(cu(a) for a in u['u_gibbs']))
+    after = core.arena.state_dict()
+    t = lambda a: torch.tensor(a, dtype=torch.float64, requires_grad=True)
+    Wt, bht, bvt = (t(a) for a in p['rbm'])
+    tgt = torch.tensor(codes_bm[:, 1:].reshape(B * T, -1))
+    (R.rbm_free_energy_cost_mean(tgt, torch.tensor(ref['sample']), Wt, bht, bvt) / 5).backward()
+    gn = float(torch.sqrt(Wt.grad.pow(2).sum() + bht.grad.pow(2).sum() + bvt.grad.pow(2).sum()))
+    scale = 5.0 / max(gn, 5.0)
+    np.testing.assert_allclose(after['generator/rbm/W'].numpy(), p['rbm'][0] - 0.1 * scale * Wt.grad.numpy(),
+                               rtol=1e-4, atol=1e-6)
+    for n in ('generator/Wuh', 'generator/Wuv', 'generator/rnn/cell_0/kernel'):
+        assert torch.equal(before[n], after[n])
+
+
+def test_joint_generate_runs_and_is_binary():
+    model = make('joint', encoder='DBN', encoder_hidden=[168, 84], generator='RBM', num_hidden=64, num_hidden_rnn=(32,))
+    x = cu(O.synthetic_pianoroll(3, 5, seed=2))
+    s = model.generate(x, 4)
+    assert s.shape == (3, 4, 84, 5) and set(np.unique(s.cpu().numpy())) <= {0.0, 1.0}
+
+
+# ----------------------------------------------------------------------------- Feedback / Feedback-RNN (config C4)
+def _fb_case(mode, encoder):
+    kw = dict(num_hidden=128, num_hidden_rnn=(48, 32), feedback=[40, 24])
+    if encoder == 'DBN':
+        kw.update(encoder='DBN', encoder_hidden=[168, 84])
+    return make(mode, **kw)
+
+
+@pytest.mark.parametrize("mode,encoder", [('feedback', 'Pass'), ('feedback-rnn', 'Pass'), ('feedback-rnn', 'DBN')])
+def test_feedback_modes_nll_gradients_and_generation(mode, encoder):
+    B, T, S = 4, 6, 5
+    model = _fb_case(mode, encoder)
+    core = model._model
+    rng = np.random.default_rng(9)
+    sd, esd = sd_np(core.arena), sd_np(core.encoder_arena)
+    x = O.synthetic_pianoroll(B, T, seed=12, density=0.1)
+    kind = 'dense' if mode == 'feedback' else 'rnn'
+    M = 5
+    # per-track encodings of the zero-padded inputs (time-major rows for the DBN uniforms)
+    pad = np.concatenate([np.zeros((B, 1, 84, M), np.float32), x], axis=1)        # [B,T+1,84,M]
+    u_enc = None
+    if encoder == 'DBN':
+        u_enc = [[rng.random(((T + 1) * B, 168), dtype=np.float32), rng.random(((T + 1) * B, 84), dtype=np.float32)]
+                 for _ in range(M)]
+        xe = []
+        for m, t in enumerate(model.tracks):
+            rbms = [tuple(a.astype(f64) for a in r) for r in dbn_params(esd, f'encoder/{t}', 2)]
+            flat = pad[..., m].transpose(1, 0, 2).reshape((T + 1) * B, 84).astype(f64)
+            _, h = O.dbn_forward(flat, rbms, [a.astype(f64) for a in u_enc[m]])
+            xe.append(h.reshape(T + 1, B, 84).transpose(1, 0, 2))
+    else:
+        xe = [pad[..., m].astype(f64) for m in range(M)]
+    gp = [O.cast_params(rnn_nade_params(sd, f'generator/{t}', 2), f64) for t in model.tracks]
+    if kind == 'dense':
+        fbp = [(sd[f'feedback/dense_{l}/kernel'].astype(f64), sd[f'feedback/dense_{l}/bias'].astype(f64)) for l in range(2)]
+    else:
+        fbp = [(sd[f'feedback/rnn/cell_{l}/kernel'].astype(f64), sd[f'feedback/rnn/cell_{l}/bias'].astype(f64))
+               for l in range(2)]
+    tt = lambda tree: R.to_torch(tree, torch.float64, requires_grad=True)
+    gpt, fbt = [tt(p) for p in gp], tt(fbp)
+    loss, nll = R.feedback_loss([torch.tensor(a) for a in xe], gpt, fbt, kind)
+    cu_enc = None if u_enc is None else [[cu(a) for a in uu] for uu in u_enc]
+    out = model.evaluate(cu(x), u_enc=cu_enc)
+    np.testing.assert_allclose(out['nll'].cpu().numpy(), nll.detach().numpy(), rtol=1e-4)
+    # gradients of every generator + the feedback module
+    leaves = R.flat_params(gpt) + R.flat_params(fbt)
+    grads = torch.autograd.grad(loss, leaves)
+    core.arena.grad.zero_()
+    l = core._forward_backward(core._check_x(cu(x), None), keep=1.0, u_drop=None, seed=0, u_enc=cu_enc)
+    assert abs(float(l) - float(loss)) / float(loss) < 1e-5
+    named = core.arena.named()
+    fb_names = [f'feedback/dense_{i}/{n}' for i in range(2) for n in ('kernel', 'bias')] if kind == 'dense' else \
+        [f'feedback/rnn/cell_{i}/{n}' for i in range(2) for n in ('kernel', 'bias')]
+    for name, g in zip(fb_names, grads[-4:]):
+        got = named[name].grad.cpu().double()
+        assert float((got - g).norm() / g.norm()) < 2e-4, name
+    g0 = grads[0]                                           # first generator's layer-0 kernel
+    got = named[f'generator/{model.tracks[0]}/rnn/cell_0/kernel'].grad.cpu().double()
+    assert float((got - g0).norm() / g0.norm()) < 2e-4
+    # generation: sampled encodings bit-exact (Pass encoders decode = identity)
+    if encoder == 'Pass':
+        u = rng.random((S, M, B, 84), dtype=np.float32)
+        got = model.generate(cu(x), S, u=cu(u)).cpu().numpy()
+        ref = O.feedback_generate(xe, gp, fbp, kind, S, u.astype(f64))
+        np.testing.assert_array_equal(got, ref)
+
+
+def test_feedback_training_reduces_loss():
+    model = _fb_case('feedback-rnn', 'Pass')
+    step = model.train_generators('adam', 0.01)
+    x = cu(O.synthetic_pianoroll(4, 6, seed=1))
+    l0 = float(step(x, keep=1.0))
+    for _ in range(6):
+        l1 = float(step(x, keep=1.0))
+    assert l1 < l0
