@@ -39,6 +39,9 @@ unsigned long long mnn_launch_count(void);
  * bits[M,T*B,4] target bit masks. Any of xin/xtr/bits may be NULL. D <= 128. */
 int mnn_pack_pianoroll(const float* x, float* xin, float* xtr, uint32_t* bits, int B, int T, int D, int M,
                        mnn_stream_t stream);
+/* Same, x given as bytes (bool / uint8 piano-rolls as stored by prepare_data.py:56). */
+int mnn_pack_pianoroll_u8(const uint8_t* x, float* xin, float* xtr, uint32_t* bits, int B, int T, int D, int M,
+                          mnn_stream_t stream);
 /* Bit masks of an already flattened binary matrix v[N,D] (element (n,d) at v[n*ld + d*dim_stride]). */
 int mnn_pack_rows(const float* v, long long ld, int dim_stride, uint32_t* bits, int N, int D, mnn_stream_t stream);
 

@@ -32,6 +32,7 @@ SIGNATURES = {
     "mnn_last_error_string": [],
     "mnn_launch_count": [],
     "mnn_pack_pianoroll": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "mnn_pack_pianoroll_u8": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
     "mnn_pack_rows": [_p, _ll, _i, _p, _i, _i, _p],
     "mnn_gemm_f32": [_p, _ll, _i, _p, _ll, _i, _p, _ll, _p, _f, _f, _i, _i, _i, _p],
     "mnn_gemm_tc_supported": [_p, _ll, _p, _ll],

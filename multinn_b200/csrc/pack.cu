@@ -10,7 +10,8 @@
 
 namespace mnn {
 
-__global__ void pack_kernel(const float* __restrict__ x, float* __restrict__ xin, float* __restrict__ xtr,
+template <typename TIn>
+__global__ void pack_kernel(const TIn* __restrict__ x, float* __restrict__ xin, float* __restrict__ xtr,
                             uint32_t* __restrict__ bits, int B, int T, int D, int M) {
   extern __shared__ uint32_t msk[];  // [warps][M][4]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -21,10 +22,10 @@ __global__ void pack_kernel(const float* __restrict__ x, float* __restrict__ xin
     const int b = (int)(row / T), t = (int)(row % T);
     for (int i = lane; i < M * 4; i += 32) mw[i] = 0u;
     __syncwarp();
-    const float* src = x + (size_t)row * I;
+    const TIn* src = x + (size_t)row * I;
     float* dst = xin ? xin + ((size_t)(t + 1) * B + b) * I : nullptr;
     for (int e = lane; e < I; e += 32) {
-      const float v = __ldg(src + e);
+      const float v = (float)__ldg(src + e);
       if (dst) dst[e] = v;
       const int d = e / M, m = e - d * M;
       if (xtr) xtr[(((size_t)m * (T + 1) + (t + 1)) * B + b) * D + d] = v;
@@ -59,8 +60,8 @@ __global__ void pack_rows_kernel(const float* __restrict__ v, long long ld, int 
 
 using namespace mnn;
 
-extern "C" int mnn_pack_pianoroll(const float* x, float* xin, float* xtr, uint32_t* bits, int B, int T, int D, int M,
-                                  cudaStream_t stream) {
+template <typename TIn>
+static int pack_impl(const TIn* x, float* xin, float* xtr, uint32_t* bits, int B, int T, int D, int M, cudaStream_t stream) {
   MNN_REQUIRE(x && (xin || xtr || bits), MNN_ERR_ARG, "pack_pianoroll: null pointer");
   MNN_REQUIRE(B > 0 && T > 0 && D > 0 && M > 0, MNN_ERR_ARG, "pack_pianoroll: non-positive size");
   MNN_REQUIRE(D <= 128, MNN_ERR_UNSUPPORTED, "pack_pianoroll: num_dims > 128 not instantiated");
@@ -73,9 +74,21 @@ extern "C" int mnn_pack_pianoroll(const float* x, float* xin, float* xtr, uint32
   const long long rows = (long long)B * T;
   long long grid = (rows + warps - 1) / warps;
   if (grid > 148 * 8) grid = 148 * 8;
-  pack_kernel<<<(unsigned)grid, warps * 32, (size_t)warps * M * 4 * sizeof(uint32_t), stream>>>(x, xin, xtr, bits, B, T,
-                                                                                            D, M);
+  pack_kernel<TIn><<<(unsigned)grid, warps * 32, (size_t)warps * M * 4 * sizeof(uint32_t), stream>>>(x, xin, xtr, bits, B,
+                                                                                                 T, D, M);
   return mnn_check_launch("pack_pianoroll");
+}
+
+extern "C" int mnn_pack_pianoroll(const float* x, float* xin, float* xtr, uint32_t* bits, int B, int T, int D, int M,
+                                  cudaStream_t stream) {
+  return pack_impl<float>(x, xin, xtr, bits, B, T, D, M, stream);
+}
+
+// Same for piano-rolls kept as bytes (the reference's .npy files are bool arrays, prepare_data.py:56; they are fed to the
+// float32 placeholder as they are): 4x less host->device traffic.
+extern "C" int mnn_pack_pianoroll_u8(const uint8_t* x, float* xin, float* xtr, uint32_t* bits, int B, int T, int D, int M,
+                                     cudaStream_t stream) {
+  return pack_impl<uint8_t>(x, xin, xtr, bits, B, T, D, M, stream);
 }
 
 extern "C" int mnn_pack_rows(const float* v, long long ld, int dim_stride, uint32_t* bits, int N, int D,

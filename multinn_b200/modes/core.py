@@ -94,6 +94,8 @@ class MultINNCore(Model, abc.ABC):
                                       'use full lengths)')
         if not x.is_cuda:
             raise ValueError('x must be a CUDA tensor: multinn_b200 has no CPU path')
+        if x.dtype in (torch.uint8, torch.bool):          # bool / byte piano-rolls as stored by prepare_data.py:56
+            return x.contiguous()
         return x.contiguous().float()
 
     def _stage_inputs(self, x, stacked=False, per_track=False, bits=False):

@@ -13,7 +13,7 @@ def _ptr(t):
         return None
     if not t.is_cuda:
         raise ValueError("multinn_b200 ops need CUDA tensors (no CPU fallback)")
-    if t.dtype not in (torch.float32, torch.int32, torch.uint8, torch.float64):
+    if t.dtype not in (torch.float32, torch.int32, torch.uint8, torch.bool, torch.float64):
         raise ValueError(f"unsupported dtype {t.dtype}")
     return t.data_ptr()
 
@@ -31,7 +31,8 @@ def pack_pianoroll(x, xin=None, xtr=None, bits=None):
     """x[B,T,D,M] -> xin[T+1,B,D*M], xtr[M,T+1,B,D], bits[M,T*B,4] (any subset)."""
     B, T, D, M = x.shape
     assert x.is_contiguous()
-    check(lib.mnn_pack_pianoroll(_ptr(x), _ptr(xin), _ptr(xtr), _ptr(bits), B, T, D, M, _stream()), "pack_pianoroll")
+    fn = lib.mnn_pack_pianoroll if x.dtype == torch.float32 else lib.mnn_pack_pianoroll_u8
+    check(fn(_ptr(x), _ptr(xin), _ptr(xtr), _ptr(bits), B, T, D, M, _stream()), "pack_pianoroll")
 
 
 def pack_rows(v, bits, D=None, dim_stride=1):

@@ -30,6 +30,28 @@ def world():
     return 0, 1
 
 
+def shard_batch(x, rank=None, world_size=None):
+    """Data-parallel partition of a global batch along dim 0: rank r gets rows [r*B/G, (r+1)*B/G).
+    Equal shards are required so that the mean of per-rank mean-loss gradients is the global-batch gradient."""
+    r, w = world()
+    rank = r if rank is None else rank
+    world_size = w if world_size is None else world_size
+    B = x.shape[0]
+    if B % world_size:
+        raise ValueError(f'global batch {B} is not divisible by the world size {world_size}')
+    per = B // world_size
+    return x[rank * per:(rank + 1) * per]
+
+
+def allreduce_sum_(flat):
+    """The one exchange step of a training step: in-place sum-allreduce of the flat gradient bucket (NCCL on GPUs,
+    gloo in the CPU tests). Returns the factor that turns the sum of per-rank means into the global mean."""
+    _, ws = world()
+    if ws > 1:
+        dist.all_reduce(flat)
+    return 1.0 / ws
+
+
 class GradientApplier:
     """compute_gradients(): allreduce -> global norm -> clip -> apply, over one contiguous arena range."""
 
@@ -52,11 +74,7 @@ class GradientApplier:
 
     def apply(self):
         g = self._rng(self.arena.grad)
-        rank, ws = world()
-        grad_scale = 1.0
-        if ws > 1:
-            dist.all_reduce(g)                          # sum of per-rank mean-loss grads; averaged below
-            grad_scale = 1.0 / ws
+        grad_scale = allreduce_sum_(g)                  # sum of per-rank mean-loss grads; averaged in the optimiser kernel
         ops.sqnorm_into(g, self.sqnorm)
         self.step_count += 1
         p = self._rng(self.arena.flat)

@@ -194,3 +194,13 @@ def test_checkpoint_roundtrip(tmp_path):
     other.arena.flat.mul_(0.5)
     other.load(str(tmp_path / 'ck.pt'))
     assert torch.equal(other.evaluate(x)['nll'], a)
+
+
+def test_byte_pianorolls_equal_float_pianorolls():
+    """bool / uint8 inputs (how the reference's .npy files store the data) give the same result as float32 inputs."""
+    model = make('composer', H=128, Rnn=(32,))
+    x = O.synthetic_pianoroll(3, 6, seed=2, density=0.1)
+    a = model.evaluate(torch.from_numpy(x).cuda())['nll'].clone()
+    b = model.evaluate(torch.from_numpy(x.astype(np.uint8)).cuda())['nll'].clone()
+    c = model.evaluate(torch.from_numpy(x.astype(bool)).cuda())['nll'].clone()
+    assert torch.equal(a, b) and torch.equal(a, c)
