@@ -233,10 +233,10 @@ def run_gpu(args):
             'final_loss': final_loss,
         }
         if world == 1 and not args.no_cpu:
-            v, cores, _, sec = cpu_port_run(args.cpu_batch, T, 1, 1)
+            v, cores, _, sec = cpu_port_run(args.cpu_batch, T, 4, 1)
             out['cpu_baseline'] = {'value': v, 'unit': 'time-steps/s', 'cores': cores, 'kind': 'port',
-                                   'sample': f'[{args.cpu_batch},{T},84,5] slice, 1 warm-up + 1 timed step '
-                                             f'({sec:.2f} s), torch-CPU fp32 restatement of the TF1 graph'}
+                                   'sample': f'[{args.cpu_batch},{T},84,5] slice, 1 warm-up + 4 timed steps '
+                                             f'({sec:.2f} s/step), torch-CPU fp32 restatement of the TF1 graph'}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -294,7 +294,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='C5', choices=sorted(WORKLOADS))
-    ap.add_argument('--cpu-batch', type=int, default=256, help='batch rows of the bounded CPU sample')
+    ap.add_argument('--cpu-batch', type=int, default=64, help='batch rows of the bounded CPU sample')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
