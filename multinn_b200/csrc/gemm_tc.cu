@@ -130,7 +130,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(BN, A_MN, B_MN);
+      const uint32_t idesc = idesc_tf32(BN, A_MN, B_MN), idesc2 = idesc_tf32(2 * BN, A_MN, B_MN);
       // K-major (SWIZZLE_128B): 8-row groups 1024 B apart (SBO), LBO unused (=16 B like CUTLASS); k-step = +32 B in the row.
       // MN-major (SWIZZLE_128B_BASE32B): 32-element column chunks BK*128 B apart (LBO), 4-k-row atoms 512 B apart (SBO);
       // one K=8 instruction spans two atoms, k-step = +1024 B.
@@ -153,19 +153,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(bar_conv + 8 * stage, phase);
           tc_fence_after();
           const uint32_t a_raw = smem0 + stage * C_::STAGE_BYTES, a_lo = a_raw + C_::A_BYTES;
-          const uint32_t b_raw = a_raw + 2 * C_::A_BYTES, b_lo = b_raw + C_::B_BYTES;
+          const uint32_t b_raw = a_raw + 2 * C_::A_BYTES;
 #pragma unroll
           for (int j = 0; j < BK / 8; ++j) {
             const uint64_t da = smem_desc(a_raw + j * a_kstep, a_lbo, a_sbo, a_lay);
             const uint64_t db = smem_desc(b_raw + j * b_kstep, b_lbo, b_sbo, b_lay);
-            const uint64_t dbl = smem_desc(b_lo + j * b_kstep, b_lbo, b_sbo, b_lay);
             const uint32_t first = (kb > kb0 || j > 0) ? 1u : 0u;
-            umma_tf32(tmem_x, da, dbl, idesc, first);
+            // the lo tile of B sits right behind the raw tile in the same layout, so [B_hi ; B_lo] is ONE operand of
+            // 2*BN rows: a single N = 2*BN instruction yields A_hi.B_hi (columns [0,BN) = main) and A_hi.B_lo
+            // (columns [BN,2BN) = aux) while reading A from shared memory once
+            umma_tf32(tmem_d, da, db, idesc2, first);
             if (p.n_products == 3) {
               const uint64_t dal = smem_desc(a_lo + j * a_kstep, a_lbo, a_sbo, a_lay);
               umma_tf32(tmem_x, dal, db, idesc, 1u);
             }
-            umma_tf32(tmem_d, da, db, idesc, first);
           }
           umma_commit(bar_empty + 8 * stage);   // smem stage reusable once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }

@@ -128,7 +128,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(BN, false, false);
+      const uint32_t idesc = idesc_tf32(BN, false, false), idesc2 = idesc_tf32(2 * BN, false, false);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int s = 0; s < n_steps; ++s) {
@@ -141,15 +141,15 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_wait(bar_conv + 8 * stage, phase);
             tc_fence_after();
             const uint32_t a_raw = smem0 + stage * C_::STAGE_BYTES, a_lo = a_raw + C_::A_BYTES;
-            const uint32_t b_raw = a_raw + 2 * C_::A_BYTES, b_lo = b_raw + C_::B_BYTES;
+            const uint32_t b_raw = a_raw + 2 * C_::A_BYTES;
 #pragma unroll
             for (int j = 0; j < BK / 8; ++j) {
               const uint64_t da = smem_desc(a_raw + j * 32, 16, 1024, 2), dal = smem_desc(a_lo + j * 32, 16, 1024, 2);
-              const uint64_t db = smem_desc(b_raw + j * 32, 16, 1024, 2), dbl = smem_desc(b_lo + j * 32, 16, 1024, 2);
+              const uint64_t db = smem_desc(b_raw + j * 32, 16, 1024, 2);
               const uint32_t first = (kb > 0 || j > 0) ? 1u : 0u;
-              umma_tf32(tmem_x, da, dbl, idesc, first);
+              // [B_hi ; B_lo] is one contiguous 2*BN-row operand: main and aux accumulators in a single instruction
+              umma_tf32(tmem_d, da, db, idesc2, first);
               umma_tf32(tmem_x, dal, db, idesc, 1u);
-              umma_tf32(tmem_d, da, db, idesc, first);
             }
             umma_commit(bar_empty + 8 * stage);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }

@@ -185,14 +185,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1) nade_fwd_kernel(NadeArgs p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K5 backward. Thread k owns hidden unit k: its w_dec column and its dW_dec column accumulators live in registers
-// (the i loop is fully unrolled), its dW_enc column accumulators in shared memory, so no reduction over k is ever
-// needed. Walks i = D-1..0 and reverses the prefix (a -= w_enc[i-1]) at each set target bit. Requires the forward
-// kernel to have written dl into the d b_dec columns of dfc.
-// Rows are staged in batches of kBwdRows through a cp.async double buffer (b_enc row, dl row, target mask), so the
-// global-load latency of batch b+1 hides behind the arithmetic of batch b; two rows are walked at a time to give
-// every thread two independent dependency chains.
-constexpr int kBwdRows = 8;
+// K5 backward. 2-D thread layout: thread (ig, kq) owns hidden units k = 4*kq..4*kq+3 and the dims of group ig
+// (G = 4 groups of DG = D/4 consecutive dims): its w_dec / dW_dec tiles [DG][4] live in registers, so every step of
+// the walk over dims is 8 packed FFMA2 (two rows in flight) against one uniform branch. Per row the thread walks its
+// dims i = hi..lo, reversing the prefix (a -= w_enc[i-1]) at the set target bits inside its group; boundaries come
+// from ONE 32-bit word (the group's slice of the row mask), the walk enters one unrolled run of DG steps through a
+// DG-entry jump table. With gA_i = dh_i * h_i * (1 - h_i):  d b_enc = sum_i gA_i,  dW_enc[j] += v_j * sum_{i>j} gA_i.
+// Each group produces its own total; totals are exchanged through shared memory once per batch of rows so that the
+// suffix sums crossing group borders and d b_enc can be completed (fix-up pass). Row data (b_enc row, dl row, mask)
+// is staged through a cp.async double buffer one batch ahead. Requires the forward kernel to have written dl into
+// the d b_dec columns of dfc.
+constexpr int kBwdRows = 4;
+constexpr int kBwdGroups = 4;
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src));
@@ -200,179 +204,263 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src));
 }
+// sigmoid from the two MUFU ops directly (ex2.approx.ftz underflows to 0 for very negative arguments -> 1/(1+0))
+__device__ __forceinline__ float sigmoid_mufu(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+__device__ __forceinline__ float4 sigmoid_mufu4(float4 a) {
+  return make_float4(sigmoid_mufu(a.x), sigmoid_mufu(a.y), sigmoid_mufu(a.z), sigmoid_mufu(a.w));
+}
+// acc += (d, d, d, d) * v as two FFMA2
+__device__ __forceinline__ void fma4(float4& acc, float d, const float4& v) {
+  const float2 dd = make_float2(d, d);
+  const float2 lo = ffma2(dd, make_float2(v.x, v.y), make_float2(acc.x, acc.y));
+  const float2 hi = ffma2(dd, make_float2(v.z, v.w), make_float2(acc.z, acc.w));
+  acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+__device__ __forceinline__ void sub4(float4& a, const float4& b) { a.x -= b.x; a.y -= b.y; a.z -= b.z; a.w -= b.w; }
+// S += dh * h * (1 - h)
+__device__ __forceinline__ void flush_seg(float4& S, const float4& dh, const float4& h) {
+  S.x = fmaf(dh.x * h.x, 1.f - h.x, S.x); S.y = fmaf(dh.y * h.y, 1.f - h.y, S.y);
+  S.z = fmaf(dh.z * h.z, 1.f - h.z, S.z); S.w = fmaf(dh.w * h.w, 1.f - h.w, S.w);
+}
+
+template <int H, int D>
+struct BwdCfg {
+  static constexpr int G = kBwdGroups, DG = D / G, DGP = (DG + 3) / 4 * 4, KQ = H / 4, R = kBwdRows;
+  static constexpr size_t kFloats = (size_t)2 * D * H      // wenc_s, acce_s
+                                    + 2 * R * H            // a_s double buffer
+                                    + 2 * R * G * DGP      // dl_s double buffer (per-group padded slices)
+                                    + R * G * H;           // tot_s
+  static constexpr size_t SMEM = kFloats * sizeof(float) + 2 * R * 8 * sizeof(uint32_t);  // + shifted masks (5 words, padded to 8)
+};
 
 template <int H, int D>
 __global__ void __launch_bounds__(H, 1) nade_bwd_kernel(NadeArgs p) {
-  static_assert(D % 4 == 0, "D must be a multiple of 4");
+  using C_ = BwdCfg<H, D>;
+  constexpr int G = C_::G, DG = C_::DG, DGP = C_::DGP, KQ = C_::KQ, R = C_::R;
+  static_assert(D % G == 0 && DG <= 31, "num_dims must be a multiple of 4 and at most 124");
+  static_assert(KQ * G == H, "one thread per (hidden-unit quad, dim group)");
   extern __shared__ __align__(16) float smem[];
   float* wenc_s = smem;                            // [D][H]
-  float* acce_s = smem + (size_t)D * H;            // [D][H]
-  float* a_s = acce_s + (size_t)D * H;             // [2][kBwdRows][H]
-  float* dl_s = a_s + 2 * kBwdRows * H;            // [2][kBwdRows][D]
-  uint32_t* mk_s = reinterpret_cast<uint32_t*>(dl_s + 2 * kBwdRows * D);  // [2][kBwdRows][kNW]
+  float* acce_s = wenc_s + (size_t)D * H;          // [D][H]
+  float* a_s = acce_s + (size_t)D * H;             // [2][R][H]
+  float* dl_s = a_s + 2 * R * H;                   // [2][R][G][DGP]
+  float* tot_s = dl_s + 2 * R * G * DGP;           // [R][G][H]
+  uint32_t* mk_s = reinterpret_cast<uint32_t*>(tot_s + R * G * H);  // [2][R][8]: words 0..4 = (mask << 1), bit i = v_{i-1}
 
   const int m = blockIdx.x % p.M;
   const int cta = blockIdx.x / p.M;
   const int nctas = (gridDim.x - m + p.M - 1) / p.M;
-  const int k = threadIdx.x;
+  const int tid = threadIdx.x;
+  const int kq = tid % KQ, ig = tid / KQ;          // a warp shares ig (KQ is a multiple of 32)
+  const int k0 = 4 * kq, lo = ig * DG;
   const float* gwe = p.w_enc + (size_t)m * D * H;
   const float* gwd = p.w_dec + (size_t)m * D * H;
 
-  float wdec[D], accw[D];
+  float4 wd[DG], aw[DG];
 #pragma unroll
-  for (int i = 0; i < D; ++i) {
-    wdec[i] = __ldg(gwd + (size_t)i * H + k);
-    accw[i] = 0.f;
-    wenc_s[i * H + k] = __ldg(gwe + (size_t)i * H + k);
-    acce_s[i * H + k] = 0.f;
+  for (int ii = 0; ii < DG; ++ii) {
+    wd[ii] = __ldg(reinterpret_cast<const float4*>(gwd + (size_t)(lo + ii) * H + k0));
+    aw[ii] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int c = tid; c < D * H / 4; c += H) {
+    reinterpret_cast<float4*>(wenc_s)[c] = __ldg(reinterpret_cast<const float4*>(gwe) + c);
+    reinterpret_cast<float4*>(acce_s)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const uint32_t* bits = p.bits + (size_t)m * p.N * kNW;
   const int enc_col = p.enc_col0 + m * H, dec_col = p.dec_col0 + m * D;
-  const int nbatches = (p.N + kBwdRows - 1) / kBwdRows;
+  const int nbatches = (p.N + R - 1) / R;
 
   auto prefetch = [&](int batch, int buf) {
-    const int row0 = batch * kBwdRows;
-    float* ab = a_s + (size_t)buf * kBwdRows * H;
-    float* db = dl_s + (size_t)buf * kBwdRows * D;
-    uint32_t* mb = mk_s + buf * kBwdRows * kNW;
-    for (int c = k; c < kBwdRows * H / 4; c += H) {          // b_enc rows, 16 B chunks
+    const int row0 = batch * R;
+    float* ab = a_s + (size_t)buf * R * H;
+    float* db = dl_s + (size_t)buf * R * G * DGP;
+    uint32_t* mb = mk_s + buf * R * 8;
+    for (int c = tid; c < R * H / 4; c += H) {               // b_enc rows, 16 B chunks
       const int r = c / (H / 4), off = (c % (H / 4)) * 4, row = row0 + r;
       if (row < p.N) cp_async16(ab + r * H + off, p.fc + (size_t)row * p.ld + enc_col + off);
       else *reinterpret_cast<float4*>(ab + r * H + off) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int c = k; c < kBwdRows * D; c += H) {              // dl rows
+    for (int c = tid; c < R * D; c += H) {                   // dl rows -> per-group padded slices
       const int r = c / D, i = c - r * D, row = row0 + r;
-      if (row < p.N) cp_async4(db + c, p.dfc + (size_t)row * p.ld + dec_col + i);
-      else db[c] = 0.f;
+      float* dst = db + (r * G + i / DG) * DGP + (i % DG);
+      if (row < p.N) cp_async4(dst, p.dfc + (size_t)row * p.ld + dec_col + i);
+      else *dst = 0.f;
     }
-    if (k < kBwdRows) {
-      const int row = row0 + k;
-      if (row < p.N) cp_async16(mb + k * kNW, bits + (size_t)row * kNW);
-      else *reinterpret_cast<uint4*>(mb + k * kNW) = make_uint4(0u, 0u, 0u, 0u);
+    if (tid < R) {
+      const int row = row0 + tid;
+      uint4 mm = make_uint4(0u, 0u, 0u, 0u);
+      if (row < p.N) mm = __ldg(reinterpret_cast<const uint4*>(bits + (size_t)row * kNW));
+      uint32_t* d = mb + tid * 8;
+      d[0] = mm.x << 1;
+      d[1] = __funnelshift_l(mm.x, mm.y, 1);
+      d[2] = __funnelshift_l(mm.y, mm.z, 1);
+      d[3] = __funnelshift_l(mm.z, mm.w, 1);
+      d[4] = mm.w >> 31;
+      d[5] = 0u;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // the group's slice of a shifted row mask: bit q = v_{lo+q-1}, q = 0..DG-1
+  auto group_bits = [&](const uint32_t* sm5) {
+    const uint32_t w0 = sm5[lo >> 5], w1 = sm5[(lo >> 5) + 1];
+    return __funnelshift_r(w0, w1, lo & 31) & ((1u << DG) - 1u);
   };
 
   int buf = 0;
   if (cta < nbatches) prefetch(cta, 0);
-  __syncthreads();   // weights staged
   for (int b = cta; b < nbatches; b += nctas) {
-    const int nb = b + nctas;
-    if (nb < nbatches) {
-      prefetch(nb, buf ^ 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
-    const int row0 = b * kBwdRows;
-    const float* ab = a_s + (size_t)buf * kBwdRows * H;
-    const float* db = dl_s + (size_t)buf * kBwdRows * D;
-    const uint32_t* mb = mk_s + buf * kBwdRows * kNW;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();   // batch b staged and visible; everyone is done with batch b - nctas (fix-up included)
+    if (b + nctas < nbatches) prefetch(b + nctas, buf ^ 1);
+    const int row0 = b * R;
+    const float* ab = a_s + (size_t)buf * R * H;
+    const float* db = dl_s + (size_t)buf * R * G * DGP;
+    const uint32_t* mb = mk_s + buf * R * 8;
+
 #pragma unroll 1
-    for (int r = 0; r < kBwdRows; r += 2) {
-      if (row0 + r >= p.N) break;
-      uint32_t mk0[kNW], mk1[kNW];
+    for (int r = 0; r < R; r += 2) {
+      const uint32_t* sm0 = mb + r * 8;
+      const uint32_t* sm1 = mb + (r + 1) * 8;
+      float4 a0 = *reinterpret_cast<const float4*>(ab + r * H + k0);
+      float4 a1 = *reinterpret_cast<const float4*>(ab + (r + 1) * H + k0);
+      // forward prefix up to the group's top dim hi = lo + DG - 1: all set target bits j < hi, i.e. shifted bits 1..hi
+      {
+        const int hi = lo + DG - 1;
 #pragma unroll
-      for (int w = 0; w < kNW; ++w) { mk0[w] = mb[r * kNW + w]; mk1[w] = mb[(r + 1) * kNW + w]; }
-      float a0 = ab[r * H + k], a1 = ab[(r + 1) * H + k];
-      // forward prefix over set bits j < D-1 (bit D-1 opens no segment that any dim reads)
-#pragma unroll
-      for (int w = 0; w < kNW; ++w) {
-        uint32_t x0 = mk0[w], x1 = mk1[w];
-        if (w * 32 + 32 > D - 1) {
-          const int keep = (D - 1) - w * 32;  // number of low bits to keep (may be <= 0)
-          const uint32_t msk = keep <= 0 ? 0u : (keep >= 32 ? 0xffffffffu : ((1u << keep) - 1u));
-          x0 &= msk; x1 &= msk;
-        }
-        while (x0) { const int j = __ffs(x0) - 1; x0 &= x0 - 1; a0 += wenc_s[(w * 32 + j) * H + k]; }
-        while (x1) { const int j = __ffs(x1) - 1; x1 &= x1 - 1; a1 += wenc_s[(w * 32 + j) * H + k]; }
-      }
-      float h0 = sigmoid_fast(a0), h1 = sigmoid_fast(a1);
-      float ga0 = 0.f, ga1 = 0.f, dh0 = 0.f, dh1 = 0.f;
-      const float* dl0 = db + r * D;
-      const float* dl1 = db + (r + 1) * D;
-      // Segment boundaries (a set target bit j ends the segment that dims > j read) are rare, so the walk over dims is
-      // a jump-table entry into ONE unrolled run of FMAs (Duff's device): the hot code stays a few KB instead of one
-      // boundary block per dim, which overflowed the instruction cache (ncu: stall_no_instruction dominated).
-      uint32_t rm[kNW];   // boundaries still ahead: bit j set <=> stop after dim j + 1
-#pragma unroll
-      for (int w = 0; w < kNW; ++w) {
-        rm[w] = mk0[w] | mk1[w];
-        if (w * 32 + 32 > D - 1) {
-          const int keep = (D - 1) - w * 32;
-          rm[w] &= keep <= 0 ? 0u : (keep >= 32 ? 0xffffffffu : ((1u << keep) - 1u));
+        for (int w = 0; w < kNW; ++w) {
+          if (w * 32 > hi) break;    // warp-uniform
+          const int nb = hi - w * 32 + 1;   // shifted bits w*32 .. hi
+          const uint32_t keep = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
+          uint32_t x0 = sm0[w] & keep, x1 = sm1[w] & keep;
+          if (w == 0) { x0 &= ~1u; x1 &= ~1u; }
+          while (x0) {
+            const int j = w * 32 + __ffs(x0) - 2;   // shifted bit s <-> target bit s - 1
+            x0 &= x0 - 1;
+            add4(a0, *reinterpret_cast<const float4*>(wenc_s + (size_t)j * H + k0));
+          }
+          while (x1) {
+            const int j = w * 32 + __ffs(x1) - 2;
+            x1 &= x1 - 1;
+            add4(a1, *reinterpret_cast<const float4*>(wenc_s + (size_t)j * H + k0));
+          }
         }
       }
-      int i = D - 1;
+      float4 h0 = sigmoid_mufu4(a0), h1 = sigmoid_mufu4(a1);
+      float4 dh0 = make_float4(0.f, 0.f, 0.f, 0.f), dh1 = dh0, S0 = dh0, S1 = dh0;
+      // boundaries inside the group: bit q (1 <= q < DG) set <=> v_{lo+q-1} = 1 <=> new segment below local dim q
+      const uint32_t bm0 = group_bits(sm0) & ~1u, bm1 = group_bits(sm1) & ~1u;
+      uint32_t rm = bm0 | bm1;
+      const float* dl0 = db + (r * G + ig) * DGP;
+      const float* dl1 = db + ((r + 1) * G + ig) * DGP;
+      int i = DG - 1;
 #pragma unroll 1
       for (;;) {
-        int s = 0;   // stop position: process dims i..s, then handle the boundary in front of dim s (if s > 0)
-#pragma unroll
-        for (int w = kNW - 1; w >= 0; --w)
-          if (s == 0 && rm[w]) {
-            const int bpos = 31 - __clz(rm[w]);
-            rm[w] &= ~(1u << bpos);
-            s = w * 32 + bpos + 1;
-          }
+        int s = 0;   // process local dims i..s, then handle the boundary below dim s (if s > 0)
+        if (rm) {
+          s = 31 - __clz(rm);
+          rm &= ~(1u << s);
+        }
         float4 q0 = *reinterpret_cast<const float4*>(dl0 + (i & ~3));
         float4 q1 = *reinterpret_cast<const float4*>(dl1 + (i & ~3));
 #define MNN_BWD_STEP(I)                                                                                   \
   case (I):                                                                                               \
-    if constexpr ((I) < D) {                                                                              \
+    if constexpr ((I) < DG) {                                                                             \
       if (((I) & 3) == 3) {                                                                               \
         q0 = *reinterpret_cast<const float4*>(dl0 + ((I) & ~3));                                          \
         q1 = *reinterpret_cast<const float4*>(dl1 + ((I) & ~3));                                          \
       }                                                                                                   \
       const float d0 = ((I) & 3) == 3 ? q0.w : (((I) & 3) == 2 ? q0.z : (((I) & 3) == 1 ? q0.y : q0.x));  \
       const float d1 = ((I) & 3) == 3 ? q1.w : (((I) & 3) == 2 ? q1.z : (((I) & 3) == 1 ? q1.y : q1.x));  \
-      dh0 = fmaf(d0, wdec[(I) < D ? (I) : 0], dh0);                                                       \
-      dh1 = fmaf(d1, wdec[(I) < D ? (I) : 0], dh1);                                                       \
-      accw[(I) < D ? (I) : 0] = fmaf(d0, h0, fmaf(d1, h1, accw[(I) < D ? (I) : 0]));                      \
+      fma4(dh0, d0, wd[(I) < DG ? (I) : 0]);                                                              \
+      fma4(dh1, d1, wd[(I) < DG ? (I) : 0]);                                                              \
+      fma4(aw[(I) < DG ? (I) : 0], d0, h0);                                                               \
+      fma4(aw[(I) < DG ? (I) : 0], d1, h1);                                                               \
       if ((I) == s) break;                                                                                \
     }
 #define MNN_BWD_STEP4(I) MNN_BWD_STEP((I) + 3) MNN_BWD_STEP((I) + 2) MNN_BWD_STEP((I) + 1) MNN_BWD_STEP(I)
-#define MNN_BWD_STEP16(I) MNN_BWD_STEP4((I) + 12) MNN_BWD_STEP4((I) + 8) MNN_BWD_STEP4((I) + 4) MNN_BWD_STEP4(I)
         switch (i) {
-          MNN_BWD_STEP16(112) MNN_BWD_STEP16(96) MNN_BWD_STEP16(80) MNN_BWD_STEP16(64)
-          MNN_BWD_STEP16(48) MNN_BWD_STEP16(32) MNN_BWD_STEP16(16) MNN_BWD_STEP16(0)
+          MNN_BWD_STEP4(28) MNN_BWD_STEP4(24) MNN_BWD_STEP4(20) MNN_BWD_STEP4(16)
+          MNN_BWD_STEP4(12) MNN_BWD_STEP4(8) MNN_BWD_STEP4(4) MNN_BWD_STEP4(0)
           default: break;
         }
-#undef MNN_BWD_STEP16
 #undef MNN_BWD_STEP4
 #undef MNN_BWD_STEP
         if (s == 0) break;
-        if (pick_word(mk0, (s - 1) >> 5) & (1u << ((s - 1) & 31))) {  // block-uniform
-          ga0 += dh0 * h0 * (1.f - h0);
-          dh0 = 0.f;
-          acce_s[(s - 1) * H + k] += ga0;
-          a0 -= wenc_s[(s - 1) * H + k];
-          h0 = sigmoid_fast(a0);
+        const int j = lo + s - 1;   // the set target bit that ends the segment
+        if (bm0 & (1u << s)) {      // block-uniform within the warp (a warp shares ig and the row)
+          flush_seg(S0, dh0, h0);
+          dh0 = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4* ae = reinterpret_cast<float4*>(acce_s + (size_t)j * H + k0);
+          float4 acc = *ae;
+          add4(acc, S0);
+          *ae = acc;
+          sub4(a0, *reinterpret_cast<const float4*>(wenc_s + (size_t)j * H + k0));
+          h0 = sigmoid_mufu4(a0);
         }
-        if (pick_word(mk1, (s - 1) >> 5) & (1u << ((s - 1) & 31))) {
-          ga1 += dh1 * h1 * (1.f - h1);
-          dh1 = 0.f;
-          acce_s[(s - 1) * H + k] += ga1;
-          a1 -= wenc_s[(s - 1) * H + k];
-          h1 = sigmoid_fast(a1);
+        if (bm1 & (1u << s)) {
+          flush_seg(S1, dh1, h1);
+          dh1 = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4* ae = reinterpret_cast<float4*>(acce_s + (size_t)j * H + k0);
+          float4 acc = *ae;
+          add4(acc, S1);
+          *ae = acc;
+          sub4(a1, *reinterpret_cast<const float4*>(wenc_s + (size_t)j * H + k0));
+          h1 = sigmoid_mufu4(a1);
         }
         i = s - 1;
       }
-      ga0 += dh0 * h0 * (1.f - h0);
-      ga1 += dh1 * h1 * (1.f - h1);
-      p.dfc[(size_t)(row0 + r) * p.ld + enc_col + k] = ga0;
-      if (row0 + r + 1 < p.N) p.dfc[(size_t)(row0 + r + 1) * p.ld + enc_col + k] = ga1;
+      flush_seg(S0, dh0, h0);
+      flush_seg(S1, dh1, h1);
+      *reinterpret_cast<float4*>(tot_s + ((size_t)r * G + ig) * H + k0) = S0;
+      *reinterpret_cast<float4*>(tot_s + ((size_t)(r + 1) * G + ig) * H + k0) = S1;
     }
-    __syncthreads();   // everyone is done with `buf` before it is refilled two iterations from now
+    __syncthreads();   // group totals of the batch are complete
+
+    // fix-up: suffix sums that cross group borders, then d b_enc
+    if (ig < G - 1) {
+#pragma unroll 1
+      for (int r = 0; r < R; ++r) {
+        // set target bits j in [lo, lo + DG): shifted bits lo+1 .. lo+DG
+        const uint32_t* sm5 = mb + r * 8;
+        const int l1 = lo + 1;
+        uint32_t x = __funnelshift_r(sm5[l1 >> 5], sm5[(l1 >> 5) + 1], l1 & 31) & ((1u << DG) - 1u);
+        if (!x) continue;
+        float4 higher = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int g = ig + 1; g < G; ++g) add4(higher, *reinterpret_cast<const float4*>(tot_s + ((size_t)r * G + g) * H + k0));
+        while (x) {
+          const int j = lo + __ffs(x) - 1;
+          x &= x - 1;
+          float4* ae = reinterpret_cast<float4*>(acce_s + (size_t)j * H + k0);
+          float4 acc = *ae;
+          add4(acc, higher);
+          *ae = acc;
+        }
+      }
+    }
+    for (int r = ig; r < R; r += G) {
+      const int row = row0 + r;
+      if (row < p.N) {
+        float4 t = *reinterpret_cast<const float4*>(tot_s + ((size_t)r * G) * H + k0);
+#pragma unroll
+        for (int g = 1; g < G; ++g) add4(t, *reinterpret_cast<const float4*>(tot_s + ((size_t)r * G + g) * H + k0));
+        *reinterpret_cast<float4*>(p.dfc + (size_t)row * p.ld + enc_col + k0) = t;
+      }
+    }
     buf ^= 1;
   }
+  __syncthreads();
   float* gdd = p.dw_dec + (size_t)m * D * H;
   float* gde = p.dw_enc + (size_t)m * D * H;
 #pragma unroll
-  for (int i = 0; i < D; ++i) {
-    atomicAdd(gdd + (size_t)i * H + k, accw[i]);
-    atomicAdd(gde + (size_t)i * H + k, acce_s[i * H + k]);
-  }
+  for (int ii = 0; ii < DG; ++ii) atomicAdd(reinterpret_cast<float4*>(gdd + (size_t)(lo + ii) * H + k0), aw[ii]);
+  for (int c = tid; c < D * H / 4; c += H)
+    atomicAdd(reinterpret_cast<float4*>(gde) + c, reinterpret_cast<const float4*>(acce_s)[c]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -530,8 +618,7 @@ extern "C" int mnn_nade_logprob_fwd(const uint32_t* bits, const float* fc, long 
 
 template <int H, int D>
 static int launch_bwd(const NadeArgs& a, cudaStream_t stream) {
-  const size_t smem = ((size_t)2 * D * H + 2 * kBwdRows * H + 2 * kBwdRows * D) * sizeof(float) +
-                      2 * kBwdRows * kNW * sizeof(uint32_t);
+  const size_t smem = BwdCfg<H, D>::SMEM;
   cudaFuncSetAttribute(nade_bwd_kernel<H, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int grid = num_sms();
   const int need = a.M * ((a.N + kBwdRows - 1) / kBwdRows);
