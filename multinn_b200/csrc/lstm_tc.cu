@@ -196,6 +196,35 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int n_blk = w % p.blocks, m_blk = w / p.blocks;
         const int b = m_blk * BM + q * 32 + lane;
         const bool row_ok = b < B;
+        // the operands of the NEXT step's epilogue for this item stream from HBM (they were written long ago): pull
+        // them into L2 now, off the critical path of the recurrence
+        if (persistent && s + 1 < n_steps && row_ok) {
+          const int tn = FWD ? t + 1 : t - 1;
+          if (FWD) {
+            constexpr int UBp = BN / 4;
+            const float* gn = p.gates + ((size_t)tn * B + b) * 4 * R + n_blk * UBp;
+            if (n_blk * UBp < R) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) prefetch_l2(gn + g * R);
+              if (p.u) prefetch_l2(p.u + (size_t)tn * BR + (size_t)b * R + n_blk * UBp);
+            }
+          } else {
+            const int u0 = n_blk * BN;
+            if (u0 < R) {
+              const float* gn = p.gates + ((size_t)tn * B + b) * 4 * R + u0;
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+#pragma unroll
+                for (int c = 0; c < BN; c += 32) prefetch_l2(gn + g * R + c);
+#pragma unroll
+              for (int c = 0; c < BN; c += 32) {
+                prefetch_l2(p.cbuf + (size_t)tn * BR + (size_t)b * R + u0 + c);
+                if (p.dout) prefetch_l2(p.dout + (size_t)tn * BR + (size_t)b * R + u0 + c);
+                if (p.dscale) prefetch_l2(p.dscale + (size_t)tn * BR + (size_t)b * R + u0 + c);
+              }
+            }
+          }
+        }
         mbar_wait(bar_tfull + 8 * acc, acc_phase);
         tc_fence_after();
         const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * BN);
@@ -233,11 +262,11 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               float cv[8], hv[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float gi = sigmoid_acc(pre[0][i]), gj = tanh_acc(pre[1][i]);
-                const float gf = sigmoid_acc(pre[2][i]), go = sigmoid_acc(pre[3][i]);
+                const float gi = sigmoid_fast(pre[0][i]), gj = tanh_fast(pre[1][i]);
+                const float gf = sigmoid_fast(pre[2][i]), go = sigmoid_fast(pre[3][i]);
                 pre[0][i] = gi; pre[1][i] = gj; pre[2][i] = gf; pre[3][i] = go;
                 cv[i] = gj * gi + cp[i] * gf;
-                hv[i] = tanh_acc(cv[i]) * go;
+                hv[i] = tanh_fast(cv[i]) * go;
               }
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
@@ -331,7 +360,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               ld8(cprev + unit, cp); ld8(cnow + unit, cn); ld8(p.dc + sidx + unit, dc);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float tcn = tanh_acc(cn[i]);
+                const float tcn = tanh_fast(cn[i]);
                 const float dcc = dc[i] + dh[i] * go[i] * (1.f - tcn * tcn);
                 const float di = dcc * gj[i] * gi[i] * (1.f - gi[i]);
                 const float dj = dcc * gi[i] * (1.f - gj[i] * gj[i]);

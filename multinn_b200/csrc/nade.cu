@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) nade_fwd_kernel(NadeArgs p) {
 // suffix sums crossing group borders and d b_enc can be completed (fix-up pass). Row data (b_enc row, dl row, mask)
 // is staged through a cp.async double buffer one batch ahead. Requires the forward kernel to have written dl into
 // the d b_dec columns of dfc.
-constexpr int kBwdRows = 4;
+constexpr int kBwdRows = 8;
 constexpr int kBwdGroups = 4;
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
@@ -276,21 +276,42 @@ __global__ void __launch_bounds__(H, 1) nade_bwd_kernel(NadeArgs p) {
   const int enc_col = p.enc_col0 + m * H, dec_col = p.dec_col0 + m * D;
   const int nbatches = (p.N + R - 1) / R;
 
+  // staging slots of this thread (loop-invariant: chunk c = tid + it * H of the batch)
+  constexpr int A_IT = (R * H / 4 + H - 1) / H, D_IT = (R * D + H - 1) / H;
+  int a_r[A_IT], a_off[A_IT], d_r[D_IT], d_i[D_IT], d_dst[D_IT];
+#pragma unroll
+  for (int it = 0; it < A_IT; ++it) {
+    const int c = tid + it * H;
+    a_r[it] = c / (H / 4);
+    a_off[it] = (c % (H / 4)) * 4;
+  }
+#pragma unroll
+  for (int it = 0; it < D_IT; ++it) {
+    const int c = tid + it * H;
+    d_r[it] = c < R * D ? c / D : -1;
+    d_i[it] = c - (c / D) * D;
+    d_dst[it] = ((c / D) * G + d_i[it] / DG) * DGP + (d_i[it] % DG);
+  }
+  const float* fc_enc = p.fc + enc_col;
+  const float* dfc_dec = p.dfc + dec_col;
   auto prefetch = [&](int batch, int buf) {
     const int row0 = batch * R;
     float* ab = a_s + (size_t)buf * R * H;
     float* db = dl_s + (size_t)buf * R * G * DGP;
     uint32_t* mb = mk_s + buf * R * 8;
-    for (int c = tid; c < R * H / 4; c += H) {               // b_enc rows, 16 B chunks
-      const int r = c / (H / 4), off = (c % (H / 4)) * 4, row = row0 + r;
-      if (row < p.N) cp_async16(ab + r * H + off, p.fc + (size_t)row * p.ld + enc_col + off);
-      else *reinterpret_cast<float4*>(ab + r * H + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int it = 0; it < A_IT; ++it) {                      // b_enc rows, 16 B chunks
+      const int row = row0 + a_r[it];
+      float* dst = ab + a_r[it] * H + a_off[it];
+      if (row < p.N) cp_async16(dst, fc_enc + (size_t)row * p.ld + a_off[it]);
+      else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int c = tid; c < R * D; c += H) {                   // dl rows -> per-group padded slices
-      const int r = c / D, i = c - r * D, row = row0 + r;
-      float* dst = db + (r * G + i / DG) * DGP + (i % DG);
-      if (row < p.N) cp_async4(dst, p.dfc + (size_t)row * p.ld + dec_col + i);
-      else *dst = 0.f;
+#pragma unroll
+    for (int it = 0; it < D_IT; ++it) {                      // dl rows -> per-group padded slices
+      if (d_r[it] < 0) continue;
+      const int row = row0 + d_r[it];
+      if (row < p.N) cp_async4(db + d_dst[it], dfc_dec + (size_t)row * p.ld + d_i[it]);
+      else db[d_dst[it]] = 0.f;
     }
     if (tid < R) {
       const int row = row0 + tid;
