@@ -16,6 +16,7 @@
 // expressed through the UMMA instruction descriptor's a_major/b_major bits, so no transposed copies exist.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -268,6 +269,237 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------------------ 2-CTA variant
+// The same pipeline on a CTA PAIR (cluster of 2, tcgen05 cta_group::2): output tile 256 x 256, each CTA holds 128 rows
+// of A and 128 of the 256 B rows per stage and ends with the accumulators of its own 128 output rows (main and aux,
+// 256 TMEM columns each). Why: a 128x128 tf32 instruction reads 8 KB of operands from shared memory per 64 clk -- all of
+// the 128 B/clk the SM has -- before the TMA writes and the hi/lo conversion are counted, so the 1-CTA kernel cannot
+// exceed ~55 % tensor utilisation; a 256x256 pair instruction reads 8 KB per CTA per 128 clk.
+//   * every role exists in both CTAs; only the leader's (rank 0) MMA thread issues, its commits are multicast to both CTAs
+//   * converters of both CTAs arrive on the LEADER's conv barrier (256 arrivals) -> "both halves of the stage are ready"
+//   * epilogue threads of both CTAs arrive on the LEADER's tempty barrier (256 arrivals) -> "both TMEM halves are drained"
+constexpr int BN2 = 256;
+struct Cfg2 {
+  static constexpr int A_BYTES = BM * BK * 4;         // this CTA's 128 rows of A
+  static constexpr int B_BYTES = (BN2 / 2) * BK * 4;  // this CTA's 128 rows of B
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = 3;
+  static constexpr int TMEM_COLS = 2 * BN2;           // main + aux, single buffered
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024;
+};
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+  using C_ = Cfg2;
+  constexpr int STAGES = C_::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[3 * STAGES + 2];
+  __shared__ uint32_t tmem_base_s;
+
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  const uint32_t bar_full = smem_u32(&bars[0]);              // [STAGES] local TMA completion
+  const uint32_t bar_conv = smem_u32(&bars[STAGES]);         // [STAGES] leader: 2 x 128 converter arrivals
+  const uint32_t bar_empty = smem_u32(&bars[2 * STAGES]);    // [STAGES] multicast MMA commit
+  const uint32_t bar_tfull = smem_u32(&bars[3 * STAGES]);    // multicast MMA commit
+  const uint32_t bar_tempty = smem_u32(&bars[3 * STAGES + 1]);  // leader: 2 x 128 epilogue arrivals
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_conv + 8 * s, 2 * (kConvThreads / 32));   // one elected arrive per converter warp
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tfull, 1);
+    mbar_init(bar_tempty, 2 * (kEpiThreads / 32));        // one elected arrive per epilogue warp
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"((uint32_t)C_::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();   // barriers of both CTAs initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int n_items = p.tiles_m * p.tiles_n * p.splits;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (own halves of A and B)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = cluster_id; w < n_items; w += n_clusters) {
+        const int n_blk = w % p.tiles_n, m_blk = (w / p.tiles_n) % p.tiles_m, split = w / (p.tiles_n * p.tiles_m);
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int m0 = m_blk * 2 * BM + (int)rank * BM, n0 = n_blk * BN2 + (int)rank * (BN2 / 2);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t full = bar_full + 8 * stage;
+          mbar_expect_tx(full, C_::A_BYTES + C_::B_BYTES);
+          const uint32_t a_dst = smem0 + stage * C_::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + 2 * C_::A_BYTES;
+          const int k0 = kb * BK;
+          if (!A_MN) {
+            tma_load_2d(a_dst, &map_a, full, k0, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 32; ++c) tma_load_2d(a_dst + c * (BK * 128), &map_a, full, m0 + 32 * c, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d(b_dst, &map_b, full, k0, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN2 / 64; ++c) tma_load_2d(b_dst + c * (BK * 128), &map_b, full, n0 + 32 * c, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer: one thread of the LEADER CTA
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = idesc_tf32(BN2, A_MN, B_MN, 2 * BM);
+      const uint32_t a_lbo = A_MN ? BK * 128 : 16, b_lbo = B_MN ? BK * 128 : 16;
+      const uint32_t a_sbo = A_MN ? 512 : 1024, b_sbo = B_MN ? 512 : 1024;
+      const uint32_t a_lay = A_MN ? 1 : 2, b_lay = B_MN ? 1 : 2;
+      const uint32_t a_kstep = A_MN ? 1024 : 32, b_kstep = B_MN ? 1024 : 32;
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      const uint32_t tmem_d = tmem_base, tmem_x = tmem_base + BN2;
+      for (int w = cluster_id; w < n_items; w += n_clusters) {
+        const int split = w / (p.tiles_n * p.tiles_m);
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(bar_tempty, acc_phase ^ 1);
+        tc_fence_after();
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_conv + 8 * stage, phase);   // both CTAs: TMA landed and lo tiles written
+          tc_fence_after();
+          const uint32_t a_raw = smem0 + stage * C_::STAGE_BYTES, a_lo = a_raw + C_::A_BYTES;
+          const uint32_t b_raw = a_raw + 2 * C_::A_BYTES, b_lo = b_raw + C_::B_BYTES;
+#pragma unroll
+          for (int j = 0; j < BK / 8; ++j) {
+            const uint64_t da = smem_desc(a_raw + j * a_kstep, a_lbo, a_sbo, a_lay);
+            const uint64_t db = smem_desc(b_raw + j * b_kstep, b_lbo, b_sbo, b_lay);
+            const uint64_t dbl = smem_desc(b_lo + j * b_kstep, b_lbo, b_sbo, b_lay);
+            const uint32_t first = (kb > kb0 || j > 0) ? 1u : 0u;
+            umma_tf32_2cta(tmem_x, da, dbl, idesc, first);
+            if (p.n_products == 3) {
+              const uint64_t dal = smem_desc(a_lo + j * a_kstep, a_lbo, a_sbo, a_lay);
+              umma_tf32_2cta(tmem_x, dal, db, idesc, 1u);
+            }
+            umma_tf32_2cta(tmem_d, da, db, idesc, first);
+          }
+          umma_commit_2cta(bar_empty + 8 * stage);   // both CTAs may refill this stage
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2cta(bar_tfull);                 // both CTAs' accumulator halves complete
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ converters: lo = x - trunc_tf32(x)
+    const int t = threadIdx.x - 8 * 32;
+    int stage = 0;
+    uint32_t phase = 0;
+    const int a_vec = (p.n_products == 3) ? C_::A_BYTES / 16 : 0;
+    constexpr int b_vec = C_::B_BYTES / 16;
+    const uint32_t conv_leader = mapa_cluster(bar_conv, 0);
+    for (int w = cluster_id; w < n_items; w += n_clusters) {
+      const int split = w / (p.tiles_n * p.tiles_m);
+      const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(bar_full + 8 * stage, phase);
+        uint8_t* base = smem_gen + (size_t)stage * C_::STAGE_BYTES;
+        const float4* a_raw = reinterpret_cast<const float4*>(base);
+        float4* a_lo = reinterpret_cast<float4*>(base + C_::A_BYTES);
+        const float4* b_raw = reinterpret_cast<const float4*>(base + 2 * C_::A_BYTES);
+        float4* b_lo = reinterpret_cast<float4*>(base + 2 * C_::A_BYTES + C_::B_BYTES);
+#pragma unroll 4
+        for (int i = t; i < a_vec; i += kConvThreads) a_lo[i] = tf32_lo4(a_raw[i]);
+#pragma unroll 4
+        for (int i = t; i < b_vec; i += kConvThreads) b_lo[i] = tf32_lo4(b_raw[i]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the pair's UMMA
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(conv_leader + 8 * stage);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue: this CTA's 128 rows x 256 columns
+    const int q = warp - 4;
+    uint32_t acc_phase = 0;
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    const uint32_t tempty_leader = mapa_cluster(bar_tempty, 0);
+    for (int w = cluster_id; w < n_items; w += n_clusters) {
+      const int n_blk = w % p.tiles_n, m_blk = (w / p.tiles_n) % p.tiles_m, split = w / (p.tiles_n * p.tiles_m);
+      const int row = m_blk * 2 * BM + (int)rank * BM + q * 32 + lane;
+      const int n0 = n_blk * BN2;
+      mbar_wait(bar_tfull, acc_phase);
+      tc_fence_after();
+      const bool add_bias = p.bias != nullptr && (!p.atomic || split == 0);
+#pragma unroll 1
+      for (int c = 0; c < BN2 / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;   // warp-uniform
+        float v[32], vx[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN2 + c * 32), vx);
+        if (row < p.M) {
+          float* dst = p.C + (size_t)row * p.ldc + col0;
+          const bool full = col0 + 32 <= p.N;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float o = p.alpha * (v[i] + vx[i]);
+            if (add_bias && (full || col0 + i < p.N)) o += __ldg(p.bias + col0 + i);
+            v[i] = o;
+          }
+          if (p.atomic) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (full || col0 + i < p.N) atomicAdd(dst + i, v[i]);
+          } else if (full && vec_ok) {
+            float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              if (p.beta != 0.f) {
+                const float4 old = d4[i];
+                o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
+              }
+              d4[i] = o;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < p.N) dst[i] = (p.beta != 0.f) ? v[i] + p.beta * dst[i] : v[i];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader);
+      acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // nobody leaves (or frees TMEM) while the peer may still signal or read
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C_::TMEM_COLS)
+                 : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -359,6 +591,41 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p,
   return mnn_check_launch("gemm_tc");
 }
 
+static int num_clusters2(const void* fn) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * num_sms());
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg2::SMEM;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms() / 2; }
+  return n;
+}
+
+template <bool A_MN, bool B_MN>
+static int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, cudaStream_t stream) {
+  static int max_clusters = 0;
+  if (!max_clusters) {
+    cudaFuncSetAttribute(gemm_tc2_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2::SMEM);
+    max_clusters = num_clusters2(reinterpret_cast<const void*>(gemm_tc2_kernel<A_MN, B_MN>));
+  }
+  const int items = p.tiles_m * p.tiles_n * p.splits;
+  const int clusters = items < max_clusters ? items : max_clusters;
+  gemm_tc2_kernel<A_MN, B_MN><<<2 * clusters, kThreads, Cfg2::SMEM, stream>>>(ma, mb, p);
+  return mnn_check_launch("gemm_tc2");
+}
+
+static int dispatch_major2(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const Params& p,
+                           cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch2<false, false>(ma, mb, p, s);
+  if (!a_mn && b_mn) return launch2<false, true>(ma, mb, p, s);
+  if (a_mn && !b_mn) return launch2<true, false>(ma, mb, p, s);
+  return launch2<true, true>(ma, mb, p, s);
+}
+
 template <int BN>
 static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const Params& p,
                           cudaStream_t s) {
@@ -394,18 +661,24 @@ extern "C" int mnn_gemm_tc(const float* A, long long lda, int transA, const floa
               "gemm_tc: TMA needs 16-byte aligned operand pointers and row strides that are multiples of 4 floats");
   const bool a_mn = transA != 0;   // A stored [K,M]: M contiguous
   const bool b_mn = transB == 0;   // B stored [K,N]: N contiguous
-  const int BN = N > 64 ? 128 : 64;
+  static const bool force_1cta = getenv("MNN_GEMM_1CTA") != nullptr;
+  // 256x256 tiles on CTA pairs: their accumulators fill TMEM (no epilogue overlap), so short-K shapes stay on the
+  // double-buffered 128x128 kernel (measured crossover: K ~ 512)
+  const bool pair = !force_1cta && M >= 256 && N > 128 && K >= 512;
+  const int BN = pair ? BN2 : (N > 64 ? 128 : 64);
+  const int TM = pair ? 2 * BM : BM;
+  const int units = pair ? num_sms() / 2 : num_sms();
 
   Params p{};
   p.C = C; p.bias = bias; p.ldc = ldc; p.alpha = alpha; p.beta = beta; p.M = M; p.N = N; p.K = K;
-  p.tiles_m = (M + BM - 1) / BM;
+  p.tiles_m = (M + TM - 1) / TM;
   p.tiles_n = (N + BN - 1) / BN;
   p.kb_total = (K + BK - 1) / BK;
   p.n_products = a_exact ? 2 : 3;
   const int tiles = p.tiles_m * p.tiles_n;
   int splits = 1;
-  if (tiles * 2 <= num_sms() && p.kb_total >= 32) {
-    splits = num_sms() / tiles;
+  if (tiles * 2 <= units && p.kb_total >= 32) {
+    splits = units / tiles;
     const int maxs = p.kb_total / 8;
     if (splits > maxs) splits = maxs;
     if (splits < 1) splits = 1;
@@ -421,13 +694,15 @@ extern "C" int mnn_gemm_tc(const float* A, long long lda, int transA, const floa
 
   CUtensorMap ma, mb;
   int rc;
+  const int box_n = pair ? BN2 / 2 : BN;
   if (!a_mn) rc = make_map(A, lda, K, M, BM, false, &ma);    // [M rows][K]   box {32 k, 128 rows}
   else rc = make_map(A, lda, M, K, BK, true, &ma);           // [K rows][M]   box {32 m, 32 k}
   if (rc) return rc;
-  if (!b_mn) rc = make_map(B, ldb, K, N, BN, false, &mb);    // [N rows][K]   box {32 k, BN rows}
+  if (!b_mn) rc = make_map(B, ldb, K, N, box_n, false, &mb); // [N rows][K]   box {32 k, BN (or BN/2 per CTA) rows}
   else rc = make_map(B, ldb, N, K, BK, true, &mb);           // [K rows][N]   box {32 n, 32 k}
   if (rc) return rc;
 
+  if (pair) return dispatch_major2(a_mn, b_mn, ma, mb, p, stream);
   if (BN == 128) return dispatch_major<128>(a_mn, b_mn, ma, mb, p, stream);
   return dispatch_major<64>(a_mn, b_mn, ma, mb, p, stream);
 }

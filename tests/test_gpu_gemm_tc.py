@@ -34,7 +34,7 @@ def _run(M, N, K, ta, tb, bias=False, beta=0.0, a_exact=False, seed=0, alpha=1.0
 
 @pytest.mark.parametrize("ta,tb", [(0, 1), (0, 0), (1, 0), (1, 1)])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 256, 64), (256, 64, 96), (300, 200, 100), (77, 340, 420),
-                                   (1000, 1700, 256), (2048, 2048, 512)])
+                                   (1000, 1700, 256), (2048, 2048, 512), (4224, 1024, 512), (700, 520, 932)])
 def test_gemm_tc_majors(M, N, K, ta, tb):
     err = _run(M, N, K, ta, tb)
     assert err < 4e-6, err

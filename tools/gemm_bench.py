@@ -22,7 +22,10 @@ SHAPES = [  # name, M, N, K, transA, transB, a_exact
 
 def main():
     only = sys.argv[1:] or ['tc', 'f32']
+    pick = os.environ.get('GB_ONLY')
     for name, M, Nn, K, ta, tb, ex in SHAPES:
+        if pick and not any(t in name for t in pick.split(',')):
+            continue
         A = torch.randn((K, M) if ta else (M, K), device='cuda')
         B = torch.randn((Nn, K) if tb else (K, Nn), device='cuda')
         C = torch.empty(M, Nn, device='cuda')
