@@ -33,6 +33,21 @@ __device__ __forceinline__ float tanh_acc(float x) {
   return tanhf(x);
 }
 
+// sigmoid / tanh straight from MUFU.EX2 + MUFU.RCP (4-5 instructions, absolute error ~1e-7; ex2.approx.ftz underflows to
+// 0 and overflows to +inf cleanly, so the saturated ends come out as exactly 0 / 1 / -1)
+__device__ __forceinline__ float sigmoid_mufu(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+__device__ __forceinline__ float tanh_mufu(float x) {   // 2 * sigmoid(2x) - 1
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -2.8853900817779268f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return fmaf(2.0f, r, -1.0f);
+}
+
 // tanh from the same two MUFU ops: 1 - 2 / (1 + e^{2x}) away from 0 (absolute error ~1e-7), odd Taylor polynomial
 // near 0 where that form cancels (relative error < 1e-7 for |x| < 0.04).
 __device__ __forceinline__ float tanh_fast(float x) {

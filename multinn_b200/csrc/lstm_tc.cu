@@ -10,6 +10,10 @@
 // is Wh transposed and permuted so that the four gate columns of a unit block are adjacent (prepared once per call).
 // Backward work item (slab m, unit block n): accumulator[128 rows, BN units] = dG_{t+1}[slab] . Wh^T, then the cell
 // backward for step t writes dG_t in place of the saved gate activations.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
 #include "multinn_b200.h"
 #include "tc_common.cuh"
 
@@ -44,7 +48,20 @@ struct LstmParams {
   int slabs, blocks;    // work items per step
   int kb_total;         // k-blocks per item
   unsigned int* flags;  // [slabs] completed-item counters (persistent launches), zeroed by the host
+  unsigned long long* trace;  // debug (MNN_LSTM_TRACE): [cta][step][16] globaltimer stamps, or null
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr int kTraceSteps = 8, kTraceS0 = 16, kTraceEv = 16;
+#define MNN_TRACE(ev)                                                                                        \
+  do {                                                                                                       \
+    if (p.trace && s >= kTraceS0 && s < kTraceS0 + kTraceSteps)                                              \
+      p.trace[((size_t)blockIdx.x * kTraceSteps + (s - kTraceS0)) * kTraceEv + (ev)] = gtimer();             \
+  } while (0)
 
 __device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
   unsigned int v;
@@ -400,6 +417,356 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------------------ forward on CTA pairs
+// The forward recurrence on CTA pairs (cluster of 2, tcgen05 cta_group::2): one work item = (256-row batch slab,
+// block of 64 units = 256 gate columns); each CTA of the pair holds 128 rows of h_{t-1} and 128 of the 256 WhP^T rows
+// per stage and ends with the accumulators of its own 128 batch rows (main + aux = all 512 TMEM columns). The pair
+// instruction reads half as many operand bytes from shared memory per flop as the 128x128 one, which is what bounds the
+// 1-CTA kernel. The converter warps have nothing to convert while the cell epilogue runs (the next step's h does not
+// exist yet), so they take the second half of the item's units: 8 epilogue warps per CTA.
+constexpr int kL2UB = 64;   // units per item
+constexpr size_t kPairSmem = 2 * 7 * (size_t)(BM * 128) + 1024;   // epilogue tiles (224 KB) alias the 3 x 64 KB stages
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLThreads, 1)
+lstm_tc2_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_c,
+                    const __grid_constant__ CUtensorMap map_o, const LstmParams p) {
+  constexpr int BNP = 4 * kL2UB;                       // 256 gate columns per item
+  constexpr int A_BYTES = BM * BK * 4, B_BYTES = (BNP / 2) * BK * 4;
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES, STAGES = 3;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[3 * STAGES + 2];
+  __shared__ __align__(8) uint64_t ebars[3];   // [0],[1]: epilogue tile loads of the two halves; [2]: tiles free again
+  __shared__ uint32_t tmem_base_s;
+
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const uint32_t bar_full = smem_u32(&bars[0]), bar_conv = smem_u32(&bars[STAGES]);
+  const uint32_t bar_empty = smem_u32(&bars[2 * STAGES]), bar_tfull = smem_u32(&bars[3 * STAGES]);
+  const uint32_t bar_tempty = smem_u32(&bars[3 * STAGES + 1]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_conv + 8 * s, 2 * 4);      // one elected arrive per converter warp of both CTAs
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tfull, 1);
+    mbar_init(bar_tempty, 2 * 8);
+    mbar_init(smem_u32(&ebars[0]), 1);
+    mbar_init(smem_u32(&ebars[1]), 1);
+    mbar_init(smem_u32(&ebars[2]), 2);              // one elected arrive per epilogue warp of both CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int n_items = p.slabs * p.blocks;     // slabs of 256 rows
+  const int n_steps = p.t1 - p.t0;
+  const int R = p.R, B = p.B;
+  const size_t BR = (size_t)B * R;
+
+  // ---- cell epilogue of one item half (eh): units [n_blk*64 + eh*32, +32) of this CTA's 128 rows.
+  // A TMEM lane is a batch row, so a thread owns a row; touching global memory row-per-thread costs 32 cache lines per
+  // warp instruction (measured: 22 us of a 41 us step). All tile I/O therefore goes through shared memory with TMA:
+  // the mainloop stages are idle once the item's MMAs are done, and hold per half 7 tiles of [128 rows x 32 units]
+  // (SWIZZLE_128B: 16-byte chunk c of row r at chunk c ^ (r & 7)): the four gate pre-activations and c_{t-1} are
+  // loaded, overwritten in place with the gate activations and c_t, h_t and the dropped-out output are added, and
+  // everything is stored back with TMA; only dscale (mask / keep) is written directly.
+  constexpr int TILE = BM * 128;                       // 16 KB
+  constexpr int HALF_BYTES = 7 * TILE;                 // gates i, j, f, o | c | h | out
+  auto epilogue_half = [&](int s, int t, int n_blk, int m_blk, int q, int eh, uint32_t ein_phase, uint32_t tempty_leader) {
+    const int r = q * 32 + lane;                       // row inside this CTA's 128
+    const int row_g = m_blk * 2 * BM + (int)rank * BM; // first batch row of this CTA
+    const int b = row_g + r;
+    const int unit0 = n_blk * kL2UB + eh * 32;
+    const uint32_t ebase = smem0 + (uint32_t)eh * HALF_BYTES;
+    uint8_t* egen = smem_gen + (size_t)eh * HALF_BYTES;
+    const uint32_t bar_ein = smem_u32(&ebars[eh]);
+    const bool leader = (lane == 0 && q == 0);
+    mbar_wait(bar_ein, ein_phase);   // gate pre-activation and c_{t-1} tiles (loaded by the producer warp as stages free up)
+    if (eh == 0 && threadIdx.x == 128) MNN_TRACE(11);
+    const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float inv_keep = 1.0f / p.keep;
+    uint8_t* rowp = egen + r * 128;
+    const int sw = r & 7;
+#pragma unroll 1
+    for (int ug = 0; ug < 4; ++ug) {
+      const int ul = eh * 32 + ug * 8;                 // unit offset inside the item
+      float pre[4][8];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float m8[8], x8[8];
+        tmem_ld8(tacc + (uint32_t)(g * kL2UB + ul), m8);
+        tmem_ld8(tacc + (uint32_t)(BNP + g * kL2UB + ul), x8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pre[g][i] = m8[i] + x8[i];
+      }
+      const int c0 = ((2 * ug) ^ sw) << 4, c1 = ((2 * ug + 1) ^ sw) << 4;   // swizzled chunk offsets of this row
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float4 p0 = *reinterpret_cast<const float4*>(rowp + g * TILE + c0);
+        const float4 p1 = *reinterpret_cast<const float4*>(rowp + g * TILE + c1);
+        pre[g][0] += p0.x; pre[g][1] += p0.y; pre[g][2] += p0.z; pre[g][3] += p0.w;
+        pre[g][4] += p1.x; pre[g][5] += p1.y; pre[g][6] += p1.z; pre[g][7] += p1.w;
+      }
+      const float4 cc0 = *reinterpret_cast<const float4*>(rowp + 4 * TILE + c0);
+      const float4 cc1 = *reinterpret_cast<const float4*>(rowp + 4 * TILE + c1);
+      const float cp[8] = {cc0.x, cc0.y, cc0.z, cc0.w, cc1.x, cc1.y, cc1.z, cc1.w};
+      float cv[8], hv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float gi = sigmoid_mufu(pre[0][i]), gj = tanh_mufu(pre[1][i]);
+        const float gf = sigmoid_mufu(pre[2][i]), go = sigmoid_mufu(pre[3][i]);
+        pre[0][i] = gi; pre[1][i] = gj; pre[2][i] = gf; pre[3][i] = go;
+        cv[i] = gj * gi + cp[i] * gf;
+        hv[i] = tanh_mufu(cv[i]) * go;
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        *reinterpret_cast<float4*>(rowp + g * TILE + c0) = make_float4(pre[g][0], pre[g][1], pre[g][2], pre[g][3]);
+        *reinterpret_cast<float4*>(rowp + g * TILE + c1) = make_float4(pre[g][4], pre[g][5], pre[g][6], pre[g][7]);
+      }
+      *reinterpret_cast<float4*>(rowp + 4 * TILE + c0) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+      *reinterpret_cast<float4*>(rowp + 4 * TILE + c1) = make_float4(cv[4], cv[5], cv[6], cv[7]);
+      *reinterpret_cast<float4*>(rowp + 5 * TILE + c0) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+      *reinterpret_cast<float4*>(rowp + 5 * TILE + c1) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+      if (p.out) {
+        float ov[8];
+        if (p.keep < 1.0f) {
+          const size_t e = (size_t)t * BR + (size_t)b * R + unit0 + ug * 8;
+          float uu[8], dv[8];
+          if (p.u) {
+            const float4 u0 = __ldg(reinterpret_cast<const float4*>(p.u + e));
+            const float4 u1 = __ldg(reinterpret_cast<const float4*>(p.u + e + 4));
+            uu[0] = u0.x; uu[1] = u0.y; uu[2] = u0.z; uu[3] = u0.w;
+            uu[4] = u1.x; uu[5] = u1.y; uu[6] = u1.z; uu[7] = u1.w;
+          } else {
+#pragma unroll
+            for (int h4 = 0; h4 < 2; ++h4) {
+              const unsigned long long ctr = (unsigned long long)(e >> 2) + h4;
+              const uint4 r4 = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u),
+                                             make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+              uu[4 * h4] = u01(r4.x); uu[4 * h4 + 1] = u01(r4.y);
+              uu[4 * h4 + 2] = u01(r4.z); uu[4 * h4 + 3] = u01(r4.w);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            dv[i] = floorf(p.keep + uu[i]) * inv_keep;   // tf.nn.dropout: x / keep * floor(keep + u)
+            ov[i] = hv[i] * dv[i];
+          }
+          float* dsp = p.dscale + e;
+          *reinterpret_cast<float4*>(dsp) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+          *reinterpret_cast<float4*>(dsp + 4) = make_float4(dv[4], dv[5], dv[6], dv[7]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ov[i] = hv[i];
+        }
+        *reinterpret_cast<float4*>(rowp + 6 * TILE + c0) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+        *reinterpret_cast<float4*>(rowp + 6 * TILE + c1) = make_float4(ov[4], ov[5], ov[6], ov[7]);
+      }
+    }
+    if (eh == 0 && threadIdx.x == 128) MNN_TRACE(7);
+    if (eh == 1 && threadIdx.x == 256) MNN_TRACE(10);
+    // tiles complete -> TMA stores; the flag may only be raised once h_t is globally visible
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    if (eh == 0) asm volatile("bar.sync 2, 128;" ::: "memory"); else asm volatile("bar.sync 3, 128;" ::: "memory");
+    if (leader) {
+      // h_t first, in its own bulk group: only it gates the next step; each half raises the slab's flag itself
+      tma_store_2d(&map_a, ebase + 5 * TILE, unit0, (t + 1) * B + row_g);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#pragma unroll
+      for (int g = 0; g < 4; ++g) tma_store_2d(&map_g, ebase + g * TILE, g * R + unit0, t * B + row_g);
+      tma_store_2d(&map_c, ebase + 4 * TILE, unit0, (t + 1) * B + row_g);
+      if (p.out) tma_store_2d(&map_o, ebase + 6 * TILE, unit0, t * B + row_g);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");   // the h_t tile is written
+      asm volatile("fence.proxy.async;" ::: "memory");
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.flags + m_blk) : "memory");
+      if (eh == 0) MNN_TRACE(8);
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // remaining tile stores have read shared memory
+      mbar_arrive(smem_u32(&ebars[2]));                                 // -> the stages may be refilled
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(tempty_leader);
+  };
+  // pull the next step's epilogue operands of this item half into L2 (they stream from HBM)
+  auto prefetch_next = [&](int t, int n_blk, int m_blk, int q, int eh) {
+    const int b = m_blk * 2 * BM + (int)rank * BM + q * 32 + lane;
+    const int unit = n_blk * kL2UB + eh * 32;
+    if (b >= B || unit >= R) return;
+    const float* gn = p.gates + ((size_t)(t + 1) * B + b) * 4 * R + unit;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) prefetch_l2(gn + g * R);
+    if (p.u) prefetch_l2(p.u + (size_t)(t + 1) * BR + (size_t)b * R + unit);
+  };
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0, item_no = 0;
+      uint32_t phase = 0;
+      for (int s = 0; s < n_steps; ++s) {
+        const int t = p.t0 + s;
+        for (int w = cluster_id; w < n_items; w += n_clusters) {
+          const int n_blk = w % p.blocks, m_blk = w / p.blocks;
+          if (s > 0) {
+            const unsigned int target = (unsigned int)s * (unsigned int)p.blocks * 4u;   // 2 CTAs x 2 halves per item
+            while (ld_acquire(p.flags + m_blk) < target) __nanosleep(32);
+            asm volatile("fence.proxy.async;" ::: "memory");   // other CTAs' generic-proxy stores -> our TMA reads
+          }
+          MNN_TRACE(0);
+          if (item_no > 0) mbar_wait(smem_u32(&ebars[2]), (uint32_t)(item_no - 1) & 1u);   // previous epilogue's tiles drained
+          const int row0 = t * p.B + m_blk * 2 * BM + (int)rank * BM;
+          const int brow0 = n_blk * BNP + (int)rank * (BNP / 2);
+          for (int kb = 0; kb < p.kb_total; ++kb) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            const uint32_t full = bar_full + 8 * stage;
+            mbar_expect_tx(full, A_BYTES + B_BYTES);
+            const uint32_t a_dst = smem0 + stage * STAGE_BYTES;
+            tma_load_2d(a_dst, &map_a, full, kb * BK, row0);
+            tma_load_2d(a_dst + 2 * A_BYTES, &map_b, full, kb * BK, brow0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          MNN_TRACE(1);
+          // epilogue inputs: the stage buffers are done for this item as their last MMAs retire; fill the tiles that
+          // alias each stage the moment it frees (tile k of half eh lives at eh*7*TILE + k*TILE; stage st at st*4*TILE)
+          {
+            const int row_g = m_blk * 2 * BM + (int)rank * BM;
+            const uint32_t ein0 = smem_u32(&ebars[0]), ein1 = smem_u32(&ebars[1]);
+            mbar_expect_tx(ein0, 5 * TILE);
+            mbar_expect_tx(ein1, 5 * TILE);
+            int st = stage;
+            uint32_t ph = phase;
+            for (int i = 0; i < STAGES; ++i) {
+              mbar_wait(bar_empty + 8 * st, ph ^ 1);
+              for (int k = 0; k < 4; ++k) {
+                const int tile = st * 4 + k;                 // 16 KB slot index in the dynamic region
+                const int eh = tile >= 7 ? 1 : 0, k7 = tile - 7 * eh;
+                if (k7 > 4) continue;                        // h / out slots: outputs only
+                const uint32_t dst = smem0 + (uint32_t)tile * TILE;
+                const int unit0 = n_blk * kL2UB + eh * 32;
+                if (k7 < 4) tma_load_2d(dst, &map_g, eh ? ein1 : ein0, k7 * R + unit0, t * B + row_g);
+                else tma_load_2d(dst, &map_c, eh ? ein1 : ein0, unit0, t * B + row_g);
+              }
+              if (++st == STAGES) { st = 0; ph ^= 1; }
+            }
+          }
+          ++item_no;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA)
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = idesc_tf32(BNP, false, false, 2 * BM);
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      const uint32_t tmem_d = tmem_base, tmem_x = tmem_base + BNP;
+      for (int s = 0; s < n_steps; ++s) {
+        for (int w = cluster_id; w < n_items; w += n_clusters) {
+          mbar_wait(bar_tempty, acc_phase ^ 1);
+          tc_fence_after();
+          for (int kb = 0; kb < p.kb_total; ++kb) {
+            mbar_wait(bar_conv + 8 * stage, phase);
+            tc_fence_after();
+            if (kb == 0) MNN_TRACE(4);
+            const uint32_t a_raw = smem0 + stage * STAGE_BYTES, a_lo = a_raw + A_BYTES;
+            const uint32_t b_raw = a_raw + 2 * A_BYTES, b_lo = b_raw + B_BYTES;
+#pragma unroll
+            for (int j = 0; j < BK / 8; ++j) {
+              const uint64_t da = smem_desc(a_raw + j * 32, 16, 1024, 2), dal = smem_desc(a_lo + j * 32, 16, 1024, 2);
+              const uint64_t db = smem_desc(b_raw + j * 32, 16, 1024, 2), dbl = smem_desc(b_lo + j * 32, 16, 1024, 2);
+              const uint32_t first = (kb > 0 || j > 0) ? 1u : 0u;
+              umma_tf32_2cta(tmem_x, da, dbl, idesc, first);
+              umma_tf32_2cta(tmem_x, dal, db, idesc, 1u);
+              umma_tf32_2cta(tmem_d, da, db, idesc, first);
+            }
+            umma_commit_2cta(bar_empty + 8 * stage);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit_2cta(bar_tfull);
+          MNN_TRACE(5);
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ converters, then the second epilogue half
+    const int tc = threadIdx.x - 8 * 32;
+    const int q = warp - 8;
+    int stage = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    const uint32_t conv_leader = mapa_cluster(bar_conv, 0), tempty_leader = mapa_cluster(bar_tempty, 0);
+    for (int s = 0; s < n_steps; ++s) {
+      const int t = p.t0 + s;
+      for (int w = cluster_id; w < n_items; w += n_clusters) {
+        const int n_blk = w % p.blocks, m_blk = w / p.blocks;
+        for (int kb = 0; kb < p.kb_total; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          if (kb == 0 && tc == 0) MNN_TRACE(2);
+          uint8_t* base = smem_gen + (size_t)stage * STAGE_BYTES;
+          const float4* a_raw = reinterpret_cast<const float4*>(base);
+          float4* a_lo = reinterpret_cast<float4*>(base + A_BYTES);
+          const float4* b_raw = reinterpret_cast<const float4*>(base + 2 * A_BYTES);
+          float4* b_lo = reinterpret_cast<float4*>(base + 2 * A_BYTES + B_BYTES);
+#pragma unroll 4
+          for (int i = tc; i < A_BYTES / 16; i += 128) a_lo[i] = tf32_lo4(a_raw[i]);
+#pragma unroll 4
+          for (int i = tc; i < B_BYTES / 16; i += 128) b_lo[i] = tf32_lo4(b_raw[i]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(conv_leader + 8 * stage);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (tc == 0) MNN_TRACE(3);
+        if (s + 1 < n_steps) prefetch_next(t, n_blk, m_blk, q, 1);
+        mbar_wait(bar_tfull, acc_phase);
+        tc_fence_after();
+        if (tc == 0) MNN_TRACE(9);
+        epilogue_half(s, t, n_blk, m_blk, q, 1, acc_phase, tempty_leader);
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ first epilogue half
+    const int q = warp - 4;
+    uint32_t acc_phase = 0;
+    const uint32_t tempty_leader = mapa_cluster(bar_tempty, 0);
+    for (int s = 0; s < n_steps; ++s) {
+      const int t = p.t0 + s;
+      for (int w = cluster_id; w < n_items; w += n_clusters) {
+        const int n_blk = w % p.blocks, m_blk = w / p.blocks;
+        if (s + 1 < n_steps) prefetch_next(t, n_blk, m_blk, q, 0);
+        mbar_wait(bar_tfull, acc_phase);
+        tc_fence_after();
+        if (threadIdx.x == 128) MNN_TRACE(6);
+        epilogue_half(s, t, n_blk, m_blk, q, 0, acc_phase, tempty_leader);
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // WhP^T[(n*4 + g)*UB + u][k] = Wh[k][g*R + n*UB + u]  (zero rows for units >= R)
 __global__ void lstm_prep_wh_kernel(const float* __restrict__ wh, float* __restrict__ whp, int R, int UB, int blocks) {
   const size_t total = (size_t)blocks * 4 * UB * R;
@@ -478,12 +845,54 @@ static int fwd_unit_block(int B, int R) {
 using namespace mnn;
 using namespace mnn::tc;
 
+// bytes reserved for the permuted recurrent weights at the head of the workspace (largest unit-block padding)
+static size_t whp_region_bytes(int R) {
+  size_t mx = 0;
+  for (int UB : {16, 32, kL2UB}) {
+    const size_t b = (size_t)((R + UB - 1) / UB) * 4 * UB * R * sizeof(float);
+    if (b > mx) mx = b;
+  }
+  return (mx + 255) / 256 * 256;
+}
+
 extern "C" size_t mnn_lstm_workspace_bytes(int B, int R) {
-  const int UB = fwd_unit_block(B, R);
-  const int blocks = (R + UB - 1) / UB;
-  const size_t whp = (size_t)blocks * 4 * UB * R * sizeof(float);
   const size_t flags = ((size_t)((B + BM - 1) / BM) * sizeof(unsigned int) + 255) / 256 * 256;
-  return (whp + 255) / 256 * 256 + flags;
+  return whp_region_bytes(R) + flags;
+}
+
+// forward on CTA pairs: needs every cluster co-resident (the CTAs of a slab wait on one another)
+static int pair_fwd_clusters() {
+  static int n = -1;
+  if (n < 0) {
+    constexpr size_t smem = kPairSmem;
+    cudaFuncSetAttribute(lstm_tc2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * mnn_tc_num_sms());
+    cfg.blockDim = dim3(kLThreads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int c = 0;
+    if (cudaOccupancyMaxActiveClusters(&c, reinterpret_cast<const void*>(lstm_tc2_fwd_kernel), &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      c = 0;
+    }
+    n = c;
+  }
+  return n;
+}
+
+static bool use_pair_fwd(int B, int R, int T, int persistent) {
+  static const char* env = getenv("MNN_LSTM_PAIR");   // "1": force (tests), "0": never
+  // TMA tile stores need whole 256-row slabs and whole 64-unit blocks; one item per cluster per step because the
+  // epilogue tiles alias the mainloop stages
+  if (!persistent || T < 2 || R % kL2UB != 0 || B % (2 * BM) != 0) return false;
+  if (env && env[0] == '0') return false;
+  if ((B / (2 * BM)) * (R / kL2UB) > pair_fwd_clusters()) return false;
+  if (env && env[0] == '1') return true;
+  return B >= 1024;
 }
 
 extern "C" int mnn_lstm_tc_supported(int B, int R) { return R % 8 == 0 && R >= 8 && B > 0; }
@@ -494,14 +903,71 @@ extern "C" int mnn_lstm_seq_fwd_tc(float* gates, const float* wh, float* hbuf, f
   MNN_REQUIRE(gates && wh && hbuf && cbuf && ws, MNN_ERR_ARG, "lstm_seq_fwd_tc: null pointer");
   MNN_REQUIRE(T > 0 && mnn_lstm_tc_supported(B, R), MNN_ERR_UNSUPPORTED, "lstm_seq_fwd_tc: needs num_units % 8 == 0");
   MNN_REQUIRE(!(out && keep < 1.f && !dscale), MNN_ERR_ARG, "lstm_seq_fwd_tc: dscale required when keep < 1");
-  const int UB = fwd_unit_block(B, R);
+  const bool pair = use_pair_fwd(B, R, T, persistent);
+  const int UB = pair ? kL2UB : fwd_unit_block(B, R);
   const int blocks = (R + UB - 1) / UB;
   float* whp = reinterpret_cast<float*>(ws);
-  const size_t whp_bytes = ((size_t)blocks * 4 * UB * R * sizeof(float) + 255) / 256 * 256;
-  unsigned int* flags = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(ws) + whp_bytes);
+  unsigned int* flags = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(ws) + whp_region_bytes(R));
   lstm_prep_wh_kernel<<<296, 256, 0, stream>>>(wh, whp, R, UB, blocks);
   int rc = mnn_check_launch("lstm_prep_wh");
   if (rc) return rc;
+  if (pair) {
+    LstmParams p{};
+    p.gates = gates; p.hbuf = hbuf; p.cbuf = cbuf; p.out = out; p.dscale = dscale; p.u = u; p.keep = keep; p.seed = seed;
+    p.T = T; p.B = B; p.R = R; p.t0 = 0; p.t1 = T;
+    p.slabs = (B + 2 * BM - 1) / (2 * BM); p.blocks = blocks; p.kb_total = (R + BK - 1) / BK; p.flags = flags;
+    CUtensorMap ma, mb;
+    rc = mnn_tc_make_map(hbuf, R, R, (long long)(T + 1) * B, BM, false, &ma);
+    if (rc) return rc;
+    rc = mnn_tc_make_map(whp, R, R, (long long)blocks * 4 * UB, BM, false, &mb);
+    if (rc) return rc;
+    CUtensorMap mg, mc, mo;
+    rc = mnn_tc_make_map(gates, 4LL * R, 4LL * R, (long long)T * B, BM, false, &mg);
+    if (rc) return rc;
+    rc = mnn_tc_make_map(cbuf, R, R, (long long)(T + 1) * B, BM, false, &mc);
+    if (rc) return rc;
+    rc = mnn_tc_make_map(out ? out : hbuf, R, R, (long long)T * B, BM, false, &mo);
+    if (rc) return rc;
+    cudaMemsetAsync(flags, 0, (size_t)p.slabs * sizeof(unsigned int), stream);
+    const int items = p.slabs * p.blocks;
+    static const char* trace_path = getenv("MNN_LSTM_TRACE");   // debug only: allocates and synchronises
+    const size_t trace_n = (size_t)2 * mnn_tc_num_sms() * kTraceSteps * kTraceEv;
+    if (trace_path) {
+      cudaMalloc(&p.trace, trace_n * sizeof(unsigned long long));
+      cudaMemsetAsync(p.trace, 0, trace_n * sizeof(unsigned long long), stream);
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * (items < pair_fwd_clusters() ? items : pair_fwd_clusters()));   // all clusters co-resident
+    cfg.blockDim = dim3(kLThreads);
+    cfg.dynamicSmemBytes = kPairSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_tc2_fwd_kernel, ma, mb, mg, mc, mo, p);
+    if (e != cudaSuccess) {
+      mnn_set_error(cudaGetErrorString(e));
+      return (int)e;
+    }
+    if (trace_path) {
+      cudaStreamSynchronize(stream);
+      std::vector<unsigned long long> h(trace_n);
+      cudaMemcpy(h.data(), p.trace, trace_n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      cudaFree(p.trace);
+      if (FILE* f = fopen(trace_path, "a")) {
+        fprintf(f, "# lstm pair fwd B=%d R=%d T=%d ctas=%d\n", B, R, T, (int)cfg.gridDim.x);
+        for (unsigned c = 0; c < cfg.gridDim.x; ++c)
+          for (int st = 0; st < kTraceSteps; ++st) {
+            fprintf(f, "%u %d", c, st);
+            for (int ev = 0; ev < kTraceEv; ++ev) fprintf(f, " %llu", h[((size_t)c * kTraceSteps + st) * kTraceEv + ev]);
+            fprintf(f, "\n");
+          }
+        fclose(f);
+      }
+    }
+    return mnn_check_launch("lstm_seq_fwd(pair)");
+  }
 
   LstmParams p{};
   p.gates = gates; p.hbuf = hbuf; p.cbuf = cbuf; p.out = out; p.dscale = dscale; p.u = u; p.keep = keep; p.seed = seed;
@@ -531,8 +997,7 @@ extern "C" int mnn_lstm_seq_bwd_tc(float* gates, const float* wh, const float* c
 
   const int slabs = (B + BM - 1) / BM;
   const int BN = (slabs * ((R + 63) / 64) >= 96) ? 64 : 32;
-  const int UBf = fwd_unit_block(B, R);
-  const size_t whp_bytes = ((size_t)((R + UBf - 1) / UBf) * 4 * UBf * R * sizeof(float) + 255) / 256 * 256;
+  const size_t whp_bytes = whp_region_bytes(R);
   LstmParams p{};
   p.gates = gates; p.cbuf = const_cast<float*>(cbuf); p.dout = dout; p.dscale = const_cast<float*>(dscale); p.dc = dc_work;
   p.T = T; p.B = B; p.R = R; p.t0 = 0; p.t1 = T - 1;

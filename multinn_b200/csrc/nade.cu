@@ -204,13 +204,6 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src));
 }
-// sigmoid from the two MUFU ops directly (ex2.approx.ftz underflows to 0 for very negative arguments -> 1/(1+0))
-__device__ __forceinline__ float sigmoid_mufu(float x) {
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-  return r;
-}
 __device__ __forceinline__ float4 sigmoid_mufu4(float4 a) {
   return make_float4(sigmoid_mufu(a.x), sigmoid_mufu(a.y), sigmoid_mufu(a.z), sigmoid_mufu(a.w));
 }
