@@ -566,6 +566,36 @@ static int make_map(const float* ptr, long long ld, long long inner, long long o
   return MNN_OK;
 }
 
+// 2-D fp32 tensor map with an arbitrary box and no swizzle (small elementwise tiles staged by the LSTM cell phases)
+static int make_map_plain(const float* ptr, long long ld, long long inner, long long outer, int box_inner, int box_outer,
+                          CUtensorMap* out) {
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  static std::mutex mu;
+  const MapKey key{ptr, ld, inner, outer, (box_inner << 16) | box_outer};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return MNN_OK; }
+  }
+  EncodeTiledFn enc = get_encode();
+  MNN_REQUIRE(enc != nullptr, MNN_ERR_UNSUPPORTED, "tensor map: cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mnn_set_error("tensor map: cuTensorMapEncodeTiled failed");
+    return MNN_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, *out);
+  return MNN_OK;
+}
+
 static int num_sms() {
   static int n = 0;
   if (!n) {
@@ -643,6 +673,10 @@ using namespace mnn;
 int mnn_tc_make_map(const float* ptr, long long ld, long long inner, long long outer, int box_outer, bool mn_major,
                     CUtensorMap* out) {
   return mnn::tc::make_map(ptr, ld, inner, outer, box_outer, mn_major, out);
+}
+int mnn_tc_make_map_plain(const float* ptr, long long ld, long long inner, long long outer, int box_inner, int box_outer,
+                           CUtensorMap* out) {
+  return mnn::tc::make_map_plain(ptr, ld, inner, outer, box_inner, box_outer, out);
 }
 int mnn_tc_num_sms() { return mnn::tc::num_sms(); }
 

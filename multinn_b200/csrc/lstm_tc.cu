@@ -767,6 +767,304 @@ lstm_tc2_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------------------------------------ BPTT on CTA pairs
+// The backward recurrence dh_t = dG_{t+1} . Wh^T has a long reduction (K = 4R) and a narrow output (N = R), so whole
+// output tiles leave most SMs idle. It runs in two phases per step, both spread over every CTA:
+//   phase A  (slab of 256 rows, tile of 256 units, K split): pair MMA (cta_group::2, 3xTF32) -> partial dh in TMEM ->
+//            swizzled shared tiles -> TMA reduce-add (fp32 add at L2) into dh_acc[B,R]; per-slab counter cntA
+//   phase B  (32 rows x 16 units per WARP): when the slab's partials are all in, TMA-load the dh_acc, gate, c, dout,
+//            dscale and dc tiles, run the cell backward, TMA-store dG_t (in place of the gate activations), dc and a
+//            zeroed dh_acc tile; per-slab counter cntB releases the next step's phase A
+// No thread ever touches global memory row-per-thread; all tile traffic is TMA.
+struct Lstm3Params {
+  const float* dout;      // null: no gradient from above
+  const float* dscale;    // null: no dropout
+  int T, B, R;
+  int slabs, ntiles, splits, kb_per_split;   // phase A: slabs of 256 rows, tiles of 256 units, K = 4R in `splits` parts
+  unsigned int* cntA;     // [slabs]
+  unsigned int* cntB;     // [slabs]
+};
+constexpr int kCellRows = 32, kCellUnits = 16, kCellTile = kCellRows * kCellUnits * 4;   // 2 KB tiles
+constexpr size_t kBwd3Smem = 3 * 64 * 1024 + 1024;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLThreads, 1)
+lstm_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_dhr, const __grid_constant__ CUtensorMap map_dh,
+                    const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_c,
+                    const __grid_constant__ CUtensorMap map_do, const __grid_constant__ CUtensorMap map_ds,
+                    const __grid_constant__ CUtensorMap map_dc, const Lstm3Params p) {
+  constexpr int NA = 256;
+  constexpr int A_BYTES = BM * BK * 4, B_BYTES = (NA / 2) * BK * 4;
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES, STAGES = 3;
+  constexpr int TILE = BM * 128;                      // 16 KB partial-out tile [128 rows x 32 units], SWIZZLE_128B
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[3 * STAGES + 2];
+  __shared__ __align__(8) uint64_t cbar[8];            // per cell warp: tile loads landed
+  __shared__ __align__(8) uint64_t bfree;              // cell tiles drained -> stages may be refilled
+  __shared__ uint32_t tmem_base_s;
+
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const uint32_t bar_full = smem_u32(&bars[0]), bar_conv = smem_u32(&bars[STAGES]);
+  const uint32_t bar_empty = smem_u32(&bars[2 * STAGES]), bar_tfull = smem_u32(&bars[3 * STAGES]);
+  const uint32_t bar_tempty = smem_u32(&bars[3 * STAGES + 1]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_conv + 8 * s, 2 * 4);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tfull, 1);
+    mbar_init(bar_tempty, 2 * 8);
+    for (int w = 0; w < 8; ++w) mbar_init(smem_u32(&cbar[w]), 1);
+    mbar_init(smem_u32(&bfree), 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int R = p.R, B = p.B;
+  const int n_itemsA = p.slabs * p.ntiles * p.splits;      // <= n_clusters (host): at most one phase-A item per pair
+  const int n_steps = p.T - 1;                             // t = T-2 .. 0 (dG_{T-1} comes from lstm_last_bwd_kernel)
+  const int kb_total = (4 * R + BK - 1) / BK;
+  const bool has_item = cluster_id < n_itemsA;
+  const int ks = cluster_id % p.splits, nt = (cluster_id / p.splits) % p.ntiles, mA = cluster_id / (p.splits * p.ntiles);
+  const int kb0 = ks * p.kb_per_split, kb1 = min(kb_total, kb0 + p.kb_per_split);
+  const unsigned int perA = (unsigned int)(p.ntiles * p.splits * 4);             // 2 CTAs x 2 halves per item
+  const int chunks = R / kCellUnits, rblocks = B / kCellRows;
+  const unsigned int perB = (unsigned int)((2 * BM / kCellRows) * chunks);       // cell items per slab
+  const int n_cells = rblocks * chunks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (phase A operands)
+    if (lane == 0 && has_item) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int s = 0; s < n_steps; ++s) {
+        const int t = p.T - 2 - s;
+        if (s > 0) {
+          const unsigned int target = (unsigned int)s * perB;                    // dG_{t+1} of the slab is complete
+          while (ld_acquire(p.cntB + mA) < target) __nanosleep(32);
+          asm volatile("fence.proxy.async;" ::: "memory");
+          mbar_wait(smem_u32(&bfree), (uint32_t)(s - 1) & 1u);                  // this CTA's cell tiles are drained
+        }
+        const int row0 = (t + 1) * B + mA * 2 * BM + (int)rank * BM;
+        const int brow0 = nt * NA + (int)rank * (NA / 2);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t full = bar_full + 8 * stage;
+          mbar_expect_tx(full, A_BYTES + B_BYTES);
+          const uint32_t a_dst = smem0 + stage * STAGE_BYTES;
+          tma_load_2d(a_dst, &map_a, full, kb * BK, row0);
+          tma_load_2d(a_dst + 2 * A_BYTES, &map_b, full, kb * BK, brow0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA)
+    if (lane == 0 && rank == 0 && has_item) {
+      const uint32_t idesc = idesc_tf32(NA, false, false, 2 * BM);
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      const uint32_t tmem_d = tmem_base, tmem_x = tmem_base + NA;
+      for (int s = 0; s < n_steps; ++s) {
+        mbar_wait(bar_tempty, acc_phase ^ 1);
+        tc_fence_after();
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_conv + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t a_raw = smem0 + stage * STAGE_BYTES, a_lo = a_raw + A_BYTES;
+          const uint32_t b_raw = a_raw + 2 * A_BYTES, b_lo = b_raw + B_BYTES;
+#pragma unroll
+          for (int j = 0; j < BK / 8; ++j) {
+            const uint64_t da = smem_desc(a_raw + j * 32, 16, 1024, 2), dal = smem_desc(a_lo + j * 32, 16, 1024, 2);
+            const uint64_t db = smem_desc(b_raw + j * 32, 16, 1024, 2), dbl = smem_desc(b_lo + j * 32, 16, 1024, 2);
+            const uint32_t first = (kb > kb0 || j > 0) ? 1u : 0u;
+            umma_tf32_2cta(tmem_x, da, dbl, idesc, first);
+            umma_tf32_2cta(tmem_x, dal, db, idesc, 1u);
+            umma_tf32_2cta(tmem_d, da, db, idesc, first);
+          }
+          umma_commit_2cta(bar_empty + 8 * stage);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2cta(bar_tfull);
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ converters (warps 8-11), phase-A epilogue, cells
+    const int cw = warp - 4;                 // cell warp 0..7
+    const int eh = cw >> 2, q = cw & 3;      // phase-A epilogue: column half, TMEM lane quadrant
+    const int tc = threadIdx.x - 8 * 32;
+    int stage = 0;
+    uint32_t phase = 0, acc_phase = 0, cphase = 0;
+    const uint32_t conv_leader = mapa_cluster(bar_conv, 0), tempty_leader = mapa_cluster(bar_tempty, 0);
+    const uint32_t my_cbar = smem_u32(&cbar[cw]);
+    const uint32_t cell0 = smem0 + (uint32_t)cw * 10 * kCellTile;
+    uint8_t* cellg = smem_gen + (size_t)cw * 10 * kCellTile;
+    const int gw = blockIdx.x * 8 + cw, n_gw = gridDim.x * 8;
+    for (int s = 0; s < n_steps; ++s) {
+      const int t = p.T - 2 - s;
+      if (has_item) {
+        if (warp >= 8) {
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(bar_full + 8 * stage, phase);
+            uint8_t* base = smem_gen + (size_t)stage * STAGE_BYTES;
+            const float4* a_raw = reinterpret_cast<const float4*>(base);
+            float4* a_lo = reinterpret_cast<float4*>(base + A_BYTES);
+            const float4* b_raw = reinterpret_cast<const float4*>(base + 2 * A_BYTES);
+            float4* b_lo = reinterpret_cast<float4*>(base + 2 * A_BYTES + B_BYTES);
+#pragma unroll 4
+            for (int i = tc; i < A_BYTES / 16; i += 128) a_lo[i] = tf32_lo4(a_raw[i]);
+#pragma unroll 4
+            for (int i = tc; i < B_BYTES / 16; i += 128) b_lo[i] = tf32_lo4(b_raw[i]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(conv_leader + 8 * stage);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        // ---- phase-A epilogue: this CTA's 128 rows, columns [eh*128, +128) of the tile -> 4 swizzled tiles -> reduce-add
+        mbar_wait(bar_tfull, acc_phase);
+        tc_fence_after();
+        {
+          const int r = q * 32 + lane, sw = r & 7;
+          const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            float v[32], vx[32];
+            tmem_ld32(tacc + (uint32_t)(eh * 128 + c * 32), v);
+            tmem_ld32(tacc + (uint32_t)(NA + eh * 128 + c * 32), vx);
+            uint8_t* rowp = smem_gen + (size_t)(eh * 4 + c) * TILE + r * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(rowp + ((j ^ sw) << 4)) =
+                  make_float4(v[4 * j] + vx[4 * j], v[4 * j + 1] + vx[4 * j + 1], v[4 * j + 2] + vx[4 * j + 2],
+                              v[4 * j + 3] + vx[4 * j + 3]);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          tc_fence_before();
+          if (eh == 0) asm volatile("bar.sync 2, 128;" ::: "memory"); else asm volatile("bar.sync 3, 128;" ::: "memory");
+          if (lane == 0 && q == 0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              tma_reduce_add_2d(&map_dhr, smem0 + (uint32_t)(eh * 4 + c) * TILE, nt * NA + eh * 128 + c * 32,
+                                mA * 2 * BM + (int)rank * BM);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            asm volatile("fence.proxy.async;" ::: "memory");
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.cntA + mA) : "memory");
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty_leader);
+        }
+        acc_phase ^= 1;
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // both halves' partial tiles are out of shared memory
+      }
+      // ---- phase B: cell backward on [32 rows x 16 units] tiles, one warp per tile
+      for (int it = gw; it < n_cells; it += n_gw) {
+        const int uc = it % chunks, rb = it / chunks;
+        const int row0 = rb * kCellRows, u0 = uc * kCellUnits;
+        const int m = row0 / (2 * BM);
+        if (lane == 0) {
+          const unsigned int target = (unsigned int)(s + 1) * perA;
+          while (ld_acquire(p.cntA + m) < target) __nanosleep(20);
+          asm volatile("fence.proxy.async;" ::: "memory");
+          const int ntl = 8 + (p.dout ? 1 : 0) + (p.dscale ? 1 : 0);
+          mbar_expect_tx(my_cbar, ntl * kCellTile);
+          tma_load_2d(cell0, &map_dh, my_cbar, u0, row0);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) tma_load_2d(cell0 + (1 + g) * kCellTile, &map_g, my_cbar, g * R + u0, t * B + row0);
+          tma_load_2d(cell0 + 5 * kCellTile, &map_c, my_cbar, u0, t * B + row0);
+          tma_load_2d(cell0 + 6 * kCellTile, &map_c, my_cbar, u0, (t + 1) * B + row0);
+          if (p.dout) tma_load_2d(cell0 + 7 * kCellTile, &map_do, my_cbar, u0, t * B + row0);
+          if (p.dscale) tma_load_2d(cell0 + 8 * kCellTile, &map_ds, my_cbar, u0, t * B + row0);
+          tma_load_2d(cell0 + 9 * kCellTile, &map_dc, my_cbar, u0, row0);
+        }
+        mbar_wait(my_cbar, cphase);
+        cphase ^= 1;
+        uint8_t* rowp = cellg + lane * (kCellUnits * 4);
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          auto ld8 = [&](int tile, float (&v)[8]) {
+            const float4 a = *reinterpret_cast<const float4*>(rowp + tile * kCellTile + h8 * 32);
+            const float4 c = *reinterpret_cast<const float4*>(rowp + tile * kCellTile + h8 * 32 + 16);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+          };
+          auto st8 = [&](int tile, const float (&v)[8]) {
+            *reinterpret_cast<float4*>(rowp + tile * kCellTile + h8 * 32) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(rowp + tile * kCellTile + h8 * 32 + 16) = make_float4(v[4], v[5], v[6], v[7]);
+          };
+          float dh[8], gi[8], gj[8], gf[8], go[8], cp[8], cn[8], dc[8];
+          ld8(0, dh); ld8(1, gi); ld8(2, gj); ld8(3, gf); ld8(4, go); ld8(5, cp); ld8(6, cn); ld8(9, dc);
+          if (p.dout) {
+            float d8[8];
+            ld8(7, d8);
+            if (p.dscale) {
+              float s8[8];
+              ld8(8, s8);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) dh[i] = fmaf(d8[i], s8[i], dh[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) dh[i] += d8[i];
+            }
+          }
+          float zero[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float tcn = tanh_mufu(cn[i]);
+            const float dcc = dc[i] + dh[i] * go[i] * (1.f - tcn * tcn);
+            const float di = dcc * gj[i] * gi[i] * (1.f - gi[i]);
+            const float dj = dcc * gi[i] * (1.f - gj[i] * gj[i]);
+            const float df = dcc * cp[i] * gf[i] * (1.f - gf[i]);
+            const float d_o = dh[i] * tcn * go[i] * (1.f - go[i]);
+            gi[i] = di; gj[i] = dj; go[i] = d_o;
+            dc[i] = dcc * gf[i];
+            gf[i] = df;
+            zero[i] = 0.f;
+          }
+          st8(1, gi); st8(2, gj); st8(3, gf); st8(4, go); st8(9, dc); st8(0, zero);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) tma_store_2d(&map_g, cell0 + (1 + g) * kCellTile, g * R + u0, t * B + row0);
+          tma_store_2d(&map_dc, cell0 + 9 * kCellTile, u0, row0);
+          tma_store_2d(&map_dh, cell0, u0, row0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          asm volatile("fence.proxy.async;" ::: "memory");
+          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.cntB + m) : "memory");
+        }
+        __syncwarp();
+      }
+      if (lane == 0) mbar_arrive(smem_u32(&bfree));
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // WhP^T[(n*4 + g)*UB + u][k] = Wh[k][g*R + n*UB + u]  (zero rows for units >= R)
 __global__ void lstm_prep_wh_kernel(const float* __restrict__ wh, float* __restrict__ whp, int R, int UB, int blocks) {
   const size_t total = (size_t)blocks * 4 * UB * R;
@@ -855,9 +1153,41 @@ static size_t whp_region_bytes(int R) {
   return (mx + 255) / 256 * 256;
 }
 
+// workspace: [permuted weights | 4 KB of counters: flags @0, cntA @1024, cntB @2048 | dh_acc[B,R]]
+constexpr size_t kCounterBytes = 4096;
 extern "C" size_t mnn_lstm_workspace_bytes(int B, int R) {
-  const size_t flags = ((size_t)((B + BM - 1) / BM) * sizeof(unsigned int) + 255) / 256 * 256;
-  return whp_region_bytes(R) + flags;
+  return whp_region_bytes(R) + kCounterBytes + (size_t)B * R * sizeof(float);
+}
+
+static int pair_bwd_clusters() {
+  static int n = -1;
+  if (n < 0) {
+    cudaFuncSetAttribute(lstm_tc3_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwd3Smem);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * mnn_tc_num_sms());
+    cfg.blockDim = dim3(kLThreads);
+    cfg.dynamicSmemBytes = kBwd3Smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int c = 0;
+    if (cudaOccupancyMaxActiveClusters(&c, reinterpret_cast<const void*>(lstm_tc3_bwd_kernel), &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      c = 0;
+    }
+    n = c;
+  }
+  return n;
+}
+
+static bool use_pair_bwd(int B, int R, int T, int persistent) {
+  static const char* env = getenv("MNN_LSTM_PAIR_BWD");   // "0": never
+  if (!persistent || T < 3 || R % 256 != 0 || B % (2 * BM) != 0) return false;
+  if (env && env[0] == '0') return false;
+  if ((B / (2 * BM)) * (R / 256) > pair_bwd_clusters()) return false;
+  if ((B / (2 * BM)) > 256) return false;                 // counters
+  return true;
 }
 
 // forward on CTA pairs: needs every cluster co-resident (the CTAs of a slab wait on one another)
@@ -994,6 +1324,50 @@ extern "C" int mnn_lstm_seq_bwd_tc(float* gates, const float* wh, const float* c
                                                          dscale ? dscale + (size_t)(T - 1) * BR : nullptr, dc_work, B, R);
   int rc = mnn_check_launch("lstm_last_bwd");
   if (rc || T == 1) return rc;
+
+  if (use_pair_bwd(B, R, T, persistent)) {
+    uint8_t* cnt = reinterpret_cast<uint8_t*>(ws) + whp_region_bytes(R);
+    float* dh_acc = reinterpret_cast<float*>(cnt + kCounterBytes);
+    Lstm3Params q{};
+    q.dout = dout; q.dscale = dscale; q.T = T; q.B = B; q.R = R;
+    q.slabs = B / (2 * BM); q.ntiles = R / 256;
+    const int kb_total = 4 * R / BK, clusters = pair_bwd_clusters();
+    int splits = clusters / (q.slabs * q.ntiles);
+    if (splits > kb_total / 2) splits = kb_total / 2;
+    if (splits < 1) splits = 1;
+    q.kb_per_split = (kb_total + splits - 1) / splits;
+    q.splits = (kb_total + q.kb_per_split - 1) / q.kb_per_split;
+    q.cntA = reinterpret_cast<unsigned int*>(cnt + 1024);
+    q.cntB = reinterpret_cast<unsigned int*>(cnt + 2048);
+    cudaMemsetAsync(cnt + 1024, 0, 2048, stream);
+    cudaMemsetAsync(dh_acc, 0, BR * sizeof(float), stream);
+    CUtensorMap ma, mb, mdhr, mdh, mg, mc, mdo, mds, mdc;
+    const long long TB = (long long)T * B;
+    if ((rc = mnn_tc_make_map(gates, 4LL * R, 4LL * R, TB, BM, false, &ma))) return rc;
+    if ((rc = mnn_tc_make_map(wh, 4LL * R, 4LL * R, R, BM, false, &mb))) return rc;
+    if ((rc = mnn_tc_make_map(dh_acc, R, R, B, BM, false, &mdhr))) return rc;
+    if ((rc = mnn_tc_make_map_plain(dh_acc, R, R, B, kCellUnits, kCellRows, &mdh))) return rc;
+    if ((rc = mnn_tc_make_map_plain(gates, 4LL * R, 4LL * R, TB, kCellUnits, kCellRows, &mg))) return rc;
+    if ((rc = mnn_tc_make_map_plain(cbuf, R, R, TB + B, kCellUnits, kCellRows, &mc))) return rc;
+    if ((rc = mnn_tc_make_map_plain(dout ? dout : cbuf, R, R, TB, kCellUnits, kCellRows, &mdo))) return rc;
+    if ((rc = mnn_tc_make_map_plain(dscale ? dscale : cbuf, R, R, TB, kCellUnits, kCellRows, &mds))) return rc;
+    if ((rc = mnn_tc_make_map_plain(dc_work, R, R, B, kCellUnits, kCellRows, &mdc))) return rc;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kLThreads);
+    cfg.dynamicSmemBytes = kBwd3Smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_tc3_bwd_kernel, ma, mb, mdhr, mdh, mg, mc, mdo, mds, mdc, q);
+    if (e != cudaSuccess) {
+      mnn_set_error(cudaGetErrorString(e));
+      return (int)e;
+    }
+    return mnn_check_launch("lstm_seq_bwd(pair)");
+  }
 
   const int slabs = (B + BM - 1) / BM;
   const int BN = (slabs * ((R + 63) / 64) >= 96) ? 64 : 32;

@@ -44,6 +44,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
                "r"(c1)
                : "memory");
 }
+// shared -> global tile reduction: global[tile] += shared[tile] (fp32 add done at L2)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -164,4 +170,6 @@ __device__ __forceinline__ uint32_t idesc_tf32(int n, bool a_mn, bool b_mn, int 
 // box {32, box_outer}; SWIZZLE_128B for K-major tiles, SWIZZLE_128B_ATOM_32B for MN-major tiles.
 int mnn_tc_make_map(const float* ptr, long long ld, long long inner, long long outer, int box_outer, bool mn_major,
                     CUtensorMap* out);
+int mnn_tc_make_map_plain(const float* ptr, long long ld, long long inner, long long outer, int box_inner, int box_outer,
+                           CUtensorMap* out);
 int mnn_tc_num_sms();

@@ -205,7 +205,8 @@ def _lstm_case(T, B, I, R, seed):
 
 @pytest.mark.parametrize("mode,persistent", [("simt", False), ("tc", False), ("tc", True)])
 @pytest.mark.parametrize("T,B,I,Rn,keep", [(9, 5, 84, 64, 1.0), (6, 33, 420, 512, 1.0), (7, 4, 30, 32, 0.8),
-                                           (12, 300, 64, 256, 0.9), (5, 130, 20, 48, 1.0), (3, 1100, 16, 96, 1.0), (4, 1024, 24, 512, 0.9)])
+                                           (12, 300, 64, 256, 0.9), (5, 130, 20, 48, 1.0), (3, 1100, 16, 96, 1.0), (4, 1024, 24, 512, 0.9), (5, 256, 24, 256, 0.9),
+                                           (3, 512, 16, 256, 1.0)])
 def test_lstm_sequence_fwd_bwd(T, B, I, Rn, keep, mode, persistent):
     ops = _ops()
     x, kernel, bias = _lstm_case(T, B, I, Rn, seed=T * B)
