@@ -772,7 +772,7 @@ lstm_tc2_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 // output tiles leave most SMs idle. It runs in two phases per step, both spread over every CTA:
 //   phase A  (slab of 256 rows, tile of 256 units, K split): pair MMA (cta_group::2, 3xTF32) -> partial dh in TMEM ->
 //            swizzled shared tiles -> TMA reduce-add (fp32 add at L2) into dh_acc[B,R]; per-slab counter cntA
-//   phase B  (32 rows x 16 units per WARP): when the slab's partials are all in, TMA-load the dh_acc, gate, c, dout,
+//   phase B  (16 rows x 16 units per WARP, double buffered): when the slab's partials are all in, TMA-load the dh_acc, gate, c, dout,
 //            dscale and dc tiles, run the cell backward, TMA-store dG_t (in place of the gate activations), dc and a
 //            zeroed dh_acc tile; per-slab counter cntB releases the next step's phase A
 // No thread ever touches global memory row-per-thread; all tile traffic is TMA.
@@ -783,8 +783,9 @@ struct Lstm3Params {
   int slabs, ntiles, splits, kb_per_split;   // phase A: slabs of 256 rows, tiles of 256 units, K = 4R in `splits` parts
   unsigned int* cntA;     // [slabs]
   unsigned int* cntB;     // [slabs]
+  unsigned long long* trace;   // debug (MNN_LSTM_TRACE)
 };
-constexpr int kCellRows = 32, kCellUnits = 16, kCellTile = kCellRows * kCellUnits * 4;   // 2 KB tiles
+constexpr int kCellRows = 16, kCellUnits = 16, kCellTile = kCellRows * kCellUnits * 4;   // 1 KB tiles
 constexpr size_t kBwd3Smem = 3 * 64 * 1024 + 1024;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLThreads, 1)
@@ -799,7 +800,7 @@ lstm_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   constexpr int TILE = BM * 128;                      // 16 KB partial-out tile [128 rows x 32 units], SWIZZLE_128B
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[3 * STAGES + 2];
-  __shared__ __align__(8) uint64_t cbar[8];            // per cell warp: tile loads landed
+  __shared__ __align__(8) uint64_t cbar[16];           // per cell warp and buffer: tile loads landed
   __shared__ __align__(8) uint64_t bfree;              // cell tiles drained -> stages may be refilled
   __shared__ uint32_t tmem_base_s;
 
@@ -820,7 +821,7 @@ lstm_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     mbar_init(bar_tfull, 1);
     mbar_init(bar_tempty, 2 * 8);
-    for (int w = 0; w < 8; ++w) mbar_init(smem_u32(&cbar[w]), 1);
+    for (int w = 0; w < 16; ++w) mbar_init(smem_u32(&cbar[w]), 1);
     mbar_init(smem_u32(&bfree), 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -860,6 +861,7 @@ lstm_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           asm volatile("fence.proxy.async;" ::: "memory");
           mbar_wait(smem_u32(&bfree), (uint32_t)(s - 1) & 1u);                  // this CTA's cell tiles are drained
         }
+        MNN_TRACE(0);
         const int row0 = (t + 1) * B + mA * 2 * BM + (int)rank * BM;
         const int brow0 = nt * NA + (int)rank * (NA / 2);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -886,6 +888,7 @@ lstm_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_conv + 8 * stage, phase);
           tc_fence_after();
+          if (kb == kb0) MNN_TRACE(1);
           const uint32_t a_raw = smem0 + stage * STAGE_BYTES, a_lo = a_raw + A_BYTES;
           const uint32_t b_raw = a_raw + 2 * A_BYTES, b_lo = b_raw + B_BYTES;
 #pragma unroll
@@ -901,6 +904,7 @@ lstm_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit_2cta(bar_tfull);
+        MNN_TRACE(2);
         acc_phase ^= 1;
       }
     }
@@ -910,14 +914,27 @@ lstm_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int eh = cw >> 2, q = cw & 3;      // phase-A epilogue: column half, TMEM lane quadrant
     const int tc = threadIdx.x - 8 * 32;
     int stage = 0;
-    uint32_t phase = 0, acc_phase = 0, cphase = 0;
+    uint32_t phase = 0, acc_phase = 0, cphase[2] = {0u, 0u};
     const uint32_t conv_leader = mapa_cluster(bar_conv, 0), tempty_leader = mapa_cluster(bar_tempty, 0);
-    const uint32_t my_cbar = smem_u32(&cbar[cw]);
-    const uint32_t cell0 = smem0 + (uint32_t)cw * 10 * kCellTile;
-    uint8_t* cellg = smem_gen + (size_t)cw * 10 * kCellTile;
+    const uint32_t my_cbar = smem_u32(&cbar[2 * cw]);
+    const uint32_t cell0 = smem0 + (uint32_t)cw * 20 * kCellTile;   // two buffers of 10 tiles
+    uint8_t* cellg = smem_gen + (size_t)cw * 20 * kCellTile;
     const int gw = blockIdx.x * 8 + cw, n_gw = gridDim.x * 8;
     for (int s = 0; s < n_steps; ++s) {
       const int t = p.T - 2 - s;
+      // this step's cell tiles stream from HBM (saved activations, c, dout, dscale): pull them into L2 while phase A runs
+      if (lane == 0) {
+        for (int it = gw; it < n_cells; it += n_gw) {
+          const int row0 = (it / chunks) * kCellRows, u0 = (it % chunks) * kCellUnits;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) tma_prefetch_l2_2d(&map_g, g * R + u0, t * B + row0);
+          tma_prefetch_l2_2d(&map_c, u0, t * B + row0);
+          if (s == 0) tma_prefetch_l2_2d(&map_c, u0, (t + 1) * B + row0);
+          if (p.dout) tma_prefetch_l2_2d(&map_do, u0, t * B + row0);
+          if (p.dscale) tma_prefetch_l2_2d(&map_ds, u0, t * B + row0);
+        }
+      }
+      __syncwarp();
       if (has_item) {
         if (warp >= 8) {
           for (int kb = kb0; kb < kb1; ++kb) {
@@ -940,6 +957,7 @@ lstm_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // ---- phase-A epilogue: this CTA's 128 rows, columns [eh*128, +128) of the tile -> 4 swizzled tiles -> reduce-add
         mbar_wait(bar_tfull, acc_phase);
         tc_fence_after();
+        if (threadIdx.x == 128) MNN_TRACE(3);
         {
           const int r = q * 32 + lane, sw = r & 7;
           const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -967,6 +985,7 @@ lstm_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             asm volatile("fence.proxy.async;" ::: "memory");
             asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.cntA + mA) : "memory");
+            if (threadIdx.x == 128) MNN_TRACE(4);
           }
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(tempty_leader);
@@ -974,85 +993,109 @@ lstm_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         acc_phase ^= 1;
         asm volatile("bar.sync 1, 256;" ::: "memory");   // both halves' partial tiles are out of shared memory
       }
-      // ---- phase B: cell backward on [32 rows x 16 units] tiles, one warp per tile
-      for (int it = gw; it < n_cells; it += n_gw) {
-        const int uc = it % chunks, rb = it / chunks;
-        const int row0 = rb * kCellRows, u0 = uc * kCellUnits;
-        const int m = row0 / (2 * BM);
-        if (lane == 0) {
+      // ---- phase B: cell backward on [16 rows x 16 units] tiles, one warp per tile; the loads of the warp's next tile
+      // are in flight while the current one is computed, and the stores are only waited for once, at the end
+      {
+        auto issue_loads = [&](int it, int buf) {   // lane 0
+          const int uc = it % chunks, rb = it / chunks;
+          const int row0 = rb * kCellRows, u0 = uc * kCellUnits;
+          const int m = row0 / (2 * BM);
           const unsigned int target = (unsigned int)(s + 1) * perA;
           while (ld_acquire(p.cntA + m) < target) __nanosleep(20);
           asm volatile("fence.proxy.async;" ::: "memory");
+          if (threadIdx.x == 128 && it == gw) MNN_TRACE(5);
+          const uint32_t bar = my_cbar + 8 * buf, dst = cell0 + (uint32_t)buf * 10 * kCellTile;
           const int ntl = 8 + (p.dout ? 1 : 0) + (p.dscale ? 1 : 0);
-          mbar_expect_tx(my_cbar, ntl * kCellTile);
-          tma_load_2d(cell0, &map_dh, my_cbar, u0, row0);
+          mbar_expect_tx(bar, ntl * kCellTile);
+          tma_load_2d(dst, &map_dh, bar, u0, row0);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) tma_load_2d(cell0 + (1 + g) * kCellTile, &map_g, my_cbar, g * R + u0, t * B + row0);
-          tma_load_2d(cell0 + 5 * kCellTile, &map_c, my_cbar, u0, t * B + row0);
-          tma_load_2d(cell0 + 6 * kCellTile, &map_c, my_cbar, u0, (t + 1) * B + row0);
-          if (p.dout) tma_load_2d(cell0 + 7 * kCellTile, &map_do, my_cbar, u0, t * B + row0);
-          if (p.dscale) tma_load_2d(cell0 + 8 * kCellTile, &map_ds, my_cbar, u0, t * B + row0);
-          tma_load_2d(cell0 + 9 * kCellTile, &map_dc, my_cbar, u0, row0);
-        }
-        mbar_wait(my_cbar, cphase);
-        cphase ^= 1;
-        uint8_t* rowp = cellg + lane * (kCellUnits * 4);
+          for (int g = 0; g < 4; ++g) tma_load_2d(dst + (1 + g) * kCellTile, &map_g, bar, g * R + u0, t * B + row0);
+          tma_load_2d(dst + 5 * kCellTile, &map_c, bar, u0, t * B + row0);
+          tma_load_2d(dst + 6 * kCellTile, &map_c, bar, u0, (t + 1) * B + row0);
+          if (p.dout) tma_load_2d(dst + 7 * kCellTile, &map_do, bar, u0, t * B + row0);
+          if (p.dscale) tma_load_2d(dst + 8 * kCellTile, &map_ds, bar, u0, t * B + row0);
+          tma_load_2d(dst + 9 * kCellTile, &map_dc, bar, u0, row0);
+        };
+        if (lane == 0 && gw < n_cells) issue_loads(gw, 0);
+        int kk = 0;
+        for (int it = gw; it < n_cells; it += n_gw, ++kk) {
+          const int buf = kk & 1;
+          const int uc = it % chunks, rb = it / chunks;
+          const int row0 = rb * kCellRows, u0 = uc * kCellUnits;
+          if (lane == 0 && it + n_gw < n_cells) {
+            // the other buffer was last used by tile kk-1: its stores must have read shared memory
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            issue_loads(it + n_gw, buf ^ 1);
+          }
+          mbar_wait(my_cbar + 8 * buf, cphase[buf]);
+          cphase[buf] ^= 1;
+          if (threadIdx.x == 128 && it == gw) MNN_TRACE(6);
+          // elementwise: a tile is 64 chunks of 16 bytes, lane L takes chunks L and L + 32 of every tile (conflict-free)
+          uint8_t* tb = cellg + (size_t)buf * 10 * kCellTile + lane * 16;
 #pragma unroll
-        for (int h8 = 0; h8 < 2; ++h8) {
-          auto ld8 = [&](int tile, float (&v)[8]) {
-            const float4 a = *reinterpret_cast<const float4*>(rowp + tile * kCellTile + h8 * 32);
-            const float4 c = *reinterpret_cast<const float4*>(rowp + tile * kCellTile + h8 * 32 + 16);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
-          };
-          auto st8 = [&](int tile, const float (&v)[8]) {
-            *reinterpret_cast<float4*>(rowp + tile * kCellTile + h8 * 32) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(rowp + tile * kCellTile + h8 * 32 + 16) = make_float4(v[4], v[5], v[6], v[7]);
-          };
-          float dh[8], gi[8], gj[8], gf[8], go[8], cp[8], cn[8], dc[8];
-          ld8(0, dh); ld8(1, gi); ld8(2, gj); ld8(3, gf); ld8(4, go); ld8(5, cp); ld8(6, cn); ld8(9, dc);
-          if (p.dout) {
-            float d8[8];
-            ld8(7, d8);
-            if (p.dscale) {
-              float s8[8];
-              ld8(8, s8);
+          for (int h = 0; h < 2; ++h) {
+            auto ld4 = [&](int tile) { return *reinterpret_cast<const float4*>(tb + tile * kCellTile + h * 512); };
+            auto st4 = [&](int tile, float4 v) { *reinterpret_cast<float4*>(tb + tile * kCellTile + h * 512) = v; };
+            const float4 Dh = ld4(0), Gi = ld4(1), Gj = ld4(2), Gf = ld4(3), Go = ld4(4), Cp = ld4(5), Cn = ld4(6), Dc = ld4(9);
+            float dh[4] = {Dh.x, Dh.y, Dh.z, Dh.w};
+            const float gi[4] = {Gi.x, Gi.y, Gi.z, Gi.w}, gj[4] = {Gj.x, Gj.y, Gj.z, Gj.w}, gf[4] = {Gf.x, Gf.y, Gf.z, Gf.w};
+            const float go[4] = {Go.x, Go.y, Go.z, Go.w}, cp[4] = {Cp.x, Cp.y, Cp.z, Cp.w}, cn[4] = {Cn.x, Cn.y, Cn.z, Cn.w};
+            const float dc[4] = {Dc.x, Dc.y, Dc.z, Dc.w};
+            if (p.dout) {
+              const float4 D = ld4(7);
+              const float d4[4] = {D.x, D.y, D.z, D.w};
+              if (p.dscale) {
+                const float4 S = ld4(8);
+                const float s4[4] = {S.x, S.y, S.z, S.w};
 #pragma unroll
-              for (int i = 0; i < 8; ++i) dh[i] = fmaf(d8[i], s8[i], dh[i]);
-            } else {
+                for (int i = 0; i < 4; ++i) dh[i] = fmaf(d4[i], s4[i], dh[i]);
+              } else {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) dh[i] += d8[i];
+                for (int i = 0; i < 4; ++i) dh[i] += d4[i];
+              }
             }
-          }
-          float zero[8];
+            float di[4], dj[4], df[4], d_o[4], dcn[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float tcn = tanh_mufu(cn[i]);
-            const float dcc = dc[i] + dh[i] * go[i] * (1.f - tcn * tcn);
-            const float di = dcc * gj[i] * gi[i] * (1.f - gi[i]);
-            const float dj = dcc * gi[i] * (1.f - gj[i] * gj[i]);
-            const float df = dcc * cp[i] * gf[i] * (1.f - gf[i]);
-            const float d_o = dh[i] * tcn * go[i] * (1.f - go[i]);
-            gi[i] = di; gj[i] = dj; go[i] = d_o;
-            dc[i] = dcc * gf[i];
-            gf[i] = df;
-            zero[i] = 0.f;
+            for (int i = 0; i < 4; ++i) {
+              const float tcn = tanh_mufu(cn[i]);
+              const float dcc = dc[i] + dh[i] * go[i] * (1.f - tcn * tcn);
+              di[i] = dcc * gj[i] * gi[i] * (1.f - gi[i]);
+              dj[i] = dcc * gi[i] * (1.f - gj[i] * gj[i]);
+              df[i] = dcc * cp[i] * gf[i] * (1.f - gf[i]);
+              d_o[i] = dh[i] * tcn * go[i] * (1.f - go[i]);
+              dcn[i] = dcc * gf[i];
+            }
+            st4(1, make_float4(di[0], di[1], di[2], di[3]));
+            st4(2, make_float4(dj[0], dj[1], dj[2], dj[3]));
+            st4(3, make_float4(df[0], df[1], df[2], df[3]));
+            st4(4, make_float4(d_o[0], d_o[1], d_o[2], d_o[3]));
+            st4(9, make_float4(dcn[0], dcn[1], dcn[2], dcn[3]));
+            st4(0, make_float4(0.f, 0.f, 0.f, 0.f));
           }
-          st8(1, gi); st8(2, gj); st8(3, gf); st8(4, go); st8(9, dc); st8(0, zero);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (threadIdx.x == 128 && it == gw) MNN_TRACE(7);
+          if (lane == 0) {
+            const uint32_t src = cell0 + (uint32_t)buf * 10 * kCellTile;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) tma_store_2d(&map_g, src + (1 + g) * kCellTile, g * R + u0, t * B + row0);
+            tma_store_2d(&map_dc, src + 9 * kCellTile, u0, row0);
+            tma_store_2d(&map_dh, src, u0, row0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) tma_store_2d(&map_g, cell0 + (1 + g) * kCellTile, g * R + u0, t * B + row0);
-          tma_store_2d(&map_dc, cell0 + 9 * kCellTile, u0, row0);
-          tma_store_2d(&map_dh, cell0, u0, row0);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (lane == 0 && gw < n_cells) {
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every tile of this warp is written
           asm volatile("fence.proxy.async;" ::: "memory");
-          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.cntB + m) : "memory");
+          for (int it = gw; it < n_cells; it += n_gw) {
+            const int m = ((it / chunks) * kCellRows) / (2 * BM);
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.cntB + m) : "memory");
+          }
+          if (threadIdx.x == 128) MNN_TRACE(8);
         }
         __syncwarp();
       }
+      if (threadIdx.x == 128) MNN_TRACE(9);
       if (lane == 0) mbar_arrive(smem_u32(&bfree));
     }
   }
@@ -1361,10 +1404,32 @@ extern "C" int mnn_lstm_seq_bwd_tc(float* gates, const float* wh, const float* c
     at[0].id = cudaLaunchAttributeCooperative;
     at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
+    static const char* trace_path = getenv("MNN_LSTM_TRACE");   // debug only: allocates and synchronises
+    const size_t trace_n = (size_t)2 * mnn_tc_num_sms() * kTraceSteps * kTraceEv;
+    if (trace_path) {
+      cudaMalloc(&q.trace, trace_n * sizeof(unsigned long long));
+      cudaMemsetAsync(q.trace, 0, trace_n * sizeof(unsigned long long), stream);
+    }
     cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_tc3_bwd_kernel, ma, mb, mdhr, mdh, mg, mc, mdo, mds, mdc, q);
     if (e != cudaSuccess) {
       mnn_set_error(cudaGetErrorString(e));
       return (int)e;
+    }
+    if (trace_path) {
+      cudaStreamSynchronize(stream);
+      std::vector<unsigned long long> h(trace_n);
+      cudaMemcpy(h.data(), q.trace, trace_n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      cudaFree(q.trace);
+      if (FILE* f = fopen(trace_path, "a")) {
+        fprintf(f, "# lstm pair bwd B=%d R=%d T=%d ctas=%d splits=%d\n", B, R, T, (int)cfg.gridDim.x, q.splits);
+        for (unsigned c = 0; c < cfg.gridDim.x; ++c)
+          for (int st = 0; st < kTraceSteps; ++st) {
+            fprintf(f, "%u %d", c, st);
+            for (int ev = 0; ev < kTraceEv; ++ev) fprintf(f, " %llu", h[((size_t)c * kTraceSteps + st) * kTraceEv + ev]);
+            fprintf(f, "\n");
+          }
+        fclose(f);
+      }
     }
     return mnn_check_launch("lstm_seq_bwd(pair)");
   }

@@ -23,10 +23,24 @@ for R in (512, 256):
         ops.lstm_seq_fwd(gates, wh, hbuf, cbuf, out=out, dscale=ds, keep=0.9, seed=1)
         e1.record()
         torch.cuda.synchronize()
-    print(f'R={R}: {e0.elapsed_time(e1) / T * 1e3:.1f} us/step')
+    print(f'R={R}: fwd {e0.elapsed_time(e1) / T * 1e3:.1f} us/step')
+    dout = torch.randn(T, B, R, device='cuda') * 0.01
+    dc = torch.empty(B, R, device='cuda')
+    for _ in range(2):
+        g2 = gates.clone()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.lstm_seq_bwd(g2, wh, cbuf, dout, ds, dc, dc)
+        e1.record()
+        torch.cuda.synchronize()
+    print(f'R={R}: bwd {e0.elapsed_time(e1) / T * 1e3:.1f} us/step')
 path = os.environ.get('MNN_LSTM_TRACE')
 if path and os.path.exists(path):
-    blocks = open(path).read().split('# lstm pair fwd')[1:]
+    FW = ['flag_ok', 'tma_issued', 'conv_first_full', 'conv_done', 'mma_first', 'mma_commit', 'epi0_tfull',
+          'epi0_done', 'published', 'epi1_tfull', 'epi1_done', 'epi0_tiles_in']
+    BW = ['cntB_ok', 'mma_first', 'mma_commit', 'epiA_tfull', 'cntA_inc', 'cell_cntA_ok', 'cell_tiles_in', 'cell_done',
+          'cell_cntB_inc', 'cells_all_done']
+    blocks = open(path).read().split('# lstm pair ')[1:]
     for blk in blocks[1::2]:          # second (warm) call of each shape
         lines = blk.strip().split('\n')
         print('#', lines[0])
@@ -37,8 +51,7 @@ if path and os.path.exists(path):
             sel = rows[:, 1] == st
             e = ev[sel]
             t0 = np.nanmin(e[:, 0])
-            names = ['flag_ok', 'tma_issued', 'conv_first_full', 'conv_done', 'mma_first', 'mma_commit', 'epi0_tfull',
-                     'epi0_done', 'published', 'epi1_tfull', 'epi1_done', 'epi0_tiles_in']
+            names = FW if lines[0].startswith('fwd') else BW
             print(f' step {st}: ' + ' | '.join(f'{n} {np.nanmin(e[:, i]) - t0:.0f}/{np.nanmean(e[:, i]) - t0:.0f}/{np.nanmax(e[:, i]) - t0:.0f}'
                                                 for i, n in enumerate(names)))
         # step period
