@@ -30,9 +30,23 @@ NADE_FLOPS_FWD = 9_139_200
 # split of DENSE_FLOPS_FWD: batched GEMMs (input projections + Dense) vs the sequential recurrence h.Wh
 BATCHED_FLOPS_FWD = 2 * (420 * 2048 + 512 * 1024 + 256 * 1700)   # 3 639 296
 RECUR_FLOPS_FWD = 2 * (512 * 2048 + 256 * 1024)                  # 2 621 440
-# what one training step really asks of mnn_gemm_tc: fwd + data-grad + weight-grad, minus the layer-0 data-grad that
-# nothing consumes (the inputs are data)
-GEMM_TC_FLOPS_STEP = 3 * BATCHED_FLOPS_FWD - 2 * 420 * 2048
+# what one training step really asks of mnn_gemm_tc per time-step: forward input projections + Dense, their data
+# gradients (none for layer 0: the inputs are data) and ALL weight gradients (the recurrent ones are batched GEMMs too)
+GEMM_TC_FLOPS_STEP = (BATCHED_FLOPS_FWD                                   # forward
+                      + 2 * (256 * 1700 + 512 * 1024)                     # dout = dfc.K^T, d_in2 = dG2.W2x^T
+                      + 2 * (932 * 2048 + 768 * 1024 + 256 * 1700))       # dW1, dW2 (x and h rows), dK
+# NADE in the segment form the kernels run (exact for any input): decode dots D*H MACs per track, forward; the backward
+# needs the same dots twice (d h and d W_dec)
+NADE_SEG_FLOPS_FWD = 2 * M * D * H
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # CUDA-core FMA peak of a B200 at 1965 MHz (SIMT kernels)
+
+
+def profiled_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu --set full capture (profiles/*traffic.json), or None."""
+    p = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    if os.path.exists(p):
+        return json.load(open(p)).get(kernel)
+    return None
 
 
 def peaks():
@@ -201,6 +215,22 @@ def run_gpu(args):
     # ---- per-phase device times of one more step (CUDA events on the launching stream) -> roofline
     phases = profile_phases(model, xdev[0], args)
 
+    # ---- autoregressive sampling (BASELINE configs[4]: 512 steps from a 32-step intro); a 64-step sample is timed
+    sampling = None
+    if not args.no_sampling:
+        intro = xdev[0][:, :32].contiguous()
+        model.generate(intro, 4, seed=1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        model.generate(intro, 64, seed=2)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 64 * 1e3
+        sampling = {'batch_per_gpu': Bl, 'intro_steps': 32, 'timed_steps': 64, 'us_per_generated_step': us,
+                    'generated_time_steps_per_s': world * Bl / (us * 1e-6),
+                    'note': 'random-init weights sample ~50 % dense frames: the worst case for the segment-form sampler'}
+
     if rank == 0:
         pk = peaks()
         tps = B * T / (ms * 1e-3)
@@ -219,17 +249,18 @@ def run_gpu(args):
                     'h2d_bytes_per_step': hosts[0].numel() * hosts[0].element_size(), 'd2h_bytes_per_step': 4},
             'gpu_launches': int(launches),
             'clocks': clk,
-            'roofline': {'bound': 'tensor', 'kernel': 'mnn::tc::gemm_tc_kernel (tcgen05 3xTF32: input projections, Dense, '
-                                                      'data- and weight-gradient GEMMs)',
+            'roofline': {'bound': 'tensor', 'kernel': 'mnn::tc::gemm_tc2_kernel / gemm_tc_kernel (tcgen05 3xTF32, cta_group::2 '
+                                                      'pair tiles for K >= 512: input projections, Dense, data- and '
+                                                      'weight-gradient GEMMs; largest kernel class of the step)',
                          'achieved': gemm_tf, 'peak': pk['tf_sust'], 'unit': 'TFLOP/s', 'frac': gemm_tf / pk['tf_sust'],
-                         'traffic': None, 'peak_source': pk['src'] + ' (cuBLAS bf16, sustained)',
+                         'traffic': profiled_traffic('gemm_tc'), 'peak_source': pk['src'] + ' (cuBLAS bf16, sustained)',
                          'launches_per_step': n_gemm, 'avg_launch_ms': gemm_ms / n_gemm,
                          'algorithmic_flops_per_step': GEMM_TC_FLOPS_STEP * n_rows,
-                         'note': 'fp32-accurate path: every algorithmic MAC costs 2-3 tf32 MMAs, so the tensor pipe does '
-                                 '~2.8x the algorithmic flops counted here; tf32 peak is half the bf16 peak',
-                         'recurrence_tflops': 3 * RECUR_FLOPS_FWD * n_rows / ((phases.get('recur_fwd_ms', 0) +
-                                              phases.get('recur_bwd_ms', 0) or 1) * 1e-3) / 1e12,
+                         'note': 'fp32-accurate path: every algorithmic MAC costs 2-3 tf32 MMAs (tf32 runs at half the '
+                                 'bf16 rate), so the ceiling against the bf16 denominator is 1/6 (1/4 with binary A)',
                          'phases_ms': phases},
+            'kernels': kernel_table(phases, n_rows, pk),
+            'sampling': sampling,
             'final_loss': final_loss,
         }
         if world == 1 and not args.no_cpu:
@@ -240,6 +271,32 @@ def run_gpu(args):
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def kernel_table(ph, n_rows, pk):
+    """Per-kernel-class roofline fractions of one training step (per-GPU rows), from the CUDA-event phase times."""
+    def row(name, ms, bound, work, peak, unit, note=''):
+        if not ms:
+            return None
+        ach = work / (ms * 1e-3)
+        return {'kernel': name, 'ms': ms, 'bound': bound, 'achieved': ach, 'peak': peak, 'unit': unit,
+                'frac': ach / peak, 'note': note}
+    rec_ms = ph.get('recur_fwd_ms', 0) + ph.get('recur_bwd_ms', 0)
+    rows = [
+        row('gemm_tc2 / gemm_tc (3xTF32)', ph.get('gemm_ms'), 'tensor', GEMM_TC_FLOPS_STEP * n_rows / 1e12, pk['tf_sust'],
+            'TFLOP/s', 'algorithmic flops; x2-3 tf32 MMAs each'),
+        row('lstm_tc2_fwd + lstm_tc3_bwd (pair recurrence)', rec_ms, 'tensor', 2 * RECUR_FLOPS_FWD * n_rows / 1e12,
+            pk['tf_sust'], 'TFLOP/s', 'h.Wh and dG.Wh^T; latency chain per time step, see DESIGN.md'),
+        row('nade_fwd (segment form)', ph.get('nade_fwd_ms'), 'fma', NADE_SEG_FLOPS_FWD * n_rows / 1e12, FP32_PEAK_TFLOPS,
+            'TFLOP/s', 'SIMT: useful decode-dot flops vs the CUDA-core fp32 peak'),
+        row('nade_bwd (segment form)', ph.get('nade_bwd_ms'), 'fma', 2 * NADE_SEG_FLOPS_FWD * n_rows / 1e12,
+            FP32_PEAK_TFLOPS, 'TFLOP/s', 'SIMT: useful flops vs the CUDA-core fp32 peak'),
+        row('nade_fwd HBM', ph.get('nade_fwd_ms'), 'hbm', n_rows * (1700 * 4 + M * D * 4 + 80 + 20) / 1e9, pk['hbm'], 'GB/s',
+            'reads fc, writes d b_dec + nll'),
+        row('pack (input staging)', ph.get('pack_ms'), 'hbm', n_rows * (420 + 1680 + 80) / 1e9, pk['hbm'], 'GB/s'),
+        row('colsum (bias grads)', ph.get('colsum_ms'), 'hbm', n_rows * (2048 + 1024 + 1700) * 4 / 1e9, pk['hbm'], 'GB/s'),
+    ]
+    return [r for r in rows if r]
 
 
 def profile_phases(model, x, args):
@@ -294,8 +351,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='C5', choices=sorted(WORKLOADS))
-    ap.add_argument('--cpu-batch', type=int, default=64, help='batch rows of the bounded CPU sample')
+    ap.add_argument('--cpu-batch', type=int, default=128, help='batch rows of the bounded CPU sample')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-sampling', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -491,8 +491,11 @@ struct NadeSampleArgs {
   unsigned long long seed, offset; int use_philox;
 };
 
+// 1024 threads: every dim of a row is a dependent chain (dot -> reduce -> sigmoid -> compare -> maybe 8 more sigmoids), so
+// the kernel lives on warps in flight: 32 warps per SM instead of 8 (weights of one track fill shared memory: 1 CTA/SM).
+constexpr int kSampleThreads = 1024;
 template <int NCH>
-__global__ void __launch_bounds__(256, 1) nade_sample_kernel(NadeSampleArgs p) {
+__global__ void __launch_bounds__(kSampleThreads, 1) nade_sample_kernel(NadeSampleArgs p) {
   constexpr int H = NCH * 128;
   extern __shared__ __align__(16) float smem[];
   const int D = p.D;
@@ -667,15 +670,16 @@ extern "C" int mnn_nade_sample(const float* fc, long long ld, int enc_col0, int 
                    nll, N, M, D, seed, offset, use_philox};
   const size_t smem = (size_t)2 * D * H * sizeof(float);
   int grid = num_sms();
-  const int need = M * ((N + 7) / 8);
+  const int wpc = kSampleThreads / 32;
+  const int need = M * ((N + wpc - 1) / wpc);
   if (grid > need) grid = need;
   if (grid < M) grid = M;
   if (H == 256) {
     cudaFuncSetAttribute(nade_sample_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    nade_sample_kernel<2><<<grid, 256, smem, stream>>>(a);
+    nade_sample_kernel<2><<<grid, kSampleThreads, smem, stream>>>(a);
   } else {
     cudaFuncSetAttribute(nade_sample_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    nade_sample_kernel<1><<<grid, 256, smem, stream>>>(a);
+    nade_sample_kernel<1><<<grid, kSampleThreads, smem, stream>>>(a);
   }
   return mnn_check_launch("nade_sample");
 }
