@@ -39,6 +39,7 @@ struct Params {
   int tiles_m, tiles_n, splits, kb_total, kb_per_split;
   int n_products;  // 3, or 2 when A is exactly representable in tf32 (binary piano-roll rows)
   int atomic;      // split-K: red.global.add into C
+  int tma_store;   // pair kernel: C tiles leave through shared memory + TMA (needs beta == 0, no split-K, aligned C)
 };
 
 template <int BN>
@@ -285,12 +286,14 @@ struct Cfg2 {
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = 3;
   static constexpr int TMEM_COLS = 2 * BN2;           // main + aux, single buffered
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024;
+  static constexpr int CTILE = BM * 128;              // [128 rows x 32 cols] fp32 staging tile of the TMA-store epilogue
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 2 * CTILE + 1024;
 };
 
 template <bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const __grid_constant__ CUtensorMap map_c, const Params p) {
   using C_ = Cfg2;
   constexpr int STAGES = C_::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -437,6 +440,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // ------------------------------------------------------------------ epilogue: this CTA's 128 rows x 256 columns
     const int q = warp - 4;
     uint32_t acc_phase = 0;
+    int store_no = 0;
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
     const uint32_t tempty_leader = mapa_cluster(bar_tempty, 0);
     for (int w = cluster_id; w < n_items; w += n_clusters) {
@@ -446,6 +450,38 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       mbar_wait(bar_tfull, acc_phase);
       tc_fence_after();
       const bool add_bias = p.bias != nullptr && (!p.atomic || split == 0);
+      if (p.tma_store) {
+        // row-per-thread global stores touch 32 cache lines per warp instruction (4 us per tile, as long as a K = 256
+        // mainloop); instead: registers -> swizzled [128 x 32] staging tile -> TMA store, double buffered
+        const int r = q * 32 + lane, sw = r & 7;
+        const int row_t = m_blk * 2 * BM + (int)rank * BM;
+#pragma unroll 1
+        for (int c = 0; c < BN2 / 32; ++c) {
+          const int col0 = n0 + c * 32;
+          if (col0 >= p.N) break;   // warp-uniform
+          float v[32], vx[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN2 + c * 32), vx);
+          float bv = 0.f;
+          if (p.bias != nullptr && col0 + lane < p.N) bv = __ldg(p.bias + col0 + lane);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaf(p.alpha, v[i] + vx[i], __shfl_sync(0xffffffffu, bv, i));
+          const int buf = store_no & 1;
+          if (threadIdx.x == 4 * 32 && store_no >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          asm volatile("bar.sync 2, 128;" ::: "memory");   // staging buffer `buf` has been read by its previous store
+          uint8_t* rowp = smem_gen + (size_t)STAGES * C_::STAGE_BYTES + (size_t)buf * C_::CTILE + r * 128;
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj)
+            *reinterpret_cast<float4*>(rowp + ((jj ^ sw) << 4)) = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (threadIdx.x == 4 * 32) {
+            tma_store_2d(&map_c, smem0 + STAGES * C_::STAGE_BYTES + buf * C_::CTILE, col0, row_t);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          ++store_no;
+        }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < BN2 / 32; ++c) {
         const int col0 = n0 + c * 32;
@@ -484,11 +520,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           }
         }
       }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_leader);
       acc_phase ^= 1;
     }
+    if (threadIdx.x == 4 * 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -636,7 +674,7 @@ static int num_clusters2(const void* fn) {
 }
 
 template <bool A_MN, bool B_MN>
-static int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, cudaStream_t stream) {
+static int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const Params& p, cudaStream_t stream) {
   static int max_clusters = 0;
   if (!max_clusters) {
     cudaFuncSetAttribute(gemm_tc2_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2::SMEM);
@@ -644,16 +682,16 @@ static int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p
   }
   const int items = p.tiles_m * p.tiles_n * p.splits;
   const int clusters = items < max_clusters ? items : max_clusters;
-  gemm_tc2_kernel<A_MN, B_MN><<<2 * clusters, kThreads, Cfg2::SMEM, stream>>>(ma, mb, p);
+  gemm_tc2_kernel<A_MN, B_MN><<<2 * clusters, kThreads, Cfg2::SMEM, stream>>>(ma, mb, mc, p);
   return mnn_check_launch("gemm_tc2");
 }
 
-static int dispatch_major2(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const Params& p,
-                           cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch2<false, false>(ma, mb, p, s);
-  if (!a_mn && b_mn) return launch2<false, true>(ma, mb, p, s);
-  if (a_mn && !b_mn) return launch2<true, false>(ma, mb, p, s);
-  return launch2<true, true>(ma, mb, p, s);
+static int dispatch_major2(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc,
+                           const Params& p, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch2<false, false>(ma, mb, mc, p, s);
+  if (!a_mn && b_mn) return launch2<false, true>(ma, mb, mc, p, s);
+  if (a_mn && !b_mn) return launch2<true, false>(ma, mb, mc, p, s);
+  return launch2<true, true>(ma, mb, mc, p, s);
 }
 
 template <int BN>
@@ -696,9 +734,10 @@ extern "C" int mnn_gemm_tc(const float* A, long long lda, int transA, const floa
   const bool a_mn = transA != 0;   // A stored [K,M]: M contiguous
   const bool b_mn = transB == 0;   // B stored [K,N]: N contiguous
   static const bool force_1cta = getenv("MNN_GEMM_1CTA") != nullptr;
-  // 256x256 tiles on CTA pairs: their accumulators fill TMEM (no epilogue overlap), so short-K shapes stay on the
-  // double-buffered 128x128 kernel (measured crossover: K ~ 512)
-  const bool pair = !force_1cta && M >= 256 && N > 128 && K >= 512;
+  static const char* kmin_env = getenv("MNN_GEMM_PAIR_KMIN");
+  static const int pair_kmin = kmin_env ? atoi(kmin_env) : 64;
+  // 256x256 tiles on CTA pairs; with the TMA-store epilogue they win down to K = 256 (Dense forward: 2.28 vs 3.67 ms)
+  const bool pair = !force_1cta && M >= 256 && N > 128 && K >= pair_kmin;
   const int BN = pair ? BN2 : (N > 64 ? 128 : 64);
   const int TM = pair ? 2 * BM : BM;
   const int units = pair ? num_sms() / 2 : num_sms();
@@ -736,7 +775,15 @@ extern "C" int mnn_gemm_tc(const float* A, long long lda, int transA, const floa
   else rc = make_map(B, ldb, N, K, BK, true, &mb);           // [K rows][N]   box {32 n, 32 k}
   if (rc) return rc;
 
-  if (pair) return dispatch_major2(a_mn, b_mn, ma, mb, p, stream);
+  if (pair) {
+    CUtensorMap mc = ma;
+    p.tma_store = (!p.atomic && beta == 0.f && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
+    if (p.tma_store) {
+      rc = make_map(C, ldc, N, M, BM, false, &mc);             // [M rows][N]   box {32 n, 128 rows}
+      if (rc) return rc;
+    }
+    return dispatch_major2(a_mn, b_mn, ma, mb, mc, p, stream);
+  }
   if (BN == 128) return dispatch_major<128>(a_mn, b_mn, ma, mb, p, stream);
   return dispatch_major<64>(a_mn, b_mn, ma, mb, p, stream);
 }

@@ -87,8 +87,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) nade_fwd_kernel(NadeArgs p) {
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         a[r][c] = __ldg(reinterpret_cast<const float4*>(be + c * 128 + lane * 4));
-        h[r][c] = make_float4(sigmoid_fast(a[r][c].x), sigmoid_fast(a[r][c].y),
-                              sigmoid_fast(a[r][c].z), sigmoid_fast(a[r][c].w));
+        h[r][c] = make_float4(sigmoid_mufu(a[r][c].x), sigmoid_mufu(a[r][c].y),
+                              sigmoid_mufu(a[r][c].z), sigmoid_mufu(a[r][c].w));
       }
     }
     const int erow = row0 + er;
@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) nade_fwd_kernel(NadeArgs p) {
     const size_t erow_c = (size_t)min(erow, p.N - 1);
     float nll_acc = 0.f;
 
+#pragma unroll 1
     for (int c8 = 0; c8 < nchunks; ++c8) {
       const int i0 = c8 * 8;
       // prefetch this lane's decoder bias
@@ -120,8 +121,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) nade_fwd_kernel(NadeArgs p) {
             for (int c = 0; c < NCH; ++c) {
               const float4 w = *reinterpret_cast<const float4*>(we + c * 128 + lane * 4);
               a[r][c].x += w.x; a[r][c].y += w.y; a[r][c].z += w.z; a[r][c].w += w.w;
-              h[r][c] = make_float4(sigmoid_fast(a[r][c].x), sigmoid_fast(a[r][c].y),
-                                    sigmoid_fast(a[r][c].z), sigmoid_fast(a[r][c].w));
+              h[r][c] = make_float4(sigmoid_mufu(a[r][c].x), sigmoid_mufu(a[r][c].y),
+                                    sigmoid_mufu(a[r][c].z), sigmoid_mufu(a[r][c].w));
             }
           }
         }
