@@ -157,7 +157,10 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch:      # development aid: time one shard of a larger data-parallel job on one GPU (e.g. --batch 256 = dp8)
+        wl['B'] = args.batch
+        wl['name'] += f' [batch overridden to {args.batch}]'
     B, T = wl['B'], wl['T']
     assert B % world == 0
     Bl = B // world
@@ -264,9 +267,9 @@ def run_gpu(args):
             'final_loss': final_loss,
         }
         if world == 1 and not args.no_cpu:
-            v, cores, _, sec = cpu_port_run(args.cpu_batch, T, 4, 1)
+            v, cores, _, sec = cpu_port_run(args.cpu_batch, T, 3, 1)
             out['cpu_baseline'] = {'value': v, 'unit': 'time-steps/s', 'cores': cores, 'kind': 'port',
-                                   'sample': f'[{args.cpu_batch},{T},84,5] slice, 1 warm-up + 4 timed steps '
+                                   'sample': f'[{args.cpu_batch},{T},84,5] slice, 1 warm-up + 3 timed steps '
                                              f'({sec:.2f} s/step), torch-CPU fp32 restatement of the TF1 graph'}
         print(json.dumps(out))
     if world > 1:
@@ -354,6 +357,7 @@ def main():
     ap.add_argument('--cpu-batch', type=int, default=128, help='batch rows of the bounded CPU sample')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-sampling', action='store_true')
+    ap.add_argument('--batch', type=int, default=0, help='override the global batch (development aid)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

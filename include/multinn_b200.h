@@ -59,6 +59,11 @@ int mnn_gemm_tc(const float* A, long long lda, int transA, const float* B, long 
                 long long ldc, const float* bias, float alpha, float beta, int M, int N, int K, int a_exact,
                 mnn_stream_t stream);
 
+/* Caps the grids of this thread's following mnn_gemm_tc launches at `sms` SMs (0 = whole device): a projection GEMM of
+ * one time chunk can then run beside the persistent recurrence kernels of other streams (layer wavefront at small
+ * per-GPU batches) instead of queueing CTAs behind them. Host-side, thread-local; no reference counterpart. */
+int mnn_set_sm_budget(int sms);
+
 /* K2 -- LSTM temporal unit. common/rnn.py:104-145 (CudnnCompatibleLSTMCell, gate blocks i,j,f,o, forget_bias 0;
  * DropoutWrapper output_keep_prob; MultiRNNCell), driven like dynamic_decode at generators/rnn_nade.py:204-218.
  * One cell step: gates[B,4R] in = pre-activations, out = activations; out = h/keep*floor(keep+u). */
@@ -86,6 +91,12 @@ int mnn_lstm_seq_fwd_tc(float* gates, const float* wh, float* hbuf, float* cbuf,
                         int persistent, mnn_stream_t stream);
 int mnn_lstm_seq_bwd_tc(float* gates, const float* wh, const float* cbuf, const float* dout, const float* dscale,
                         float* dc_work, int T, int B, int R, void* ws, int persistent, mnn_stream_t stream);
+/* BPTT of one time chunk [t0, t0+T) of a longer sequence (pointers at the chunk's first slot). has_next != 0: the chunk
+ * after it has already been back-propagated, i.e. gates slot T holds dG of step t0+T and dc_work the carried cell
+ * gradient, so the chunk's last step takes its recurrent term like every other step. */
+int mnn_lstm_seq_bwd_tc_chunk(float* gates, const float* wh, const float* cbuf, const float* dout, const float* dscale,
+                              float* dc_work, int T, int B, int R, void* ws, int persistent, int has_next,
+                              mnn_stream_t stream);
 /* out[c] (+)= sum_r A[r,c] (bias gradients); deterministic two-stage sum, ws >= mnn_colsum_workspace_bytes(cols). */
 size_t mnn_colsum_workspace_bytes(int cols);
 int mnn_colsum(const float* A, long long ld, int rows, int cols, float* out, int accumulate, void* ws,

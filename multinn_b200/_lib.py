@@ -35,6 +35,7 @@ SIGNATURES = {
     "mnn_pack_pianoroll_u8": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
     "mnn_pack_rows": [_p, _ll, _i, _p, _i, _i, _p],
     "mnn_gemm_f32": [_p, _ll, _i, _p, _ll, _i, _p, _ll, _p, _f, _f, _i, _i, _i, _p],
+    "mnn_set_sm_budget": [_i],
     "mnn_gemm_tc_supported": [_p, _ll, _p, _ll],
     "mnn_gemm_tc": [_p, _ll, _i, _p, _ll, _i, _p, _ll, _p, _f, _f, _i, _i, _i, _i, _p],
     "mnn_lstm_cell_fwd": [_p, _p, _p, _p, _p, _p, _p, _f, _u64, _u64, _i, _i, _p],
@@ -44,6 +45,7 @@ SIGNATURES = {
     "mnn_lstm_tc_supported": [_i, _i],
     "mnn_lstm_seq_fwd_tc": [_p, _p, _p, _p, _p, _p, _p, _f, _u64, _i, _i, _i, _p, _i, _p],
     "mnn_lstm_seq_bwd_tc": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _i, _p],
+    "mnn_lstm_seq_bwd_tc_chunk": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _i, _i, _p],
     "mnn_colsum_workspace_bytes": [_i],
     "mnn_colsum": [_p, _ll, _i, _i, _p, _i, _p, _p],
     "mnn_nade_logprob_fwd": [_p, _p, _ll, _i, _i, _p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _p],

@@ -89,6 +89,23 @@ class RNN:
         return ws
 
     # ------------------------------------------------------------------ whole-sequence forward / BPTT
+    # At small per-GPU batches (data-parallel shards) a recurrence step is a fixed latency chain that keeps well under
+    # half of the SMs busy, so the layers are run as a WAVEFRONT over time chunks: layer l works on chunk c while
+    # layer l+1 works on chunk c-1 on another stream (SURVEY 7 "hard parts": recurrence latency at B/8).
+    WAVEFRONT_MAX_BATCH = 256
+    WAVEFRONT_CHUNK = 32
+    WAVEFRONT_GEMM_SMS = 32
+
+    def _use_wavefront(self, T, B):
+        return (self.num_layers > 1 and B <= self.WAVEFRONT_MAX_BATCH and T % self.WAVEFRONT_CHUNK == 0
+                and T >= 2 * self.WAVEFRONT_CHUNK)
+
+    def _streams(self, device):
+        st = self.__dict__.get('_wave_streams')
+        if st is None:
+            st = self._wave_streams = [torch.cuda.Stream(device=device) for _ in range(self.num_layers)]
+        return st
+
     def forward_sequence(self, x, keep=1.0, u=None, seed=0, initial_state=None):
         """x[T,B,I] time-major -> outputs[T,B,R_top] (dropped out when keep < 1), final state.
         u: optional list (per layer) of [T,B,R_l] uniforms for reproducible dropout; else Philox(seed).
@@ -97,57 +114,146 @@ class RNN:
         assert I == self._num_inputs and x.is_contiguous()
         dropout = keep < 1.0
         ws = self._workspace(T, B, x.device, dropout)
-        inp = x.view(T * B, I)
-        for l, r in enumerate(self._num_units):
-            w = ws[l]
-            kern, bias = self.kernels[l].data, self.biases[l].data
-            i_l = inp.shape[1]
-            gates = w['gates'].view(T * B, 4 * r)
-            ops.gemm(inp, kern[:i_l], gates, bias=bias, a_exact=(l == 0 and self._binary_inputs))   # hoisted input projection
+        for l, w in enumerate(ws):
             if initial_state is None:
                 w['hbuf'][0].zero_()
                 w['cbuf'][0].zero_()
             else:
                 w['cbuf'][0].copy_(initial_state[l][0])
                 w['hbuf'][0].copy_(initial_state[l][1])
-            ops.lstm_seq_fwd(w['gates'], kern[i_l:], w['hbuf'], w['cbuf'],
-                             out=w['out'] if dropout else None, dscale=w['dscale'] if dropout else None,
-                             u=None if u is None else u[l], keep=keep, seed=seed + 7919 * l)
-            out = w['out'] if dropout else w['hbuf'][1:]
-            inp = out.view(T * B, r)
+        outs = [w['out'] if dropout else w['hbuf'][1:] for w in ws]
+        # layer 0: hoisted input projection over all T*B rows
+        r0 = self._num_units[0]
+        ops.gemm(x.view(T * B, I), self.kernels[0].data[:I], ws[0]['gates'].view(T * B, 4 * r0), bias=self.biases[0].data,
+                 a_exact=self._binary_inputs)
+        if self._use_wavefront(T, B):
+            self._forward_wavefront(ws, outs, T, B, keep, u, seed, dropout)
+        else:
+            for l, r in enumerate(self._num_units):
+                w = ws[l]
+                kern = self.kernels[l].data
+                i_l = self.in_dims()[l]
+                if l > 0:
+                    ops.gemm(outs[l - 1].view(T * B, i_l), kern[:i_l], w['gates'].view(T * B, 4 * r), bias=self.biases[l].data)
+                ops.lstm_seq_fwd(w['gates'], kern[i_l:], w['hbuf'], w['cbuf'],
+                                 out=w['out'] if dropout else None, dscale=w['dscale'] if dropout else None,
+                                 u=None if u is None else u[l], keep=keep, seed=seed + 7919 * l)
         self._saved = (x, ws, dropout)
         state = [LSTMStateTuple(w['cbuf'][T], w['hbuf'][T]) for w in ws]
-        return out, state
+        return outs[-1], state
+
+    def _forward_wavefront(self, ws, outs, T, B, keep, u, seed, dropout):
+        C = self.WAVEFRONT_CHUNK
+        nch = T // C
+        main = torch.cuda.current_stream()
+        streams = self._streams(ws[0]['gates'].device)
+        start = torch.cuda.Event()
+        start.record(main)
+        done = [[torch.cuda.Event() for _ in range(nch)] for _ in range(self.num_layers)]
+        for c in range(nch):
+            t0, t1 = c * C, (c + 1) * C
+            for l, r in enumerate(self._num_units):
+                w = ws[l]
+                kern = self.kernels[l].data
+                i_l = self.in_dims()[l]
+                with torch.cuda.stream(streams[l]):
+                    if c == 0:
+                        streams[l].wait_event(start)
+                    if l > 0:
+                        streams[l].wait_event(done[l - 1][c])
+                        ops.set_sm_budget(self.WAVEFRONT_GEMM_SMS)
+                        try:
+                            ops.gemm(outs[l - 1][t0:t1].reshape(C * B, i_l), kern[:i_l],
+                                     w['gates'][t0:t1].view(C * B, 4 * r), bias=self.biases[l].data)
+                        finally:
+                            ops.set_sm_budget(0)
+                    ops.lstm_seq_fwd(w['gates'][t0:t1], kern[i_l:], w['hbuf'][t0:t1 + 1], w['cbuf'][t0:t1 + 1],
+                                     out=w['out'][t0:t1] if dropout else None,
+                                     dscale=w['dscale'][t0:t1] if dropout else None,
+                                     u=None if u is None else u[l][t0:t1], keep=keep,
+                                     seed=seed + 7919 * l + 104729 * c)
+                    done[l][c].record(streams[l])
+        for l in range(self.num_layers):
+            main.wait_event(done[l][nch - 1])
 
     def backward_sequence(self, dout, need_dx=False):
         """dout[T,B,R_top] = grad wrt the (dropped-out) top outputs. Writes kernel/bias grads; returns dx or None."""
         x, ws, dropout = self._saved
         T, B, I = x.shape
-        dx = None
+        for l, r in enumerate(self._num_units):
+            w = ws[l]
+            w.setdefault('dh_work', torch.empty(B, r, device=x.device))
+            w.setdefault('dc_work', torch.empty(B, r, device=x.device))
+            i_l = self.in_dims()[l]
+            if (l > 0 or need_dx) and (w.get('d_in') is None or w['d_in'].shape != (T, B, i_l)):
+                w['d_in'] = torch.empty(T, B, i_l, device=x.device)
+        if self._use_wavefront(T, B):
+            self._backward_wavefront(ws, dout, T, B, dropout, need_dx)
+        else:
+            d = dout
+            for l in reversed(range(self.num_layers)):
+                w = ws[l]
+                kern = self.kernels[l]
+                i_l = self.in_dims()[l]
+                ops.lstm_seq_bwd(w['gates'], kern.data[i_l:], w['cbuf'], d, w['dscale'] if dropout else None,
+                                 w['dh_work'], w['dc_work'])
+                if l > 0 or need_dx:
+                    ops.gemm(w['gates'].view(T * B, -1), kern.data[:i_l], w['d_in'].view(T * B, i_l), transB=True)   # dx = dG Wx^T
+                    d = w['d_in']
+        # weight gradients: batched GEMMs over all T*B rows
         for l in reversed(range(self.num_layers)):
             r = self._num_units[l]
             w = ws[l]
             kern = self.kernels[l]
             i_l = self.in_dims()[l]
-            dh_work = w.setdefault('dh_work', torch.empty(B, r, device=x.device))
-            dc_work = w.setdefault('dc_work', torch.empty(B, r, device=x.device))
-            ops.lstm_seq_bwd(w['gates'], kern.data[i_l:], w['cbuf'], dout, w['dscale'] if dropout else None,
-                             dh_work, dc_work)
             dg = w['gates'].view(T * B, 4 * r)                       # now d(pre-activations)
             inp = x.view(T * B, I) if l == 0 else \
                 (ws[l - 1]['out'] if dropout else ws[l - 1]['hbuf'][1:]).view(T * B, i_l)
             ops.gemm(inp, dg, kern.grad[:i_l], transA=True, a_exact=(l == 0 and self._binary_inputs))   # dWx = x^T dG
             ops.gemm(w['hbuf'][:T].view(T * B, r), dg, kern.grad[i_l:], transA=True)   # dWh = h_{t-1}^T dG
             ops.colsum(dg, self.biases[l].grad)
-            if l > 0 or need_dx:
-                d_in = w.get('d_in')
-                if d_in is None or d_in.shape != (T, B, i_l):
-                    d_in = w['d_in'] = torch.empty(T, B, i_l, device=x.device)
-                ops.gemm(dg, kern.data[:i_l], d_in.view(T * B, i_l), transB=True)    # dx = dG Wx^T
-                dout = d_in
-                if l == 0:
-                    dx = d_in
-        return dx
+        return ws[0]['d_in'] if need_dx else None
+
+    def _backward_wavefront(self, ws, dout, T, B, dropout, need_dx):
+        """BPTT as a wavefront over time chunks: layer l back-propagates chunk c while layer l-1 works on chunk c+1."""
+        C = self.WAVEFRONT_CHUNK
+        nch = T // C
+        L = self.num_layers
+        main = torch.cuda.current_stream()
+        streams = self._streams(ws[0]['gates'].device)
+        start = torch.cuda.Event()
+        start.record(main)
+        done = [[torch.cuda.Event() for _ in range(nch)] for _ in range(L)]
+        budgets = [0] * L
+        if L == 2:
+            budgets = [72, 36]          # SMs for the persistent BPTT kernels of the two layers (they must co-reside)
+        for c in reversed(range(nch)):
+            t0, t1 = c * C, (c + 1) * C
+            for l in reversed(range(L)):
+                w = ws[l]
+                kern = self.kernels[l]
+                i_l = self.in_dims()[l]
+                r = self._num_units[l]
+                d = dout if l == L - 1 else ws[l + 1]['d_in']
+                with torch.cuda.stream(streams[l]):
+                    if c == nch - 1:
+                        streams[l].wait_event(start)
+                    if l < L - 1:
+                        streams[l].wait_event(done[l + 1][c])
+                    ops.set_sm_budget(budgets[l])
+                    try:
+                        ops.lstm_seq_bwd(w['gates'][t0:t1], kern.data[i_l:], w['cbuf'][t0:t1 + 1], d[t0:t1],
+                                         w['dscale'][t0:t1] if dropout else None, w['dh_work'], w['dc_work'],
+                                         has_next=c < nch - 1)
+                        if l > 0 or need_dx:
+                            ops.set_sm_budget(self.WAVEFRONT_GEMM_SMS)
+                            ops.gemm(w['gates'][t0:t1].view(C * B, 4 * r), kern.data[:i_l],
+                                     w['d_in'][t0:t1].view(C * B, i_l), transB=True)
+                    finally:
+                        ops.set_sm_budget(0)
+                    done[l][c].record(streams[l])
+        for l in range(L):
+            main.wait_event(done[l][0])
 
     # ------------------------------------------------------------------ one step (generation)
     def step(self, x, state, scratch=None):

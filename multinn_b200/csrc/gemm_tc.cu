@@ -634,7 +634,7 @@ static int make_map_plain(const float* ptr, long long ld, long long inner, long 
   return MNN_OK;
 }
 
-static int num_sms() {
+static int device_sms() {
   static int n = 0;
   if (!n) {
     int dev = 0;
@@ -643,6 +643,13 @@ static int num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+// SM budget of the calling thread's persistent GEMM grids (mnn_set_sm_budget): lets a GEMM run beside co-resident
+// persistent recurrence kernels of other streams instead of queueing CTAs behind them
+static thread_local int g_sm_budget = 0;
+static int num_sms() {
+  const int n = device_sms();
+  return (g_sm_budget > 0 && g_sm_budget < n) ? g_sm_budget : n;
 }
 
 template <int BN, bool A_MN, bool B_MN>
@@ -661,7 +668,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p,
 
 static int num_clusters2(const void* fn) {
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * num_sms());
+  cfg.gridDim = dim3(2 * device_sms());
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = Cfg2::SMEM;
   cudaLaunchAttribute at[1];
@@ -669,7 +676,7 @@ static int num_clusters2(const void* fn) {
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms() / 2; }
+  if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = device_sms() / 2; }
   return n;
 }
 
@@ -681,7 +688,8 @@ static int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorM
     max_clusters = num_clusters2(reinterpret_cast<const void*>(gemm_tc2_kernel<A_MN, B_MN>));
   }
   const int items = p.tiles_m * p.tiles_n * p.splits;
-  const int clusters = items < max_clusters ? items : max_clusters;
+  int clusters = items < max_clusters ? items : max_clusters;
+  if (clusters > num_sms() / 2) clusters = num_sms() / 2 > 0 ? num_sms() / 2 : 1;
   gemm_tc2_kernel<A_MN, B_MN><<<2 * clusters, kThreads, Cfg2::SMEM, stream>>>(ma, mb, mc, p);
   return mnn_check_launch("gemm_tc2");
 }
@@ -716,7 +724,14 @@ int mnn_tc_make_map_plain(const float* ptr, long long ld, long long inner, long 
                            CUtensorMap* out) {
   return mnn::tc::make_map_plain(ptr, ld, inner, outer, box_inner, box_outer, out);
 }
-int mnn_tc_num_sms() { return mnn::tc::num_sms(); }
+int mnn_tc_num_sms() { return mnn::tc::device_sms(); }
+
+int mnn_tc_sm_budget() { return mnn::tc::g_sm_budget; }
+
+extern "C" int mnn_set_sm_budget(int sms) {
+  mnn::tc::g_sm_budget = sms > 0 ? sms : 0;
+  return MNN_OK;
+}
 
 extern "C" int mnn_gemm_tc_supported(const float* A, long long lda, const float* B, long long ldb) {
   return ((lda & 3) == 0) && ((ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&

@@ -780,6 +780,7 @@ struct Lstm3Params {
   const float* dout;      // null: no gradient from above
   const float* dscale;    // null: no dropout
   int T, B, R;
+  int t_top;              // first (highest) step of the launch: T-2, or T-1 when a later chunk follows (dG_T readable)
   int slabs, ntiles, splits, kb_per_split;   // phase A: slabs of 256 rows, tiles of 256 units, K = 4R in `splits` parts
   unsigned int* cntA;     // [slabs]
   unsigned int* cntB;     // [slabs]
@@ -838,7 +839,7 @@ lstm_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
   const int R = p.R, B = p.B;
   const int n_itemsA = p.slabs * p.ntiles * p.splits;      // <= n_clusters (host): at most one phase-A item per pair
-  const int n_steps = p.T - 1;                             // t = T-2 .. 0 (dG_{T-1} comes from lstm_last_bwd_kernel)
+  const int n_steps = p.t_top + 1;                         // t = t_top .. 0
   const int kb_total = (4 * R + BK - 1) / BK;
   const bool has_item = cluster_id < n_itemsA;
   const int ks = cluster_id % p.splits, nt = (cluster_id / p.splits) % p.ntiles, mA = cluster_id / (p.splits * p.ntiles);
@@ -854,7 +855,7 @@ lstm_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int s = 0; s < n_steps; ++s) {
-        const int t = p.T - 2 - s;
+        const int t = p.t_top - s;
         if (s > 0) {
           const unsigned int target = (unsigned int)s * perB;                    // dG_{t+1} of the slab is complete
           while (ld_acquire(p.cntB + mA) < target) __nanosleep(32);
@@ -921,7 +922,7 @@ lstm_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint8_t* cellg = smem_gen + (size_t)cw * 20 * kCellTile;
     const int gw = blockIdx.x * 8 + cw, n_gw = gridDim.x * 8;
     for (int s = 0; s < n_steps; ++s) {
-      const int t = p.T - 2 - s;
+      const int t = p.t_top - s;
       // this step's cell tiles stream from HBM (saved activations, c, dout, dscale): pull them into L2 while phase A runs
       if (lane == 0) {
         for (int it = gw; it < n_cells; it += n_gw) {
@@ -1355,26 +1356,35 @@ extern "C" int mnn_lstm_seq_fwd_tc(float* gates, const float* wh, float* hbuf, f
   return launch_lstm<64, true>(ma, mb, p, persistent, stream);
 }
 
-extern "C" int mnn_lstm_seq_bwd_tc(float* gates, const float* wh, const float* cbuf, const float* dout,
-                                   const float* dscale, float* dc_work, int T, int B, int R, void* ws, int persistent,
-                                   cudaStream_t stream) {
+extern "C" int mnn_lstm_seq_bwd_tc_chunk(float* gates, const float* wh, const float* cbuf, const float* dout,
+                                         const float* dscale, float* dc_work, int T, int B, int R, void* ws, int persistent,
+                                         int has_next, cudaStream_t stream) {
   MNN_REQUIRE(gates && wh && cbuf && dc_work && ws, MNN_ERR_ARG, "lstm_seq_bwd_tc: null pointer");
+  // has_next: this is a time chunk [t0, t0+T) of a longer sequence whose later chunk has already been back-propagated:
+  // gates slot T holds dG of the next step and dc_work the carried cell gradient, so step T-1 is an ordinary step
   MNN_REQUIRE(T > 0 && mnn_lstm_tc_supported(B, R), MNN_ERR_UNSUPPORTED, "lstm_seq_bwd_tc: needs num_units % 8 == 0");
   const size_t BR = (size_t)B * R;
   const int n = B * R;
-  lstm_last_bwd_kernel<<<(n + 255) / 256, 256, 0, stream>>>(gates + (size_t)(T - 1) * B * 4 * R, cbuf + (size_t)(T - 1) * BR,
-                                                         cbuf + (size_t)T * BR, dout ? dout + (size_t)(T - 1) * BR : nullptr,
-                                                         dscale ? dscale + (size_t)(T - 1) * BR : nullptr, dc_work, B, R);
-  int rc = mnn_check_launch("lstm_last_bwd");
-  if (rc || T == 1) return rc;
+  int rc = MNN_OK;
+  if (!has_next) {
+    lstm_last_bwd_kernel<<<(n + 255) / 256, 256, 0, stream>>>(gates + (size_t)(T - 1) * B * 4 * R, cbuf + (size_t)(T - 1) * BR,
+                                                           cbuf + (size_t)T * BR, dout ? dout + (size_t)(T - 1) * BR : nullptr,
+                                                           dscale ? dscale + (size_t)(T - 1) * BR : nullptr, dc_work, B, R);
+    rc = mnn_check_launch("lstm_last_bwd");
+    if (rc || T == 1) return rc;
+  }
+  const int t_top = has_next ? T - 1 : T - 2;
 
   if (use_pair_bwd(B, R, T, persistent)) {
     uint8_t* cnt = reinterpret_cast<uint8_t*>(ws) + whp_region_bytes(R);
     float* dh_acc = reinterpret_cast<float*>(cnt + kCounterBytes);
     Lstm3Params q{};
-    q.dout = dout; q.dscale = dscale; q.T = T; q.B = B; q.R = R;
+    q.dout = dout; q.dscale = dscale; q.T = T; q.B = B; q.R = R; q.t_top = t_top;
     q.slabs = B / (2 * BM); q.ntiles = R / 256;
-    const int kb_total = 4 * R / BK, clusters = pair_bwd_clusters();
+    int clusters = pair_bwd_clusters();
+    if (mnn_tc_sm_budget() > 0 && clusters > mnn_tc_sm_budget() / 2) clusters = mnn_tc_sm_budget() / 2;
+    if (clusters < q.slabs * q.ntiles) clusters = q.slabs * q.ntiles;
+    const int kb_total = 4 * R / BK;
     int splits = clusters / (q.slabs * q.ntiles);
     if (splits > kb_total / 2) splits = kb_total / 2;
     if (splits < 1) splits = 1;
@@ -1386,7 +1396,7 @@ extern "C" int mnn_lstm_seq_bwd_tc(float* gates, const float* wh, const float* c
     cudaMemsetAsync(dh_acc, 0, BR * sizeof(float), stream);
     CUtensorMap ma, mb, mdhr, mdh, mg, mc, mdo, mds, mdc;
     const long long TB = (long long)T * B;
-    if ((rc = mnn_tc_make_map(gates, 4LL * R, 4LL * R, TB, BM, false, &ma))) return rc;
+    if ((rc = mnn_tc_make_map(gates, 4LL * R, 4LL * R, TB + (has_next ? B : 0), BM, false, &ma))) return rc;
     if ((rc = mnn_tc_make_map(wh, 4LL * R, 4LL * R, R, BM, false, &mb))) return rc;
     if ((rc = mnn_tc_make_map(dh_acc, R, R, B, BM, false, &mdhr))) return rc;
     if ((rc = mnn_tc_make_map_plain(dh_acc, R, R, B, kCellUnits, kCellRows, &mdh))) return rc;
@@ -1439,14 +1449,20 @@ extern "C" int mnn_lstm_seq_bwd_tc(float* gates, const float* wh, const float* c
   const size_t whp_bytes = whp_region_bytes(R);
   LstmParams p{};
   p.gates = gates; p.cbuf = const_cast<float*>(cbuf); p.dout = dout; p.dscale = const_cast<float*>(dscale); p.dc = dc_work;
-  p.T = T; p.B = B; p.R = R; p.t0 = 0; p.t1 = T - 1;
+  p.T = T; p.B = B; p.R = R; p.t0 = 0; p.t1 = t_top + 1;
   p.slabs = slabs; p.blocks = (R + BN - 1) / BN; p.kb_total = (4 * R + BK - 1) / BK;
   p.flags = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(ws) + whp_bytes);
   CUtensorMap ma, mb;
-  rc = mnn_tc_make_map(gates, 4LL * R, 4LL * R, (long long)T * B, BM, false, &ma);
+  rc = mnn_tc_make_map(gates, 4LL * R, 4LL * R, (long long)(T + (has_next ? 1 : 0)) * B, BM, false, &ma);
   if (rc) return rc;
   rc = mnn_tc_make_map(wh, 4LL * R, 4LL * R, R, BN, false, &mb);
   if (rc) return rc;
   if (BN == 64) return launch_lstm<64, false>(ma, mb, p, persistent, stream);
   return launch_lstm<32, false>(ma, mb, p, persistent, stream);
+}
+
+extern "C" int mnn_lstm_seq_bwd_tc(float* gates, const float* wh, const float* cbuf, const float* dout,
+                                   const float* dscale, float* dc_work, int T, int B, int R, void* ws, int persistent,
+                                   cudaStream_t stream) {
+  return mnn_lstm_seq_bwd_tc_chunk(gates, wh, cbuf, dout, dscale, dc_work, T, B, R, ws, persistent, 0, stream);
 }

@@ -177,3 +177,4 @@ int mnn_tc_make_map(const float* ptr, long long ld, long long inner, long long o
 int mnn_tc_make_map_plain(const float* ptr, long long ld, long long inner, long long outer, int box_inner, int box_outer,
                            CUtensorMap* out);
 int mnn_tc_num_sms();
+int mnn_tc_sm_budget();   // mnn_set_sm_budget of the calling thread (0 = whole device)

@@ -61,6 +61,11 @@ def gemm(A, B, C, transA=False, transB=False, bias=None, alpha=1.0, beta=0.0, a_
                            _rowstride(C), _ptr(bias), float(alpha), float(beta), M, N, K, _stream()), "gemm_f32")
 
 
+def set_sm_budget(sms):
+    """Cap the persistent GEMM grids launched by this thread at `sms` SMs (0 = all)."""
+    check(lib.mnn_set_sm_budget(int(sms)), "set_sm_budget")
+
+
 _colsum_ws = {}
 
 
@@ -109,15 +114,18 @@ def lstm_seq_fwd(gates, wh, hbuf, cbuf, out=None, dscale=None, u=None, keep=1.0,
                                float(keep), seed, T, B, R4 // 4, _stream()), "lstm_seq_fwd")
 
 
-def lstm_seq_bwd(gates, wh, cbuf, dout, dscale, dh_work, dc_work, mode=None, persistent=None):
+def lstm_seq_bwd(gates, wh, cbuf, dout, dscale, dh_work, dc_work, mode=None, persistent=None, has_next=False):
+    """has_next: `gates` is a time chunk of a longer buffer whose following chunk was already back-propagated."""
     T, B, R4 = gates.shape
     mode = mode or LSTM_MODE
     if mode == "tc" and lib.mnn_lstm_tc_supported(B, R4 // 4):
         pers = LSTM_PERSISTENT if persistent is None else persistent
-        check(lib.mnn_lstm_seq_bwd_tc(_ptr(gates), _ptr(wh), _ptr(cbuf), _ptr(dout), _ptr(dscale), _ptr(dc_work), T, B,
-                                      R4 // 4, _ptr(_lstm_workspace(B, R4 // 4, gates.device)), int(pers), _stream()),
-              "lstm_seq_bwd_tc")
+        check(lib.mnn_lstm_seq_bwd_tc_chunk(_ptr(gates), _ptr(wh), _ptr(cbuf), _ptr(dout), _ptr(dscale), _ptr(dc_work),
+                                            T, B, R4 // 4, _ptr(_lstm_workspace(B, R4 // 4, gates.device)), int(pers),
+                                            int(has_next), _stream()), "lstm_seq_bwd_tc")
         return
+    if has_next:
+        raise ValueError("chunked BPTT needs the tensor-core recurrence (num_units % 8 == 0)")
     check(lib.mnn_lstm_seq_bwd(_ptr(gates), _ptr(wh), _ptr(cbuf), _ptr(dout), _ptr(dscale), _ptr(dh_work),
                                _ptr(dc_work), T, B, R4 // 4, _stream()), "lstm_seq_bwd")
 
