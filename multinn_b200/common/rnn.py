@@ -9,6 +9,8 @@ x.Wx + b of a whole sequence is ONE GEMM over all T*B rows (hoisted out of the r
 sequential. Gate pre-activations are overwritten by their activations (saved for BPTT) and then by their
 gradients, so the recurrence keeps a single [T,B,4R] buffer per layer.
 """
+import os
+
 import torch
 
 from .. import ops
@@ -92,13 +94,14 @@ class RNN:
     # At small per-GPU batches (data-parallel shards) a recurrence step is a fixed latency chain that keeps well under
     # half of the SMs busy, so the layers are run as a WAVEFRONT over time chunks: layer l works on chunk c while
     # layer l+1 works on chunk c-1 on another stream (SURVEY 7 "hard parts": recurrence latency at B/8).
-    WAVEFRONT_MAX_BATCH = 256
+    WAVEFRONT_MAX_BATCH = int(os.environ.get('MNN_WAVEFRONT_MAX_BATCH', 1024))   # forward; measured gain up to 1024
+    WAVEFRONT_MAX_BATCH_BWD = 512                                                # BPTT: the SM budgets cost more above
     WAVEFRONT_CHUNK = 32
     WAVEFRONT_GEMM_SMS = 32
 
-    def _use_wavefront(self, T, B):
-        return (self.num_layers > 1 and B <= self.WAVEFRONT_MAX_BATCH and T % self.WAVEFRONT_CHUNK == 0
-                and T >= 2 * self.WAVEFRONT_CHUNK)
+    def _use_wavefront(self, T, B, backward=False):
+        mb = min(self.WAVEFRONT_MAX_BATCH, self.WAVEFRONT_MAX_BATCH_BWD) if backward else self.WAVEFRONT_MAX_BATCH
+        return (self.num_layers > 1 and B <= mb and T % self.WAVEFRONT_CHUNK == 0 and T >= 2 * self.WAVEFRONT_CHUNK)
 
     def _streams(self, device):
         st = self.__dict__.get('_wave_streams')
@@ -167,11 +170,15 @@ class RNN:
                                      w['gates'][t0:t1].view(C * B, 4 * r), bias=self.biases[l].data)
                         finally:
                             ops.set_sm_budget(0)
-                    ops.lstm_seq_fwd(w['gates'][t0:t1], kern[i_l:], w['hbuf'][t0:t1 + 1], w['cbuf'][t0:t1 + 1],
-                                     out=w['out'][t0:t1] if dropout else None,
-                                     dscale=w['dscale'][t0:t1] if dropout else None,
-                                     u=None if u is None else u[l][t0:t1], keep=keep,
-                                     seed=seed + 7919 * l + 104729 * c)
+                    ops.set_sm_budget(96 if l == 0 else 48)     # wavefront mode: kernels pick co-resident configurations
+                    try:
+                        ops.lstm_seq_fwd(w['gates'][t0:t1], kern[i_l:], w['hbuf'][t0:t1 + 1], w['cbuf'][t0:t1 + 1],
+                                         out=w['out'][t0:t1] if dropout else None,
+                                         dscale=w['dscale'][t0:t1] if dropout else None,
+                                         u=None if u is None else u[l][t0:t1], keep=keep,
+                                         seed=seed + 7919 * l + 104729 * c)
+                    finally:
+                        ops.set_sm_budget(0)
                     done[l][c].record(streams[l])
         for l in range(self.num_layers):
             main.wait_event(done[l][nch - 1])
@@ -187,7 +194,7 @@ class RNN:
             i_l = self.in_dims()[l]
             if (l > 0 or need_dx) and (w.get('d_in') is None or w['d_in'].shape != (T, B, i_l)):
                 w['d_in'] = torch.empty(T, B, i_l, device=x.device)
-        if self._use_wavefront(T, B):
+        if self._use_wavefront(T, B, backward=True):
             self._backward_wavefront(ws, dout, T, B, dropout, need_dx)
         else:
             d = dout

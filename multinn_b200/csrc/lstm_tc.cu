@@ -1266,7 +1266,9 @@ static bool use_pair_fwd(int B, int R, int T, int persistent) {
   if (env && env[0] == '0') return false;
   if ((B / (2 * BM)) * (R / kL2UB) > pair_fwd_clusters()) return false;
   if (env && env[0] == '1') return true;
-  return B >= 1024;
+  // below 1024 rows the 1-CTA kernel's smaller items win, unless the caller runs the layers as a wavefront (SM budget
+  // set): then the pair kernel's few CTAs leave room for the other layer
+  return B >= 1024 || (mnn_tc_sm_budget() > 0 && B >= 512);
 }
 
 extern "C" int mnn_lstm_tc_supported(int B, int R) { return R % 8 == 0 && R >= 8 && B > 0; }
