@@ -436,7 +436,7 @@ lstm_tc2_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES, STAGES = 3;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[3 * STAGES + 2];
-  __shared__ __align__(8) uint64_t ebars[3];   // [0],[1]: epilogue tile loads of the two halves; [2]: tiles free again
+  __shared__ __align__(8) uint64_t ebars[4];   // [0],[1]: tile loads of the two halves; [2]: tiles read out; [3]: tile stores complete
   __shared__ uint32_t tmem_base_s;
 
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -458,7 +458,8 @@ lstm_tc2_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     mbar_init(bar_tempty, 2 * 8);
     mbar_init(smem_u32(&ebars[0]), 1);
     mbar_init(smem_u32(&ebars[1]), 1);
-    mbar_init(smem_u32(&ebars[2]), 2);              // one elected arrive per epilogue warp of both CTAs
+    mbar_init(smem_u32(&ebars[2]), 2);
+    mbar_init(smem_u32(&ebars[3]), 2);              // one elected arrive per epilogue warp of both CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -540,8 +541,13 @@ lstm_tc2_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
       *reinterpret_cast<float4*>(rowp + 4 * TILE + c0) = make_float4(cv[0], cv[1], cv[2], cv[3]);
       *reinterpret_cast<float4*>(rowp + 4 * TILE + c1) = make_float4(cv[4], cv[5], cv[6], cv[7]);
-      *reinterpret_cast<float4*>(rowp + 5 * TILE + c0) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-      *reinterpret_cast<float4*>(rowp + 5 * TILE + c1) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+      // h_t gates the next step of the whole slab: it goes straight to global memory (8 stores per thread) so that the
+      // flag can be raised without waiting for a TMA store to complete; everything else leaves through the tiles
+      {
+        float* hdst = p.hbuf + (size_t)(t + 1) * BR + (size_t)b * R + unit0 + ug * 8;
+        *reinterpret_cast<float4*>(hdst) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+        *reinterpret_cast<float4*>(hdst + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+      }
       if (p.out) {
         float ov[8];
         if (p.keep < 1.0f) {
@@ -583,22 +589,20 @@ lstm_tc2_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // tiles complete -> TMA stores; the flag may only be raised once h_t is globally visible
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
+    __threadfence();                                 // this thread's h_t stores are visible device-wide
     if (eh == 0) asm volatile("bar.sync 2, 128;" ::: "memory"); else asm volatile("bar.sync 3, 128;" ::: "memory");
     if (leader) {
-      // h_t first, in its own bulk group: only it gates the next step; each half raises the slab's flag itself
-      tma_store_2d(&map_a, ebase + 5 * TILE, unit0, (t + 1) * B + row_g);
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.flags + m_blk) : "memory");
+      if (eh == 0) MNN_TRACE(8);
 #pragma unroll
       for (int g = 0; g < 4; ++g) tma_store_2d(&map_g, ebase + g * TILE, g * R + unit0, t * B + row_g);
       tma_store_2d(&map_c, ebase + 4 * TILE, unit0, (t + 1) * B + row_g);
       if (p.out) tma_store_2d(&map_o, ebase + 6 * TILE, unit0, t * B + row_g);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");   // the h_t tile is written
-      asm volatile("fence.proxy.async;" ::: "memory");
-      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.flags + m_blk) : "memory");
-      if (eh == 0) MNN_TRACE(8);
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // remaining tile stores have read shared memory
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // tile stores have read shared memory
       mbar_arrive(smem_u32(&ebars[2]));                                 // -> the stages may be refilled
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");        // c_t (and the rest) is written: the next step's
+      mbar_arrive(smem_u32(&ebars[3]));                                 // tile loads of this item may be issued
     }
     __syncwarp();
     if (lane == 0) mbar_arrive_cluster(tempty_leader);
@@ -646,6 +650,7 @@ lstm_tc2_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           {
             const int row_g = m_blk * 2 * BM + (int)rank * BM;
             const uint32_t ein0 = smem_u32(&ebars[0]), ein1 = smem_u32(&ebars[1]);
+            if (item_no > 0) mbar_wait(smem_u32(&ebars[3]), (uint32_t)(item_no - 1) & 1u);   // c_{t-1} tile is in memory
             mbar_expect_tx(ein0, 5 * TILE);
             mbar_expect_tx(ein1, 5 * TILE);
             int st = stage;
