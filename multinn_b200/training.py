@@ -89,3 +89,52 @@ class GradientApplier:
         """Global gradient norm of the last step (after averaging over ranks)."""
         _, ws = world()
         return float(self.sqnorm.sqrt()) / ws
+
+
+class BatchPrefetcher:
+    """Overlaps the host->device copy of the NEXT batch with the current training step: `put(host)` enqueues the copy
+    on a side stream into one of two device buffers, `get()` makes the current stream wait for it and returns the
+    buffer. The reference feeds NumPy batches through feed_dict each sess.run (train.py:186-189); this is the
+    equivalent input path for pinned host batches (bool/uint8 or float32 piano-rolls)."""
+
+    def __init__(self, device='cuda'):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.bufs = [None, None]
+        self.ready = [None, None]       # copy finished (side stream)
+        self.released = [None, None]    # last consumer enqueued (main stream)
+        self.head = 0                   # next slot to fill
+        self.tail = 0                   # next slot to hand out
+        self.pending = 0
+
+    def put(self, host):
+        if self.pending >= 2:
+            raise RuntimeError('BatchPrefetcher holds two batches already: call get() first')
+        i = self.head
+        if self.bufs[i] is None or self.bufs[i].shape != host.shape or self.bufs[i].dtype != host.dtype:
+            self.bufs[i] = torch.empty(host.shape, dtype=host.dtype, device=self.device)
+        if self.released[i] is not None:
+            self.stream.wait_event(self.released[i])        # the step that read this buffer has been enqueued and run
+        with torch.cuda.stream(self.stream):
+            self.bufs[i].copy_(host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.ready[i] = ev
+        self.head ^= 1
+        self.pending += 1
+
+    def get(self):
+        if self.pending == 0:
+            raise RuntimeError('BatchPrefetcher is empty: call put() first')
+        i = self.tail
+        torch.cuda.current_stream().wait_event(self.ready[i])
+        self.tail ^= 1
+        self.pending -= 1
+        self._last = i
+        return self.bufs[i]
+
+    def release(self):
+        """Call after the step that consumes the last `get()` buffer has been enqueued."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.released[self._last] = ev

@@ -233,3 +233,19 @@ def test_layer_wavefront_equals_layerwise(B, Rn, keep):
     (l1, g1), (l0, g0) = results
     assert abs(l1 - l0) / l0 < 1e-6
     assert float((g1 - g0).norm() / g0.norm()) < 1e-5
+
+
+def test_batch_prefetcher_roundtrip():
+    from multinn_b200.training import BatchPrefetcher
+    pf = BatchPrefetcher()
+    hosts = [torch.from_numpy(O.synthetic_pianoroll(3, 4, seed=s).astype(np.uint8)).pin_memory() for s in range(3)]
+    pf.put(hosts[0])
+    for i in range(3):
+        x = pf.get()
+        if i + 1 < 3:
+            pf.put(hosts[i + 1])
+        y = x.float().sum()          # consumer work on the current stream
+        pf.release()
+        assert torch.equal(x.cpu(), hosts[i]) and float(y) == float(hosts[i].sum())
+    with pytest.raises(RuntimeError):
+        pf.get()
