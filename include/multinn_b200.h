@@ -144,6 +144,9 @@ int mnn_sum(const float* x, size_t n, void* ws, float* out, float scale, int acc
 int mnn_sqnorm(const float* x, size_t n, void* ws, float* out, mnn_stream_t stream);
 int mnn_clip_adam(float* p, const float* g, float* m, float* v, size_t n, const float* sqnorm, float grad_scale,
                   float clip_norm, float lr, float beta1, float beta2, float eps, int step, mnn_stream_t stream);
+/* x[r*ld + c] *= w[r % period], c < ncols. Variable sequence lengths: utils/sequences.py:6-37 drops the rows t >= lengths[b]
+ * from every per-row result (flatten_maybe_padded_sequences); here such rows get weight 0 in the NLL and in dNLL/dl. */
+int mnn_scale_rows(float* x, long long ld, int ncols, const float* w, long long rows, int period, mnn_stream_t stream);
 /* y += alpha * x (CD-k assign_add, common/rbm.py:322-330). */
 int mnn_axpy(float* y, const float* x, float alpha, size_t n, mnn_stream_t stream);
 int mnn_clip_sgd(float* p, const float* g, size_t n, const float* sqnorm, float grad_scale, float clip_norm,

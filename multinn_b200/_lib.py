@@ -58,6 +58,7 @@ SIGNATURES = {
     "mnn_sum": [_p, _sz, _p, _p, _f, _i, _p],
     "mnn_sqnorm": [_p, _sz, _p, _p, _p],
     "mnn_clip_adam": [_p, _p, _p, _p, _sz, _p, _f, _f, _f, _f, _f, _f, _i, _p],
+    "mnn_scale_rows": [_p, _ll, _i, _p, _ll, _i, _p],
     "mnn_axpy": [_p, _p, _f, _sz, _p],
     "mnn_clip_sgd": [_p, _p, _sz, _p, _f, _f, _f, _p],
 }

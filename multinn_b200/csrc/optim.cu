@@ -131,3 +131,28 @@ extern "C" int mnn_clip_sgd(float* p, const float* g, size_t n, const float* sqn
   clip_sgd_kernel<<<nb, 256, 0, stream>>>(p, g, n, sqnorm, grad_scale, clip_norm, lr);
   return mnn_check_launch("clip_sgd");
 }
+
+
+// ------------------------------------------------------------------------------------------------ padded rows
+// x[r*ld + c] *= w[r % period] for c < ncols: drops the rows past a sequence's length from per-row results and
+// gradients (flatten_maybe_padded_sequences keeps only rows t < lengths[b], reference utils/sequences.py:6-37).
+namespace mnn {
+__global__ void scale_rows_kernel(float* x, long long ld, int ncols, const float* w, long long rows, int period) {
+  const long long total = rows * ncols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / ncols;
+    const int c = (int)(i - r * ncols);
+    x[r * ld + c] *= __ldg(w + (r % period));
+  }
+}
+}  // namespace mnn
+
+extern "C" int mnn_scale_rows(float* x, long long ld, int ncols, const float* w, long long rows, int period,
+                              cudaStream_t stream) {
+  MNN_REQUIRE(x && w, MNN_ERR_ARG, "scale_rows: null pointer");
+  MNN_REQUIRE(rows > 0 && ncols > 0 && period > 0, MNN_ERR_ARG, "scale_rows: non-positive size");
+  const long long total = rows * ncols;
+  const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  mnn::scale_rows_kernel<<<grid, 256, 0, stream>>>(x, ld, ncols, w, rows, period);
+  return mnn_check_launch("scale_rows");
+}

@@ -84,9 +84,9 @@ class RnnNade(RnnEstimator):
 
     def _get_state(self, inputs, lengths=None, initial_state=None, last_outputs=False, keep=1.0, u_drop=None,
                    seed=0, training=False):
-        """rnn_nade.py:173-232. inputs[T,B,I] time-major (or [B,I] = one step). Full lengths only."""
-        if lengths is not None:
-            raise NotImplementedError('variable `lengths` (padded flatten) is a next-row item; pass None')
+        """rnn_nade.py:173-232. inputs[T,B,I] time-major (or [B,I] = one step). dynamic_decode(impute_finished=False)
+        computes the rows past a sequence's length too; `log_prob` / `forward_backward` take `lengths` and
+        give those rows weight 0 (flatten_maybe_padded_sequences drops them, utils/sequences.py:6-37)."""
         if inputs.dim() == 2:
             inputs = inputs.unsqueeze(0)
         T, B, _ = inputs.shape
@@ -105,10 +105,28 @@ class RnnNade(RnnEstimator):
         return self._state_from_fc(fc, rnn_state)
 
     # -------------------------------------------------------------- teacher-forced likelihood
-    def log_prob(self, inputs, bits, keep=1.0, u_drop=None, seed=0, cond_probs=False):
+    @staticmethod
+    def row_weights(lengths, T, B, device):
+        """w[t*B + b] = 1 if t < lengths[b] else 0 (tf.sequence_mask, utils/sequences.py:29), and the number of valid
+        rows; None for full lengths (the reshape branch, sequences.py:22-24)."""
+        if lengths is None:
+            return None, T * B
+        lengths = torch.as_tensor(lengths).to('cpu', torch.int64)
+        if lengths.numel() != B:
+            raise ValueError(f'lengths must hold one entry per sequence ({B}), got {lengths.numel()}')
+        if int(lengths.min()) >= T:
+            return None, T * B
+        if int(lengths.min()) < 0:
+            raise ValueError('negative sequence length')
+        w = (torch.arange(T)[:, None] < lengths[None, :]).to(torch.float32).reshape(-1)
+        return w.to(device), int(lengths.clamp(max=T).sum())
+
+    def log_prob(self, inputs, bits, keep=1.0, u_drop=None, seed=0, cond_probs=False, lengths=None):
         """rnn_nade.py:279-302 / rnn_multinade.py:258-290. inputs[T,B,I], bits[M,T*B,4] target masks.
-        Returns (nll[M,N'] positive, cond_p[M,N',D] or None); rows n' = t*B + b."""
+        Returns (nll[M,N'] positive, cond_p[M,N',D] or None); rows n' = t*B + b. With `lengths`, the NLL of the rows
+        t >= lengths[b] is 0 (the reference removes those rows)."""
         T, B, _ = inputs.shape
+        w, _ = self.row_weights(lengths, T, B, inputs.device)
         self._get_state(inputs, keep=keep, u_drop=u_drop, seed=seed)
         ws = self._ws[(T * B, False)]
         cp = None
@@ -116,20 +134,28 @@ class RnnNade(RnnEstimator):
             cp = torch.empty(self._num_tracks, T * B, self._num_dims, device=inputs.device)
         ops.nade_logprob_fwd(bits, ws['fc'], self.enc_col0, self.dec_col0, self._bank.w_enc.data,
                              self._bank.w_dec.data, ws['nll'], cond_p=cp)
+        if w is not None:
+            ops.scale_rows(ws['nll'].view(-1, 1), w, period=T * B)
         return ws['nll'], cp
 
-    def forward_backward(self, inputs, bits, keep=None, u_drop=None, seed=0, loss_scale=1.0, need_dx=False):
+    def forward_backward(self, inputs, bits, keep=None, u_drop=None, seed=0, loss_scale=1.0, need_dx=False,
+                         lengths=None):
         """One training pass: loss = loss_scale * mean_m mean_n NLL (statistical.py:34; rnn_multinade.py:200-203)
         and its gradient wrt every trainable parameter (written into the arena's grad buffer; NADE weight grads
-        are ACCUMULATED, so the caller zeroes the grad buffer once per step). Returns (loss[1], nll[M,N'], dx)."""
+        are ACCUMULATED, so the caller zeroes the grad buffer once per step). Returns (loss[1], nll[M,N'], dx).
+        `lengths`: the means run over the valid rows only; padded rows get zero NLL and zero logit gradient."""
         keep = self._keep_prob if keep is None else keep
         T, B, _ = inputs.shape
         N, M = T * B, self._num_tracks
+        w, nvalid = self.row_weights(lengths, T, B, inputs.device)
         self._get_state(inputs, keep=keep, u_drop=u_drop, seed=seed, training=True)
         ws = self._ws[(N, True)]
-        gscale = loss_scale / (N * M)
+        gscale = loss_scale / (nvalid * M)
         ops.nade_logprob_fwd(bits, ws['fc'], self.enc_col0, self.dec_col0, self._bank.w_enc.data,
                              self._bank.w_dec.data, ws['nll'], dfc=ws['dfc'], gscale=gscale)
+        if w is not None:       # every NADE gradient is linear in the logit gradient the forward wrote into dfc's b_dec columns
+            ops.scale_rows(ws['nll'].view(-1, 1), w, period=N)
+            ops.scale_rows(ws['dfc'][:, self.dec_col0:], w)
         ops.sum_into(ws['nll'], ws['loss'], scale=gscale)
         ops.nade_logprob_bwd(bits, ws['fc'], self.enc_col0, self.dec_col0, self._bank.w_enc.data,
                              self._bank.w_dec.data, ws['dfc'], self._bank.w_enc.grad, self._bank.w_dec.grad)

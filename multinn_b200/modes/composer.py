@@ -11,6 +11,8 @@ class MultINNComposer(MultINNCore):
         super().__init__(config, params, name=name, **kw)
         self._mode = 'composer'
 
+    _supports_lengths = True
+
     def _init_encoders(self, encoder_class):
         nh = self._params['encoder']['num_hidden']
         encs = [encoder_class(num_dims=self.num_dims, num_hidden=nh, track_name=t, arena=self._enc_arena,
@@ -31,27 +33,32 @@ class MultINNComposer(MultINNCore):
         if self.encoder_type != 'Pass':
             raise NotImplementedError('Composer with DBN encoders: use feedback/joint modes or Pass encoders')
 
-    def _forward_backward(self, x, keep, u_drop, seed, **extra):
+    def _forward_backward(self, x, keep, u_drop, seed, lengths=None, **extra):
         self._require_pass()
         B, T, D, M = x.shape
         st = self._stage_inputs(x, stacked=True, bits=True)
         # inputs = slots 0..T-1 ([0, x_0..x_{T-2}]), targets = slots 1..T (multinn_composer.py:82-86)
-        loss, nll, _ = self._generator.forward_backward(st['xin'][:T], st['bits'], keep=keep, u_drop=u_drop, seed=seed)
+        loss, nll, _ = self._generator.forward_backward(st['xin'][:T], st['bits'], keep=keep, u_drop=u_drop, seed=seed,
+                                                        lengths=lengths)
         self._last_nll = (nll, T, B)
         return loss
 
     def evaluate(self, x, lengths=None, cond_probs=False):
         """is_train=False forward: per-row NLL[N,M] (rows n = b*T + t), `batch/loss` = mean over tracks of the
-        per-track means (metrics/statistical.py:34, rnn_multinade.py:200-203)."""
+        per-track means (metrics/statistical.py:34, rnn_multinade.py:200-203). With variable `lengths` the rows
+        t >= lengths[b] are removed (utils/sequences.py:29-37): `nll` then holds the valid rows only, b-major."""
         self._require_pass()
         x = self._check_x(x, lengths)
         B, T, D, M = x.shape
         st = self._stage_inputs(x, stacked=True, bits=True)
-        nll, cp = self._generator.log_prob(st['xin'][:T], st['bits'], cond_probs=cond_probs)
+        nll, cp = self._generator.log_prob(st['xin'][:T], st['bits'], cond_probs=cond_probs, lengths=lengths)
+        keep_rows = self.valid_rows(lengths, T, B, x.device)
         out = {'nll': self.rows_to_reference_order(nll, T, B)}
-        out['batch/loss'] = out['log_likelihood'] = out['nll'].mean(0).mean()
         if cp is not None:
             out['cond_probs'] = cp.view(M, T, B, D).permute(2, 1, 3, 0).reshape(B * T, D, M)
+        if keep_rows is not None:
+            out = {k: v[keep_rows] for k, v in out.items()}
+        out['batch/loss'] = out['log_likelihood'] = out['nll'].mean(0).mean()
         self._metrics.update(out)
         return out
 

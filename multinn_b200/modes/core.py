@@ -85,13 +85,15 @@ class MultINNCore(Model, abc.ABC):
     def _init_generators(self, generator_class):
         ...
 
+    _supports_lengths = False
+
     # ------------------------------------------------------------------ input staging (K0)
     def _check_x(self, x, lengths):
         if x.dim() != 4 or x.shape[2] != self.num_dims or x.shape[3] != self.num_tracks:
             raise ValueError(f'x must be [batch, time, {self.num_dims}, {self.num_tracks}], got {tuple(x.shape)}')
-        if lengths is not None and int(lengths.min()) != x.shape[1]:
-            raise NotImplementedError('variable sequence lengths are not supported yet (all BASELINE configs '
-                                      'use full lengths)')
+        if lengths is not None and int(torch.as_tensor(lengths).min()) < x.shape[1] and not self._supports_lengths:
+            raise NotImplementedError(f'variable sequence lengths are not supported in {self._mode} mode yet '
+                                      '(Composer and Jamming NADE paths support them)')
         if not x.is_cuda:
             raise ValueError('x must be a CUDA tensor: multinn_b200 has no CPU path')
         if x.dtype in (torch.uint8, torch.bool):          # bool / byte piano-rolls as stored by prepare_data.py:56
@@ -127,6 +129,18 @@ class MultINNCore(Model, abc.ABC):
         M = t.shape[0]
         return t.view(M, T, B).permute(2, 1, 0).reshape(B * T, M)
 
+    @staticmethod
+    def valid_rows(lengths, T, B, device):
+        """Indices of the rows flatten_maybe_padded_sequences keeps, in its order n = b*T + t (utils/sequences.py:29-31);
+        None for full lengths."""
+        if lengths is None:
+            return None
+        lengths = torch.as_tensor(lengths).to('cpu', torch.int64)
+        if int(lengths.min()) >= T:
+            return None
+        mask = torch.arange(T)[None, :] < lengths[:, None]
+        return mask.reshape(-1).nonzero().squeeze(1).to(device)
+
     # ------------------------------------------------------------------ training
     def _make_optimizer(self, optimizer, lr):
         if isinstance(optimizer, str):
@@ -145,6 +159,8 @@ class MultINNCore(Model, abc.ABC):
             self._applier.zero_grad()
             s = counter[0] if seed is None else seed
             counter[0] += 1
+            if lengths is not None and self._supports_lengths:
+                extra['lengths'] = lengths
             loss = self._forward_backward(x, keep=self._keep_prob if keep is None else keep, u_drop=u_drop,
                                           seed=s * 1000003, **extra)
             self._applier.apply()

@@ -11,6 +11,8 @@ class MultINNJamming(MultINNCore):
         super().__init__(config, params, name=name, **kw)
         self._mode = 'jamming'
 
+    _supports_lengths = True
+
     def _init_encoders(self, encoder_class):
         nh = self._params['encoder']['num_hidden']
         encs = [encoder_class(num_dims=self.num_dims, num_hidden=nh, track_name=t, arena=self._enc_arena,
@@ -28,7 +30,7 @@ class MultINNJamming(MultINNCore):
         if self.encoder_type != 'Pass':
             raise NotImplementedError('Jamming with DBN encoders is not wired yet')
 
-    def _forward_backward(self, x, keep, u_drop, seed, **extra):
+    def _forward_backward(self, x, keep, u_drop, seed, lengths=None, **extra):
         self._require_pass()
         B, T, D, M = x.shape
         st = self._stage_inputs(x, per_track=True, bits=True)
@@ -37,7 +39,7 @@ class MultINNJamming(MultINNCore):
         for m, gen in enumerate(self._generators):
             loss, nll, _ = gen.forward_backward(st['xtr'][m, :T], st['bits'][m:m + 1], keep=keep,
                                                 u_drop=None if u_drop is None else u_drop[m],
-                                                seed=seed + 104729 * m, loss_scale=1.0 / M)
+                                                seed=seed + 104729 * m, loss_scale=1.0 / M, lengths=lengths)
             total += loss
             nlls.append(nll)
         return total
@@ -49,9 +51,12 @@ class MultINNJamming(MultINNCore):
         st = self._stage_inputs(x, per_track=True, bits=True)
         nll = torch.empty(M, T * B, device=x.device)
         for m, gen in enumerate(self._generators):
-            n, _ = gen.log_prob(st['xtr'][m, :T], st['bits'][m:m + 1])
+            n, _ = gen.log_prob(st['xtr'][m, :T], st['bits'][m:m + 1], lengths=lengths)
             nll[m] = n[0]
         out = {'nll': self.rows_to_reference_order(nll, T, B)}
+        keep_rows = self.valid_rows(lengths, T, B, x.device)
+        if keep_rows is not None:
+            out['nll'] = out['nll'][keep_rows]
         out['batch/loss'] = out['log_likelihood'] = out['nll'].mean(0).mean()     # multinn_core.py:402-405
         self._metrics.update(out)
         return out

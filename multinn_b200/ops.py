@@ -206,6 +206,13 @@ def clip_adam(p, g, m, v, sqnorm, step, lr, grad_scale=1.0, clip_norm=5.0, beta1
           "clip_adam")
 
 
+def scale_rows(x, w, ncols=None, period=None):
+    """x[r, :ncols] *= w[r % period] on a row-major 2-D view x (row stride free)."""
+    rows = x.shape[0]
+    check(lib.mnn_scale_rows(_ptr(x), _rowstride(x), int(ncols if ncols is not None else x.shape[1]), _ptr(w), rows,
+                             int(period if period is not None else w.numel()), _stream()), "scale_rows")
+
+
 def axpy(y, x, alpha):
     """y += alpha * x (contiguous tensors of equal size)."""
     assert y.is_contiguous() and x.is_contiguous() and y.numel() == x.numel()

@@ -165,10 +165,19 @@ def composer_inputs_targets(x):
     return pad[:, :-1], pad[:, 1:]
 
 
-def composer_forward(x, params, keep=1.0, u_drop=None):
+def flatten_valid_rows(lengths, T):
+    """utils/sequences.py:29-31: indices of tf.where(tf.sequence_mask(lengths)) into the [B*T] row order n = b*T + t
+    (b-major, rows t >= lengths[b] removed)."""
+    lengths = np.asarray(lengths)
+    return np.concatenate([b * T + np.arange(int(l)) for b, l in enumerate(lengths)]).astype(np.int64)
+
+
+def composer_forward(x, params, keep=1.0, u_drop=None, lengths=None):
     """Composer LSTM-MultiNADE teacher-forced forward (SURVEY 3.2 stack).
     params: dict(lstm=[(kernel,bias)..], dense=(K,b), nade=[(w_enc,w_dec)..M]).
-    Returns dict(nll[N,M], cond_p[M,N,D], loss, fc_out[N,*]); rows n = b*T + t (utils/sequences.py:22-24)."""
+    Returns dict(nll[N,M], cond_p[M,N,D], loss, fc_out[N,*]); rows n = b*T + t (utils/sequences.py:22-24).
+    lengths[B] (max == T): rows past a sequence's length are dropped from every per-row result and from the loss mean
+    (dynamic_decode still computes them; flatten_maybe_padded_sequences removes them)."""
     B, T, D, M = x.shape
     inp, tgt = composer_inputs_targets(x)
     outs, _ = rnn_scan(inp, params['lstm'], keep, u_drop)
@@ -181,6 +190,9 @@ def composer_forward(x, params, keep=1.0, u_drop=None):
     cp = np.zeros((M, B * T, D), x.dtype)
     for m in range(M):                                              # rnn_multinade.py:281-288
         nll[:, m], cp[m] = nade_log_prob(tgt_flat[:, :, m], be[m], bd[m], *params['nade'][m])
+    if lengths is not None and int(np.min(lengths)) != T:           # sequences.py:33-37
+        keep_rows = flatten_valid_rows(lengths, T)
+        nll, cp, fc = nll[keep_rows], cp[:, keep_rows], fc[keep_rows]
     loss = np.mean([nll[:, m].mean() for m in range(M)])            # statistical.py:34; rnn_multinade.py:200-203
     return dict(nll=nll, cond_p=cp, loss=loss, fc_out=fc)
 

@@ -72,9 +72,10 @@ def rnn_scan(inputs, layers, keep=1.0, u=None, state=None):
     return torch.stack(outs, 1), state
 
 
-def composer_loss(x, params, keep=1.0, u_drop=None):
+def composer_loss(x, params, keep=1.0, u_drop=None, lengths=None):
     """Composer LSTM-MultiNADE training graph. x[B,T,D,M] tensor.
-    params: dict(lstm=[(k,b)], dense=(K,b), nade=[(w_enc,w_dec)]). Returns (loss, nll[N,M])."""
+    params: dict(lstm=[(k,b)], dense=(K,b), nade=[(w_enc,w_dec)]). Returns (loss, nll[N,M]).
+    lengths: rows t >= lengths[b] are dropped before the means (utils/sequences.py:6-37)."""
     B, T, D, M = x.shape
     stack = x.reshape(B, T, D * M)
     pad = torch.cat([torch.zeros(B, 1, D * M, dtype=x.dtype), stack], 1)
@@ -90,22 +91,28 @@ def composer_loss(x, params, keep=1.0, u_drop=None):
         bd = fc[:, M * H + m * D:M * H + (m + 1) * D]
         nll, _ = nade_log_prob(tgt_flat[:, :, m], be, bd, *params['nade'][m])
         nlls.append(nll)
+    if lengths is not None and int(min(lengths)) != T:
+        keep_rows = torch.cat([b * T + torch.arange(int(l)) for b, l in enumerate(lengths)])
+        nlls = [n[keep_rows] for n in nlls]
     loss = torch.stack([n.mean() for n in nlls]).mean()
     return loss, torch.stack(nlls, 1)
 
 
-def rnn_nade_loss(inp, tgt, params, keep=1.0, u_drop=None):
-    """Single-track RNN-NADE (Jamming generator), generators/rnn_nade.py:279-302."""
+def rnn_nade_loss(inp, tgt, params, keep=1.0, u_drop=None, lengths=None):
+    """Single-track RNN-NADE (Jamming generator), generators/rnn_nade.py:279-302; padded rows dropped
+    (rnn_nade.py:225, utils/sequences.py:29-37)."""
     B, T, D = tgt.shape
     outs, _ = rnn_scan(inp, params['lstm'], keep, u_drop)
     K, b = params['dense']
     fc = outs.reshape(B * T, -1) @ K + b
     H = params['nade'][0].shape[1]
     nll, _ = nade_log_prob(tgt.reshape(B * T, D), fc[:, :H], fc[:, H:H + D], *params['nade'])
+    if lengths is not None and int(min(lengths)) != T:
+        nll = nll[torch.cat([b * T + torch.arange(int(l)) for b, l in enumerate(lengths)])]
     return nll.mean(), nll
 
 
-def jamming_loss(x, params_list, keep=1.0, u_drop=None):
+def jamming_loss(x, params_list, keep=1.0, u_drop=None, lengths=None):
     """Jamming: M independent RNN-NADEs, loss = mean of track losses (multinn_core.py:402-405)."""
     B, T, D, M = x.shape
     losses, nlls = [], []
@@ -113,7 +120,7 @@ def jamming_loss(x, params_list, keep=1.0, u_drop=None):
         xm = x[..., m]
         pad = torch.cat([torch.zeros(B, 1, D, dtype=x.dtype), xm], 1)
         l, n = rnn_nade_loss(pad[:, :-1], pad[:, 1:], params_list[m], keep,
-                             None if u_drop is None else u_drop[m])
+                             None if u_drop is None else u_drop[m], lengths)
         losses.append(l)
         nlls.append(n)
     return torch.stack(losses).mean(), torch.stack(nlls, 1)

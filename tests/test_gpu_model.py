@@ -249,3 +249,57 @@ def test_batch_prefetcher_roundtrip():
         assert torch.equal(x.cpu(), hosts[i]) and float(y) == float(hosts[i].sum())
     with pytest.raises(RuntimeError):
         pf.get()
+
+
+def test_composer_variable_lengths_nll_and_gradients():
+    """Variable `lengths` (utils/sequences.py:6-37): per-row NLL of the kept rows, the loss (mean over kept rows) and
+    every gradient vs the oracle; the rows past a sequence's length are removed in the reference's b-major order."""
+    B, T, H, Rn = 5, 9, 128, (64, 32)
+    lengths = np.array([9, 4, 7, 1, 9], dtype=np.int32)
+    model = make('composer', H=H, Rnn=Rn)
+    p32 = arena_to_params(model, 'generator', 2, True)
+    x = O.synthetic_pianoroll(B, T, seed=11, density=0.15)
+    ref = O.composer_forward(x.astype(np.float64), O.cast_params(p32, np.float64), lengths=lengths)
+    out = model.evaluate(torch.from_numpy(x).cuda(), lengths=torch.from_numpy(lengths))
+    assert out['nll'].shape == (int(lengths.sum()), 5)
+    np.testing.assert_allclose(out['nll'].cpu().numpy(), ref['nll'], rtol=1e-4)
+    assert abs(float(out['batch/loss']) - ref['loss']) / ref['loss'] < 1e-5
+    params = R.to_torch(p32, torch.float64, requires_grad=True)
+    loss, _ = R.composer_loss(torch.tensor(x, dtype=torch.float64), params, lengths=lengths)
+    assert abs(float(loss) - ref['loss']) / ref['loss'] < 1e-9
+    grads = torch.autograd.grad(loss, R.flat_params(params))
+    core = model._model
+    xd = core._check_x(torch.from_numpy(x).cuda(), lengths)
+    core.arena.grad.zero_()
+    l = core._forward_backward(xd, keep=1.0, u_drop=None, seed=0, lengths=lengths)
+    assert abs(float(l) - float(loss)) / float(loss) < 1e-5
+    named = core.arena.named()
+    names = ['generator/rnn/cell_0/kernel', 'generator/rnn/cell_0/bias', 'generator/rnn/cell_1/kernel',
+             'generator/rnn/cell_1/bias', 'generator/dense/kernel', 'generator/dense/bias']
+    for n, g in zip(names, grads[:6]):
+        got = named[n].grad.cpu().double()
+        assert float((got - g).norm() / g.norm()) < 1e-4, n
+    gwe = torch.stack([grads[6 + 2 * m] for m in range(5)])
+    gwd = torch.stack([grads[7 + 2 * m] for m in range(5)])
+    assert float((named['generator/nade/w_enc'].grad.cpu().double() - gwe).norm() / gwe.norm()) < 1e-4
+    assert float((named['generator/nade/w_dec'].grad.cpu().double() - gwd).norm() / gwd.norm()) < 1e-4
+    # full lengths given explicitly take the reshape branch: identical to lengths=None
+    a = model.evaluate(torch.from_numpy(x).cuda(), lengths=torch.full((B,), T))['nll']
+    b = model.evaluate(torch.from_numpy(x).cuda())['nll']
+    assert torch.equal(a, b)
+
+
+def test_variable_lengths_training_step_and_unsupported_modes():
+    B, T = 4, 6
+    lengths = np.array([6, 2, 5, 3], dtype=np.int32)
+    model = make('jamming', H=128, Rnn=(32,))
+    plist = [arena_to_params(model, f'generator/{t}', 1, False) for t in model.tracks]
+    tp = [R.to_torch(p, torch.float64, requires_grad=True) for p in plist]
+    x = O.synthetic_pianoroll(B, T, seed=8, density=0.1)
+    l_ref, _ = R.jamming_loss(torch.tensor(x, dtype=torch.float64), tp, lengths=lengths)
+    step = model.train_generators('adam', 0.01)
+    got = step(torch.from_numpy(x).cuda(), lengths=lengths, keep=1.0)
+    assert abs(float(got) - float(l_ref)) / float(l_ref) < 1e-5
+    joint = make('joint', encoder='DBN', generator='RBM', H=64, Rnn=(32,))
+    with pytest.raises(NotImplementedError):
+        joint.evaluate(torch.from_numpy(x).cuda(), lengths=torch.from_numpy(lengths))

@@ -191,3 +191,29 @@ def test_composer_generate_shapes_and_determinism():
     a = O.composer_generate(x, p, S, u)
     b = O.composer_generate(x, p, S, u)
     assert a.shape == (B, S, D, M) and np.array_equal(a, b) and set(np.unique(a)) <= {0., 1.}
+
+
+def test_variable_lengths_drop_padded_rows():
+    """utils/sequences.py:6-37: rows t >= lengths[b] are removed in b-major order; the values of the padded frames
+    after a sequence's end cannot change any kept row (the recurrence is causal); full lengths = plain reshape."""
+    B, T, D, M, H = 3, 5, 5, 2, 4
+    lengths = np.array([5, 2, 3])
+    x = O.synthetic_pianoroll(B, T, D, M, density=0.3).astype(np.float64)
+    p = O.cast_params(O.init_composer_params(D, M, H, (6, 4), seed=7), np.float64)
+    rows = O.flatten_valid_rows(lengths, T)
+    np.testing.assert_array_equal(rows, [0, 1, 2, 3, 4, 5, 6, 10, 11, 12])
+    full = O.composer_forward(x, p)
+    out = O.composer_forward(x, p, lengths=lengths)
+    np.testing.assert_array_equal(out['nll'], full['nll'][rows])
+    np.testing.assert_allclose(out['loss'], full['nll'][rows].mean(), rtol=1e-13)
+    x2 = x.copy()
+    x2[1, 2:] = 1 - x2[1, 2:]                    # garbage after the end of sequence 1
+    x2[2, 3:] = 1 - x2[2, 3:]
+    out2 = O.composer_forward(x2, p, lengths=lengths)
+    np.testing.assert_array_equal(out2['nll'], out['nll'])
+    same = O.composer_forward(x, p, lengths=np.full(B, T))
+    np.testing.assert_array_equal(same['nll'], full['nll'])
+    tp = R.to_torch(p, torch.float64)
+    loss, nll = R.composer_loss(torch.tensor(x), tp, lengths=lengths)
+    np.testing.assert_allclose(float(loss), out['loss'], rtol=1e-12)
+    np.testing.assert_allclose(nll.numpy(), out['nll'], rtol=1e-12)
