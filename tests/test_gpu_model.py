@@ -300,6 +300,6 @@ def test_variable_lengths_training_step_and_unsupported_modes():
     step = model.train_generators('adam', 0.01)
     got = step(torch.from_numpy(x).cuda(), lengths=lengths, keep=1.0)
     assert abs(float(got) - float(l_ref)) / float(l_ref) < 1e-5
-    joint = make('joint', encoder='DBN', generator='RBM', H=64, Rnn=(32,))
+    joint = make('joint', encoder='DBN', encoder_hidden=[168, 84], generator='RBM', H=64, Rnn=(32,))
     with pytest.raises(NotImplementedError):
         joint.evaluate(torch.from_numpy(x).cuda(), lengths=torch.from_numpy(lengths))
