@@ -106,15 +106,17 @@ int mnn_colsum(const float* A, long long ld, int rows, int cols, float* out, int
  * (_cond_prob), utils/auxiliary.py:9-11 (safe_log), generators/rnn_multinade.py:231-290 (bias split, per-track
  * loop). fc[N,ld] is the Dense output read in place: b_enc of track m at column enc_col0 + m*H, b_dec at
  * dec_col0 + m*D. w_enc/w_dec[M,D,H]. Outputs nll[M,N] (positive), cond_p[M,N,D] (optional). When dfc != NULL
- * (training) the d b_dec columns of dfc[N,ld] receive gscale * dNLL/dl. */
+ * (training) the d b_dec columns of dfc[N,ld] receive gscale * dNLL/dl. track_stride (0 = N): rows between
+ * consecutive tracks in bits / nll / cond_p, so that a chunk of N rows of longer [M,TS,..] buffers can be processed
+ * (all row pointers pre-offset by the caller). The grid honours mnn_set_sm_budget. */
 int mnn_nade_logprob_fwd(const uint32_t* bits, const float* fc, long long ld, int enc_col0, int dec_col0,
                          const float* w_enc, const float* w_dec, float* nll, float* cond_p, float* dfc, float gscale,
-                         int N, int M, int D, int H, mnn_stream_t stream);
+                         int N, int M, int D, int H, long long track_stride, mnn_stream_t stream);
 /* K5 -- its backward (what tf.gradients builds through nade.py:199-226). Needs the d b_dec columns written by
  * the forward; writes the d b_enc columns of dfc and ACCUMULATES into dw_enc/dw_dec[M,D,H]. */
 int mnn_nade_logprob_bwd(const uint32_t* bits, const float* fc, long long ld, int enc_col0, int dec_col0,
                          const float* w_enc, const float* w_dec, float* dfc, float* dw_enc, float* dw_dec, int N,
-                         int M, int D, int H, mnn_stream_t stream);
+                         int M, int D, int H, long long track_stride, mnn_stream_t stream);
 /* K6 -- NADE ancestral sampling, common/nade.py:231-308 (+ tfp Bernoulli(logits).sample(), :283-287;
  * rnn_multinade.py:292-317 stacks tracks with axis=2). u[M,N,D] uniforms; u == NULL and use_philox == 0 means
  * temperature=None (p >= .5). out[row*out_ld + i*out_dim_stride + m*out_track_stride] in {0,1}. */

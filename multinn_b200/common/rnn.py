@@ -99,20 +99,54 @@ class RNN:
     WAVEFRONT_CHUNK = 32
     WAVEFRONT_GEMM_SMS = 32
 
+    # Time-chunk PIPELINE (small per-GPU batches): while the recurrences walk the chunks on their (high-priority)
+    # streams, the batched work either side of them -- Dense, NADE forward/backward, data- and weight-gradient GEMMs,
+    # bias column sums -- runs chunk by chunk on a low-priority "bulk" stream inside an SM budget that leaves the
+    # recurrence kernels' SMs free. The recurrences hold ~100 SMs but are a latency chain; the bulk work fills the rest.
+    PIPE_MAX_BATCH = int(os.environ.get('MNN_PIPE_MAX_BATCH', 512))
+    PIPE_FWD_BUDGETS = tuple(int(v) for v in os.environ.get('MNN_PIPE_FWD_BUDGETS', '96,48').split(','))
+    PIPE_BWD_BUDGETS = tuple(int(v) for v in os.environ.get('MNN_PIPE_BWD_BUDGETS', '72,36').split(','))
+    PIPE_BULK_SMS_FWD = int(os.environ.get('MNN_PIPE_BULK_SMS_FWD', 44))
+    PIPE_BULK_SMS_BWD = int(os.environ.get('MNN_PIPE_BULK_SMS_BWD', 36))
+    PIPE_SLOW_HOOKS = int(os.environ.get('MNN_PIPE_SLOW_HOOKS', 2))     # forward chunk hooks that start under the recurrence
+    PIPE_FULL_WGRADS = int(os.environ.get('MNN_PIPE_FULL_WGRADS', 2))   # last BPTT chunks whose weight grads use every SM
+
+    TRACE = None        # debug (tools/pipeline_trace.py): list collecting (label, timing event) of the chunk schedule
+
+    @classmethod
+    def _event(cls, label=None):
+        if cls.TRACE is None:
+            return torch.cuda.Event()
+        ev = torch.cuda.Event(enable_timing=True)
+        cls.TRACE.append((label, ev))
+        return ev
+
     def _use_wavefront(self, T, B, backward=False):
         mb = min(self.WAVEFRONT_MAX_BATCH, self.WAVEFRONT_MAX_BATCH_BWD) if backward else self.WAVEFRONT_MAX_BATCH
         return (self.num_layers > 1 and B <= mb and T % self.WAVEFRONT_CHUNK == 0 and T >= 2 * self.WAVEFRONT_CHUNK)
 
+    def use_pipeline(self, T, B):
+        return B <= self.PIPE_MAX_BATCH and self._use_wavefront(T, B) and self._use_wavefront(T, B, backward=True)
+
     def _streams(self, device):
         st = self.__dict__.get('_wave_streams')
         if st is None:
-            st = self._wave_streams = [torch.cuda.Stream(device=device) for _ in range(self.num_layers)]
+            st = self._wave_streams = [torch.cuda.Stream(device=device, priority=-1) for _ in range(self.num_layers)]
         return st
 
-    def forward_sequence(self, x, keep=1.0, u=None, seed=0, initial_state=None):
+    def bulk_stream(self, device):
+        st = self.__dict__.get('_bulk_stream')
+        if st is None:
+            st = self._bulk_stream = torch.cuda.Stream(device=device, priority=0)
+        return st
+
+    def forward_sequence(self, x, keep=1.0, u=None, seed=0, initial_state=None, chunk_hook=None):
         """x[T,B,I] time-major -> outputs[T,B,R_top] (dropped out when keep < 1), final state.
         u: optional list (per layer) of [T,B,R_l] uniforms for reproducible dropout; else Philox(seed).
-        Saves what BPTT needs (call `backward_sequence` next)."""
+        Saves what BPTT needs (call `backward_sequence` next).
+        chunk_hook(c, nch, t0, t1, done_event, outs_top): pipeline mode (`use_pipeline`), called once per time chunk after
+        the top layer's chunk has been enqueued; the hook enqueues the consumer work of steps [t0, t1) on `bulk_stream`
+        behind `done_event`."""
         T, B, I = x.shape
         assert I == self._num_inputs and x.is_contiguous()
         dropout = keep < 1.0
@@ -130,7 +164,8 @@ class RNN:
         ops.gemm(x.view(T * B, I), self.kernels[0].data[:I], ws[0]['gates'].view(T * B, 4 * r0), bias=self.biases[0].data,
                  a_exact=self._binary_inputs)
         if self._use_wavefront(T, B):
-            self._forward_wavefront(ws, outs, T, B, keep, u, seed, dropout)
+            hook = chunk_hook if (chunk_hook is not None and self.use_pipeline(T, B)) else None
+            self._forward_wavefront(ws, outs, T, B, keep, u, seed, dropout, hook)
         else:
             for l, r in enumerate(self._num_units):
                 w = ws[l]
@@ -145,14 +180,15 @@ class RNN:
         state = [LSTMStateTuple(w['cbuf'][T], w['hbuf'][T]) for w in ws]
         return outs[-1], state
 
-    def _forward_wavefront(self, ws, outs, T, B, keep, u, seed, dropout):
+    def _forward_wavefront(self, ws, outs, T, B, keep, u, seed, dropout, hook=None):
         C = self.WAVEFRONT_CHUNK
         nch = T // C
+        budgets = self.PIPE_FWD_BUDGETS if hook is not None else (96, 48)
         main = torch.cuda.current_stream()
         streams = self._streams(ws[0]['gates'].device)
-        start = torch.cuda.Event()
+        start = self._event('fwd start')
         start.record(main)
-        done = [[torch.cuda.Event() for _ in range(nch)] for _ in range(self.num_layers)]
+        done = [[self._event(f'fwd L{l} chunk {c}') for c in range(nch)] for l in range(self.num_layers)]
         for c in range(nch):
             t0, t1 = c * C, (c + 1) * C
             for l, r in enumerate(self._num_units):
@@ -170,7 +206,7 @@ class RNN:
                                      w['gates'][t0:t1].view(C * B, 4 * r), bias=self.biases[l].data)
                         finally:
                             ops.set_sm_budget(0)
-                    ops.set_sm_budget(96 if l == 0 else 48)     # wavefront mode: kernels pick co-resident configurations
+                    ops.set_sm_budget(budgets[min(l, len(budgets) - 1)])   # wavefront mode: co-resident configurations
                     try:
                         ops.lstm_seq_fwd(w['gates'][t0:t1], kern[i_l:], w['hbuf'][t0:t1 + 1], w['cbuf'][t0:t1 + 1],
                                          out=w['out'][t0:t1] if dropout else None,
@@ -180,11 +216,15 @@ class RNN:
                     finally:
                         ops.set_sm_budget(0)
                     done[l][c].record(streams[l])
+            if hook is not None:
+                hook(c, nch, t0, t1, done[self.num_layers - 1][c], outs[-1])
         for l in range(self.num_layers):
             main.wait_event(done[l][nch - 1])
 
-    def backward_sequence(self, dout, need_dx=False):
-        """dout[T,B,R_top] = grad wrt the (dropped-out) top outputs. Writes kernel/bias grads; returns dx or None."""
+    def backward_sequence(self, dout, need_dx=False, pipelined=False):
+        """dout[T,B,R_top] = grad wrt the (dropped-out) top outputs. Writes kernel/bias grads; returns dx or None.
+        pipelined: weight / bias gradients are ACCUMULATED chunk by chunk on the bulk stream while BPTT walks the
+        earlier chunks (the caller zeroed the gradient buffers, as GradientApplier.zero_grad does every step)."""
         x, ws, dropout = self._saved
         T, B, I = x.shape
         for l, r in enumerate(self._num_units):
@@ -194,8 +234,11 @@ class RNN:
             i_l = self.in_dims()[l]
             if (l > 0 or need_dx) and (w.get('d_in') is None or w['d_in'].shape != (T, B, i_l)):
                 w['d_in'] = torch.empty(T, B, i_l, device=x.device)
+        pipelined = pipelined and self.use_pipeline(T, B)
         if self._use_wavefront(T, B, backward=True):
-            self._backward_wavefront(ws, dout, T, B, dropout, need_dx)
+            self._backward_wavefront(ws, dout, T, B, dropout, need_dx, x if pipelined else None)
+            if pipelined:
+                return ws[0]['d_in'] if need_dx else None
         else:
             d = dout
             for l in reversed(range(self.num_layers)):
@@ -209,31 +252,40 @@ class RNN:
                     d = w['d_in']
         # weight gradients: batched GEMMs over all T*B rows
         for l in reversed(range(self.num_layers)):
-            r = self._num_units[l]
-            w = ws[l]
-            kern = self.kernels[l]
-            i_l = self.in_dims()[l]
-            dg = w['gates'].view(T * B, 4 * r)                       # now d(pre-activations)
-            inp = x.view(T * B, I) if l == 0 else \
-                (ws[l - 1]['out'] if dropout else ws[l - 1]['hbuf'][1:]).view(T * B, i_l)
-            ops.gemm(inp, dg, kern.grad[:i_l], transA=True, a_exact=(l == 0 and self._binary_inputs))   # dWx = x^T dG
-            ops.gemm(w['hbuf'][:T].view(T * B, r), dg, kern.grad[i_l:], transA=True)   # dWh = h_{t-1}^T dG
-            ops.colsum(dg, self.biases[l].grad)
+            self._weight_grads(l, x, ws, dropout, 0, T, B, beta=0.0)
         return ws[0]['d_in'] if need_dx else None
 
-    def _backward_wavefront(self, ws, dout, T, B, dropout, need_dx):
-        """BPTT as a wavefront over time chunks: layer l back-propagates chunk c while layer l-1 works on chunk c+1."""
+    def _weight_grads(self, l, x, ws, dropout, t0, t1, B, beta):
+        """dWx_l (+)= in_l^T dG_l, dWh_l (+)= h_{l,t-1}^T dG_l, db_l (+)= colsum(dG_l) over steps [t0, t1)."""
+        r = self._num_units[l]
+        w = ws[l]
+        kern = self.kernels[l]
+        i_l = self.in_dims()[l]
+        rows = (t1 - t0) * B
+        dg = w['gates'][t0:t1].view(rows, 4 * r)                       # now d(pre-activations)
+        inp = x[t0:t1].view(rows, -1) if l == 0 else \
+            (ws[l - 1]['out'] if dropout else ws[l - 1]['hbuf'][1:])[t0:t1].reshape(rows, i_l)
+        ops.gemm(inp, dg, kern.grad[:i_l], transA=True, beta=beta, a_exact=(l == 0 and self._binary_inputs))
+        ops.gemm(w['hbuf'][t0:t1].view(rows, r), dg, kern.grad[i_l:], transA=True, beta=beta)
+        ops.colsum(dg, self.biases[l].grad, accumulate=beta != 0.0)
+
+    def _backward_wavefront(self, ws, dout, T, B, dropout, need_dx, x_pipe=None):
+        """BPTT as a wavefront over time chunks: layer l back-propagates chunk c while layer l-1 works on chunk c+1.
+        x_pipe (pipeline mode): the layer-0 inputs; weight gradients of finished chunks run on the bulk stream."""
         C = self.WAVEFRONT_CHUNK
         nch = T // C
         L = self.num_layers
         main = torch.cuda.current_stream()
         streams = self._streams(ws[0]['gates'].device)
-        start = torch.cuda.Event()
+        start = self._event('bwd start')
         start.record(main)
-        done = [[torch.cuda.Event() for _ in range(nch)] for _ in range(L)]
+        done = [[self._event(f'bwd L{l} chunk {c}') for c in range(nch)] for l in range(L)]
         budgets = [0] * L
         if L == 2:
             budgets = [72, 36]          # SMs for the persistent BPTT kernels of the two layers (they must co-reside)
+            if x_pipe is not None:
+                budgets = list(self.PIPE_BWD_BUDGETS)
+        bulk = self.bulk_stream(ws[0]['gates'].device) if x_pipe is not None else None
         for c in reversed(range(nch)):
             t0, t1 = c * C, (c + 1) * C
             for l in reversed(range(L)):
@@ -259,8 +311,22 @@ class RNN:
                     finally:
                         ops.set_sm_budget(0)
                     done[l][c].record(streams[l])
+                if bulk is not None:
+                    with torch.cuda.stream(bulk):
+                        bulk.wait_event(done[l][c])
+                        ops.set_sm_budget(0 if c < self.PIPE_FULL_WGRADS else self.PIPE_BULK_SMS_BWD)
+                        try:
+                            self._weight_grads(l, x_pipe, ws, dropout, t0, t1, B, beta=1.0)
+                        finally:
+                            ops.set_sm_budget(0)
+                        if self.TRACE is not None:
+                            self._event(f'bwd wgrads L{l} chunk {c}').record(bulk)
         for l in range(L):
             main.wait_event(done[l][0])
+        if bulk is not None:
+            ev = self._event('bwd bulk end')
+            ev.record(bulk)
+            main.wait_event(ev)
 
     # ------------------------------------------------------------------ one step (generation)
     def step(self, x, state, scratch=None):

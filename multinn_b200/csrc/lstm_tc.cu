@@ -71,10 +71,16 @@ __device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
 
 // Shared skeleton of both directions. FWD: A = h slot t (rows t*B + m*128), B = WhP^T rows n*BN..; BWD: A = dG slot t+1,
 // B = Wh rows n*BN.. (both operands K-major).
-template <int BN, bool FWD>
+// SHARE (one item per CTA and step, the small-batch regime): the mainloop and the cell epilogue of an item cannot
+// overlap anyway (the next step's h does not exist yet), so all 8 worker warps convert during the mainloop and all 8 run
+// the epilogue (warps 4-7 the even 8-unit groups, warps 8-11 the odd ones; a warp reads the TMEM lanes of quadrant
+// warp % 4). Measured at B=256, R=512 (globaltimer trace): conversion by 4 warps bounded the mainloop at 0.55 us per
+// k-block (9.5 us per step) and the 4-warp row-per-thread epilogue took 7.4 us.
+template <int BN, bool FWD, bool SHARE>
 __global__ void __launch_bounds__(kLThreads, 1)
 lstm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const LstmParams p) {
   using C_ = LCfg<BN>;
+  constexpr int kConvThreads = SHARE ? 256 : 128;
   constexpr int STAGES = C_::STAGES;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[3 * STAGES + 4];
@@ -90,12 +96,12 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_conv + 8 * s, 128);
+      mbar_init(bar_conv + 8 * s, kConvThreads);
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 128);
+      mbar_init(bar_tempty + 8 * a, kConvThreads);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -129,6 +135,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             while (ld_acquire(p.flags + m_blk) < target) __nanosleep(32);
             asm volatile("fence.proxy.async;" ::: "memory");   // other CTAs' generic-proxy stores -> our TMA reads
           }
+          if (w == blockIdx.x) MNN_TRACE(0);
           const int row0 = a_slot * p.B + m_blk * BM;
           for (int kb = 0; kb < p.kb_total; ++kb) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -139,6 +146,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tma_load_2d(a_dst + 2 * C_::A_BYTES, &map_b, full, kb * BK, n_blk * BN);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
+          if (w == blockIdx.x) MNN_TRACE(1);
         }
       }
     }
@@ -157,6 +165,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_wait(bar_full + 8 * stage, phase);
             mbar_wait(bar_conv + 8 * stage, phase);
             tc_fence_after();
+            if (kb == 0 && w == blockIdx.x) MNN_TRACE(4);
             const uint32_t a_raw = smem0 + stage * C_::STAGE_BYTES, a_lo = a_raw + C_::A_BYTES;
             const uint32_t b_raw = a_raw + 2 * C_::A_BYTES;
 #pragma unroll
@@ -172,39 +181,22 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           umma_commit(bar_tfull + 8 * acc);
+          if (w == blockIdx.x) MNN_TRACE(5);
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       }
     }
-  } else if (warp >= 8) {
-    // ------------------------------------------------------------------ converters: lo = x - trunc_tf32(x)
-    const int tc = threadIdx.x - 8 * 32;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int s = 0; s < n_steps; ++s) {
-      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-        for (int kb = 0; kb < p.kb_total; ++kb) {
-          mbar_wait(bar_full + 8 * stage, phase);
-          uint8_t* base = smem_gen + (size_t)stage * C_::STAGE_BYTES;
-          const float4* a_raw = reinterpret_cast<const float4*>(base);
-          float4* a_lo = reinterpret_cast<float4*>(base + C_::A_BYTES);
-          const float4* b_raw = reinterpret_cast<const float4*>(base + 2 * C_::A_BYTES);
-          float4* b_lo = reinterpret_cast<float4*>(base + 2 * C_::A_BYTES + C_::B_BYTES);
-#pragma unroll 4
-          for (int i = tc; i < C_::A_BYTES / 16; i += 128) a_lo[i] = tf32_lo4(a_raw[i]);
-#pragma unroll 4
-          for (int i = tc; i < C_::B_BYTES / 16; i += 128) b_lo[i] = tf32_lo4(b_raw[i]);
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(bar_conv + 8 * stage);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue: the LSTM cell (fwd) / its backward
-    const int q = warp - 4;
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    // ------------------------------------------------------------------ worker warps: hi/lo converters (lo = x - trunc_tf32(x))
+    // and the epilogue = the LSTM cell (fwd) / its backward. !SHARE: warps 8-11 convert, warps 4-7 run the epilogue.
+    const int q = warp & 3;                    // TMEM lane quadrant of this warp
+    const int hf = (warp - 4) >> 2;            // 0: warps 4-7, 1: warps 8-11
+    const bool conv_role = SHARE || hf == 1, epi_role = SHARE || hf == 0;
+    const int tc = SHARE ? threadIdx.x - 4 * 32 : threadIdx.x - 8 * 32;
+    const int ug0 = SHARE ? hf : 0;
+    constexpr int UGS = SHARE ? 2 : 1;
+    int acc = 0, stage = 0;
+    uint32_t acc_phase = 0, phase = 0;
     const int R = p.R, B = p.B;
     const size_t BR = (size_t)B * R;
     for (int s = 0; s < n_steps; ++s) {
@@ -215,7 +207,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const bool row_ok = b < B;
         // the operands of the NEXT step's epilogue for this item stream from HBM (they were written long ago): pull
         // them into L2 now, off the critical path of the recurrence
-        if (persistent && s + 1 < n_steps && row_ok) {
+        if (hf == 0 && persistent && s + 1 < n_steps && row_ok) {
           const int tn = FWD ? t + 1 : t - 1;
           if (FWD) {
             constexpr int UBp = BN / 4;
@@ -242,8 +234,31 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           }
         }
+        if (conv_role) {
+          for (int kb = 0; kb < p.kb_total; ++kb) {
+            mbar_wait(bar_full + 8 * stage, phase);
+            if (tc == 0 && w == blockIdx.x) {
+              if (kb == 0) MNN_TRACE(2);
+              if (kb == p.kb_total - 1) MNN_TRACE(3);
+            }
+            uint8_t* base = smem_gen + (size_t)stage * C_::STAGE_BYTES;
+            const float4* a_raw = reinterpret_cast<const float4*>(base);
+            float4* a_lo = reinterpret_cast<float4*>(base + C_::A_BYTES);
+            const float4* b_raw = reinterpret_cast<const float4*>(base + 2 * C_::A_BYTES);
+            float4* b_lo = reinterpret_cast<float4*>(base + 2 * C_::A_BYTES + C_::B_BYTES);
+#pragma unroll 4
+            for (int i = tc; i < C_::A_BYTES / 16; i += kConvThreads) a_lo[i] = tf32_lo4(a_raw[i]);
+#pragma unroll 4
+            for (int i = tc; i < C_::B_BYTES / 16; i += kConvThreads) b_lo[i] = tf32_lo4(b_raw[i]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(bar_conv + 8 * stage);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        if (!epi_role) continue;
         mbar_wait(bar_tfull + 8 * acc, acc_phase);
         tc_fence_after();
+        if (threadIdx.x == 128 && w == blockIdx.x) MNN_TRACE(6);
         const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * BN);
         if (FWD) {
           constexpr int UB = BN / 4;
@@ -253,7 +268,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           float* cnew = p.cbuf + (size_t)(t + 1) * BR + sidx;
           float* hnew = p.hbuf + (size_t)(t + 1) * BR + sidx;
 #pragma unroll 1
-          for (int ug = 0; ug < UB / 8; ++ug) {
+          for (int ug = ug0; ug < UB / 8; ug += UGS) {
             const int unit = n_blk * UB + ug * 8;
             if (unit >= R) break;   // warp-uniform (R % 8 == 0)
             float pre[4][8];
@@ -339,7 +354,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const float* cprev = p.cbuf + (size_t)t * BR + sidx;
           const float* cnow = p.cbuf + (size_t)(t + 1) * BR + sidx;
 #pragma unroll 1
-          for (int ug = 0; ug < BN / 8; ++ug) {
+          for (int ug = ug0; ug < BN / 8; ug += UGS) {
             const int unit = n_blk * BN + ug * 8;
             if (unit >= R) break;
             float dh[8];
@@ -395,13 +410,16 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tc_fence_before();
         mbar_arrive(bar_tempty + 8 * acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (threadIdx.x == 128 && w == blockIdx.x) MNN_TRACE(7);
         if (persistent) {
           // publish this item's h_t / dG_t rows to the CTAs of the same slab
           __threadfence();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (SHARE) asm volatile("bar.sync 1, 256;" ::: "memory");
+          else asm volatile("bar.sync 1, 128;" ::: "memory");
           if (threadIdx.x == 4 * 32) {
             asm volatile("fence.proxy.async;" ::: "memory");
             atomicAdd(p.flags + m_blk, 1u);
+            if (w == blockIdx.x) MNN_TRACE(8);
           }
         }
       }
@@ -1150,32 +1168,61 @@ static int launch_lstm(const CUtensorMap& ma, const CUtensorMap& mb, LstmParams 
   using C_ = LCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(lstm_tc_kernel<BN, FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_::SMEM);
+    cudaFuncSetAttribute(lstm_tc_kernel<BN, FWD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_::SMEM);
+    cudaFuncSetAttribute(lstm_tc_kernel<BN, FWD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_::SMEM);
     attr_set = true;
   }
   const int items = p.slabs * p.blocks;
   const int grid = items < mnn_tc_num_sms() ? items : mnn_tc_num_sms();
   const int t0 = p.t0, t1 = p.t1;
+  static const char* share_env = getenv("MNN_LSTM_SHARE");   // "0": never (debug)
+  const bool share = items <= grid && !(share_env && share_env[0] == '0');
   if (persistent && t1 - t0 > 1) {
     cudaMemsetAsync(p.flags, 0, (size_t)p.slabs * sizeof(unsigned int), stream);
+    static const char* trace_path = getenv("MNN_LSTM_TRACE");   // debug only: allocates and synchronises
+    const size_t trace_n = (size_t)grid * kTraceSteps * kTraceEv;
+    if (trace_path) {
+      cudaMalloc(&p.trace, trace_n * sizeof(unsigned long long));
+      cudaMemsetAsync(p.trace, 0, trace_n * sizeof(unsigned long long), stream);
+    }
     void* args[3] = {const_cast<CUtensorMap*>(&ma), const_cast<CUtensorMap*>(&mb), &p};
-    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_tc_kernel<BN, FWD>), dim3(grid),
-                                                dim3(kLThreads), args, C_::SMEM, stream);
+    cudaError_t e = cudaLaunchCooperativeKernel(
+        share ? reinterpret_cast<void*>(lstm_tc_kernel<BN, FWD, true>) : reinterpret_cast<void*>(lstm_tc_kernel<BN, FWD, false>),
+        dim3(grid), dim3(kLThreads), args, C_::SMEM, stream);
     if (e != cudaSuccess) {
       mnn_set_error(cudaGetErrorString(e));
       return (int)e;
+    }
+    if (trace_path) {
+      cudaStreamSynchronize(stream);
+      std::vector<unsigned long long> h(trace_n);
+      cudaMemcpy(h.data(), p.trace, trace_n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      cudaFree(p.trace);
+      if (FILE* f = fopen(trace_path, "a")) {
+        fprintf(f, "# lstm 1cta %s B=%d R=%d T=%d ctas=%d BN=%d share=%d\n", FWD ? "fwd" : "bwd", p.B, p.R, t1 - t0, grid, BN,
+                (int)share);
+        for (int c = 0; c < grid; ++c)
+          for (int st = 0; st < kTraceSteps; ++st) {
+            fprintf(f, "%d %d", c, st);
+            for (int ev = 0; ev < kTraceEv; ++ev) fprintf(f, " %llu", h[((size_t)c * kTraceSteps + st) * kTraceEv + ev]);
+            fprintf(f, "\n");
+          }
+        fclose(f);
+      }
     }
     return mnn_check_launch(FWD ? "lstm_seq_fwd(persistent)" : "lstm_seq_bwd(persistent)");
   }
   if (FWD) {
     for (int t = t0; t < t1; ++t) {
       p.t0 = t; p.t1 = t + 1;
-      lstm_tc_kernel<BN, FWD><<<grid, kLThreads, C_::SMEM, stream>>>(ma, mb, p);
+      if (share) lstm_tc_kernel<BN, FWD, true><<<grid, kLThreads, C_::SMEM, stream>>>(ma, mb, p);
+      else lstm_tc_kernel<BN, FWD, false><<<grid, kLThreads, C_::SMEM, stream>>>(ma, mb, p);
     }
   } else {
     for (int t = t1 - 1; t >= t0; --t) {
       p.t0 = t; p.t1 = t + 1;
-      lstm_tc_kernel<BN, FWD><<<grid, kLThreads, C_::SMEM, stream>>>(ma, mb, p);
+      if (share) lstm_tc_kernel<BN, FWD, true><<<grid, kLThreads, C_::SMEM, stream>>>(ma, mb, p);
+      else lstm_tc_kernel<BN, FWD, false><<<grid, kLThreads, C_::SMEM, stream>>>(ma, mb, p);
     }
   }
   return mnn_check_launch(FWD ? "lstm_seq_fwd" : "lstm_seq_bwd", t1 - t0);
@@ -1183,6 +1230,10 @@ static int launch_lstm(const CUtensorMap& ma, const CUtensorMap& mb, LstmParams 
 
 static int fwd_unit_block(int B, int R) {
   const int slabs = (B + BM - 1) / BM;
+  // an SM budget below the number of 16-unit items: 32-unit items, half as many CTAs (the caller wants the SMs for the
+  // bulk work it runs beside the recurrence)
+  const int budget = mnn_tc_sm_budget();
+  if (budget > 0 && slabs * ((R + 15) / 16) > budget) return 32;
   return (slabs * ((R + 31) / 32) >= 96) ? 32 : 16;
 }
 

@@ -10,6 +10,8 @@
 #include "common.cuh"
 #include "multinn_b200.h"
 
+int mnn_tc_sm_budget();   // gemm_tc.cu: mnn_set_sm_budget of the calling thread (0 = whole device)
+
 namespace mnn {
 
 constexpr int kNW = 4;          // 32-bit mask words per (row, track): D <= 128
@@ -17,19 +19,20 @@ constexpr int kFwdThreads = 384;
 constexpr int kFwdRows = 4;     // rows per warp
 
 struct NadeArgs {
-  const uint32_t* bits;  // [M][N][kNW]
+  const uint32_t* bits;  // [M][TS][kNW]  (TS = tstride rows per track >= N: a row chunk of a longer buffer)
   const float* fc;       // [N][ld]   b_enc(m) at col enc_col0 + m*H, b_dec(m) at dec_col0 + m*D
   long long ld;
   int enc_col0, dec_col0;
   const float* w_enc;    // [M][D][H]
   const float* w_dec;    // [M][D][H]
-  float* nll;            // [M][N]
-  float* cond_p;         // [M][N][D] or null
+  float* nll;            // [M][TS]
+  float* cond_p;         // [M][TS][D] or null
   float* dfc;            // [N][ld] or null: d b_dec columns written by fwd, d b_enc columns by bwd
   float* dw_enc;         // [M][D][H] accumulated (bwd)
   float* dw_dec;         // [M][D][H] accumulated (bwd)
   float gscale;          // d loss / d nll[n,m]
   int N, M, D;
+  long long tstride;     // rows between consecutive tracks in bits / nll / cond_p
 };
 
 __device__ __forceinline__ uint32_t pick_word(const uint32_t (&w)[kNW], int idx) {
@@ -65,7 +68,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) nade_fwd_kernel(NadeArgs p) {
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int ngroups = (p.N + kFwdRows - 1) / kFwdRows;
-  const uint32_t* bits = p.bits + (size_t)m * p.N * kNW;
+  const uint32_t* bits = p.bits + (size_t)m * p.tstride * kNW;
   const int enc_col = p.enc_col0 + m * H, dec_col = p.dec_col0 + m * D;
   const int nchunks = (D + 7) / 8;
   const int er = lane >> 3, eii = lane & 7;  // epilogue ownership
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) nade_fwd_kernel(NadeArgs p) {
         const float lp = v ? logf(kSafeLogEps + pr) : logf(kSafeLogEps + q);
         if (e_ok) {
           nll_acc -= lp;
-          if (p.cond_p) p.cond_p[((size_t)m * p.N + erow) * D + ei] = pr;
+          if (p.cond_p) p.cond_p[((size_t)m * p.tstride + erow) * D + ei] = pr;
           if (p.dfc) {
             // d(-lp)/dl with dp/dl = p(1-p)   (safe_log eps kept, nade.py:210)
             const float pq = pr * q;
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) nade_fwd_kernel(NadeArgs p) {
     nll_acc += __shfl_xor_sync(0xffffffffu, nll_acc, 1);
     nll_acc += __shfl_xor_sync(0xffffffffu, nll_acc, 2);
     nll_acc += __shfl_xor_sync(0xffffffffu, nll_acc, 4);
-    if (eii == 0 && erow_ok) p.nll[(size_t)m * p.N + erow] = nll_acc;
+    if (eii == 0 && erow_ok) p.nll[(size_t)m * p.tstride + erow] = nll_acc;
   }
 }
 
@@ -266,7 +269,7 @@ __global__ void __launch_bounds__(H, 1) nade_bwd_kernel(NadeArgs p) {
     reinterpret_cast<float4*>(wenc_s)[c] = __ldg(reinterpret_cast<const float4*>(gwe) + c);
     reinterpret_cast<float4*>(acce_s)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  const uint32_t* bits = p.bits + (size_t)m * p.N * kNW;
+  const uint32_t* bits = p.bits + (size_t)m * p.tstride * kNW;
   const int enc_col = p.enc_col0 + m * H, dec_col = p.dec_col0 + m * D;
   const int nbatches = (p.N + R - 1) / R;
 
@@ -586,7 +589,7 @@ __global__ void __launch_bounds__(kSampleThreads, 1) nade_sample_kernel(NadeSamp
 }
 
 static int g_num_sms = 0;
-static int num_sms() {
+static int device_sms() {
   if (!g_num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -594,6 +597,12 @@ static int num_sms() {
     if (g_num_sms <= 0) g_num_sms = 148;
   }
   return g_num_sms;
+}
+// grids of the persistent NADE kernels honour the caller's SM budget so that they can run beside the recurrence
+// kernels of other streams (time-chunk pipeline at small per-GPU batches)
+static int num_sms() {
+  const int n = device_sms(), b = ::mnn_tc_sm_budget();
+  return (b > 0 && b < n) ? b : n;
 }
 
 }  // namespace mnn
@@ -612,11 +621,14 @@ static int check_nade_common(int N, int M, int D, int H, long long ld, int enc_c
 
 extern "C" int mnn_nade_logprob_fwd(const uint32_t* bits, const float* fc, long long ld, int enc_col0, int dec_col0,
                                     const float* w_enc, const float* w_dec, float* nll, float* cond_p, float* dfc,
-                                    float gscale, int N, int M, int D, int H, cudaStream_t stream) {
+                                    float gscale, int N, int M, int D, int H, long long track_stride,
+                                    cudaStream_t stream) {
   MNN_REQUIRE(bits && fc && w_enc && w_dec && nll, MNN_ERR_ARG, "nade_logprob_fwd: null pointer");
   int rc = check_nade_common(N, M, D, H, ld, enc_col0, dec_col0);
   if (rc) return rc;
-  NadeArgs a{bits, fc, ld, enc_col0, dec_col0, w_enc, w_dec, nll, cond_p, dfc, nullptr, nullptr, gscale, N, M, D};
+  MNN_REQUIRE(track_stride == 0 || track_stride >= N, MNN_ERR_ARG, "nade_logprob_fwd: track_stride < N");
+  NadeArgs a{bits, fc, ld, enc_col0, dec_col0, w_enc, w_dec, nll, cond_p, dfc, nullptr, nullptr, gscale, N, M, D,
+             track_stride ? track_stride : N};
   const size_t smem = (size_t)2 * D * H * sizeof(float);
   const int groups = (N + kFwdRows - 1) / kFwdRows;
   const int warps_per_cta = kFwdThreads / 32;
@@ -648,11 +660,13 @@ static int launch_bwd(const NadeArgs& a, cudaStream_t stream) {
 
 extern "C" int mnn_nade_logprob_bwd(const uint32_t* bits, const float* fc, long long ld, int enc_col0, int dec_col0,
                                     const float* w_enc, const float* w_dec, float* dfc, float* dw_enc, float* dw_dec,
-                                    int N, int M, int D, int H, cudaStream_t stream) {
+                                    int N, int M, int D, int H, long long track_stride, cudaStream_t stream) {
   MNN_REQUIRE(bits && fc && w_enc && w_dec && dfc && dw_enc && dw_dec, MNN_ERR_ARG, "nade_logprob_bwd: null pointer");
   int rc = check_nade_common(N, M, D, H, ld, enc_col0, dec_col0);
   if (rc) return rc;
-  NadeArgs a{bits, fc, ld, enc_col0, dec_col0, w_enc, w_dec, nullptr, nullptr, dfc, dw_enc, dw_dec, 0.f, N, M, D};
+  MNN_REQUIRE(track_stride == 0 || track_stride >= N, MNN_ERR_ARG, "nade_logprob_bwd: track_stride < N");
+  NadeArgs a{bits, fc, ld, enc_col0, dec_col0, w_enc, w_dec, nullptr, nullptr, dfc, dw_enc, dw_dec, 0.f, N, M, D,
+             track_stride ? track_stride : N};
   if (H == 256 && D == 84) return launch_bwd<256, 84>(a, stream);
   if (H == 128 && D == 84) return launch_bwd<128, 84>(a, stream);
   if (H == 128 && D == 20) return launch_bwd<128, 20>(a, stream);

@@ -148,6 +148,8 @@ class RnnNade(RnnEstimator):
         T, B, _ = inputs.shape
         N, M = T * B, self._num_tracks
         w, nvalid = self.row_weights(lengths, T, B, inputs.device)
+        if w is None and self._rnn.use_pipeline(T, B):
+            return self._forward_backward_pipelined(inputs, bits, keep, u_drop, seed, loss_scale, need_dx)
         self._get_state(inputs, keep=keep, u_drop=u_drop, seed=seed, training=True)
         ws = self._ws[(N, True)]
         gscale = loss_scale / (nvalid * M)
@@ -165,6 +167,54 @@ class RnnNade(RnnEstimator):
         ops.gemm(ws['dfc'], self._fc_kernel.data, ws['dout'], transB=True)
         dx = self._rnn.backward_sequence(ws['dout'].view(T, B, -1), need_dx=need_dx)
         return ws['loss'], ws['nll'], dx
+
+    def _forward_backward_pipelined(self, inputs, bits, keep, u_drop, seed, loss_scale, need_dx):
+        """Same results as the phase-by-phase path, scheduled as a pipeline over time chunks (small per-GPU batches, where
+        the recurrences are latency chains that leave SMs idle): as soon as the top LSTM layer has finished a chunk, its
+        Dense forward, NADE forward + backward, Dense weight/bias gradients (accumulated) and the gradient wrt the LSTM
+        outputs run on the bulk stream beside the recurrences of the later chunks; BPTT then overlaps the LSTM weight
+        gradients of the chunks it has left behind (common/rnn.py)."""
+        T, B, _ = inputs.shape
+        N, M = T * B, self._num_tracks
+        rnn = self._rnn
+        ws = self._workspace(N, inputs.device, True)
+        gscale = loss_scale / (N * M)
+        fc, dfc, nll, dout = ws['fc'], ws['dfc'], ws['nll'], ws['dout']
+        bulk = rnn.bulk_stream(inputs.device)
+        main = torch.cuda.current_stream()
+        ready = rnn._event('step start')
+        ready.record(main)                   # zeroed gradient buffers, staged inputs
+        bulk.wait_event(ready)
+        last = [None]
+
+        def hook(c, nch, t0, t1, done, outs_top):
+            r0, r1 = t0 * B, t1 * B
+            oc = outs_top[t0:t1].reshape(r1 - r0, -1)
+            with torch.cuda.stream(bulk):
+                bulk.wait_event(done)
+                ops.set_sm_budget(rnn.PIPE_BULK_SMS_FWD if c < rnn.PIPE_SLOW_HOOKS else 0)
+                try:
+                    ops.gemm(oc, self._fc_kernel.data, fc[r0:r1], bias=self._fc_bias.data)
+                    ops.nade_logprob_fwd(bits[:, r0:r1], fc[r0:r1], self.enc_col0, self.dec_col0, self._bank.w_enc.data,
+                                         self._bank.w_dec.data, nll[:, r0:r1], dfc=dfc[r0:r1], gscale=gscale)
+                    ops.nade_logprob_bwd(bits[:, r0:r1], fc[r0:r1], self.enc_col0, self.dec_col0, self._bank.w_enc.data,
+                                         self._bank.w_dec.data, dfc[r0:r1], self._bank.w_enc.grad, self._bank.w_dec.grad)
+                    ops.gemm(dfc[r0:r1], self._fc_kernel.data, dout[r0:r1], transB=True)
+                    ops.gemm(oc, dfc[r0:r1], self._fc_kernel.grad, transA=True, beta=1.0)
+                    ops.colsum(dfc[r0:r1], self._fc_bias.grad, accumulate=True)
+                finally:
+                    ops.set_sm_budget(0)
+                if c == nch - 1 or rnn.TRACE is not None:
+                    last[0] = rnn._event(f'fwd hook {c}')
+                    last[0].record(bulk)
+
+        outs, rnn_state = rnn.forward_sequence(inputs.contiguous(), keep=keep, u=u_drop, seed=seed, chunk_hook=hook)
+        self._outs = outs
+        self._state_from_fc(fc, rnn_state)
+        main.wait_event(last[0])
+        ops.sum_into(nll, ws['loss'], scale=gscale)
+        dx = rnn.backward_sequence(dout.view(T, B, -1), need_dx=need_dx, pipelined=True)
+        return ws['loss'], nll, dx
 
     # -------------------------------------------------------------- generation
     def single_step(self, inputs, initial_state):

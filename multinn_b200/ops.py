@@ -131,18 +131,25 @@ def lstm_seq_bwd(gates, wh, cbuf, dout, dscale, dh_work, dc_work, mode=None, per
 
 
 def nade_logprob_fwd(bits, fc, enc_col0, dec_col0, w_enc, w_dec, nll, cond_p=None, dfc=None, gscale=0.0):
+    """bits[M,N,4], nll[M,N], cond_p[M,N,D] may be row slices ([:, r0:r1]) of longer buffers; fc/dfc the same rows."""
     M, D, H = w_enc.shape
     N = fc.shape[0]
+    ts = bits.stride(0) // bits.stride(1) if M > 1 else N
+    assert bits.shape[1] == N and nll.shape[1] == N and nll.stride(1) == 1 and (M == 1 or nll.stride(0) == ts)
+    assert cond_p is None or M == 1 or (cond_p.stride(0) == ts * D and cond_p.stride(1) == D)
+    assert dfc is None or dfc.stride(0) == fc.stride(0)
     check(lib.mnn_nade_logprob_fwd(_ptr(bits), _ptr(fc), _rowstride(fc), enc_col0, dec_col0, _ptr(w_enc), _ptr(w_dec),
-                                   _ptr(nll), _ptr(cond_p), _ptr(dfc), float(gscale), N, M, D, H, _stream()),
+                                   _ptr(nll), _ptr(cond_p), _ptr(dfc), float(gscale), N, M, D, H, ts, _stream()),
           "nade_logprob_fwd")
 
 
 def nade_logprob_bwd(bits, fc, enc_col0, dec_col0, w_enc, w_dec, dfc, dw_enc, dw_dec):
     M, D, H = w_enc.shape
     N = fc.shape[0]
+    ts = bits.stride(0) // bits.stride(1) if M > 1 else N
+    assert bits.shape[1] == N and dfc.stride(0) == fc.stride(0)
     check(lib.mnn_nade_logprob_bwd(_ptr(bits), _ptr(fc), _rowstride(fc), enc_col0, dec_col0, _ptr(w_enc), _ptr(w_dec),
-                                   _ptr(dfc), _ptr(dw_enc), _ptr(dw_dec), N, M, D, H, _stream()), "nade_logprob_bwd")
+                                   _ptr(dfc), _ptr(dw_enc), _ptr(dw_dec), N, M, D, H, ts, _stream()), "nade_logprob_bwd")
 
 
 def nade_sample(fc, enc_col0, dec_col0, w_enc, w_dec, out, out_ld, out_dim_stride, out_track_stride, u=None,

@@ -207,32 +207,37 @@ def test_byte_pianorolls_equal_float_pianorolls():
 
 
 @pytest.mark.parametrize("B,Rn,keep", [(6, (64, 32), 0.9), (256, (256, 256), 1.0)])
-def test_layer_wavefront_equals_layerwise(B, Rn, keep):
-    """Small per-GPU batches run the LSTM layers as a wavefront over 32-step chunks on separate streams (chunked
-    forward, chunked BPTT with has_next, SM budgets): loss and every gradient must equal the layer-by-layer path."""
+def test_layer_wavefront_and_chunk_pipeline_equal_layerwise(B, Rn, keep):
+    """Small per-GPU batches run (a) the LSTM layers as a wavefront over 32-step chunks on separate streams (chunked
+    forward, chunked BPTT with has_next, SM budgets) and (b) the whole generator as a time-chunk pipeline (Dense / NADE
+    forward+backward / gradient GEMMs of finished chunks on a bulk stream beside the recurrences, accumulated weight
+    gradients): loss and every gradient must equal the phase-by-phase, layer-by-layer path."""
     from multinn_b200.common.rnn import RNN
     T = 64
     x = torch.from_numpy(O.synthetic_pianoroll(B, T, seed=5, density=0.08)).cuda()
     rng = np.random.default_rng(3)
     u = [torch.from_numpy(rng.random((T, B, r), dtype=np.float32)).cuda() for r in Rn] if keep < 1 else None
     results = []
-    saved = RNN.WAVEFRONT_MAX_BATCH
+    saved = RNN.WAVEFRONT_MAX_BATCH, RNN.PIPE_MAX_BATCH
     try:
-        for max_batch in (saved, 0):
-            RNN.WAVEFRONT_MAX_BATCH = max_batch
+        for wave, pipe in ((saved[0], max(saved[1], 256)), (saved[0], 0), (0, 0)):
+            RNN.WAVEFRONT_MAX_BATCH, RNN.PIPE_MAX_BATCH = wave, pipe
             model = make('composer', keep_prob=keep, H=128, Rnn=Rn)
             core = model._model
-            assert core.generators[0].rnn._use_wavefront(T, B) == (max_batch > 0)
+            rnn = core.generators[0].rnn
+            assert rnn._use_wavefront(T, B) == (wave > 0) and rnn.use_pipeline(T, B) == (pipe > 0)
             xd = core._check_x(x, None)
-            core.arena.grad.zero_()
-            loss = core._forward_backward(xd, keep=keep, u_drop=u, seed=0)
+            for _ in range(2):                       # twice: the second pass reuses workspaces, streams and events
+                core.arena.grad.zero_()
+                loss = core._forward_backward(xd, keep=keep, u_drop=u, seed=0)
             torch.cuda.synchronize()
             results.append((float(loss), core.arena.grad.clone()))
     finally:
-        RNN.WAVEFRONT_MAX_BATCH = saved
-    (l1, g1), (l0, g0) = results
-    assert abs(l1 - l0) / l0 < 1e-6
-    assert float((g1 - g0).norm() / g0.norm()) < 1e-5
+        RNN.WAVEFRONT_MAX_BATCH, RNN.PIPE_MAX_BATCH = saved
+    l0, g0 = results[-1]
+    for l1, g1 in results[:-1]:
+        assert abs(l1 - l0) / l0 < 1e-6
+        assert float((g1 - g0).norm() / g0.norm()) < 1e-5
 
 
 def test_batch_prefetcher_roundtrip():
