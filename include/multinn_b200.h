@@ -86,6 +86,10 @@ int mnn_lstm_seq_bwd(float* gates, const float* wh, const float* cbuf, const flo
  * ws >= mnn_lstm_workspace_bytes(B, R); dc_work[B,R] scratch. Philox dropout differs in stream from the elementwise path. */
 size_t mnn_lstm_workspace_bytes(int B, int R);
 int mnn_lstm_tc_supported(int B, int R);
+/* SMs (one CTA each) the persistent forward / BPTT kernel of a layer occupies under the calling thread's SM budget
+ * (mnn_set_sm_budget): the host sizes the budget of the batched work it runs beside the recurrences from these. */
+int mnn_lstm_seq_fwd_ctas(int T, int B, int R);
+int mnn_lstm_seq_bwd_ctas(int T, int B, int R);
 int mnn_lstm_seq_fwd_tc(float* gates, const float* wh, float* hbuf, float* cbuf, float* out, float* dscale,
                         const float* u, float keep, unsigned long long seed, int T, int B, int R, void* ws,
                         int persistent, mnn_stream_t stream);

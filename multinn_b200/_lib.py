@@ -43,6 +43,8 @@ SIGNATURES = {
     "mnn_lstm_seq_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "mnn_lstm_workspace_bytes": [_i, _i],
     "mnn_lstm_tc_supported": [_i, _i],
+    "mnn_lstm_seq_fwd_ctas": [_i, _i, _i],
+    "mnn_lstm_seq_bwd_ctas": [_i, _i, _i],
     "mnn_lstm_seq_fwd_tc": [_p, _p, _p, _p, _p, _p, _p, _f, _u64, _i, _i, _i, _p, _i, _p],
     "mnn_lstm_seq_bwd_tc": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _i, _p],
     "mnn_lstm_seq_bwd_tc_chunk": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _i, _i, _p],

@@ -96,7 +96,7 @@ class RNN:
     # layer l+1 works on chunk c-1 on another stream (SURVEY 7 "hard parts": recurrence latency at B/8).
     WAVEFRONT_MAX_BATCH = int(os.environ.get('MNN_WAVEFRONT_MAX_BATCH', 1024))   # forward; measured gain up to 1024
     WAVEFRONT_MAX_BATCH_BWD = 512                                                # BPTT: the SM budgets cost more above
-    WAVEFRONT_CHUNK = 32
+    WAVEFRONT_CHUNK = int(os.environ.get('MNN_WAVEFRONT_CHUNK', 32))
     WAVEFRONT_GEMM_SMS = 32
 
     # Time-chunk PIPELINE (small per-GPU batches): while the recurrences walk the chunks on their (high-priority)
@@ -105,11 +105,12 @@ class RNN:
     # recurrence kernels' SMs free. The recurrences hold ~100 SMs but are a latency chain; the bulk work fills the rest.
     PIPE_MAX_BATCH = int(os.environ.get('MNN_PIPE_MAX_BATCH', 512))
     PIPE_FWD_BUDGETS = tuple(int(v) for v in os.environ.get('MNN_PIPE_FWD_BUDGETS', '96,48').split(','))
-    PIPE_BWD_BUDGETS = tuple(int(v) for v in os.environ.get('MNN_PIPE_BWD_BUDGETS', '72,36').split(','))
-    PIPE_BULK_SMS_FWD = int(os.environ.get('MNN_PIPE_BULK_SMS_FWD', 44))
-    PIPE_BULK_SMS_BWD = int(os.environ.get('MNN_PIPE_BULK_SMS_BWD', 36))
-    PIPE_SLOW_HOOKS = int(os.environ.get('MNN_PIPE_SLOW_HOOKS', 2))     # forward chunk hooks that start under the recurrence
-    PIPE_FULL_WGRADS = int(os.environ.get('MNN_PIPE_FULL_WGRADS', 2))   # last BPTT chunks whose weight grads use every SM
+    PIPE_BWD_BUDGETS = tuple(int(v) for v in os.environ.get('MNN_PIPE_BWD_BUDGETS', '0').split(','))   # 0: by batch
+    PIPE_BULK_SMS_FWD = int(os.environ.get('MNN_PIPE_BULK_SMS_FWD', 0))    # 0: every SM the recurrence kernels leave
+    PIPE_BULK_SMS_BWD = int(os.environ.get('MNN_PIPE_BULK_SMS_BWD', 0))
+    PIPE_AUX_SMS = int(os.environ.get('MNN_PIPE_AUX_SMS', 16))          # dx GEMMs between the BPTT layers (own stream); 0: off
+    PIPE_SLOW_HOOKS = int(os.environ.get('MNN_PIPE_SLOW_HOOKS', 0))     # forward chunk hooks under the recurrence; 0: by batch
+    PIPE_FULL_WGRADS = int(os.environ.get('MNN_PIPE_FULL_WGRADS', 3))   # last BPTT chunks whose weight grads use every SM
 
     TRACE = None        # debug (tools/pipeline_trace.py): list collecting (label, timing event) of the chunk schedule
 
@@ -134,6 +135,38 @@ class RNN:
             st = self._wave_streams = [torch.cuda.Stream(device=device, priority=-1) for _ in range(self.num_layers)]
         return st
 
+    def _bwd_budgets(self, B):
+        """SM budgets of the two BPTT kernels in pipeline mode (measured: 72,36 best at B=256, 48,24 at B=512)."""
+        if self.PIPE_BWD_BUDGETS[0] > 0:
+            return self.PIPE_BWD_BUDGETS
+        return (64, 32) if B < 512 else (48, 24)
+
+    def bulk_budget(self, T, B, backward=False):
+        """SM budget of the bulk stream while the recurrences run: what the layers' persistent kernels (and the budgeted
+        GEMM that shares a layer's stream) leave free."""
+        fixed = self.PIPE_BULK_SMS_BWD if backward else self.PIPE_BULK_SMS_FWD
+        if fixed > 0:
+            return fixed
+        key = (T, B, backward)
+        cache = self.__dict__.setdefault('_bulk_budgets', {})
+        if key not in cache:
+            budgets = self._bwd_budgets(B) if backward else self.PIPE_FWD_BUDGETS
+            used = 0
+            for l, r in enumerate(self._num_units):
+                n = ops.lstm_seq_ctas(self.WAVEFRONT_CHUNK, B, r, budgets[min(l, len(budgets) - 1)], backward)
+                if backward and self.PIPE_AUX_SMS > 0:
+                    used += n + (self.PIPE_AUX_SMS if l == 1 else 0)   # dx GEMMs run on their own stream
+                else:                                                  # input projection / dx GEMM on the layer's stream
+                    used += max(n, self.WAVEFRONT_GEMM_SMS) if l > 0 else n
+            cache[key] = max(16, ops.num_sms() - used)
+        return cache[key]
+
+    def aux_stream(self, device):
+        st = self.__dict__.get('_aux_stream')
+        if st is None:
+            st = self._aux_stream = torch.cuda.Stream(device=device, priority=-1)
+        return st
+
     def bulk_stream(self, device):
         st = self.__dict__.get('_bulk_stream')
         if st is None:
@@ -144,9 +177,10 @@ class RNN:
         """x[T,B,I] time-major -> outputs[T,B,R_top] (dropped out when keep < 1), final state.
         u: optional list (per layer) of [T,B,R_l] uniforms for reproducible dropout; else Philox(seed).
         Saves what BPTT needs (call `backward_sequence` next).
-        chunk_hook(c, nch, t0, t1, done_event, outs_top): pipeline mode (`use_pipeline`), called once per time chunk after
-        the top layer's chunk has been enqueued; the hook enqueues the consumer work of steps [t0, t1) on `bulk_stream`
-        behind `done_event`."""
+        chunk_hook(t0, t1, done_event, outs_top, budget, last): pipeline mode (`use_pipeline`); called after the top layer
+        has been enqueued up to step t1, the hook enqueues the consumer work of steps [t0, t1) on `bulk_stream` behind
+        `done_event` under the SM `budget` (0 = every SM). The first PIPE_SLOW_HOOKS chunks get one budgeted call each
+        (they run beside the recurrences), the rest ONE call at full width once the recurrences are through."""
         T, B, I = x.shape
         assert I == self._num_inputs and x.is_contiguous()
         dropout = keep < 1.0
@@ -159,13 +193,14 @@ class RNN:
                 w['cbuf'][0].copy_(initial_state[l][0])
                 w['hbuf'][0].copy_(initial_state[l][1])
         outs = [w['out'] if dropout else w['hbuf'][1:] for w in ws]
-        # layer 0: hoisted input projection over all T*B rows
+        # layer 0: hoisted input projection over all T*B rows (pipeline mode: chunk 0 now, the rest beside the recurrences)
         r0 = self._num_units[0]
-        ops.gemm(x.view(T * B, I), self.kernels[0].data[:I], ws[0]['gates'].view(T * B, 4 * r0), bias=self.biases[0].data,
-                 a_exact=self._binary_inputs)
+        hook = chunk_hook if (chunk_hook is not None and self.use_pipeline(T, B)) else None
+        rows0 = (self.WAVEFRONT_CHUNK if hook is not None else T) * B
+        ops.gemm(x.view(T * B, I)[:rows0], self.kernels[0].data[:I], ws[0]['gates'].view(T * B, 4 * r0)[:rows0],
+                 bias=self.biases[0].data, a_exact=self._binary_inputs)
         if self._use_wavefront(T, B):
-            hook = chunk_hook if (chunk_hook is not None and self.use_pipeline(T, B)) else None
-            self._forward_wavefront(ws, outs, T, B, keep, u, seed, dropout, hook)
+            self._forward_wavefront(ws, outs, T, B, keep, u, seed, dropout, hook, x)
         else:
             for l, r in enumerate(self._num_units):
                 w = ws[l]
@@ -180,7 +215,7 @@ class RNN:
         state = [LSTMStateTuple(w['cbuf'][T], w['hbuf'][T]) for w in ws]
         return outs[-1], state
 
-    def _forward_wavefront(self, ws, outs, T, B, keep, u, seed, dropout, hook=None):
+    def _forward_wavefront(self, ws, outs, T, B, keep, u, seed, dropout, hook=None, x=None):
         C = self.WAVEFRONT_CHUNK
         nch = T // C
         budgets = self.PIPE_FWD_BUDGETS if hook is not None else (96, 48)
@@ -189,6 +224,27 @@ class RNN:
         start = self._event('fwd start')
         start.record(main)
         done = [[self._event(f'fwd L{l} chunk {c}') for c in range(nch)] for l in range(self.num_layers)]
+        proj = [None] * nch
+        n_slow = 0
+        if hook is not None:
+            # layer-0 input projection of the later chunks: bulk stream, inside the bulk SM budget
+            bulk = self.bulk_stream(ws[0]['gates'].device)
+            bulk_sms = self.bulk_budget(T, B)
+            n_slow = self.PIPE_SLOW_HOOKS if self.PIPE_SLOW_HOOKS > 0 else (2 if B < 512 else 3)   # measured at T=256
+            n_slow = max(0, min(n_slow * 32 // C, nch - 1))
+            I, r0 = self._num_inputs, self._num_units[0]
+            with torch.cuda.stream(bulk):
+                bulk.wait_event(start)
+                ops.set_sm_budget(bulk_sms)
+                try:
+                    for c in range(1, nch):
+                        ops.gemm(x[c * C:(c + 1) * C].view(C * B, I), self.kernels[0].data[:I],
+                                 ws[0]['gates'][c * C:(c + 1) * C].view(C * B, 4 * r0), bias=self.biases[0].data,
+                                 a_exact=self._binary_inputs)
+                        proj[c] = self._event(f'fwd L0 projection chunk {c}')
+                        proj[c].record(bulk)
+                finally:
+                    ops.set_sm_budget(0)
         for c in range(nch):
             t0, t1 = c * C, (c + 1) * C
             for l, r in enumerate(self._num_units):
@@ -198,6 +254,8 @@ class RNN:
                 with torch.cuda.stream(streams[l]):
                     if c == 0:
                         streams[l].wait_event(start)
+                    if l == 0 and proj[c] is not None:
+                        streams[l].wait_event(proj[c])
                     if l > 0:
                         streams[l].wait_event(done[l - 1][c])
                         ops.set_sm_budget(self.WAVEFRONT_GEMM_SMS)
@@ -216,8 +274,10 @@ class RNN:
                     finally:
                         ops.set_sm_budget(0)
                     done[l][c].record(streams[l])
-            if hook is not None:
-                hook(c, nch, t0, t1, done[self.num_layers - 1][c], outs[-1])
+            if hook is not None and c < n_slow:
+                hook(t0, t1, done[self.num_layers - 1][c], outs[-1], bulk_sms, False)
+        if hook is not None:
+            hook(n_slow * C, T, done[self.num_layers - 1][nch - 1], outs[-1], 0, True)
         for l in range(self.num_layers):
             main.wait_event(done[l][nch - 1])
 
@@ -284,7 +344,7 @@ class RNN:
         if L == 2:
             budgets = [72, 36]          # SMs for the persistent BPTT kernels of the two layers (they must co-reside)
             if x_pipe is not None:
-                budgets = list(self.PIPE_BWD_BUDGETS)
+                budgets = list(self._bwd_budgets(B))
         bulk = self.bulk_stream(ws[0]['gates'].device) if x_pipe is not None else None
         for c in reversed(range(nch)):
             t0, t1 = c * C, (c + 1) * C
@@ -294,6 +354,8 @@ class RNN:
                 i_l = self.in_dims()[l]
                 r = self._num_units[l]
                 d = dout if l == L - 1 else ws[l + 1]['d_in']
+                aux = self.aux_stream(w['gates'].device) if (bulk is not None and self.PIPE_AUX_SMS > 0) else None
+                cell_done = done[l][c]
                 with torch.cuda.stream(streams[l]):
                     if c == nch - 1:
                         streams[l].wait_event(start)
@@ -304,17 +366,32 @@ class RNN:
                         ops.lstm_seq_bwd(w['gates'][t0:t1], kern.data[i_l:], w['cbuf'][t0:t1 + 1], d[t0:t1],
                                          w['dscale'][t0:t1] if dropout else None, w['dh_work'], w['dc_work'],
                                          has_next=c < nch - 1)
-                        if l > 0 or need_dx:
+                        if (l > 0 or need_dx) and aux is None:
                             ops.set_sm_budget(self.WAVEFRONT_GEMM_SMS)
                             ops.gemm(w['gates'][t0:t1].view(C * B, 4 * r), kern.data[:i_l],
                                      w['d_in'][t0:t1].view(C * B, i_l), transB=True)
                     finally:
                         ops.set_sm_budget(0)
-                    done[l][c].record(streams[l])
+                    if (l > 0 or need_dx) and aux is not None:
+                        cell_done = self._event(f'bwd L{l} cells chunk {c}')
+                        cell_done.record(streams[l])
+                    else:
+                        done[l][c].record(streams[l])
+                if (l > 0 or need_dx) and aux is not None:
+                    # dx = dG Wx^T of the chunk on its own stream: the layer's next BPTT chunk does not wait for it
+                    with torch.cuda.stream(aux):
+                        aux.wait_event(cell_done)
+                        ops.set_sm_budget(self.PIPE_AUX_SMS)
+                        try:
+                            ops.gemm(w['gates'][t0:t1].view(C * B, 4 * r), kern.data[:i_l],
+                                     w['d_in'][t0:t1].view(C * B, i_l), transB=True)
+                        finally:
+                            ops.set_sm_budget(0)
+                        done[l][c].record(aux)
                 if bulk is not None:
                     with torch.cuda.stream(bulk):
-                        bulk.wait_event(done[l][c])
-                        ops.set_sm_budget(0 if c < self.PIPE_FULL_WGRADS else self.PIPE_BULK_SMS_BWD)
+                        bulk.wait_event(cell_done)
+                        ops.set_sm_budget(0 if c < max(1, self.PIPE_FULL_WGRADS * 32 // C) else self.bulk_budget(T, B, backward=True))
                         try:
                             self._weight_grads(l, x_pipe, ws, dropout, t0, t1, B, beta=1.0)
                         finally:

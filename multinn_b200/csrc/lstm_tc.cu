@@ -1329,6 +1329,35 @@ static bool use_pair_fwd(int B, int R, int T, int persistent) {
 
 extern "C" int mnn_lstm_tc_supported(int B, int R) { return R % 8 == 0 && R >= 8 && B > 0; }
 
+// CTAs (= SMs, one CTA per SM) the persistent recurrence kernels occupy under the calling thread's SM budget: lets the
+// host size the budget of the work it runs beside them (time-chunk pipeline).
+extern "C" int mnn_lstm_seq_fwd_ctas(int T, int B, int R) {
+  if (!mnn_lstm_tc_supported(B, R)) return 0;
+  const int sms = mnn_tc_num_sms();
+  if (use_pair_fwd(B, R, T, 1)) {
+    const int items = (B / (2 * BM)) * (R / kL2UB);
+    return 2 * (items < pair_fwd_clusters() ? items : pair_fwd_clusters());
+  }
+  const int UB = fwd_unit_block(B, R);
+  const int items = ((B + BM - 1) / BM) * ((R + UB - 1) / UB);
+  return items < sms ? items : sms;
+}
+extern "C" int mnn_lstm_seq_bwd_ctas(int T, int B, int R) {
+  if (!mnn_lstm_tc_supported(B, R)) return 0;
+  const int sms = mnn_tc_num_sms();
+  if (use_pair_bwd(B, R, T, 1)) {
+    const int need = (B / (2 * BM)) * (R / 256);
+    int clusters = pair_bwd_clusters();
+    if (mnn_tc_sm_budget() > 0 && clusters > mnn_tc_sm_budget() / 2) clusters = mnn_tc_sm_budget() / 2;
+    if (clusters < need) clusters = need;
+    return 2 * clusters;
+  }
+  const int slabs = (B + BM - 1) / BM;
+  const int BN = (slabs * ((R + 63) / 64) >= 96) ? 64 : 32;
+  const int items = slabs * ((R + BN - 1) / BN);
+  return items < sms ? items : sms;
+}
+
 extern "C" int mnn_lstm_seq_fwd_tc(float* gates, const float* wh, float* hbuf, float* cbuf, float* out, float* dscale,
                                    const float* u, float keep, unsigned long long seed, int T, int B, int R, void* ws,
                                    int persistent, cudaStream_t stream) {

@@ -187,12 +187,12 @@ class RnnNade(RnnEstimator):
         bulk.wait_event(ready)
         last = [None]
 
-        def hook(c, nch, t0, t1, done, outs_top):
+        def hook(t0, t1, done, outs_top, budget, is_last):
             r0, r1 = t0 * B, t1 * B
             oc = outs_top[t0:t1].reshape(r1 - r0, -1)
             with torch.cuda.stream(bulk):
                 bulk.wait_event(done)
-                ops.set_sm_budget(rnn.PIPE_BULK_SMS_FWD if c < rnn.PIPE_SLOW_HOOKS else 0)
+                ops.set_sm_budget(budget)
                 try:
                     ops.gemm(oc, self._fc_kernel.data, fc[r0:r1], bias=self._fc_bias.data)
                     ops.nade_logprob_fwd(bits[:, r0:r1], fc[r0:r1], self.enc_col0, self.dec_col0, self._bank.w_enc.data,
@@ -204,8 +204,8 @@ class RnnNade(RnnEstimator):
                     ops.colsum(dfc[r0:r1], self._fc_bias.grad, accumulate=True)
                 finally:
                     ops.set_sm_budget(0)
-                if c == nch - 1 or rnn.TRACE is not None:
-                    last[0] = rnn._event(f'fwd hook {c}')
+                if is_last or rnn.TRACE is not None:
+                    last[0] = rnn._event(f'fwd hook steps {t0}..{t1}')
                     last[0].record(bulk)
 
         outs, rnn_state = rnn.forward_sequence(inputs.contiguous(), keep=keep, u=u_drop, seed=seed, chunk_hook=hook)

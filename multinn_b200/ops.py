@@ -66,6 +66,20 @@ def set_sm_budget(sms):
     check(lib.mnn_set_sm_budget(int(sms)), "set_sm_budget")
 
 
+def lstm_seq_ctas(T, B, R, budget, backward=False):
+    """SMs the persistent recurrence kernel of one layer occupies when launched under `budget`."""
+    set_sm_budget(budget)
+    try:
+        fn = lib.mnn_lstm_seq_bwd_ctas if backward else lib.mnn_lstm_seq_fwd_ctas
+        return int(fn(int(T), int(B), int(R)))
+    finally:
+        set_sm_budget(0)
+
+
+def num_sms():
+    return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+
+
 _colsum_ws = {}
 
 

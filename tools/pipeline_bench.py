@@ -11,15 +11,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CONFIGS = [
     ('wavefront only (no pipeline)', {'MNN_PIPE_MAX_BATCH': '0'}),
     ('pipeline default', {}),
-    ('pipeline slow hooks 3', {'MNN_PIPE_SLOW_HOOKS': '3'}),
-    ('pipeline slow hooks 8 (all budgeted)', {'MNN_PIPE_SLOW_HOOKS': '8'}),
-    ('pipeline fwd 32,16 bulk 92', {'MNN_PIPE_FWD_BUDGETS': '32,16', 'MNN_PIPE_BULK_SMS_FWD': '92', 'MNN_PIPE_SLOW_HOOKS': '4'}),
-    ('pipeline fwd 32,16 bulk 92 hooks 8', {'MNN_PIPE_FWD_BUDGETS': '32,16', 'MNN_PIPE_BULK_SMS_FWD': '92', 'MNN_PIPE_SLOW_HOOKS': '8'}),
-    ('pipeline bwd 48,24 bulk 72', {'MNN_PIPE_BWD_BUDGETS': '48,24', 'MNN_PIPE_BULK_SMS_BWD': '72'}),
-    ('pipeline bwd 32,16 bulk 96', {'MNN_PIPE_BWD_BUDGETS': '32,16', 'MNN_PIPE_BULK_SMS_BWD': '96'}),
-    ('pipeline fwd 32,16/92/8 + bwd 48,24/72', {'MNN_PIPE_FWD_BUDGETS': '32,16', 'MNN_PIPE_BULK_SMS_FWD': '92', 'MNN_PIPE_SLOW_HOOKS': '8',
-                                             'MNN_PIPE_BWD_BUDGETS': '48,24', 'MNN_PIPE_BULK_SMS_BWD': '72'}),
-    ('pipeline full wgrads 2', {'MNN_PIPE_FULL_WGRADS': '2'}),
+    ('fwd 32,16', {'MNN_PIPE_FWD_BUDGETS': '32,16'}),
+    ('fwd 32,16 slow 3', {'MNN_PIPE_FWD_BUDGETS': '32,16', 'MNN_PIPE_SLOW_HOOKS': '3'}),
+    ('fwd 32,16 slow 4', {'MNN_PIPE_FWD_BUDGETS': '32,16', 'MNN_PIPE_SLOW_HOOKS': '4'}),
+    ('bwd 48,24', {'MNN_PIPE_BWD_BUDGETS': '48,24'}),
+    ('fwd 32,16 slow 3 + bwd 48,24', {'MNN_PIPE_FWD_BUDGETS': '32,16', 'MNN_PIPE_SLOW_HOOKS': '3', 'MNN_PIPE_BWD_BUDGETS': '48,24'}),
+    ('default slow 3', {'MNN_PIPE_SLOW_HOOKS': '3'}),
+    ('default slow 1', {'MNN_PIPE_SLOW_HOOKS': '1'}),
+    ('full wgrads 3', {'MNN_PIPE_FULL_WGRADS': '3'}),
+    ('full wgrads 1', {'MNN_PIPE_FULL_WGRADS': '1'}),
 ]
 
 if __name__ == '__main__':
