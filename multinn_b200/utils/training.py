@@ -1,0 +1,216 @@
+"""Training / evaluation host loop (mirrors reference multinn/utils/training.py:8-240 and the epoch loop of
+multinn/train.py:153-282). The reference drives a TF session with feed_dict batches; here `model` is a
+multinn_b200.MultINN and every batch piece is one call of the step / evaluate functions on device tensors.
+Logging, TensorBoard summaries, MIDI export and the CLI are out of scope (control plane)."""
+import pickle
+
+import numpy as np
+
+
+class TrainingStats:
+    """training.py:8-88: counters + best monitored metric; `save`/`load` keep the reference's pickle of a 4-tuple."""
+
+    def __init__(self, steps=0, epoch=0, run=0, metric_best=1e3):
+        self._steps, self._epoch, self._run, self._metric_best = steps, epoch, run, metric_best
+        self._idle_epochs = 0
+
+    steps = property(lambda s: s._steps)
+    epoch = property(lambda s: s._epoch)
+    run = property(lambda s: s._run)
+    metric_best = property(lambda s: s._metric_best)
+    idle_epochs = property(lambda s: s._idle_epochs)
+
+    def new_epoch(self):
+        self._epoch += 1
+
+    def new_step(self):
+        self._steps += 1
+
+    def new_run(self):
+        self._run += 1
+
+    def update_metric_best(self, val):
+        self._metric_best = val
+
+    def new_idle_epoch(self):
+        self._idle_epochs += 1
+
+    def reset_idle_epochs(self):
+        self._idle_epochs = 0
+
+    def load(self, filename):
+        with open(filename, 'rb') as f:
+            self._steps, self._epoch, self._run, self._metric_best = pickle.load(f)
+
+    def save(self, filename):
+        with open(filename, 'wb') as f:
+            pickle.dump((self.steps, self.epoch, self.run, self.metric_best), f)
+
+
+class LossAccumulator:
+    """training.py:91-148: mean training loss that skips NaN / +-inf values and counts them."""
+
+    def __init__(self):
+        self._sum_loss, self._num_loss = 0., 0
+        self._num_nan = self._num_posinf = self._num_neginf = self._num_total = 0
+
+    def clear(self):
+        self.__init__()
+
+    def update(self, loss):
+        self._num_total += 1
+        if np.isnan(loss):
+            self._num_nan += 1
+        elif np.isposinf(loss):
+            self._num_posinf += 1
+        elif np.isneginf(loss):
+            self._num_neginf += 1
+        else:
+            self._num_loss += 1
+            self._sum_loss += loss
+
+    def loss(self):
+        return self._sum_loss / self._num_loss if self._num_loss > 0 else np.nan
+
+    def num_bad(self):
+        return self._num_nan + self._num_posinf + self._num_neginf
+
+    def ratio_bad(self):
+        return self.num_bad() / self._num_total
+
+    def __str__(self):
+        return (f' - loss: {self.loss():7.3f} (nan: {self._num_nan}, +inf: {self._num_posinf}, -inf: {self._num_neginf}, '
+                f'bad: {100. * self.ratio_bad():.2f}%)')
+
+
+def training_pieces(X, lengths, ids, batch_size, piece_size):
+    """The batch pieces one epoch feeds (train.py:165-178): for every batch of shuffled song ids and every piece offset
+    j, the songs that still have frames past j, cut to the longest remaining length (at most `piece_size`).
+    Yields (batch_index, songs[b, max_length, D, M], lengths[b]); `batch_index` changes once per batch (quirk Q11:
+    the step counter advances per batch, not per piece)."""
+    for bi, i in enumerate(range(0, X.shape[0], batch_size)):
+        sel = ids[i:i + batch_size]
+        for j in range(0, X.shape[1], piece_size):
+            len_batch = lengths[sel] - j
+            non_empty = np.where(len_batch > 0)[0]
+            if len(non_empty) > 0:
+                len_batch = np.minimum(len_batch[non_empty], piece_size)
+                max_length = int(len_batch.max())
+                yield bi, X[sel, j:j + max_length, ...][non_empty], len_batch
+
+
+def evaluation_pieces(data, data_lengths, batch_size, piece_size):
+    """The pieces collect_metrics feeds (training.py:201-213). Quirk Q9 kept: the piece offset j is NOT subtracted from
+    the lengths, so every piece is evaluated over min(length, piece_size) frames. Lengths are capped at the frames the
+    slice really has (a ragged last piece)."""
+    for i in range(0, data.shape[0], batch_size):
+        for j in range(0, data.shape[1], piece_size):
+            seq = np.minimum(data_lengths[i:i + batch_size], piece_size)
+            max_length = int(seq.max())
+            songs = data[i:i + batch_size, j:j + max_length, :]
+            yield songs, np.minimum(seq, songs.shape[1])
+
+
+def _to_device(songs, device):
+    import torch
+    a = np.ascontiguousarray(songs)
+    if a.dtype not in (np.uint8, np.bool_, np.float32):
+        a = a.astype(np.float32)
+    return torch.from_numpy(a).to(device, non_blocking=True)
+
+
+def collect_metrics(model, data, data_lengths, batch_size, piece_size, device='cuda'):
+    """Streaming evaluation over a dataset (training.py:180-213 + metrics/statistical.py:22-34): the tf.metrics.mean
+    accumulators become (sum, count) on the device. Returns {'log_likelihood': mean NLL over all evaluated rows and
+    tracks, 'perplexity': mean exp(NLL), 'rows': count}."""
+    import torch
+    total = torch.zeros((), dtype=torch.float64, device=device)
+    total_ppl = torch.zeros((), dtype=torch.float64, device=device)
+    count = 0
+    for songs, seq in evaluation_pieces(data, data_lengths, batch_size, piece_size):
+        out = model.evaluate(_to_device(songs, device), lengths=torch.as_tensor(np.asarray(seq)))
+        nll = out['nll'].double()
+        total += nll.sum()
+        total_ppl += nll.exp().sum()
+        count += nll.numel()
+    return {'log_likelihood': float(total) / max(count, 1), 'perplexity': float(total_ppl) / max(count, 1), 'rows': count}
+
+
+def generate_music(model, sampler, intro_songs, num_songs=5, concat=True, device='cuda', u=None, seed=0):
+    """training.py:216-240: tile the intros `num_songs` times, sample, optionally prepend the intro."""
+    intro = np.tile(intro_songs, (num_songs, 1, 1, 1))
+    samples = sampler(_to_device(intro, device), u=u, seed=seed).cpu().numpy()
+    return np.concatenate([intro.astype(samples.dtype), samples], axis=1) if concat else samples
+
+
+def train_epoch(step, X_train, len_train, batch_size, piece_size, epoch, stats, loss_accum=None, device='cuda',
+                fetch_every=1):
+    """One epoch of train.py:153-200: np.random.seed(epoch), shuffle the song ids, feed every batch piece to `step`
+    (= model.train_generators(...)), advance the step counter once per batch. The reference fetches the loss after
+    every sess.run; `fetch_every` > 1 reads it back less often so that the host does not stall the device."""
+    import torch
+    loss_accum = LossAccumulator() if loss_accum is None else loss_accum
+    stats.new_epoch()
+    np.random.seed(epoch)
+    ids = np.arange(X_train.shape[0])
+    np.random.shuffle(ids)
+    loss_accum.clear()
+    pending = []
+    steps0 = stats.steps
+    n_batches = (X_train.shape[0] + batch_size - 1) // batch_size
+    for bi, songs, len_batch in training_pieces(X_train, len_train, ids, batch_size, piece_size):
+        while stats.steps < steps0 + bi:          # stats.new_step() once per finished batch (train.py:194, quirk Q11)
+            stats.new_step()
+        loss = step(_to_device(songs, device), lengths=torch.as_tensor(np.asarray(len_batch)), seed=stats.steps * 131 + epoch)
+        pending.append(loss.detach().clone())
+        if len(pending) >= fetch_every:
+            for v in torch.stack(pending).flatten().cpu().tolist():
+                loss_accum.update(v)
+            pending = []
+    if pending:
+        for v in torch.stack(pending).flatten().cpu().tolist():
+            loss_accum.update(v)
+    while stats.steps < steps0 + n_batches:
+        stats.new_step()
+    return loss_accum
+
+
+def fit(model, train, valid, training_config, stats=None, optimizer='adam', checkpoint_path=None, evaluate_epochs=1,
+        beat_size=None, device='cuda', log=None):
+    """The epoch loop of train.py:153-282 without its logging / sampling side effects: train, evaluate on the
+    validation set, keep the best checkpoint (`loglik_val < stats.metric_best`, :243-257), stop after
+    `early_stopping` epochs without improvement (:258-270). Returns (stats, history)."""
+    X_train, len_train = train
+    X_valid, len_valid = valid
+    stats = TrainingStats() if stats is None else stats
+    stats.new_run()
+    batch_size = training_config['batch_size']
+    if beat_size is None:
+        beat_size = 1.0
+    piece_size = int(training_config['piece_size'] * beat_size)
+    step = model.train_generators(optimizer, training_config['learning_rate'])
+    loss_accum = LossAccumulator()
+    history = []
+    past_epochs = stats.epoch
+    loglik_val = float('inf')
+    for epoch in range(past_epochs + 1, past_epochs + training_config['epochs'] + 1):
+        train_epoch(step, X_train, len_train, batch_size, piece_size, epoch, stats, loss_accum, device)
+        rec = {'epoch': epoch, 'steps': stats.steps, 'loss': loss_accum.loss(), 'bad': loss_accum.num_bad()}
+        if evaluate_epochs > 0 and epoch % evaluate_epochs == 0:
+            m = collect_metrics(model, X_valid, len_valid, batch_size * 2, piece_size, device)
+            loglik_val = m['log_likelihood']
+            rec['valid_log_likelihood'] = loglik_val
+        history.append(rec)
+        if log is not None:
+            log(rec)
+        if loglik_val < stats.metric_best:
+            stats.update_metric_best(loglik_val)
+            stats.reset_idle_epochs()
+            if checkpoint_path is not None:
+                model.save(checkpoint_path)
+                stats.save(checkpoint_path + '.stats')
+        else:
+            stats.new_idle_epoch()
+            if stats.idle_epochs >= training_config['early_stopping']:
+                break
+    return stats, history

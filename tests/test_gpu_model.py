@@ -308,3 +308,31 @@ def test_variable_lengths_training_step_and_unsupported_modes():
     joint = make('joint', encoder='DBN', encoder_hidden=[168, 84], generator='RBM', H=64, Rnn=(32,))
     with pytest.raises(NotImplementedError):
         joint.evaluate(torch.from_numpy(x).cuda(), lengths=torch.from_numpy(lengths))
+
+
+def test_fit_loop_on_device_with_variable_lengths(tmp_path):
+    """The epoch loop of train.py:153-282 (multinn_b200/utils/training.py) on the device: batch pieces with variable
+    lengths, streaming validation log-likelihood equal to the oracle's, the best checkpoint restorable."""
+    from multinn_b200.utils import training as U
+    rng = np.random.default_rng(7)
+    X = (rng.random((6, 12, 84, 5)) < 0.08).astype(np.uint8)
+    lengths = np.array([12, 12, 7, 12, 3, 9])
+    model = make('composer', keep_prob=1.0, H=128, Rnn=(48, 32))
+    p32 = arena_to_params(model, 'generator', 2, True)
+    m0 = U.collect_metrics(model, X[:4], lengths[:4], batch_size=4, piece_size=6)
+    # oracle: the same pieces (quirk Q9: lengths capped at the piece size, offset not subtracted)
+    tot, cnt = 0.0, 0
+    for songs, seq in U.evaluation_pieces(X[:4], lengths[:4], 4, 6):
+        ref = O.composer_forward(songs.astype(np.float64), O.cast_params(p32, np.float64), lengths=seq)
+        tot += ref['nll'].sum()
+        cnt += ref['nll'].size
+    assert m0['rows'] == cnt and abs(m0['log_likelihood'] - tot / cnt) / (tot / cnt) < 1e-5
+    cfg = {'batch_size': 3, 'piece_size': 6, 'learning_rate': 0.01, 'epochs': 3, 'early_stopping': 5}
+    stats, hist = U.fit(model, (X, lengths), (X[:4], lengths[:4]), cfg, checkpoint_path=str(tmp_path / 'best.pt'))
+    assert stats.epoch == 3 and stats.steps == 6 and len(hist) == 3
+    assert hist[-1]['loss'] < hist[0]['loss'] and hist[-1]['valid_log_likelihood'] < m0['log_likelihood']
+    assert stats.metric_best == min(h['valid_log_likelihood'] for h in hist)
+    other = make('composer', keep_prob=1.0, H=128, Rnn=(48, 32))
+    other.load(str(tmp_path / 'best.pt'))
+    best = U.collect_metrics(other, X[:4], lengths[:4], batch_size=4, piece_size=6)['log_likelihood']
+    assert abs(best - stats.metric_best) < 1e-6 * abs(best)

@@ -1,0 +1,142 @@
+"""Host-side utilities around the hot path (row f1 of the scope table): dataset reshaping / splitting, the batch pieces
+of train.py:165-178 and utils/training.py:201-213, TrainingStats / LossAccumulator, and the epoch loop with early
+stopping -- checked on CPU with a stub model (the GPU run of the same loop is in test_gpu_model.py)."""
+import numpy as np
+import pytest
+
+from multinn_b200.utils import data as D
+from multinn_b200.utils import training as U
+
+
+def test_training_pieces_follow_the_reference_loop():
+    rng = np.random.default_rng(0)
+    X = rng.random((5, 10, 3, 2)) < 0.5
+    lengths = np.array([10, 3, 7, 1, 10])
+    ids = np.array([4, 1, 0, 3, 2])
+    got = list(U.training_pieces(X, lengths, ids, batch_size=2, piece_size=4))
+    # literal restatement of train.py:165-178
+    ref = []
+    for bi, i in enumerate(range(0, 5, 2)):
+        for j in range(0, 10, 4):
+            lb = lengths[ids[i:i + 2]] - j
+            ne = np.where(lb > 0)[0]
+            if len(ne) > 0:
+                lb = np.minimum(lb[ne], 4)
+                ref.append((bi, X[ids[i:i + 2], j:j + lb.max(), ...][ne], lb))
+    assert len(got) == len(ref) == 8
+    for (b0, s0, l0), (b1, s1, l1) in zip(got, ref):
+        assert b0 == b1 and np.array_equal(s0, s1) and np.array_equal(l0, l1)
+        assert s0.shape[1] == l0.max() and (l0 > 0).all()
+
+
+def test_evaluation_pieces_keep_quirk_q9():
+    X = np.zeros((3, 8, 2, 1), dtype=np.float32)
+    lengths = np.array([8, 2, 5])
+    pieces = list(U.evaluation_pieces(X, lengths, batch_size=4, piece_size=4))
+    assert len(pieces) == 2
+    for songs, seq in pieces:                       # the offset j is never subtracted from the lengths
+        assert songs.shape == (3, 4, 2, 1) and np.array_equal(seq, [4, 2, 4])
+
+
+def test_training_stats_and_loss_accumulator(tmp_path):
+    st = U.TrainingStats()
+    st.new_run(); st.new_epoch(); st.new_step(); st.new_step(); st.update_metric_best(12.5); st.new_idle_epoch()
+    st.save(str(tmp_path / 'steps'))
+    other = U.TrainingStats()
+    other.load(str(tmp_path / 'steps'))
+    assert (other.steps, other.epoch, other.run, other.metric_best, other.idle_epochs) == (2, 1, 1, 12.5, 0)
+    acc = U.LossAccumulator()
+    for v in (1.0, float('nan'), 3.0, float('inf'), float('-inf')):
+        acc.update(v)
+    assert acc.loss() == 2.0 and acc.num_bad() == 3 and abs(acc.ratio_bad() - 0.6) < 1e-12
+    assert 'nan: 1' in str(acc) and '+inf: 1' in str(acc)
+    acc.clear()
+    assert np.isnan(acc.loss())
+
+
+def test_load_data_split_reshape_and_errors(tmp_path):
+    rng = np.random.default_rng(1)
+    songs = rng.random((7, 9, 4, 2)) < 0.3
+    np.save(tmp_path / 'songs.npy', songs)
+    np.save(tmp_path / 'lengths.npy', np.array([9, 8, 7, 6, 5, 4, 3]))
+    cfg = {'filename': str(tmp_path / 'songs'), 'source': 'npy', 'instruments': ['a', 'b'],
+           'sequence_lengths': str(tmp_path / 'lengths.npy'), 'split': {'num_train': 4, 'num_valid': 2, 'num_test': 1}}
+    (xt, lt), (xv, lv), (xs, ls) = D.load_data(cfg, step_size=2)
+    assert xt.shape == (4, 5, 8, 2) and xv.shape == (2, 5, 8, 2) and xs.shape == (1, 5, 8, 2)
+    assert np.array_equal(lt, [9, 8, 7, 6]) and np.array_equal(lv, [5, 4]) and np.array_equal(ls, [3])
+    # pixels folded into the feature axis: step t, feature p*4 + d = time 2t + p, pitch d; one zero step appended
+    assert np.array_equal(xt[1, 2, :4, 0], songs[1, 4, :, 0]) and np.array_equal(xt[1, 2, 4:, 1], songs[1, 5, :, 1])
+    assert not xt[:, 4, 4:].any()
+    cfg2 = dict(cfg, sequence_lengths=None)
+    (xt2, lt2), _, _ = D.load_data(cfg2, step_size=1)
+    assert xt2.shape == (4, 9, 4, 2) and np.array_equal(lt2, [9, 9, 9, 9])
+    with pytest.raises(ValueError):
+        D.load_data(dict(cfg, instruments=['a']), 1)
+    with pytest.raises(ValueError):
+        D.load_data(dict(cfg, source='tfrecord'), 1)
+
+
+def test_pad_to_midi_and_sampling_inputs():
+    cfg = {'pitch_range': {'lowest': 24, 'highest': 108}}
+    x = np.ones((2, 3, 168, 5), dtype=np.float32)              # num_pixels = 2
+    p = D.pad_to_midi(x, cfg)
+    assert p.shape == (2, 6, 128, 5) and p[:, :, :24].sum() == 0 and p[:, :, 108:].sum() == 0 and p[:, :, 24:108].all()
+    Xt = np.arange(6 * 10).reshape(6, 10, 1, 1).astype(np.float32)
+    Xv = -np.arange(4 * 10).reshape(4, 10, 1, 1).astype(np.float32)
+    sc = {'intro_beats': 2, 'num_save': 2, 'intro_ids': {'train': {'start': 1, 'end': 4}, 'valid': {'start': 0, 'end': 2}},
+          'save_ids': {'train': [0, 2], 'valid': [1]}}
+    intro, save_ids, labels = D.prepare_sampling_inputs(Xt, Xv, sc, beat_size=3.0)
+    assert intro.shape == (5, 6, 1, 1) and labels == ['t0', 't2', 'v1']
+    assert np.array_equal(save_ids, [0, 2, 4, 5, 7, 9])
+
+
+class _StubModel:
+    """Loss falls for three epochs, then the validation metric stalls."""
+
+    def __init__(self):
+        self.calls, self.saved, self.valid = [], [], iter([5.0, 4.0, 4.5, 4.2, 4.1, 3.0])
+        self.epoch_metric = None
+
+    def train_generators(self, optimizer, lr):
+        import torch
+
+        def step(x, lengths=None, seed=None):
+            self.calls.append((tuple(x.shape), lengths.tolist(), seed))
+            return torch.tensor([float(len(self.calls))])
+        return step
+
+    def evaluate(self, x, lengths=None):
+        import torch
+        if self.epoch_metric is None:
+            self.epoch_metric = next(self.valid)
+        return {'nll': torch.full((int(lengths.sum()), 2), self.epoch_metric)}
+
+    def save(self, path):
+        self.saved.append(path)
+
+
+def test_fit_early_stopping_checkpoints_and_step_counter(tmp_path):
+    X = (np.random.default_rng(2).random((5, 8, 3, 2)) < 0.3).astype(np.uint8)
+    lengths = np.array([8, 8, 3, 5, 8])
+    model = _StubModel()
+    orig = U.collect_metrics
+
+    def collect(model_, *a, **kw):
+        model_.epoch_metric = None
+        return orig(model_, *a, **kw)
+    U_collect, U.collect_metrics = U.collect_metrics, collect
+    try:
+        cfg = {'batch_size': 2, 'piece_size': 4, 'learning_rate': 0.01, 'epochs': 6, 'early_stopping': 2}
+        stats, hist = U.fit(model, (X, lengths), (X[:2], lengths[:2]), cfg, checkpoint_path=str(tmp_path / 'best.pt'),
+                            device='cpu')
+    finally:
+        U.collect_metrics = U_collect
+    # epochs 1, 2 improve (5.0, 4.0); 3 and 4 do not -> stop after epoch 4
+    assert [h['epoch'] for h in hist] == [1, 2, 3, 4]
+    assert stats.metric_best == 4.0 and stats.idle_epochs == 2 and len(model.saved) == 2
+    assert stats.steps == 4 * 3 and stats.run == 1            # 3 batches per epoch, one step per batch (Q11)
+    assert (tmp_path / 'best.pt.stats').exists()
+    # every fed piece: at most piece_size frames, lengths within it, the songs past their end dropped
+    for shape, lens, _ in model.calls:
+        assert shape[1] == max(lens) <= 4 and len(lens) == shape[0] and min(lens) > 0
+    assert abs(hist[0]['valid_log_likelihood'] - 5.0) < 1e-12
