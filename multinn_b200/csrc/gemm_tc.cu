@@ -40,6 +40,7 @@ struct Params {
   int n_products;  // 3, or 2 when A is exactly representable in tf32 (binary piano-roll rows)
   int atomic;      // split-K: red.global.add into C
   int tma_store;   // pair kernel: C tiles leave through shared memory + TMA (needs beta == 0, no split-K, aligned C)
+  int bf16x;       // pair kernel: cross terms hi.lo + lo.hi as bf16 MMAs (kind::f16, twice the tf32 rate)
 };
 
 template <int BN>
@@ -378,6 +379,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0, acc_phase = 0;
       const uint32_t tmem_d = tmem_base, tmem_x = tmem_base + BN2;
+      // bf16 cross-term tiles (convert_bf16_tiles): [hi | lo] of 8 KB each in the operand's "lo" region
+      const uint32_t idesc16 = idesc_bf16(BN2, A_MN, B_MN, 2 * BM);
+      const uint32_t a16_lbo = A_MN ? 4096 : 16, b16_lbo = B_MN ? 4096 : 16;
+      const uint32_t a16_sbo = A_MN ? 1024 : 512, b16_sbo = B_MN ? 1024 : 512;
+      const uint32_t a16_lay = A_MN ? 2 : 4, b16_lay = B_MN ? 2 : 4;
+      const uint32_t a16_kstep = A_MN ? 2048 : 32, b16_kstep = B_MN ? 2048 : 32;
       for (int w = cluster_id; w < n_items; w += n_clusters) {
         const int split = w / (p.tiles_n * p.tiles_m);
         const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -388,6 +395,30 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           tc_fence_after();
           const uint32_t a_raw = smem0 + stage * C_::STAGE_BYTES, a_lo = a_raw + C_::A_BYTES;
           const uint32_t b_raw = a_raw + 2 * C_::A_BYTES, b_lo = b_raw + C_::B_BYTES;
+          if (p.bf16x) {
+            // A.B ~ A_hi.B_hi (tf32, 4 x K=8) + bf16(A).bf16(B_lo) + bf16(A_lo).bf16(B) (kind::f16, 2 x K=16 each)
+#pragma unroll
+            for (int j = 0; j < BK / 16; ++j) {
+              const uint32_t first = (kb > kb0 || j > 0) ? 1u : 0u;
+              const uint64_t dah = smem_desc(a_lo + j * a16_kstep, a16_lbo, a16_sbo, a16_lay);
+              const uint64_t dbl = smem_desc(b_lo + C_::B_BYTES / 2 + j * b16_kstep, b16_lbo, b16_sbo, b16_lay);
+              umma_bf16_2cta(tmem_x, dah, dbl, idesc16, first);
+              if (p.n_products == 3) {
+                const uint64_t dal = smem_desc(a_lo + C_::A_BYTES / 2 + j * a16_kstep, a16_lbo, a16_sbo, a16_lay);
+                const uint64_t dbh = smem_desc(b_lo + j * b16_kstep, b16_lbo, b16_sbo, b16_lay);
+                umma_bf16_2cta(tmem_x, dal, dbh, idesc16, 1u);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < BK / 8; ++j) {
+              const uint64_t da = smem_desc(a_raw + j * a_kstep, a_lbo, a_sbo, a_lay);
+              const uint64_t db = smem_desc(b_raw + j * b_kstep, b_lbo, b_sbo, b_lay);
+              umma_tf32_2cta(tmem_d, da, db, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
+            }
+            umma_commit_2cta(bar_empty + 8 * stage);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
 #pragma unroll
           for (int j = 0; j < BK / 8; ++j) {
             const uint64_t da = smem_desc(a_raw + j * a_kstep, a_lbo, a_sbo, a_lay);
@@ -426,10 +457,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         float4* a_lo = reinterpret_cast<float4*>(base + C_::A_BYTES);
         const float4* b_raw = reinterpret_cast<const float4*>(base + 2 * C_::A_BYTES);
         float4* b_lo = reinterpret_cast<float4*>(base + 2 * C_::A_BYTES + C_::B_BYTES);
+        if (p.bf16x) {
+          convert_bf16_tiles<A_MN, kConvThreads>(base, base + C_::A_BYTES, t, p.n_products == 3);
+          convert_bf16_tiles<B_MN, kConvThreads>(base + 2 * C_::A_BYTES, base + 2 * C_::A_BYTES + C_::B_BYTES, t, true);
+        } else {
 #pragma unroll 4
-        for (int i = t; i < a_vec; i += kConvThreads) a_lo[i] = tf32_lo4(a_raw[i]);
+          for (int i = t; i < a_vec; i += kConvThreads) a_lo[i] = tf32_lo4(a_raw[i]);
 #pragma unroll 4
-        for (int i = t; i < b_vec; i += kConvThreads) b_lo[i] = tf32_lo4(b_raw[i]);
+          for (int i = t; i < b_vec; i += kConvThreads) b_lo[i] = tf32_lo4(b_raw[i]);
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the pair's UMMA
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(conv_leader + 8 * stage);
@@ -791,6 +827,10 @@ extern "C" int mnn_gemm_tc(const float* A, long long lda, int transA, const floa
   if (rc) return rc;
 
   if (pair) {
+    // cross terms as bf16 MMAs ("2.5 products"): on for general A; with a binary A (2 tf32 products) the extra bf16(A)
+    // tile makes the converter warps the bottleneck (measured 3.15 -> 3.33 ms). MNN_GEMM_BF16X=0 / 1 forces it off / on.
+    static const char* bf16x_env = getenv("MNN_GEMM_BF16X");
+    p.bf16x = bf16x_env ? (bf16x_env[0] == '1' ? 1 : 0) : (p.n_products == 3 ? 1 : 0);
     CUtensorMap mc = ma;
     p.tma_store = (!p.atomic && beta == 0.f && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
     if (p.tma_store) {

@@ -72,6 +72,14 @@ __device__ __forceinline__ void umma_tf32_2cta(uint32_t tmem_d, uint64_t adesc, 
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// bf16 inputs, fp32 accumulation (K = 16 per instruction, twice the tf32 rate)
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
 // arrives (once the MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
@@ -165,6 +173,60 @@ __device__ __forceinline__ float4 tf32_lo4(float4 x) {
 __device__ __forceinline__ uint32_t idesc_tf32(int n, bool a_mn, bool b_mn, int m = BM) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// kind::f16 instruction descriptor with bf16 operands: a = b = BF16 (1), fp32 accumulator
+__device__ __forceinline__ uint32_t idesc_bf16(int n, bool a_mn, bool b_mn, int m = BM) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// (bf16(x0..x3)) packed into 8 bytes, round to nearest even
+__device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) {
+  uint32_t lo, hi;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b), "f"(a));   // first source -> upper half
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(d), "f"(c));
+  return make_uint2(lo, hi);
+}
+// residual of the hardware's truncation to tf32 (exact in fp32)
+__device__ __forceinline__ float tf32_residual(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// Cross-term operands of the "2.5-product" scheme: for a [128 x 32] fp32 operand tile as TMA left it in shared memory,
+// write bf16(x) and bf16(x - trunc_tf32(x)) as two [128 x 32] bf16 tiles (8 KB each, hi then lo) in the UMMA canonical
+// layout of the same major-ness: K-major source (SWIZZLE_128B rows of 32 floats) -> K-major SWIZZLE_64B (64-byte rows,
+// 8-row atoms of 512 B); MN-major source (four {32 mn x 32 k} boxes, SWIZZLE_128B with 32-byte atoms) -> MN-major
+// SWIZZLE_128B (atoms of 64 mn x 8 k, k-groups 1 KB apart, the two 64-mn blocks 4 KB apart).
+template <bool MN, int NT>
+__device__ __forceinline__ void convert_bf16_tiles(const uint8_t* raw, uint8_t* dst, int t, bool want_lo) {
+  static_assert(NT == 128, "offsets below are hoisted for 128 converter threads");
+  const float4* src = reinterpret_cast<const float4*>(raw) + t;
+  // piece i = t + 128 n (n = 0..7). All index arithmetic that depends on t is done once; n is a compile-time constant.
+  uint32_t off_even, off_odd;
+  if (!MN) {
+    // row = (t >> 3) + 16 n, 16-byte piece (t & 7) holds logical k0 = 4 * ((t & 7) ^ (row & 7)); row & 7 = (t >> 3) & 7
+    const int r8 = (t >> 3) & 7, k0 = ((t & 7) ^ r8) << 2;
+    off_even = (uint32_t)((t >> 6) * 512 + r8 * 64 + (((k0 >> 3) ^ (r8 >> 1)) << 4) + ((k0 & 7) << 1));
+    off_odd = off_even;
+  } else {
+    // box = n >> 1, k-row = (t >> 3) + 16 (n & 1); 32-byte chunk (t & 7) >> 1 holds logical chunk ^ (k-row & 3)
+    const int krow = t >> 3, p16 = t & 7, k8 = krow & 7;
+    const int c = ((((p16 >> 1) ^ (krow & 3)) << 3) + ((p16 & 1) << 2));      // mn within the box
+    const uint32_t base = (uint32_t)((krow >> 3) * 1024 + k8 * 128 + ((c & 7) << 1));
+    const int x = (c >> 3) ^ k8;
+    off_even = base + (uint32_t)(x << 4);            // boxes 0 and 2: mn & 63 in [0, 32)
+    off_odd = base + (uint32_t)((x ^ 4) << 4);       // boxes 1 and 3: mn & 63 in [32, 64)
+  }
+#pragma unroll
+  for (int n = 0; n < BM * BK / 4 / NT; ++n) {
+    const float4 x = src[n * NT];
+    uint32_t off;
+    if (!MN) off = off_even + (uint32_t)n * 1024u;
+    else off = (((n >> 1) & 1) ? off_odd : off_even) + (uint32_t)((n >> 2) * 4096 + (n & 1) * 2048);
+    *reinterpret_cast<uint2*>(dst + off) = pack_bf16x4(x.x, x.y, x.z, x.w);
+    if (want_lo)
+      *reinterpret_cast<uint2*>(dst + BM * BK * 2 + off) =
+          pack_bf16x4(tf32_residual(x.x), tf32_residual(x.y), tf32_residual(x.z), tf32_residual(x.w));
+  }
 }
 
 }  // namespace tc
