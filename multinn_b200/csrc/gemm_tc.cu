@@ -41,6 +41,7 @@ struct Params {
   int atomic;      // split-K: red.global.add into C
   int tma_store;   // pair kernel: C tiles leave through shared memory + TMA (needs beta == 0, no split-K, aligned C)
   int bf16x;       // pair kernel: cross terms hi.lo + lo.hi as bf16 MMAs (kind::f16, twice the tf32 rate)
+  int share_conv;  // pair kernel, long K loops: the epilogue warps convert too (256 converter threads per CTA)
 };
 
 template <int BN>
@@ -291,6 +292,35 @@ struct Cfg2 {
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 2 * CTILE + 1024;
 };
 
+// one converter thread's share of a landed stage [A raw | A lo | B raw | B lo]: the tf32 residual tiles (3xTF32) or the bf16
+// cross-term tiles (bf16x); t in [0, 128) or, when the epilogue warps convert too (share_conv), [0, 256)
+template <bool A_MN, bool B_MN>
+__device__ __forceinline__ void convert_stage(uint8_t* base, int t, const Params& p) {
+  using C_ = Cfg2;
+  if (p.bf16x) {
+    if (p.share_conv) {
+      convert_bf16_tiles<A_MN, 256>(base, base + C_::A_BYTES, t, p.n_products == 3);
+      convert_bf16_tiles<B_MN, 256>(base + 2 * C_::A_BYTES, base + 2 * C_::A_BYTES + C_::B_BYTES, t, true);
+    } else {
+      convert_bf16_tiles<A_MN, 128>(base, base + C_::A_BYTES, t, p.n_products == 3);
+      convert_bf16_tiles<B_MN, 128>(base + 2 * C_::A_BYTES, base + 2 * C_::A_BYTES + C_::B_BYTES, t, true);
+    }
+  } else {
+    const float4* a_raw = reinterpret_cast<const float4*>(base);
+    float4* a_lo = reinterpret_cast<float4*>(base + C_::A_BYTES);
+    const float4* b_raw = reinterpret_cast<const float4*>(base + 2 * C_::A_BYTES);
+    float4* b_lo = reinterpret_cast<float4*>(base + 2 * C_::A_BYTES + C_::B_BYTES);
+    const int nt = p.share_conv ? 2 * kConvThreads : kConvThreads;
+    const int a_vec = (p.n_products == 3) ? C_::A_BYTES / 16 : 0;
+    constexpr int b_vec = C_::B_BYTES / 16;
+#pragma unroll 4
+    for (int i = t; i < a_vec; i += nt) a_lo[i] = tf32_lo4(a_raw[i]);
+#pragma unroll 4
+    for (int i = t; i < b_vec; i += nt) b_lo[i] = tf32_lo4(b_raw[i]);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the pair's UMMA
+}
+
 template <bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -316,7 +346,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_conv + 8 * s, 2 * (kConvThreads / 32));   // one elected arrive per converter warp
+      mbar_init(bar_conv + 8 * s, 2 * ((p.share_conv ? 2 : 1) * kConvThreads / 32));   // one elected arrive per converter warp
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_tfull, 1);
@@ -444,29 +474,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int t = threadIdx.x - 8 * 32;
     int stage = 0;
     uint32_t phase = 0;
-    const int a_vec = (p.n_products == 3) ? C_::A_BYTES / 16 : 0;
-    constexpr int b_vec = C_::B_BYTES / 16;
     const uint32_t conv_leader = mapa_cluster(bar_conv, 0);
     for (int w = cluster_id; w < n_items; w += n_clusters) {
       const int split = w / (p.tiles_n * p.tiles_m);
       const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(bar_full + 8 * stage, phase);
-        uint8_t* base = smem_gen + (size_t)stage * C_::STAGE_BYTES;
-        const float4* a_raw = reinterpret_cast<const float4*>(base);
-        float4* a_lo = reinterpret_cast<float4*>(base + C_::A_BYTES);
-        const float4* b_raw = reinterpret_cast<const float4*>(base + 2 * C_::A_BYTES);
-        float4* b_lo = reinterpret_cast<float4*>(base + 2 * C_::A_BYTES + C_::B_BYTES);
-        if (p.bf16x) {
-          convert_bf16_tiles<A_MN, kConvThreads>(base, base + C_::A_BYTES, t, p.n_products == 3);
-          convert_bf16_tiles<B_MN, kConvThreads>(base + 2 * C_::A_BYTES, base + 2 * C_::A_BYTES + C_::B_BYTES, t, true);
-        } else {
-#pragma unroll 4
-          for (int i = t; i < a_vec; i += kConvThreads) a_lo[i] = tf32_lo4(a_raw[i]);
-#pragma unroll 4
-          for (int i = t; i < b_vec; i += kConvThreads) b_lo[i] = tf32_lo4(b_raw[i]);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the pair's UMMA
+        convert_stage<A_MN, B_MN>(smem_gen + (size_t)stage * C_::STAGE_BYTES, t, p);
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(conv_leader + 8 * stage);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -479,10 +493,24 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     int store_no = 0;
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
     const uint32_t tempty_leader = mapa_cluster(bar_tempty, 0);
+    const uint32_t conv_leader = mapa_cluster(bar_conv, 0);
+    int cstage = 0;
+    uint32_t cphase = 0;
     for (int w = cluster_id; w < n_items; w += n_clusters) {
       const int n_blk = w % p.tiles_n, m_blk = (w / p.tiles_n) % p.tiles_m, split = w / (p.tiles_n * p.tiles_m);
       const int row = m_blk * 2 * BM + (int)rank * BM + q * 32 + lane;
       const int n0 = n_blk * BN2;
+      if (p.share_conv) {
+        // long K loop: the epilogue has nothing to do until the tile is complete, so these warps convert as well
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_full + 8 * cstage, cphase);
+          convert_stage<A_MN, B_MN>(smem_gen + (size_t)cstage * C_::STAGE_BYTES, (int)threadIdx.x, p);   // t in [128, 256)
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(conv_leader + 8 * cstage);
+          if (++cstage == STAGES) { cstage = 0; cphase ^= 1; }
+        }
+      }
       mbar_wait(bar_tfull, acc_phase);
       tc_fence_after();
       const bool add_bias = p.bias != nullptr && (!p.atomic || split == 0);
@@ -831,6 +859,9 @@ extern "C" int mnn_gemm_tc(const float* A, long long lda, int transA, const floa
     // tile makes the converter warps the bottleneck (measured 3.15 -> 3.33 ms). MNN_GEMM_BF16X=0 / 1 forces it off / on.
     static const char* bf16x_env = getenv("MNN_GEMM_BF16X");
     p.bf16x = bf16x_env ? (bf16x_env[0] == '1' ? 1 : 0) : (p.n_products == 3 ? 1 : 0);
+    static const char* share_env = getenv("MNN_GEMM_SHARE_KB");   // k-blocks per tile from which the epilogue warps convert too
+    static const int share_kb = share_env ? atoi(share_env) : 8;
+    p.share_conv = (share_kb > 0 && p.kb_per_split >= share_kb) ? 1 : 0;
     CUtensorMap mc = ma;
     p.tma_store = (!p.atomic && beta == 0.f && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
     if (p.tma_store) {

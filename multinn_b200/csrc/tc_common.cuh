@@ -198,17 +198,18 @@ __device__ __forceinline__ float tf32_residual(float x) { return x - __uint_as_f
 // SWIZZLE_128B (atoms of 64 mn x 8 k, k-groups 1 KB apart, the two 64-mn blocks 4 KB apart).
 template <bool MN, int NT>
 __device__ __forceinline__ void convert_bf16_tiles(const uint8_t* raw, uint8_t* dst, int t, bool want_lo) {
-  static_assert(NT == 128, "offsets below are hoisted for 128 converter threads");
+  static_assert(NT == 128 || NT == 256, "offsets below are hoisted for 128 or 256 converter threads");
   const float4* src = reinterpret_cast<const float4*>(raw) + t;
-  // piece i = t + 128 n (n = 0..7). All index arithmetic that depends on t is done once; n is a compile-time constant.
+  // piece i = t + NT n. All index arithmetic that depends on t is done once; n is a compile-time constant.
   uint32_t off_even, off_odd;
   if (!MN) {
-    // row = (t >> 3) + 16 n, 16-byte piece (t & 7) holds logical k0 = 4 * ((t & 7) ^ (row & 7)); row & 7 = (t >> 3) & 7
+    // row = (t >> 3) + (NT / 8) n, 16-byte piece (t & 7) holds logical k0 = 4 * ((t & 7) ^ (row & 7)); row & 7 = (t >> 3) & 7
     const int r8 = (t >> 3) & 7, k0 = ((t & 7) ^ r8) << 2;
     off_even = (uint32_t)((t >> 6) * 512 + r8 * 64 + (((k0 >> 3) ^ (r8 >> 1)) << 4) + ((k0 & 7) << 1));
     off_odd = off_even;
   } else {
-    // box = n >> 1, k-row = (t >> 3) + 16 (n & 1); 32-byte chunk (t & 7) >> 1 holds logical chunk ^ (k-row & 3)
+    // NT = 128: box = n >> 1, k-row = (t >> 3) + 16 (n & 1); NT = 256: box = n, k-row = t >> 3.
+    // 32-byte chunk (t & 7) >> 1 holds logical chunk ^ (k-row & 3)
     const int krow = t >> 3, p16 = t & 7, k8 = krow & 7;
     const int c = ((((p16 >> 1) ^ (krow & 3)) << 3) + ((p16 & 1) << 2));      // mn within the box
     const uint32_t base = (uint32_t)((krow >> 3) * 1024 + k8 * 128 + ((c & 7) << 1));
@@ -220,8 +221,9 @@ __device__ __forceinline__ void convert_bf16_tiles(const uint8_t* raw, uint8_t* 
   for (int n = 0; n < BM * BK / 4 / NT; ++n) {
     const float4 x = src[n * NT];
     uint32_t off;
-    if (!MN) off = off_even + (uint32_t)n * 1024u;
-    else off = (((n >> 1) & 1) ? off_odd : off_even) + (uint32_t)((n >> 2) * 4096 + (n & 1) * 2048);
+    if (!MN) off = off_even + (uint32_t)n * (NT * 8u);                         // NT / 8 rows = NT / 64 atoms of 512 B
+    else if (NT == 128) off = (((n >> 1) & 1) ? off_odd : off_even) + (uint32_t)((n >> 2) * 4096 + (n & 1) * 2048);
+    else off = ((n & 1) ? off_odd : off_even) + (uint32_t)((n >> 1) * 4096);
     *reinterpret_cast<uint2*>(dst + off) = pack_bf16x4(x.x, x.y, x.z, x.w);
     if (want_lo)
       *reinterpret_cast<uint2*>(dst + BM * BK * 2 + off) =
