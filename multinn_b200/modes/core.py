@@ -169,6 +169,86 @@ class MultINNCore(Model, abc.ABC):
 
         return step
 
+    # ------------------------------------------------------------------ encoder pre-training (train_encoders.py)
+    def _encoder_rows(self, x, lengths=None):
+        """Per-encoder training rows: the zero-padded inputs [B,T+1,..] flattened by flatten_maybe_padded_sequences
+        with the UNPADDED lengths (encoder.build(x=self._inputs[i], lengths), dbn_encoder.py:212-214): the rows
+        t < lengths[b] of the padded sequence, i.e. the zero frame and the first lengths[b] - 1 real frames. Returns a
+        list with one [rows, num_dims] tensor per encoder (CD sums do not depend on the row order)."""
+        B, T, D, M = x.shape
+        keep = None
+        if lengths is not None and int(torch.as_tensor(lengths).min()) < T + 1:
+            ln = torch.as_tensor(lengths).to('cpu', torch.int64)
+            mask = (torch.arange(T + 1)[:, None] < ln[None, :]).reshape(-1)          # time-major rows t*B + b
+            keep = mask.nonzero().squeeze(1).to(x.device)
+        if len(self._encoders) == 1:                                                 # Joint: one encoder over D*M dims
+            st = self._stage_inputs(x, stacked=True)
+            rows = [st['xin'].view((T + 1) * B, D * M)]
+        else:
+            st = self._stage_inputs(x, per_track=True)
+            rows = [st['xtr'][m].view((T + 1) * B, D) for m in range(M)]
+        if keep is None:
+            return [r[:T * B] for r in rows]                                         # full lengths: t < T
+        return [r.index_select(0, keep) for r in rows]
+
+    def train_encoders(self, optimizer=None, lr=0.01, layer=0):
+        """core/multi_encoder_nn.py:155-195 / multinn_joint.py: the encoders are pre-trained separately but in parallel,
+        layer by layer, with CD-k (`RBM.train` applies the update itself: the optimizer argument is unused there too).
+        Returns (init, step): `init(x, lengths=None)` = the init_ops (visible-bias initialisation, run once on
+        X_train[:1600], train_encoders.py:106-109); `step(x, lengths=None, u=None, seed=None)` = one CD update of
+        `layer` on every encoder, returning {'batch/loss', 'log_likelihood'} averaged over the encoders
+        (`_combine_track_metrics`). Pass encoders (no parameters) make both no-ops."""
+        trainable = [e for e in self._encoders if getattr(e, 'stochastic', False)]
+        counter = [0]
+
+        def init(x, lengths=None, u=None, seed=0):
+            x = self._check_encoder_x(x)
+            for m, (enc, rows) in enumerate(zip(self._encoders, self._encoder_rows(x, lengths))):
+                if enc in trainable:
+                    enc.init_bias(rows, layer, u=None if u is None else u[m], seed=seed + 31 * m)
+
+        def step(x, lengths=None, u=None, seed=None):
+            x = self._check_encoder_x(x)
+            s = counter[0] if seed is None else seed
+            counter[0] += 1
+            out = {'batch/loss': torch.zeros((), device=x.device), 'log_likelihood': torch.zeros((), device=x.device)}
+            for m, (enc, rows) in enumerate(zip(self._encoders, self._encoder_rows(x, lengths))):
+                if enc not in trainable:
+                    continue
+                um = None if u is None else u[m]
+                met = enc.layer_metrics(rows, layer, u=None if um is None else um['metrics'], seed=s * 7919 + 31 * m)
+                enc.train(rows, lr, layer=layer, u=None if um is None else um['train'], seed=s * 7919 + 31 * m + 1)
+                for k in out:
+                    out[k] = out[k] + met[k].reshape(()) / max(len(trainable), 1)
+            self._metrics.update({f'encoders/{k}': v for k, v in out.items()})
+            return out
+
+        return init, step
+
+    def evaluate_encoders(self, x, lengths=None, layer=0, u=None, seed=0):
+        """Encoder metrics without an update (the metrics_upd ops collect_metrics runs in train_encoders.py:178-190):
+        {'batch/loss', 'log_likelihood'} of RBM `layer`, averaged over the encoders, plus the number of rows."""
+        x = self._check_encoder_x(x)
+        trainable = [e for e in self._encoders if getattr(e, 'stochastic', False)]
+        out = {'batch/loss': torch.zeros((), device=x.device), 'log_likelihood': torch.zeros((), device=x.device)}
+        rows_n = 0
+        for m, (enc, rows) in enumerate(zip(self._encoders, self._encoder_rows(x, lengths))):
+            if enc not in trainable:
+                continue
+            met = enc.layer_metrics(rows, layer, u=None if u is None else u[m], seed=seed + 31 * m)
+            rows_n = rows.shape[0]
+            for k in out:
+                out[k] = out[k] + met[k].reshape(()) / len(trainable)
+        out['rows'] = rows_n
+        return out
+
+    def _check_encoder_x(self, x):
+        if x.dim() != 4 or x.shape[2] != self.num_dims or x.shape[3] != self.num_tracks:
+            raise ValueError(f'x must be [batch, time, {self.num_dims}, {self.num_tracks}], got {tuple(x.shape)}')
+        if not x.is_cuda:
+            raise ValueError('x must be a CUDA tensor: multinn_b200 has no CPU path')
+        return x.contiguous() if x.dtype in (torch.uint8, torch.bool) else x.contiguous().float()
+
     @abc.abstractmethod
     def _forward_backward(self, x, keep, u_drop, seed, **extra):
         """One fwd+bwd over the batch; `extra` carries mode-specific uniform-noise tensors for parity runs."""

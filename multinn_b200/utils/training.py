@@ -214,3 +214,65 @@ def fit(model, train, valid, training_config, stats=None, optimizer='adam', chec
             if stats.idle_epochs >= training_config['early_stopping']:
                 break
     return stats, history
+
+
+def fit_encoders(model, train, valid, training_config, layer=0, stats=None, checkpoint_path=None, evaluate_epochs=1,
+                 beat_size=None, device='cuda', init_songs=1600, log=None):
+    """The encoder pre-training loop of train_encoders.py:17-219 for one DBN layer: run the init_ops once on
+    X_train[:1600] (:106-109), then per epoch feed every batch piece to the CD-k update, evaluate the validation
+    log-likelihood with the streaming mean of collect_metrics, keep the best checkpoint and stop after
+    `early_stopping` idle epochs. Returns (stats, history)."""
+    import torch
+    X_train, len_train = train
+    X_valid, len_valid = valid
+    fresh = stats is None
+    stats = TrainingStats() if stats is None else stats
+    batch_size = training_config['batch_size']
+    piece_size = int(training_config['piece_size'] * (1.0 if beat_size is None else beat_size))
+    init, step = model.train_encoders(None, training_config['learning_rate'], layer=layer)
+    if fresh:
+        init(_to_device(X_train[:init_songs], device), lengths=torch.as_tensor(np.asarray(len_train[:init_songs])))
+    stats.new_run()
+    loss_accum = LossAccumulator()
+    history = []
+    loglik_val = float('inf')
+    past_epochs = stats.epoch
+    for epoch in range(past_epochs + 1, past_epochs + training_config['epochs'] + 1):
+        stats.new_epoch()
+        np.random.seed(epoch)
+        ids = np.arange(X_train.shape[0])
+        np.random.shuffle(ids)
+        loss_accum.clear()
+        steps0 = stats.steps
+        for bi, songs, len_batch in training_pieces(X_train, len_train, ids, batch_size, piece_size):
+            while stats.steps < steps0 + bi:
+                stats.new_step()
+            out = step(_to_device(songs, device), lengths=torch.as_tensor(np.asarray(len_batch)),
+                       seed=stats.steps * 131 + epoch)
+            loss_accum.update(float(out['batch/loss']))
+        while stats.steps < steps0 + (X_train.shape[0] + batch_size - 1) // batch_size:
+            stats.new_step()
+        rec = {'epoch': epoch, 'steps': stats.steps, 'loss': loss_accum.loss()}
+        if evaluate_epochs > 0 and epoch % evaluate_epochs == 0:
+            tot, cnt = 0.0, 0
+            for songs, seq in evaluation_pieces(X_valid, len_valid, batch_size * 2, piece_size):
+                m = model.evaluate_encoders(_to_device(songs, device), lengths=torch.as_tensor(np.asarray(seq)),
+                                            layer=layer, seed=epoch)
+                tot += float(m['log_likelihood']) * m['rows']
+                cnt += m['rows']
+            loglik_val = tot / max(cnt, 1)
+            rec['valid_log_likelihood'] = loglik_val
+        history.append(rec)
+        if log is not None:
+            log(rec)
+        if loglik_val < stats.metric_best:
+            stats.update_metric_best(loglik_val)
+            stats.reset_idle_epochs()
+            if checkpoint_path is not None:
+                model.save(checkpoint_path)
+                stats.save(checkpoint_path + '.stats')
+        else:
+            stats.new_idle_epoch()
+            if stats.idle_epochs >= training_config['early_stopping']:
+                break
+    return stats, history

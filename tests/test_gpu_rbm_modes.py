@@ -262,3 +262,61 @@ def test_feedback_training_reduces_loss():
     for _ in range(6):
         l1 = float(step(x, keep=1.0))
     assert l1 < l0
+
+
+def test_train_encoders_step_matches_oracle_cd_and_driver_runs(tmp_path):
+    """Encoder pre-training (train_encoders.py, multi_encoder_nn.py:155-195): the rows each encoder trains on are the
+    zero-padded inputs cut by the unpadded lengths; one `step` = the oracle's CD-k update per track; the init_ops set
+    the visible bias from the data mean; the layer-wise driver lowers the reconstruction log-loss."""
+    from multinn_b200.utils import training as U
+    rng = np.random.default_rng(11)
+    B, T, M, k = 3, 5, 5, 1
+    model = make('jamming', encoder='DBN', encoder_hidden=[24, 12], num_hidden=128, num_hidden_rnn=(16,))
+    core = model._model
+    x = O.synthetic_pianoroll(B, T, seed=3, density=0.2)
+    lengths = np.array([5, 3, 4])
+    rows = core._encoder_rows(cu(x), torch.from_numpy(lengths))
+    pad = np.concatenate([np.zeros((B, 1, 84, M), np.float32), x], 1)              # [B,T+1,D,M]
+    for m in range(M):
+        ref_rows = np.concatenate([pad[b, :lengths[b], :, m] for b in range(B)])     # b-major; order is irrelevant
+        got = rows[m].cpu().numpy()
+        assert got.shape == ref_rows.shape
+        assert np.array_equal(np.sort(got.sum(1)), np.sort(ref_rows.sum(1))) and got.sum() == ref_rows.sum()
+    full = core._encoder_rows(cu(x), None)
+    assert full[0].shape == (T * B, 84) and float(full[0][:B].abs().sum()) == 0.0      # zero frame first
+    # one CD-1 step on layer 0, supplied uniforms, against the oracle update on the same rows
+    N = rows[0].shape[0]
+    sd0 = sd_np(core.encoder_arena)
+    u = []
+    for m in range(M):
+        cd = dict(uh=rng.random((k, N, 24), dtype=np.float32), uv=rng.random((k, N, 84), dtype=np.float32),
+                  uh0=rng.random((N, 24), dtype=np.float32), uhk=rng.random((N, 24), dtype=np.float32))
+        met = dict(lower=[], up=rng.random((N, 24), dtype=np.float32), down=rng.random((N, 84), dtype=np.float32))
+        u.append(dict(train=dict(lower=[], cd={n: cu(a) for n, a in cd.items()}),
+                      metrics=dict(lower=[], up=cu(met['up']), down=cu(met['down'])), _cd=cd))
+    init, step = model.train_encoders(None, 0.05, layer=0)
+    out = step(cu(x), lengths=torch.from_numpy(lengths), u=u)
+    assert np.isfinite(float(out['batch/loss'])) and float(out['log_likelihood']) > 0
+    sd1 = sd_np(core.encoder_arena)
+    for m, t in enumerate(model.tracks):
+        W, bh, bv = (sd0[f'encoder/{t}/rbm_0/{n}'].astype(f64) for n in ('W', 'bh', 'bv'))
+        c = {n: a.astype(f64) for n, a in u[m]['_cd'].items()}
+        dW, dbv, dbh = O.rbm_cd_update(rows[m].cpu().numpy().astype(f64), W, bh, bv, k, 0.05, c['uh'], c['uv'], c['uh0'], c['uhk'])
+        np.testing.assert_allclose(sd1[f'encoder/{t}/rbm_0/W'], W + dW, rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(sd1[f'encoder/{t}/rbm_0/bv'], bv + dbv.reshape(bv.shape), rtol=1e-4, atol=1e-6)
+        np.testing.assert_array_equal(sd1[f'encoder/{t}/rbm_1/W'], sd0[f'encoder/{t}/rbm_1/W'])
+    init(cu(x), lengths=torch.from_numpy(lengths))
+    sd2 = sd_np(core.encoder_arena)
+    np.testing.assert_allclose(sd2['encoder/Drums/rbm_0/bv'].reshape(-1),
+                               O.rbm_visible_bias_init(rows[0].cpu().numpy().astype(f64)).reshape(-1), rtol=1e-4, atol=1e-5)
+    # the driver: two layers, a few epochs each
+    X = (rng.random((8, 6, 84, 5)) < 0.1).astype(np.uint8)
+    L = np.array([6, 6, 4, 6, 2, 6, 5, 6])
+    cfg = {'batch_size': 4, 'piece_size': 6, 'learning_rate': 0.1, 'epochs': 8, 'early_stopping': 20}
+    for layer in (0, 1):
+        stats, hist = U.fit_encoders(model, (X, L), (X[:4], L[:4]), cfg, layer=layer,
+                                     checkpoint_path=str(tmp_path / f'enc{layer}.pt'))
+        assert stats.epoch == 8 and stats.steps == 16 and len(hist) == 8
+        assert all(np.isfinite(h['valid_log_likelihood']) and np.isfinite(h['loss']) for h in hist)
+        if layer == 0:          # layer 1 trains on freshly sampled binary codes: too noisy at this size to assert on
+            assert min(h['valid_log_likelihood'] for h in hist[1:]) < hist[0]['valid_log_likelihood']
