@@ -262,15 +262,16 @@ def run_gpu(args):
                     'h2d_bytes_per_step': hosts[0].numel() * hosts[0].element_size(), 'd2h_bytes_per_step': 4},
             'gpu_launches': int(launches),
             'clocks': clk,
-            'roofline': {'bound': 'tensor', 'kernel': 'mnn::tc::gemm_tc2_kernel / gemm_tc_kernel (tcgen05 3xTF32, cta_group::2 '
-                                                      'pair tiles for K >= 512: input projections, Dense, data- and '
+            'roofline': {'bound': 'tensor', 'kernel': 'mnn::tc::gemm_tc2_kernel / gemm_tc_kernel (tcgen05 tf32 + bf16 cross terms, '
+                                                      'cta_group::2 pair tiles: input projections, Dense, data- and '
                                                       'weight-gradient GEMMs; largest kernel class of the step)',
                          'achieved': gemm_tf, 'peak': pk['tf_sust'], 'unit': 'TFLOP/s', 'frac': gemm_tf / pk['tf_sust'],
                          'traffic': profiled_traffic('gemm_tc'), 'peak_source': pk['src'] + ' (cuBLAS bf16, sustained)',
                          'launches_per_step': n_gemm, 'avg_launch_ms': gemm_ms / n_gemm,
                          'algorithmic_flops_per_step': GEMM_TC_FLOPS_STEP * n_rows,
-                         'note': 'fp32-accurate path: every algorithmic MAC costs 2-3 tf32 MMAs (tf32 runs at half the '
-                                 'bf16 rate), so the ceiling against the bf16 denominator is 1/6 (1/4 with binary A)',
+                         'note': 'fp32-accurate path: every algorithmic MAC costs one tf32 MMA (half the bf16 rate) plus two bf16 '
+                                 'cross-term MMAs (2 tf32 products with a binary A), so the ceiling against the bf16 '
+                                 'denominator is 1/4',
                          'phases_ms': phases},
             'kernels': kernel_table(phases, n_rows, pk),
             'sampling': sampling,
@@ -296,7 +297,7 @@ def kernel_table(ph, n_rows, pk):
                 'frac': ach / peak, 'note': note}
     rec_ms = ph.get('recur_fwd_ms', 0) + ph.get('recur_bwd_ms', 0)
     rows = [
-        row('gemm_tc2 / gemm_tc (3xTF32)', ph.get('gemm_ms'), 'tensor', GEMM_TC_FLOPS_STEP * n_rows / 1e12, pk['tf_sust'],
+        row('gemm_tc2 / gemm_tc (tf32 + bf16 cross terms)', ph.get('gemm_ms'), 'tensor', GEMM_TC_FLOPS_STEP * n_rows / 1e12, pk['tf_sust'],
             'TFLOP/s', 'algorithmic flops; x2-3 tf32 MMAs each'),
         row('lstm_tc2_fwd + lstm_tc3_bwd (pair recurrence)', rec_ms, 'tensor', 2 * RECUR_FLOPS_FWD * n_rows / 1e12,
             pk['tf_sust'], 'TFLOP/s', 'h.Wh and dG.Wh^T; latency chain per time step, see DESIGN.md'),
