@@ -104,6 +104,8 @@ class RNN:
     # bias column sums -- runs chunk by chunk on a low-priority "bulk" stream inside an SM budget that leaves the
     # recurrence kernels' SMs free. The recurrences hold ~100 SMs but are a latency chain; the bulk work fills the rest.
     PIPE_MAX_BATCH = int(os.environ.get('MNN_PIPE_MAX_BATCH', 512))
+    PIPE_TAIL_STEPS = int(os.environ.get('MNN_PIPE_TAIL_STEPS', 16))     # large batches: steps whose bulk work runs beside the top layer
+    PIPE_MAX_BATCH_FWD = int(os.environ.get('MNN_PIPE_MAX_BATCH_FWD', 1024))
     PIPE_FWD_BUDGETS = tuple(int(v) for v in os.environ.get('MNN_PIPE_FWD_BUDGETS', '96,48').split(','))
     PIPE_BWD_BUDGETS = tuple(int(v) for v in os.environ.get('MNN_PIPE_BWD_BUDGETS', '0').split(','))   # 0: by batch
     PIPE_BULK_SMS_FWD = int(os.environ.get('MNN_PIPE_BULK_SMS_FWD', 0))    # 0: every SM the recurrence kernels leave
@@ -127,7 +129,19 @@ class RNN:
         return (self.num_layers > 1 and B <= mb and T % self.WAVEFRONT_CHUNK == 0 and T >= 2 * self.WAVEFRONT_CHUNK)
 
     def use_pipeline(self, T, B):
+        """Backward half of the pipeline (chunked BPTT wavefront with the weight gradients beside it)."""
         return B <= self.PIPE_MAX_BATCH and self._use_wavefront(T, B) and self._use_wavefront(T, B, backward=True)
+
+    def use_any_pipeline(self, T, B):
+        """Does `forward_sequence` call a chunk hook for this shape (forward wavefront pipeline or top-layer tail)?"""
+        if self.use_fwd_pipeline(T, B):
+            return True
+        return (self.PIPE_TAIL_STEPS > 0 and self.PIPE_MAX_BATCH > 0 and not self._use_wavefront(T, B)
+                and T % self.WAVEFRONT_CHUNK == 0 and T >= 2 * self.WAVEFRONT_CHUNK and B >= 1024)
+
+    def use_fwd_pipeline(self, T, B):
+        """Forward half (chunk hooks beside the forward wavefront): also where BPTT runs layer by layer (B = 1024)."""
+        return self.PIPE_MAX_BATCH > 0 and B <= max(self.PIPE_MAX_BATCH, self.PIPE_MAX_BATCH_FWD) and self._use_wavefront(T, B)
 
     def _streams(self, device):
         st = self.__dict__.get('_wave_streams')
@@ -195,25 +209,66 @@ class RNN:
         outs = [w['out'] if dropout else w['hbuf'][1:] for w in ws]
         # layer 0: hoisted input projection over all T*B rows (pipeline mode: chunk 0 now, the rest beside the recurrences)
         r0 = self._num_units[0]
-        hook = chunk_hook if (chunk_hook is not None and self.use_pipeline(T, B)) else None
+        hook = chunk_hook if (chunk_hook is not None and self.use_fwd_pipeline(T, B)) else None
         rows0 = (self.WAVEFRONT_CHUNK if hook is not None else T) * B
         ops.gemm(x.view(T * B, I)[:rows0], self.kernels[0].data[:I], ws[0]['gates'].view(T * B, 4 * r0)[:rows0],
                  bias=self.biases[0].data, a_exact=self._binary_inputs)
         if self._use_wavefront(T, B):
             self._forward_wavefront(ws, outs, T, B, keep, u, seed, dropout, hook, x)
         else:
+            tail = chunk_hook is not None and self.use_any_pipeline(T, B)
             for l, r in enumerate(self._num_units):
                 w = ws[l]
                 kern = self.kernels[l].data
                 i_l = self.in_dims()[l]
                 if l > 0:
                     ops.gemm(outs[l - 1].view(T * B, i_l), kern[:i_l], w['gates'].view(T * B, 4 * r), bias=self.biases[l].data)
+                if tail and l == self.num_layers - 1:
+                    self._forward_top_chunked(w, kern[i_l:], outs, T, B, keep, u, seed, dropout, chunk_hook)
+                    continue
                 ops.lstm_seq_fwd(w['gates'], kern[i_l:], w['hbuf'], w['cbuf'],
                                  out=w['out'] if dropout else None, dscale=w['dscale'] if dropout else None,
                                  u=None if u is None else u[l], keep=keep, seed=seed + 7919 * l)
         self._saved = (x, ws, dropout)
         state = [LSTMStateTuple(w['cbuf'][T], w['hbuf'][T]) for w in ws]
         return outs[-1], state
+
+    def _forward_top_chunked(self, w, wh, outs, T, B, keep, u, seed, dropout, hook):
+        """Large batches (no layer wavefront: the recurrence kernels of two layers do not fit side by side): the TOP
+        layer's recurrence leaves SMs free (64 of 148 CTAs at B=2048, R=256), so it runs in time chunks on its own
+        stream and the consumer work of the first PIPE_TAIL_STEPS steps runs beside it on the bulk stream; the rest
+        follows as one full-width call."""
+        C = self.WAVEFRONT_CHUNK
+        nch = T // C
+        l = self.num_layers - 1
+        r = self._num_units[l]
+        main = torch.cuda.current_stream()
+        st = self._streams(w['gates'].device)[l]
+        start = self._event('fwd top start')
+        start.record(main)
+        n = ops.lstm_seq_ctas(C, B, r, 48)
+        bulk_sms = max(16, ops.num_sms() - n)
+        t_slow = min(self.PIPE_TAIL_STEPS, C)
+        done = None
+        for c in range(nch):
+            t0, t1 = c * C, (c + 1) * C
+            with torch.cuda.stream(st):
+                if c == 0:
+                    st.wait_event(start)
+                ops.set_sm_budget(48)
+                try:
+                    ops.lstm_seq_fwd(w['gates'][t0:t1], wh, w['hbuf'][t0:t1 + 1], w['cbuf'][t0:t1 + 1],
+                                     out=w['out'][t0:t1] if dropout else None,
+                                     dscale=w['dscale'][t0:t1] if dropout else None,
+                                     u=None if u is None else u[l][t0:t1], keep=keep, seed=seed + 7919 * l + 104729 * c)
+                finally:
+                    ops.set_sm_budget(0)
+                done = self._event(f'fwd top chunk {c}')
+                done.record(st)
+            if c == 0:
+                hook(0, t_slow, done, outs[-1], bulk_sms, False)
+        hook(t_slow, T, done, outs[-1], 0, True)
+        main.wait_event(done)
 
     def _forward_wavefront(self, ws, outs, T, B, keep, u, seed, dropout, hook=None, x=None):
         C = self.WAVEFRONT_CHUNK
@@ -230,7 +285,7 @@ class RNN:
             # layer-0 input projection of the later chunks: bulk stream, inside the bulk SM budget
             bulk = self.bulk_stream(ws[0]['gates'].device)
             bulk_sms = self.bulk_budget(T, B)
-            n_slow = self.PIPE_SLOW_HOOKS if self.PIPE_SLOW_HOOKS > 0 else (2 if B < 512 else 3)   # measured at T=256
+            n_slow = self.PIPE_SLOW_HOOKS if self.PIPE_SLOW_HOOKS > 0 else (2 if B < 512 else (3 if B < 1024 else 1))   # measured, T=256
             n_slow = max(0, min(n_slow * 32 // C, nch - 1))
             I, r0 = self._num_inputs, self._num_units[0]
             with torch.cuda.stream(bulk):

@@ -861,7 +861,9 @@ extern "C" int mnn_gemm_tc(const float* A, long long lda, int transA, const floa
     p.bf16x = bf16x_env ? (bf16x_env[0] == '1' ? 1 : 0) : (p.n_products == 3 ? 1 : 0);
     static const char* share_env = getenv("MNN_GEMM_SHARE_KB");   // k-blocks per tile from which the epilogue warps convert too
     static const int share_kb = share_env ? atoi(share_env) : 8;
-    p.share_conv = (share_kb > 0 && p.kb_per_split >= share_kb) ? 1 : 0;
+    // only with the bf16 tiles: in the tf32 path with a binary A just B is converted and the extra arrivals cost more
+    // than the shared work saves (dW1x 3.16 -> 3.71 ms)
+    p.share_conv = (p.bf16x && share_kb > 0 && p.kb_per_split >= share_kb) ? 1 : 0;
     CUtensorMap mc = ma;
     p.tma_store = (!p.atomic && beta == 0.f && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
     if (p.tma_store) {

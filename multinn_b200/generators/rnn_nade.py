@@ -148,7 +148,7 @@ class RnnNade(RnnEstimator):
         T, B, _ = inputs.shape
         N, M = T * B, self._num_tracks
         w, nvalid = self.row_weights(lengths, T, B, inputs.device)
-        if w is None and self._rnn.use_pipeline(T, B):
+        if w is None and self._rnn.use_any_pipeline(T, B):
             return self._forward_backward_pipelined(inputs, bits, keep, u_drop, seed, loss_scale, need_dx)
         self._get_state(inputs, keep=keep, u_drop=u_drop, seed=seed, training=True)
         ws = self._ws[(N, True)]

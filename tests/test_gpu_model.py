@@ -336,3 +336,31 @@ def test_fit_loop_on_device_with_variable_lengths(tmp_path):
     other.load(str(tmp_path / 'best.pt'))
     best = U.collect_metrics(other, X[:4], lengths[:4], batch_size=4, piece_size=6)['log_likelihood']
     assert abs(best - stats.metric_best) < 1e-6 * abs(best)
+
+
+@pytest.mark.parametrize("B", [1024, 2048])
+def test_large_batch_pipelines_equal_phase_by_phase(B):
+    """B=1024: chunk hooks beside the forward layer wavefront, BPTT layer by layer; B=2048: the top layer's recurrence
+    in time chunks with the first steps' consumer work beside it. Same loss and gradients as the unpipelined path."""
+    from multinn_b200.common.rnn import RNN
+    T, Rn = 64, (64, 32)
+    x = torch.from_numpy(O.synthetic_pianoroll(B, T, seed=6, density=0.06).astype(np.uint8)).cuda()
+    results = []
+    saved = RNN.PIPE_MAX_BATCH
+    try:
+        for pipe in (saved if saved > 0 else 512, 0):
+            RNN.PIPE_MAX_BATCH = pipe
+            model = make('composer', keep_prob=1.0, H=128, Rnn=Rn)
+            core = model._model
+            assert core.generators[0].rnn.use_any_pipeline(T, B) == (pipe > 0)
+            xd = core._check_x(x, None)
+            for _ in range(2):
+                core.arena.grad.zero_()
+                loss = core._forward_backward(xd, keep=1.0, u_drop=None, seed=0)
+            torch.cuda.synchronize()
+            results.append((float(loss), core.arena.grad.clone()))
+    finally:
+        RNN.PIPE_MAX_BATCH = saved
+    (l1, g1), (l0, g0) = results
+    assert abs(l1 - l0) / l0 < 1e-6
+    assert float((g1 - g0).norm() / g0.norm()) < 1e-5
