@@ -320,3 +320,28 @@ def test_train_encoders_step_matches_oracle_cd_and_driver_runs(tmp_path):
         assert all(np.isfinite(h['valid_log_likelihood']) and np.isfinite(h['loss']) for h in hist)
         if layer == 0:          # layer 1 trains on freshly sampled binary codes: too noisy at this size to assert on
             assert min(h['valid_log_likelihood'] for h in hist[1:]) < hist[0]['valid_log_likelihood']
+
+
+@pytest.mark.parametrize("mode", ['jamming', 'feedback', 'feedback-rnn'])
+def test_chunk_pipeline_in_multi_generator_modes(mode):
+    """T = 64 switches the per-generator time-chunk pipeline on (five generators one after another, `need_dx` through
+    the aux-stream dx GEMMs in the feedback modes): loss and every gradient equal the unpipelined path."""
+    from multinn_b200.common.rnn import RNN
+    B, T = 8, 64
+    x = cu(O.synthetic_pianoroll(B, T, seed=21, density=0.07))
+    results = []
+    saved = RNN.PIPE_MAX_BATCH
+    try:
+        for pipe in (saved if saved > 0 else 512, 0):
+            RNN.PIPE_MAX_BATCH = pipe
+            model = _fb_case(mode, 'Pass') if mode != 'jamming' else make('jamming', num_hidden=128, num_hidden_rnn=(32, 16))
+            core = model._model
+            core.arena.grad.zero_()
+            loss = core._forward_backward(core._check_x(x, None), keep=1.0, u_drop=None, seed=0)
+            torch.cuda.synchronize()
+            results.append((float(loss), core.arena.grad.clone()))
+    finally:
+        RNN.PIPE_MAX_BATCH = saved
+    (l1, g1), (l0, g0) = results
+    assert abs(l1 - l0) / l0 < 1e-6
+    assert float((g1 - g0).norm() / g0.norm()) < 1e-5
