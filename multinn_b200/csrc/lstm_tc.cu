@@ -49,6 +49,7 @@ struct LstmParams {
   int kb_total;         // k-blocks per item
   unsigned int* flags;  // [slabs] completed-item counters (persistent launches), zeroed by the host
   unsigned long long* trace;  // debug (MNN_LSTM_TRACE): [cta][step][16] globaltimer stamps, or null
+  int bf16x;            // pair forward kernel: cross terms as bf16 MMAs (2.5-product scheme, see gemm_tc.cu)
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -708,6 +709,22 @@ lstm_tc2_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             if (kb == 0) MNN_TRACE(4);
             const uint32_t a_raw = smem0 + stage * STAGE_BYTES, a_lo = a_raw + A_BYTES;
             const uint32_t b_raw = a_raw + 2 * A_BYTES, b_lo = b_raw + B_BYTES;
+            if (p.bf16x) {
+              // h.Wh ~ hi.hi (tf32) + bf16(h).bf16(Wh_lo) + bf16(h_lo).bf16(Wh) (2.5-product scheme, gemm_tc.cu)
+              const uint32_t idesc16 = idesc_bf16(BNP, false, false, 2 * BM);
+#pragma unroll
+              for (int j = 0; j < BK / 16; ++j) {
+                const uint32_t first = (kb > 0 || j > 0) ? 1u : 0u;
+                umma_bf16_2cta(tmem_x, smem_desc(a_lo + j * 32, 16, 512, 4), smem_desc(b_lo + B_BYTES / 2 + j * 32, 16, 512, 4),
+                               idesc16, first);
+                umma_bf16_2cta(tmem_x, smem_desc(a_lo + A_BYTES / 2 + j * 32, 16, 512, 4), smem_desc(b_lo + j * 32, 16, 512, 4),
+                               idesc16, 1u);
+              }
+#pragma unroll
+              for (int j = 0; j < BK / 8; ++j)
+                umma_tf32_2cta(tmem_d, smem_desc(a_raw + j * 32, 16, 1024, 2), smem_desc(b_raw + j * 32, 16, 1024, 2), idesc,
+                               (kb > 0 || j > 0) ? 1u : 0u);
+            } else {
 #pragma unroll
             for (int j = 0; j < BK / 8; ++j) {
               const uint64_t da = smem_desc(a_raw + j * 32, 16, 1024, 2), dal = smem_desc(a_lo + j * 32, 16, 1024, 2);
@@ -716,6 +733,7 @@ lstm_tc2_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               umma_tf32_2cta(tmem_x, da, dbl, idesc, first);
               umma_tf32_2cta(tmem_x, dal, db, idesc, 1u);
               umma_tf32_2cta(tmem_d, da, db, idesc, first);
+            }
             }
             umma_commit_2cta(bar_empty + 8 * stage);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -745,10 +763,15 @@ lstm_tc2_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           float4* a_lo = reinterpret_cast<float4*>(base + A_BYTES);
           const float4* b_raw = reinterpret_cast<const float4*>(base + 2 * A_BYTES);
           float4* b_lo = reinterpret_cast<float4*>(base + 2 * A_BYTES + B_BYTES);
+          if (p.bf16x) {
+            convert_bf16_tiles<false, 128>(base, base + A_BYTES, tc, true);
+            convert_bf16_tiles<false, 128>(base + 2 * A_BYTES, base + 2 * A_BYTES + B_BYTES, tc, true);
+          } else {
 #pragma unroll 4
-          for (int i = tc; i < A_BYTES / 16; i += 128) a_lo[i] = tf32_lo4(a_raw[i]);
+            for (int i = tc; i < A_BYTES / 16; i += 128) a_lo[i] = tf32_lo4(a_raw[i]);
 #pragma unroll 4
-          for (int i = tc; i < B_BYTES / 16; i += 128) b_lo[i] = tf32_lo4(b_raw[i]);
+            for (int i = tc; i < B_BYTES / 16; i += 128) b_lo[i] = tf32_lo4(b_raw[i]);
+          }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(conv_leader + 8 * stage);
@@ -808,6 +831,7 @@ struct Lstm3Params {
   unsigned int* cntA;     // [slabs]
   unsigned int* cntB;     // [slabs]
   unsigned long long* trace;   // debug (MNN_LSTM_TRACE)
+  int bf16x;              // phase A: cross terms as bf16 MMAs (2.5-product scheme, see gemm_tc.cu)
 };
 constexpr int kCellRows = 16, kCellUnits = 16, kCellTile = kCellRows * kCellUnits * 4;   // 1 KB tiles
 constexpr size_t kBwd3Smem = 3 * 64 * 1024 + 1024;
@@ -915,6 +939,23 @@ lstm_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           if (kb == kb0) MNN_TRACE(1);
           const uint32_t a_raw = smem0 + stage * STAGE_BYTES, a_lo = a_raw + A_BYTES;
           const uint32_t b_raw = a_raw + 2 * A_BYTES, b_lo = b_raw + B_BYTES;
+          if (p.bf16x) {
+            // dG.Wh^T ~ hi.hi (tf32) + bf16(dG).bf16(Wh_lo) + bf16(dG_lo).bf16(Wh): both operands K-major, bf16 tiles
+            // [hi | lo] of 8 KB each in the "lo" regions (K-major SWIZZLE_64B, convert_bf16_tiles)
+            const uint32_t idesc16 = idesc_bf16(NA, false, false, 2 * BM);
+#pragma unroll
+            for (int j = 0; j < BK / 16; ++j) {
+              const uint32_t first = (kb > kb0 || j > 0) ? 1u : 0u;
+              umma_bf16_2cta(tmem_x, smem_desc(a_lo + j * 32, 16, 512, 4), smem_desc(b_lo + B_BYTES / 2 + j * 32, 16, 512, 4),
+                             idesc16, first);
+              umma_bf16_2cta(tmem_x, smem_desc(a_lo + A_BYTES / 2 + j * 32, 16, 512, 4), smem_desc(b_lo + j * 32, 16, 512, 4),
+                             idesc16, 1u);
+            }
+#pragma unroll
+            for (int j = 0; j < BK / 8; ++j)
+              umma_tf32_2cta(tmem_d, smem_desc(a_raw + j * 32, 16, 1024, 2), smem_desc(b_raw + j * 32, 16, 1024, 2), idesc,
+                             (kb > kb0 || j > 0) ? 1u : 0u);
+          } else {
 #pragma unroll
           for (int j = 0; j < BK / 8; ++j) {
             const uint64_t da = smem_desc(a_raw + j * 32, 16, 1024, 2), dal = smem_desc(a_lo + j * 32, 16, 1024, 2);
@@ -923,6 +964,7 @@ lstm_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             umma_tf32_2cta(tmem_x, da, dbl, idesc, first);
             umma_tf32_2cta(tmem_x, dal, db, idesc, 1u);
             umma_tf32_2cta(tmem_d, da, db, idesc, first);
+          }
           }
           umma_commit_2cta(bar_empty + 8 * stage);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -968,10 +1010,15 @@ lstm_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             float4* a_lo = reinterpret_cast<float4*>(base + A_BYTES);
             const float4* b_raw = reinterpret_cast<const float4*>(base + 2 * A_BYTES);
             float4* b_lo = reinterpret_cast<float4*>(base + 2 * A_BYTES + B_BYTES);
+            if (p.bf16x) {
+              convert_bf16_tiles<false, 128>(base, base + A_BYTES, tc, true);
+              convert_bf16_tiles<false, 128>(base + 2 * A_BYTES, base + 2 * A_BYTES + B_BYTES, tc, true);
+            } else {
 #pragma unroll 4
-            for (int i = tc; i < A_BYTES / 16; i += 128) a_lo[i] = tf32_lo4(a_raw[i]);
+              for (int i = tc; i < A_BYTES / 16; i += 128) a_lo[i] = tf32_lo4(a_raw[i]);
 #pragma unroll 4
-            for (int i = tc; i < B_BYTES / 16; i += 128) b_lo[i] = tf32_lo4(b_raw[i]);
+              for (int i = tc; i < B_BYTES / 16; i += 128) b_lo[i] = tf32_lo4(b_raw[i]);
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(conv_leader + 8 * stage);
@@ -1377,6 +1424,8 @@ extern "C" int mnn_lstm_seq_fwd_tc(float* gates, const float* wh, float* hbuf, f
     p.gates = gates; p.hbuf = hbuf; p.cbuf = cbuf; p.out = out; p.dscale = dscale; p.u = u; p.keep = keep; p.seed = seed;
     p.T = T; p.B = B; p.R = R; p.t0 = 0; p.t1 = T;
     p.slabs = (B + 2 * BM - 1) / (2 * BM); p.blocks = blocks; p.kb_total = (R + BK - 1) / BK; p.flags = flags;
+    static const char* bf16x_env = getenv("MNN_LSTM_BF16X");   // "0": 3xTF32
+    p.bf16x = (bf16x_env && bf16x_env[0] == '0') ? 0 : 1;
     CUtensorMap ma, mb;
     rc = mnn_tc_make_map(hbuf, R, R, (long long)(T + 1) * B, BM, false, &ma);
     if (rc) return rc;
@@ -1477,6 +1526,8 @@ extern "C" int mnn_lstm_seq_bwd_tc_chunk(float* gates, const float* wh, const fl
     if (splits < 1) splits = 1;
     q.kb_per_split = (kb_total + splits - 1) / splits;
     q.splits = (kb_total + q.kb_per_split - 1) / q.kb_per_split;
+    static const char* bf16x_env = getenv("MNN_LSTM_BF16X");   // "0": 3xTF32 in phase A
+    q.bf16x = (bf16x_env && bf16x_env[0] == '0') ? 0 : 1;
     q.cntA = reinterpret_cast<unsigned int*>(cnt + 1024);
     q.cntB = reinterpret_cast<unsigned int*>(cnt + 2048);
     cudaMemsetAsync(cnt + 1024, 0, 2048, stream);
