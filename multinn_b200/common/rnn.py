@@ -114,6 +114,8 @@ class RNN:
     PIPE_SLOW_HOOKS = int(os.environ.get('MNN_PIPE_SLOW_HOOKS', 0))     # forward chunk hooks under the recurrence; 0: by batch
     PIPE_FULL_WGRADS = int(os.environ.get('MNN_PIPE_FULL_WGRADS', 3))   # last BPTT chunks whose weight grads use every SM
 
+    COLSUM_SIDE_STREAM = os.environ.get('MNN_COLSUM_SIDE', '1') != '0'
+
     TRACE = None        # debug (tools/pipeline_trace.py): list collecting (label, timing event) of the chunk schedule
 
     @classmethod
@@ -366,11 +368,16 @@ class RNN:
                     ops.gemm(w['gates'].view(T * B, -1), kern.data[:i_l], w['d_in'].view(T * B, i_l), transB=True)   # dx = dG Wx^T
                     d = w['d_in']
         # weight gradients: batched GEMMs over all T*B rows
+        side = self.aux_stream(x.device) if (self.COLSUM_SIDE_STREAM and x.is_cuda) else None
         for l in reversed(range(self.num_layers)):
-            self._weight_grads(l, x, ws, dropout, 0, T, B, beta=0.0)
+            self._weight_grads(l, x, ws, dropout, 0, T, B, beta=0.0, side=side)
+        if side is not None:
+            ev = torch.cuda.Event()
+            ev.record(side)
+            torch.cuda.current_stream().wait_event(ev)
         return ws[0]['d_in'] if need_dx else None
 
-    def _weight_grads(self, l, x, ws, dropout, t0, t1, B, beta):
+    def _weight_grads(self, l, x, ws, dropout, t0, t1, B, beta, side=None):
         """dWx_l (+)= in_l^T dG_l, dWh_l (+)= h_{l,t-1}^T dG_l, db_l (+)= colsum(dG_l) over steps [t0, t1)."""
         r = self._num_units[l]
         w = ws[l]
@@ -380,9 +387,18 @@ class RNN:
         dg = w['gates'][t0:t1].view(rows, 4 * r)                       # now d(pre-activations)
         inp = x[t0:t1].view(rows, -1) if l == 0 else \
             (ws[l - 1]['out'] if dropout else ws[l - 1]['hbuf'][1:])[t0:t1].reshape(rows, i_l)
+        if side is not None:
+            # the bias-gradient column sums (HBM-bound, no shared memory) run UNDER the weight-gradient GEMMs (tensor /
+            # shared-memory bound) on a side stream; both read the same dG, so one of them mostly hits L2
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                ops.colsum(dg, self.biases[l].grad, accumulate=beta != 0.0)
         ops.gemm(inp, dg, kern.grad[:i_l], transA=True, beta=beta, a_exact=(l == 0 and self._binary_inputs))
         ops.gemm(w['hbuf'][t0:t1].view(rows, r), dg, kern.grad[i_l:], transA=True, beta=beta)
-        ops.colsum(dg, self.biases[l].grad, accumulate=beta != 0.0)
+        if side is None:
+            ops.colsum(dg, self.biases[l].grad, accumulate=beta != 0.0)
 
     def _backward_wavefront(self, ws, dout, T, B, dropout, need_dx, x_pipe=None):
         """BPTT as a wavefront over time chunks: layer l back-propagates chunk c while layer l-1 works on chunk c+1.

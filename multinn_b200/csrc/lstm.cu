@@ -83,11 +83,12 @@ __global__ void lstm_cell_bwd_kernel(CellBwdArgs a) {
   a.dc[idx] = dc * gf;
 }
 
-// out[c] (+)= sum_r A[r][c]. Two deterministic stages: grid (cols/32, RB) blocks each reduce a row range into
-// ws[rb][c]; a second pass adds the RB partials in a fixed order. HBM-bound: every element of A is read once.
+// out[c] (+)= sum_r A[r][c]. Two deterministic stages: grid (cols/32, RB) blocks of 32x8 threads, every thread reduces
+// its column over every 8th row of the block's row range into ws[rb*8 + ty][c]; a second pass adds the 8*RB partials in
+// a fixed order. HBM-bound: every element of A is read once. No shared memory: the blocks fit beside a resident
+// tensor-core GEMM CTA, so the bias-gradient sums can run under the weight-gradient GEMMs on a side stream.
 __global__ void colsum_partial_kernel(const float* __restrict__ A, long long ld, int rows, int cols, int rows_per_block,
                                       float* __restrict__ ws) {
-  __shared__ float red[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -100,14 +101,7 @@ __global__ void colsum_partial_kernel(const float* __restrict__ A, long long ld,
       s3 += __ldg(A + (size_t)(r + 24) * ld + c);
     }
     for (; r < r1; r += 8) s0 += __ldg(A + (size_t)r * ld + c);
-  }
-  red[threadIdx.y][threadIdx.x] = (s0 + s1) + (s2 + s3);
-  __syncthreads();
-  if (threadIdx.y == 0 && c < cols) {
-    float t = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    ws[(size_t)blockIdx.y * cols + c] = t;
+    ws[((size_t)blockIdx.y * 8 + threadIdx.y) * cols + c] = (s0 + s1) + (s2 + s3);
   }
 }
 
@@ -179,7 +173,7 @@ extern "C" int mnn_lstm_seq_bwd(float* gates, const float* wh, const float* cbuf
   return MNN_OK;
 }
 
-extern "C" size_t mnn_colsum_workspace_bytes(int cols) { return (size_t)64 * (size_t)cols * sizeof(float); }
+extern "C" size_t mnn_colsum_workspace_bytes(int cols) { return (size_t)64 * 8 * (size_t)cols * sizeof(float); }
 
 extern "C" int mnn_colsum(const float* A, long long ld, int rows, int cols, float* out, int accumulate, void* ws,
                           cudaStream_t stream) {
@@ -191,6 +185,6 @@ extern "C" int mnn_colsum(const float* A, long long ld, int rows, int cols, floa
   rb = (rows + rpb - 1) / rpb;
   colsum_partial_kernel<<<dim3((cols + 31) / 32, rb), dim3(32, 8), 0, stream>>>(A, ld, rows, cols, rpb,
                                                                               reinterpret_cast<float*>(ws));
-  colsum_final_kernel<<<(cols + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const float*>(ws), rb, cols, out, accumulate);
+  colsum_final_kernel<<<(cols + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const float*>(ws), rb * 8, cols, out, accumulate);
   return mnn_check_launch("colsum", 2);
 }
