@@ -1,6 +1,5 @@
 """Composer MultINN (mirrors reference models/multinn/multinn_composer.py:17-199): per-track encoders, ONE
 generator with a shared temporal unit and per-track NADEs (RnnMultiNADE) over the stacked encodings."""
-import torch
 
 from ..generators.rnn_multinade import RnnMultiNADE
 from .core import MultINNCore

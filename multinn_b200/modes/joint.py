@@ -2,7 +2,6 @@
 feature axis (D*M dims, feature d*M + m) and ONE generator over its encodings."""
 import torch
 
-from ..generators.rnn_nade import RnnNade
 from ..generators.rnn_rbm import RnnRBM
 from .core import MultINNCore
 

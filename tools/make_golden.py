@@ -80,6 +80,18 @@ def composer_case():
     np.savez_compressed(os.path.join(OUT, 'composer.npz'), **d)
 
 
+def composer_lengths_case():
+    """Variable sequence lengths (utils/sequences.py:6-37) on the composer case's inputs and weights: kept rows only."""
+    g = np.load(os.path.join(OUT, 'composer.npz'))
+    B, T = g['x'].shape[:2]
+    lengths = np.array([T, 2, T - 1, 4][:B], dtype=np.int64)
+    p = dict(lstm=[(g[f'lstm{l}_kernel'], g[f'lstm{l}_bias']) for l in range(2)], dense=(g['dense_kernel'], g['dense_bias']),
+             nade=[(g[f'nade{m}_w_enc'], g[f'nade{m}_w_dec']) for m in range(5)])
+    ref = O.composer_forward(g['x'], O.cast_params(p, np.float64), lengths=lengths)
+    np.savez_compressed(os.path.join(OUT, 'composer_lengths.npz'), lengths=lengths, nll=ref['nll'],
+                        loss=np.float64(ref['loss']), rows=O.flatten_valid_rows(lengths, T))
+
+
 def rbm_case():
     rng = np.random.default_rng(103)
     N, D, H, k = 24, 84, 32, 3
@@ -113,6 +125,7 @@ if __name__ == '__main__':
     nade_case()
     lstm_case()
     composer_case()
+    composer_lengths_case()
     rbm_case()
     optim_case()
     for f in sorted(os.listdir(OUT)):
