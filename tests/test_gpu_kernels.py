@@ -146,6 +146,37 @@ def test_nade_logprob_bwd(N, D, H, M, density):
     assert rel_err(dwd.cpu().numpy(), wd_t.grad.numpy()) < 1e-4
 
 
+@pytest.mark.parametrize("budget", [0, 20])
+def test_nade_row_chunks_and_sm_budget_equal_whole_call(budget):
+    """The chunk pipeline calls the NADE kernels on row slices of the [M,N,..] buffers (track_stride > rows) under an SM
+    budget: forward results are bit-identical to one whole call, accumulated weight gradients equal within fp32 order."""
+    ops = _ops()
+    N, D, H, M = 300, 84, 256, 5
+    x, fc, we, wd = _nade_case(N, D, H, M, seed=77, density=0.07)
+    bits = _bits_of(x)
+    fcd, wed, wdd = dev(fc), dev(we), dev(wd)
+    gscale = 1.0 / (N * M)
+
+    def run(chunks):
+        nll = torch.zeros(M, N, device='cuda')
+        dfc = torch.zeros_like(fcd)
+        dwe, dwd = torch.zeros_like(wed), torch.zeros_like(wdd)
+        ops.set_sm_budget(budget)
+        try:
+            for r0, r1 in chunks:
+                ops.nade_logprob_fwd(bits[:, r0:r1], fcd[r0:r1], 0, M * H, wed, wdd, nll[:, r0:r1], dfc=dfc[r0:r1], gscale=gscale)
+                ops.nade_logprob_bwd(bits[:, r0:r1], fcd[r0:r1], 0, M * H, wed, wdd, dfc[r0:r1], dwe, dwd)
+        finally:
+            ops.set_sm_budget(0)
+        torch.cuda.synchronize()
+        return nll, dfc, dwe, dwd
+    whole = run([(0, N)])
+    parts = run([(0, 96), (96, 97), (97, 300)])
+    assert torch.equal(whole[0], parts[0]) and torch.equal(whole[1], parts[1])
+    assert rel_err(parts[2].cpu().numpy(), whole[2].cpu().numpy()) < 1e-6
+    assert rel_err(parts[3].cpu().numpy(), whole[3].cpu().numpy()) < 1e-6
+
+
 @pytest.mark.parametrize("N,D,H,M", [(200, 84, 256, 5), (37, 84, 256, 1), (64, 20, 128, 2)])
 def test_nade_sample_bit_exact(N, D, H, M):
     ops = _ops()
