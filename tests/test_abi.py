@@ -47,3 +47,31 @@ def test_product_does_not_import_oracle():
             if f.endswith('.py'):
                 s = open(os.path.join(dp, f)).read()
                 assert 'oracle' not in s.replace('# oracle', ''), f'{f} mentions the oracle'
+
+
+def test_argument_errors_are_codes_not_crashes():
+    """The boundary's error behaviour without a GPU: null pointers, non-positive sizes and unsupported shapes are
+    rejected with MNN_ERR_ARG / MNN_ERR_UNSUPPORTED before anything touches the device, and the message is readable
+    through mnn_last_error_string()."""
+    import ctypes as C
+    from multinn_b200 import _lib
+    lib = _lib.lib
+    ERR_ARG, ERR_UNSUPPORTED = -1, -2
+    assert lib.mnn_gemm_tc(None, 4, 0, None, 4, 0, None, 4, None, 1.0, 0.0, 8, 8, 8, 0, None) == ERR_ARG
+    assert 'null pointer' in _lib.last_error()
+    buf = (C.c_float * 64)()
+    p = C.cast(buf, C.c_void_p)
+    assert lib.mnn_gemm_tc(p, 4, 0, p, 4, 0, p, 4, None, 1.0, 0.0, 0, 8, 8, 0, None) == ERR_ARG
+    assert lib.mnn_gemm_tc(p, 3, 0, p, 4, 0, p, 4, None, 1.0, 0.0, 8, 8, 8, 0, None) == ERR_UNSUPPORTED   # TMA row stride
+    assert lib.mnn_nade_logprob_fwd(None, p, 4, 0, 0, p, p, p, None, None, 0.0, 8, 1, 84, 256, 0, None) == ERR_ARG
+    assert lib.mnn_nade_logprob_fwd(p, p, 4, 0, 0, p, p, p, None, None, 0.0, 8, 1, 84, 200, 0, None) == ERR_UNSUPPORTED
+    assert 'num_hidden' in _lib.last_error()
+    assert lib.mnn_nade_logprob_fwd(p, p, 4, 0, 0, p, p, p, None, None, 0.0, 8, 1, 84, 256, 4, None) == ERR_ARG   # stride < N
+    assert lib.mnn_lstm_seq_fwd_tc(p, p, p, p, None, None, None, 1.0, 0, 4, 8, 12, p, 1, None) == ERR_UNSUPPORTED   # R % 8
+    assert lib.mnn_lstm_tc_supported(8, 12) == 0 and lib.mnn_lstm_tc_supported(8, 16) == 1
+    assert lib.mnn_colsum(None, 4, 4, 4, p, 0, p, None) == ERR_ARG
+    assert lib.mnn_scale_rows(p, 4, 4, None, 4, 4, None) == ERR_ARG
+    assert lib.mnn_set_sm_budget(-5) == 0 and lib.mnn_set_sm_budget(0) == 0
+    import pytest
+    with pytest.raises(_lib.MultinnLibraryError):
+        _lib.check(ERR_ARG, 'unit test')
