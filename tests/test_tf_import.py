@@ -1,0 +1,73 @@
+"""TF1-variable import / export (scope-table row f2), CPU: round trips through TF-shaped variables with shuffled order and
+foreign scope prefixes, explicit name maps, and readable failures. (Unverified against a real TF checkpoint -- see the
+module docstring of multinn_b200/utils/tf_import.py.)"""
+import numpy as np
+import pytest
+
+from multinn_b200.multinn import MultINN, default_config, default_params
+from multinn_b200.utils import tf_import as T
+
+
+def _composer(seed):
+    return MultINN(default_config(), default_params(mode='composer', num_hidden=32, num_hidden_rnn=(16, 8), keep_prob=1.0),
+                   'composer', device='cpu', seed=seed)
+
+
+def _same(a, b):
+    sa, sb = a.state_dict(), b.state_dict()
+    return all(np.array_equal(sa[k].numpy(), sb[k].numpy()) for k in sa)
+
+
+def test_composer_round_trip_with_foreign_prefixes_and_shuffled_order():
+    src, dst = _composer(1), _composer(2)
+    assert not _same(src.arena, dst.arena)
+    tfv = T.export_tf_variables(src)
+    assert tfv['generator/rnn/multi_rnn_cell/cell_1/cudnn_compatible_lstm_cell/kernel'].shape == (24, 32)
+    assert tfv['generator/Piano/nade/w_enc'].shape == (84, 1, 32) and tfv['generator/Piano/nade/w_dec'].shape == (84, 32, 1)
+    # whatever scope prefix TF really generated, only leaves + indices + track names matter
+    renamed = {('MultINN/generators/rnn-multinade/all/' + n.split('/', 1)[1] + ':0'): a for n, a in tfv.items()}
+    keys = list(renamed)
+    np.random.default_rng(0).shuffle(keys)
+    applied = T.load_tf_variables(dst, {k: renamed[k] for k in keys})
+    assert _same(src.arena, dst.arena)
+    assert len(applied['generator/nade/w_enc']) == 5 and 'Drums' in applied['generator/nade/w_enc'][0]
+
+
+def test_jamming_tracks_are_matched_by_name():
+    mk = lambda s: MultINN(default_config(), default_params(mode='jamming', num_hidden=32, num_hidden_rnn=(8,), keep_prob=1.0),
+                           'jamming', device='cpu', seed=s)
+    src, dst = mk(3), mk(4)
+    tfv = T.export_tf_variables(src)
+    keys = sorted(tfv, reverse=True)
+    T.load_tf_variables(dst, {k: tfv[k] for k in keys})
+    assert _same(src.arena, dst.arena)
+
+
+def test_dbn_encoder_and_rnn_rbm_round_trip():
+    mk = lambda s: MultINN(default_config(), default_params(mode='joint', encoder='DBN', encoder_hidden=[24, 12], generator='RBM',
+                                                            num_hidden=16, num_hidden_rnn=(8,)), 'joint', device='cpu', seed=s)
+    src, dst = mk(5), mk(6)
+    T.load_tf_variables(dst, T.export_tf_variables(src))
+    T.load_tf_variables(dst, T.export_tf_variables(src, 'encoders'), which='encoders')
+    assert _same(src.arena, dst.arena) and _same(src.encoder_arena, dst.encoder_arena)
+    assert 'encoder/all/rbm/1/W' in T.export_tf_variables(src, 'encoders')
+
+
+def test_explicit_name_map_and_failures():
+    src, dst = _composer(7), _composer(8)
+    tfv = T.export_tf_variables(src)
+    odd = dict(tfv)
+    odd['some/other/name'] = odd.pop('generator/dense/kernel')
+    with pytest.raises(ValueError, match='dense_kernel'):
+        T.load_tf_variables(dst, odd)
+    T.load_tf_variables(dst, odd, name_map={'generator/dense/kernel': 'some/other/name'})
+    assert _same(src.arena, dst.arena)
+    bad = dict(tfv)
+    bad['generator/dense/bias'] = np.zeros(7, np.float32)
+    with pytest.raises(ValueError, match='shape'):
+        T.load_tf_variables(_composer(9), bad)
+    extra = dict(tfv)
+    extra['x/dense_3/kernel'] = np.zeros((2, 2), np.float32)
+    with pytest.raises(ValueError, match='unused TF variables'):
+        T.load_tf_variables(_composer(9), extra)
+    T.load_tf_variables(_composer(9), extra, strict=False)
