@@ -152,7 +152,8 @@ class RNN:
         return st
 
     def _bwd_budgets(self, B):
-        """SM budgets of the two BPTT kernels in pipeline mode (measured: 72,36 best at B=256, 48,24 at B=512)."""
+        """SM budgets of the two BPTT kernels in pipeline mode. Measured: at B=256 (64, 32) gives the same K-splits as
+        (72, 36) and frees 12 SMs for the bulk stream; at B=512 (48, 24) beats both."""
         if self.PIPE_BWD_BUDGETS[0] > 0:
             return self.PIPE_BWD_BUDGETS
         return (64, 32) if B < 512 else (48, 24)
@@ -193,7 +194,7 @@ class RNN:
         """x[T,B,I] time-major -> outputs[T,B,R_top] (dropped out when keep < 1), final state.
         u: optional list (per layer) of [T,B,R_l] uniforms for reproducible dropout; else Philox(seed).
         Saves what BPTT needs (call `backward_sequence` next).
-        chunk_hook(t0, t1, done_event, outs_top, budget, last): pipeline mode (`use_pipeline`); called after the top layer
+        chunk_hook(t0, t1, done_event, outs_top, budget, last): pipeline modes (`use_any_pipeline`); called after the top layer
         has been enqueued up to step t1, the hook enqueues the consumer work of steps [t0, t1) on `bulk_stream` behind
         `done_event` under the SM `budget` (0 = every SM). The first PIPE_SLOW_HOOKS chunks get one budgeted call each
         (they run beside the recurrences), the rest ONE call at full width once the recurrences are through."""
