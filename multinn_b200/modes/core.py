@@ -93,7 +93,7 @@ class MultINNCore(Model, abc.ABC):
             raise ValueError(f'x must be [batch, time, {self.num_dims}, {self.num_tracks}], got {tuple(x.shape)}')
         if lengths is not None and int(torch.as_tensor(lengths).min()) < x.shape[1] and not self._supports_lengths:
             raise NotImplementedError(f'variable sequence lengths are not supported in {self._mode} mode yet '
-                                      '(Composer and Jamming NADE paths support them)')
+                                      '(the NADE generators of the Composer, Jamming and Feedback modes support them)')
         if not x.is_cuda:
             raise ValueError('x must be a CUDA tensor: multinn_b200 has no CPU path')
         if x.dtype in (torch.uint8, torch.bool):          # bool / byte piano-rolls as stored by prepare_data.py:56

@@ -75,7 +75,10 @@ class MultINNFeedback(MultINNCore):
         self._feedback_layer.backward(dfb.reshape(T1 * B, F))
 
     # ------------------------------------------------------------------ train / eval
-    def _forward_backward(self, x, keep, u_drop, seed, u_enc=None, u_fb=None, **extra):
+    _supports_lengths = True      # the generators take `lengths` (multinn_feedback.py:93-94); the feedback module runs
+                                  # over every padded step in training (:76-80 passes no lengths)
+
+    def _forward_backward(self, x, keep, u_drop, seed, u_enc=None, u_fb=None, lengths=None, **extra):
         B, T, D, M = x.shape
         xe, stack, bits = self._encode(x, u_enc, seed)
         fb = self._apply_feedback(stack, keep=keep, u_fb=u_fb, seed=seed + 17)
@@ -86,7 +89,8 @@ class MultINNFeedback(MultINNCore):
             inp = torch.cat([xe[m][:T], fb[:T]], dim=2)                       # multinn_feedback.py:86-88
             loss, nll, dx = gen.forward_backward(inp, bits[m:m + 1], keep=keep,
                                                  u_drop=None if u_drop is None else u_drop[m],
-                                                 seed=seed + 104729 * m, loss_scale=1.0 / M, need_dx=True)
+                                                 seed=seed + 104729 * m, loss_scale=1.0 / M, need_dx=True,
+                                                 lengths=lengths)
             total += loss
             dfb[:T] += dx[:, :, E:]
         self._feedback_backward(dfb)
@@ -99,9 +103,12 @@ class MultINNFeedback(MultINNCore):
         fb = self._apply_feedback(stack, save=False)
         nll = torch.empty(M, T * B, device=x.device)
         for m, gen in enumerate(self._generators):
-            n, _ = gen.log_prob(torch.cat([xe[m][:T], fb[:T]], dim=2), bits[m:m + 1])
+            n, _ = gen.log_prob(torch.cat([xe[m][:T], fb[:T]], dim=2), bits[m:m + 1], lengths=lengths)
             nll[m] = n[0]
         out = {'nll': self.rows_to_reference_order(nll, T, B)}
+        keep_rows = self.valid_rows(lengths, T, B, x.device)
+        if keep_rows is not None:
+            out['nll'] = out['nll'][keep_rows]
         out['batch/loss'] = out['log_likelihood'] = out['nll'].mean(0).mean()
         self._metrics.update(out)
         return out

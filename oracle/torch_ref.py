@@ -202,7 +202,7 @@ def dnn_forward(x, layers):
     return x
 
 
-def feedback_loss(xe, gen_params, fb_params, kind='dense', keep=1.0, u_drop=None, u_fb=None):
+def feedback_loss(xe, gen_params, fb_params, kind='dense', keep=1.0, u_drop=None, u_fb=None, lengths=None):
     """multinn_feedback.py:54-97 / multinn_feedback_rnn.py:41-79 training graph on given per-track encodings.
     xe: list of M tensors [B,T+1,E] (zero-padded, already encoded). gen_params: list of rnn-nade param dicts (LSTM input
     = E + F). fb_params: dense -> [(K,b)..]; rnn -> [(kernel,bias)..]. Returns (loss, nll[N,M])."""
@@ -218,7 +218,8 @@ def feedback_loss(xe, gen_params, fb_params, kind='dense', keep=1.0, u_drop=None
     for m in range(M):
         inp = torch.cat([xe[m], fb], dim=2)[:, :-1]
         tgt = xe[m][:, 1:]
-        l, n = rnn_nade_loss(inp, tgt, gen_params[m], keep, None if u_drop is None else u_drop[m])
+        l, n = rnn_nade_loss(inp, tgt, gen_params[m], keep, None if u_drop is None else u_drop[m],
+                             lengths)       # the generators alone see `lengths` (multinn_feedback.py:93-94)
         losses.append(l)
         nlls.append(n)
     return torch.stack(losses).mean(), torch.stack(nlls, 1)

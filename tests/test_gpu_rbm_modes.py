@@ -345,3 +345,39 @@ def test_chunk_pipeline_in_multi_generator_modes(mode):
     (l1, g1), (l0, g0) = results
     assert abs(l1 - l0) / l0 < 1e-6
     assert float((g1 - g0).norm() / g0.norm()) < 1e-5
+
+
+@pytest.mark.parametrize("mode", ['feedback', 'feedback-rnn'])
+def test_feedback_modes_variable_lengths(mode):
+    """Variable `lengths` reach the generators only (multinn_feedback.py:93-94): kept-row NLL, loss and the gradients of
+    the feedback module and of a generator against the oracle."""
+    B, T, M = 4, 7, 5
+    lengths = np.array([7, 3, 5, 1])
+    model = _fb_case(mode, 'Pass')
+    core = model._model
+    sd = sd_np(core.arena)
+    x = O.synthetic_pianoroll(B, T, seed=14, density=0.1)
+    kind = 'dense' if mode == 'feedback' else 'rnn'
+    pad = np.concatenate([np.zeros((B, 1, 84, M), np.float32), x], axis=1)
+    xe = [pad[..., m].astype(f64) for m in range(M)]
+    gp = [O.cast_params(rnn_nade_params(sd, f'generator/{t}', 2), f64) for t in model.tracks]
+    names = [f'feedback/dense_{i}/{n}' for i in range(2) for n in ('kernel', 'bias')] if kind == 'dense' else \
+        [f'feedback/rnn/cell_{i}/{n}' for i in range(2) for n in ('kernel', 'bias')]
+    fbp = [(sd[names[2 * l]].astype(f64), sd[names[2 * l + 1]].astype(f64)) for l in range(2)]
+    tt = lambda tree: R.to_torch(tree, torch.float64, requires_grad=True)
+    gpt, fbt = [tt(p) for p in gp], tt(fbp)
+    loss, nll = R.feedback_loss([torch.tensor(a) for a in xe], gpt, fbt, kind, lengths=lengths)
+    out = model.evaluate(cu(x), lengths=torch.from_numpy(lengths))
+    assert out['nll'].shape == (int(lengths.sum()), M)
+    np.testing.assert_allclose(out['nll'].cpu().numpy(), nll.detach().numpy(), rtol=1e-4)
+    leaves = R.flat_params(gpt) + R.flat_params(fbt)
+    grads = torch.autograd.grad(loss, leaves)
+    core.arena.grad.zero_()
+    l = core._forward_backward(core._check_x(cu(x), lengths), keep=1.0, u_drop=None, seed=0, lengths=lengths)
+    assert abs(float(l) - float(loss)) / float(loss) < 1e-5
+    named = core.arena.named()
+    for name, g in zip(names, grads[-4:]):
+        got = named[name].grad.cpu().double()
+        assert float((got - g).norm() / g.norm()) < 2e-4, name
+    got = named[f'generator/{model.tracks[0]}/rnn/cell_0/kernel'].grad.cpu().double()
+    assert float((got - grads[0]).norm() / grads[0].norm()) < 2e-4
