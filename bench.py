@@ -130,7 +130,12 @@ def run_reference(args):
         return
     wl = WORKLOADS[args.workload]
     sB, sT = args.cpu_batch, wl['T']
-    v, cores, loss, sec = cpu_port_run(sB, sT, max(1, args.steps), min(args.warmup, 1))
+    steps = max(1, args.steps)
+    # bounded sample: keep the whole run within a few minutes whatever --steps asks for (calibrated on 8 rows)
+    v0, _, _, _ = cpu_port_run(8, sT, 1, 0)
+    cap = int(args.cpu_seconds * v0 / (steps * sT)) // 8 * 8
+    sB = max(8, min(sB, cap))
+    v, cores, loss, sec = cpu_port_run(sB, sT, steps, min(args.warmup, 1))
     sample = (f'[{sB},{sT},84,5] slice of the workload per step ({sec:.2f} s/step), torch-CPU fp32 op-for-op '
               f'restatement of the TF1 graph (TF 1.13.1 not installable), keep_prob 0.9')
     print(json.dumps({
@@ -366,6 +371,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='C5', choices=sorted(WORKLOADS))
     ap.add_argument('--cpu-batch', type=int, default=128, help='batch rows of the bounded CPU sample')
+    ap.add_argument('--cpu-seconds', type=float, default=150.0, help='wall-clock bound of the reference arm\'s timed steps')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-sampling', action='store_true')
     ap.add_argument('--batch', type=int, default=0, help='override the global batch (development aid)')
