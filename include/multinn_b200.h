@@ -135,6 +135,18 @@ int mnn_nade_sample(const float* fc, long long ld, int enc_col0, int dec_col0, c
 int mnn_bias_sigmoid_sample(const float* pre, long long ld_pre, const float* bias, long long ld_bias, const float* u,
                             long long ld_u, int use_philox, unsigned long long seed, unsigned long long offset,
                             float* p, long long ld_p, float* s, long long ld_s, int N, int C, mnn_stream_t stream);
+/* K7 fused -- the whole k-step Gibbs chain of common/rbm.py:192-231 (tf.while_loop of 2k {matmul, sigmoid, Bernoulli}
+ * pairs) in ONE launch: v0[N,D] -> p_v = p(v | h_k) of the last step, v_k, and optionally h_k. W[D,H] (contiguous) and its
+ * transpose are staged in shared memory; bh/bv are per-row [N,.] (ld > 0) or one broadcast row (ld == 0) or NULL;
+ * uh[k,N,H] / uv[k,N,D] contiguous uniforms (parity runs) or both NULL with use_philox (counter = (offset + row,
+ * half-step, column group), key = seed: a function of the global row only). mnn_rbm_gibbs_smem_bytes() is 0 for shapes
+ * the kernel does not take (D, H multiples of 4, <= 256, 2*D*H floats + buffers within 227 KB): callers then run the
+ * chain as GEMM + mnn_bias_sigmoid_sample half-steps. All float pointers but v0 16-byte aligned, strides % 4 == 0. */
+size_t mnn_rbm_gibbs_smem_bytes(int D, int H);
+int mnn_rbm_gibbs(const float* v0, long long ld_v, const float* W, const float* bh, long long ld_bh, const float* bv,
+                  long long ld_bv, const float* uh, const float* uv, int use_philox, unsigned long long seed,
+                  unsigned long long offset, float* p_v, long long ld_p, float* v_k, long long ld_vk, float* h_k,
+                  long long ld_hk, int N, int D, int H, int k, mnn_stream_t stream);
 /* d(pre) = dy * y * (1 - y): backward of a sigmoid layer (Dense feedback module, common/dnn.py:56-60). */
 int mnn_sigmoid_bwd(const float* y, long long ld_y, const float* dy, long long ld_dy, float* dpre, long long ld_d, int N,
                     int C, mnn_stream_t stream);

@@ -54,6 +54,8 @@ SIGNATURES = {
     "mnn_nade_logprob_bwd": [_p, _p, _ll, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _ll, _p],
     "mnn_nade_sample": [_p, _ll, _i, _i, _p, _p, _p, _i, _u64, _u64, _p, _ll, _i, _i, _p, _i, _i, _i, _i, _p],
     "mnn_bias_sigmoid_sample": [_p, _ll, _p, _ll, _p, _ll, _i, _u64, _u64, _p, _ll, _p, _ll, _i, _i, _p],
+    "mnn_rbm_gibbs_smem_bytes": [_i, _i],
+    "mnn_rbm_gibbs": [_p, _ll, _p, _p, _ll, _p, _ll, _p, _p, _i, _u64, _u64, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _p],
     "mnn_sigmoid_bwd": [_p, _ll, _p, _ll, _p, _ll, _i, _i, _p],
     "mnn_rbm_free_energy": [_p, _ll, _p, _ll, _p, _ll, _p, _ll, _p, _i, _i, _i, _p],
     "mnn_reduce_workspace_bytes": [],
@@ -65,7 +67,8 @@ SIGNATURES = {
     "mnn_clip_sgd": [_p, _p, _sz, _p, _f, _f, _f, _p],
 }
 _RESTYPES = {"mnn_last_error_string": C.c_char_p, "mnn_launch_count": C.c_ulonglong, "mnn_reduce_workspace_bytes": C.c_size_t,
-             "mnn_colsum_workspace_bytes": C.c_size_t, "mnn_lstm_workspace_bytes": C.c_size_t}
+             "mnn_colsum_workspace_bytes": C.c_size_t, "mnn_lstm_workspace_bytes": C.c_size_t,
+             "mnn_rbm_gibbs_smem_bytes": C.c_size_t}
 
 for _name, _args in SIGNATURES.items():
     _fn = getattr(lib, _name, None)

@@ -2,8 +2,10 @@
 
 Bernoulli sampling contract (TFP 0.6.0, rbm.py:375-387): sample = float(u < p), strict. Every sampling method takes
 optional uniforms `u` (parity runs) and otherwise uses the in-kernel Philox generator keyed by (seed, offset).
-The k-step Gibbs chain is `forward`/`reconstruct` half-steps: a tensor-core GEMM followed by the fused
-bias + sigmoid + Bernoulli kernel (csrc/rbm.cu).
+The k-step Gibbs chain runs as ONE launch of the fused kernel `mnn_rbm_gibbs` (W and its transpose in shared memory,
+bias + sigmoid + Bernoulli in registers, csrc/rbm.cu) when the shape fits (D, H <= 256, e.g. the 84 x 256 generator RBM
+and the 84/168 DBN layers); larger layers (the Joint encoder's 420 x 168) and single half-steps (`forward`,
+`reconstruct`) run a tensor-core GEMM followed by the fused bias + sigmoid + Bernoulli kernel.
 """
 import torch
 
@@ -70,6 +72,18 @@ class RBM(Model):
         """rbm.py:192-231: k-step Gibbs chain from v. k=None -> self.k (quirk Q1: the docstring's intent).
         u = (uh[k,N,H], uv[k,N,D]) or None. Returns (p_v of the last step, v_k); k == 0 returns (v, v)."""
         k = self._k if k is None else k
+        if k > 0 and ops.GIBBS_MODE == 'fused':
+            bh_ = self.bh.data if bh is None else bh
+            bv_ = self.bv.data if bv is None else bv
+            if ops.rbm_gibbs_supported(v, self.W.data, bh_, bv_, u):
+                N = v.shape[0]
+                p_v = torch.empty(N, self._num_dims, device=v.device)
+                vk = torch.empty(N, self._num_dims, device=v.device)
+                uu = None if u is None else (u[0][:k], u[1][:k])
+                # Philox: the chain's stream is keyed by the row, so only one offset unit per call is consumed per row
+                ops.rbm_gibbs(v, self.W.data, bh_, bv_, k, p_v=p_v, v_k=vk, u=uu,
+                              seed=self._seed if seed is None else seed, offset=self._next_offset(N))
+                return p_v, vk
         p_v, vk = v, v
         for s in range(k):
             _, hk = self.forward(vk, bh, u=None if u is None else u[0][s], seed=seed)

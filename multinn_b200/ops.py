@@ -187,6 +187,46 @@ def bias_sigmoid_sample(pre, bias=None, u=None, p=None, s=None, use_philox=False
                                       _rowstride(s) if s is not None else 0, N, Cc, _stream()), "bias_sigmoid_sample")
 
 
+GIBBS_MODE = "fused"    # "fused": one launch per k-step chain (mnn_rbm_gibbs) where the shape fits; "gemm": 2k GEMM + half-step launches
+
+
+def _bias_ld(b, N):
+    if b is None:
+        return 0
+    return b.stride(0) if (b.dim() == 2 and b.shape[0] == N and N > 1) else 0
+
+
+def rbm_gibbs_supported(v0, W, bh=None, bv=None, u=None):
+    """True if mnn_rbm_gibbs takes this chain: shape fits shared memory, operands 16-byte aligned, contiguous uniforms."""
+    D, H = W.shape
+    if not int(lib.mnn_rbm_gibbs_smem_bytes(D, H)) or not W.is_contiguous() or v0.dim() != 2 or v0.stride(1) != 1:
+        return False
+    if u is not None and not (torch.is_tensor(u[0]) and torch.is_tensor(u[1]) and u[0].dim() == 3 and u[1].dim() == 3):
+        return False
+    for t in (W, bh, bv) + (tuple(u) if u is not None else ()):
+        if t is not None and (t.data_ptr() % 16 or (t.dim() == 2 and t.shape[0] > 1 and t.stride(0) % 4)
+                              or t.stride(-1) != 1):
+            return False
+    if u is not None and not (u[0].is_contiguous() and u[1].is_contiguous()):
+        return False
+    return True
+
+
+def rbm_gibbs(v0, W, bh, bv, k, p_v=None, v_k=None, h_k=None, u=None, seed=0, offset=0):
+    """k-step Gibbs chain from v0[N,D] in one launch: fills p_v[N,D] (last step's probabilities), v_k[N,D], h_k[N,H].
+    bh/bv: [N,.] per-row or [1,.]/[.] broadcast biases. u = (uh[k,N,H], uv[k,N,D]) or None (in-kernel Philox)."""
+    N, D = v0.shape
+    H = W.shape[1]
+    uh, uv = (None, None) if u is None else (u[0], u[1])
+    if u is not None:
+        assert tuple(uh.shape[-3:]) == (k, N, H) and tuple(uv.shape[-3:]) == (k, N, D), "u = (uh[k,N,H], uv[k,N,D])"
+    check(lib.mnn_rbm_gibbs(_ptr(v0), _rowstride(v0), _ptr(W), _ptr(bh), _bias_ld(bh, N), _ptr(bv), _bias_ld(bv, N),
+                            _ptr(uh), _ptr(uv), int(u is None), seed, offset, _ptr(p_v),
+                            _rowstride(p_v) if p_v is not None else 0, _ptr(v_k),
+                            _rowstride(v_k) if v_k is not None else 0, _ptr(h_k),
+                            _rowstride(h_k) if h_k is not None else 0, N, D, H, int(k), _stream()), "rbm_gibbs")
+
+
 def sigmoid_bwd(y, dy, dpre):
     N, Cc = y.shape
     check(lib.mnn_sigmoid_bwd(_ptr(y), _rowstride(y), _ptr(dy), _rowstride(dy), _ptr(dpre), _rowstride(dpre), N, Cc,

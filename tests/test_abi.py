@@ -72,6 +72,19 @@ def test_argument_errors_are_codes_not_crashes():
     assert lib.mnn_colsum(None, 4, 4, 4, p, 0, p, None) == ERR_ARG
     assert lib.mnn_scale_rows(p, 4, 4, None, 4, 4, None) == ERR_ARG
     assert lib.mnn_set_sm_budget(-5) == 0 and lib.mnn_set_sm_budget(0) == 0
+    # fused Gibbs chain: shapes it takes / refuses, and its argument checks
+    assert lib.mnn_rbm_gibbs_smem_bytes(84, 256) == (2 * 84 * 256 + 8 * 4 * (84 + 256)) * 4
+    assert lib.mnn_rbm_gibbs_smem_bytes(168, 84) > 0 and lib.mnn_rbm_gibbs_smem_bytes(84, 168) > 0
+    assert lib.mnn_rbm_gibbs_smem_bytes(420, 168) == 0 and lib.mnn_rbm_gibbs_smem_bytes(84, 254) == 0
+    assert lib.mnn_rbm_gibbs_smem_bytes(256, 256) == 0                      # 512 KB of weights
+    g = lambda *a: lib.mnn_rbm_gibbs(*a)
+    assert g(None, 84, p, None, 0, None, 0, None, None, 1, 0, 0, p, 84, p, 84, None, 0, 8, 84, 256, 2, None) == ERR_ARG
+    assert g(p, 84, p, None, 0, None, 0, None, None, 0, 0, 0, p, 84, p, 84, None, 0, 8, 84, 256, 2, None) == ERR_ARG
+    assert 'philox' in _lib.last_error()
+    assert g(p, 84, p, None, 0, None, 0, p, None, 0, 0, 0, p, 84, p, 84, None, 0, 8, 84, 256, 2, None) == ERR_ARG   # uh without uv
+    assert g(p, 420, p, None, 0, None, 0, None, None, 1, 0, 0, p, 420, p, 420, None, 0, 8, 420, 168, 2, None) == ERR_UNSUPPORTED
+    assert g(p, 84, p, None, 0, None, 0, None, None, 1, 0, 0, p, 84, p, 84, None, 0, 8, 84, 256, 0, None) == ERR_ARG    # k == 0
+    assert g(p, 84, p, None, 0, None, 0, None, None, 1, 0, 0, p, 83, p, 84, None, 0, 8, 84, 256, 2, None) == ERR_ARG    # ld_p % 4
     import pytest
     with pytest.raises(_lib.MultinnLibraryError):
         _lib.check(ERR_ARG, 'unit test')

@@ -80,6 +80,97 @@ def test_rbm_gibbs_free_energy_and_cd():
     np.testing.assert_allclose(new['rbm/bh'], bh + dbh, rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize('N,D,H,k,rowbias', [(70, 84, 256, 3, True), (33, 84, 168, 2, False), (64, 168, 84, 2, True),
+                                             (5, 20, 64, 10, True), (1, 84, 256, 1, False), (258, 84, 128, 4, True)])
+def test_fused_gibbs_chain_equals_oracle_and_half_step_path(N, D, H, k, rowbias):
+    """mnn_rbm_gibbs (one launch per chain, W + W^T in shared memory) against the fp64 oracle chain (rbm.py:192-231) and
+    against the GEMM + half-step path, same uniforms: samples bit-exact, last-step probabilities to 2e-5."""
+    from multinn_b200 import ops
+    from multinn_b200.common.rbm import RBM
+    from multinn_b200.params import ParamArena
+    rng = np.random.default_rng(N * 1000 + D + H)
+    arena = ParamArena()
+    rbm = RBM(D, H, k=k, arena=arena, name='rbm')
+    arena.finalize('cuda', seed=7)
+    arena.load('rbm/bh', rng.standard_normal((1, H)) * 0.2)
+    arena.load('rbm/bv', rng.standard_normal((1, D)) * 0.2)
+    W, bh, bv = (sd_np(arena)[n].astype(f64) for n in ('rbm/W', 'rbm/bh', 'rbm/bv'))
+    v = (rng.random((N, D)) < 0.1).astype(np.float32)
+    v[N // 2] = 0.0                                                    # an all-zero row (every input dim skipped)
+    bh_t = (rng.standard_normal((N, H)) * 0.3).astype(np.float32) if rowbias else None
+    bv_t = (rng.standard_normal((N, D)) * 0.3).astype(np.float32) if rowbias else None
+    bh_o = bh if bh_t is None else bh_t.astype(f64)
+    bv_o = bv if bv_t is None else bv_t.astype(f64)
+    for _ in range(200):     # uniforms whose every comparison along the fp64 chain has a margin fp32 rounding cannot cross
+        uh, uv = rng.random((k, N, H), dtype=np.float32), rng.random((k, N, D), dtype=np.float32)
+        vv, margin = v.astype(f64), 1.0
+        for s_ in range(k):
+            ph = O.rbm_cond_prob_h(vv, W, bh_o)
+            hh = (uh[s_] < ph).astype(f64)
+            pv = O.rbm_cond_prob_v(hh, W, bv_o)
+            vv = (uv[s_] < pv).astype(f64)
+            margin = min(margin, float(np.abs(uh[s_] - ph).min()), float(np.abs(uv[s_] - pv).min()))
+        if margin > 2e-6:
+            break
+    assert margin > 2e-6
+    assert ops.rbm_gibbs_supported(cu(v), rbm.W.data, None, None, (cu(uh), cu(uv)))
+    args = (cu(v), None if bh_t is None else cu(bh_t), None if bv_t is None else cu(bv_t))
+    assert ops.GIBBS_MODE == 'fused'
+    p_f, v_f = rbm.sample(*args, u=(cu(uh), cu(uv)))
+    ops.GIBBS_MODE = 'gemm'
+    try:
+        p_g, v_g = rbm.sample(*args, u=(cu(uh), cu(uv)))
+    finally:
+        ops.GIBBS_MODE = 'fused'
+    rp, rv = O.rbm_gibbs(v.astype(f64), W, bh_o, bv_o, k, uh.astype(f64), uv.astype(f64))
+    np.testing.assert_array_equal(v_f.cpu().numpy(), rv)
+    np.testing.assert_array_equal(v_g.cpu().numpy(), rv)
+    np.testing.assert_allclose(p_f.cpu().numpy(), rp, rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(p_f.cpu().numpy(), p_g.cpu().numpy(), rtol=2e-5, atol=1e-7)
+    # direct call: h_k output, a strided v0 view and the k-prefix of longer uniform tensors
+    wide = torch.zeros(N, D + 12, device='cuda')
+    wide[:, 4:4 + D] = cu(v)
+    h_k = torch.empty(N, H, device='cuda')
+    v_k = torch.empty(N, D, device='cuda')
+    ops.rbm_gibbs(wide[:, 4:4 + D], rbm.W.data, args[1] if rowbias else rbm.bh.data, args[2] if rowbias else rbm.bv.data,
+                  k, v_k=v_k, h_k=h_k, u=(cu(uh), cu(uv)))
+    assert torch.equal(v_k, v_f)
+    vv = v.astype(f64)
+    for s in range(k):                                                 # oracle half-steps up to h_k
+        _, hh = O.rbm_forward(vv, W, bh_o, uh[s].astype(f64))
+        _, vv = O.rbm_reconstruct(hh, W, bv_o, uv[s].astype(f64))
+    np.testing.assert_array_equal(h_k.cpu().numpy(), hh)
+
+
+def test_fused_gibbs_philox_statistics_and_determinism():
+    from multinn_b200 import ops
+    from multinn_b200.common.rbm import RBM
+    from multinn_b200.params import ParamArena
+    arena = ParamArena()
+    rbm = RBM(84, 256, k=2, arena=arena, name='rbm')
+    arena.finalize('cuda', seed=2)
+    rbm.W.data.zero_()                              # zero weights and biases: every conditional is exactly 0.5
+    v = torch.zeros(4098, 84, device='cuda')
+    p1, v1 = rbm.sample(v)
+    assert torch.all(p1 == 0.5) and set(np.unique(v1.cpu().numpy())) <= {0.0, 1.0}
+    assert abs(float(v1.mean()) - 0.5) < 0.005
+    cols = v1.mean(0)
+    assert float((cols - 0.5).abs().max()) < 0.05   # no stuck column group
+    _, v2 = rbm.sample(v)
+    assert not torch.equal(v1, v2)                  # fresh noise on every call (quirk Q12)
+    outs = []
+    for _ in range(2):                              # same (seed, offset): the same chain
+        vk, hk = torch.empty(4098, 84, device='cuda'), torch.empty(4098, 256, device='cuda')
+        ops.rbm_gibbs(v, rbm.W.data, rbm.bh.data, rbm.bv.data, 2, v_k=vk, h_k=hk, seed=11, offset=5)
+        outs.append((vk, hk))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert abs(float(outs[0][1].mean()) - 0.5) < 0.005
+    # keyed by the global row: rows [100:200) of a chain at offset 5 == rows [0:100) at offset 105
+    vk = torch.empty(100, 84, device='cuda')
+    ops.rbm_gibbs(v[:100], rbm.W.data, rbm.bh.data, rbm.bv.data, 2, v_k=vk, seed=11, offset=105)
+    assert torch.equal(vk, outs[0][0][100:200])
+
+
 def test_rbm_philox_half_step_statistics():
     from multinn_b200.common.rbm import RBM
     from multinn_b200.params import ParamArena
