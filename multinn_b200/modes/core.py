@@ -268,6 +268,21 @@ class MultINNCore(Model, abc.ABC):
         num_steps = num_beats * dc['beat_resolution'] * pitch_span // self.num_dims
         return lambda x, u=None, seed=0: self.generate(x, num_steps, u=u, seed=seed)
 
+    def evaluator(self):
+        """multinn_core.py:343-362: returns `evaluate_music(x) -> {summary scope: value}`: x[B,T,num_dims,M] (device tensor
+        or array, data or generated samples) reshaped into bar music and scored with the musical metrics
+        (metrics/musical_tf.py:186-229). Reporting code: runs on the host in NumPy, once per sampling run."""
+        from ..metrics import musical
+        dc = self._config['data']
+        pitch_span = dc['pitch_range']['highest'] - dc['pitch_range']['lowest']
+        beat_resolution, tracks = dc['beat_resolution'], self.tracks
+
+        def evaluate_music(x):
+            x = x.detach().cpu().numpy() if torch.is_tensor(x) else x
+            return musical.metric_summary(musical.to_bars(x, beat_resolution, pitch_span), tracks)
+
+        return evaluate_music
+
     # ------------------------------------------------------------------ checkpoints (model.py:180-234: trainable vars only)
     def state_dict(self):
         return {'generators': self._arena.state_dict(), 'encoders': self._enc_arena.state_dict()}

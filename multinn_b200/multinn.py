@@ -33,7 +33,8 @@ class MultINN:
 def default_config(num_pixels=1, instruments=('Drums', 'Piano', 'Guitar', 'Bass', 'Strings'), beat_resolution=12):
     """The keys of reference configs/default_config.yaml that the hot path reads."""
     return {'data': {'beat_resolution': beat_resolution, 'pitch_range': {'lowest': 24, 'highest': 108},
-                     'instruments': list(instruments)},
+                     'instruments': list(instruments), 'programs': [0, 0, 24, 32, 48][:len(instruments)],
+                     'is_drums': [True, False, False, False, False][:len(instruments)], 'tempo': 120},
             'training': {'random_seed': 23, 'batch_size': 32, 'num_pixels': num_pixels, 'piece_size': 16,
                          'learning_rate': 0.01, 'clip_norm': 5.},
             'sampling': {'num_songs': 3, 'intro_beats': 8, 'sample_beats': 88}}

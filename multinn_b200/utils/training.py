@@ -143,6 +143,31 @@ def generate_music(model, sampler, intro_songs, num_songs=5, concat=True, device
     return np.concatenate([intro.astype(samples.dtype), samples], axis=1) if concat else samples
 
 
+def sample_songs(model, X_train, X_valid, config, epoch=0, samples_dir=None, eval_samples=False, device='cuda', u=None,
+                 seed=0, name='MultINN'):
+    """The sampling run of sample.py:40-115 after the checkpoint is loaded: intros from the train/valid splits ->
+    `model.sampler(sample_beats)` -> generate_music (intro + samples) -> pad_to_midi -> MIDI files of the `save_ids`
+    (when `samples_dir` is given) -> musical metrics of all samples (when `eval_samples`).
+    Returns dict(samples[N, steps, 128, tracks], paths, metrics, table)."""
+    from ..metrics import musical
+    from .data import pad_to_midi, prepare_sampling_inputs, save_music
+    dc, sc = config['data'], config['sampling']
+    beat_size = float(dc['beat_resolution'] / config['training']['num_pixels'])    # sample.py:39: steps per beat
+    intro_songs, save_ids, song_labels = prepare_sampling_inputs(X_train, X_valid, sc, beat_size)
+    sampler = model.sampler(num_beats=sc['sample_beats'])
+    music = generate_music(model, sampler, intro_songs, num_songs=sc['num_songs'], device=device, u=u, seed=seed)
+    samples = pad_to_midi(music, dc)
+    out = {'samples': samples, 'paths': [], 'metrics': None, 'table': None}
+    if samples_dir is not None:
+        out['paths'] = save_music(samples[save_ids], num_intro=len(save_ids) // sc['num_save'], data_config=dc,
+                                  base_path=f'eval_{name}_e{epoch}', save_dir=samples_dir, song_labels=song_labels)
+    if eval_samples:
+        bars = samples.reshape((samples.shape[0], -1, dc['beat_resolution'] * 4) + samples.shape[-2:])
+        out['metrics'] = musical.sample_metrics(bars)
+        out['table'] = musical.format_sample_metrics(out['metrics'])
+    return out
+
+
 def train_epoch(step, X_train, len_train, batch_size, piece_size, epoch, stats, loss_accum=None, device='cuda',
                 fetch_every=1):
     """One epoch of train.py:153-200: np.random.seed(epoch), shuffle the song ids, feed every batch piece to `step`

@@ -140,3 +140,125 @@ def test_fit_early_stopping_checkpoints_and_step_counter(tmp_path):
     for shape, lens, _ in model.calls:
         assert shape[1] == max(lens) <= 4 and len(lens) == shape[0] and min(lens) > 0
     assert abs(hist[0]['valid_log_likelihood'] - 5.0) < 1e-12
+
+
+# ----------------------------------------------------------------------------- sample post-processing (row f4)
+def _parse_smf(data):
+    """Minimal Standard MIDI File reader for the round-trip test: returns (format, division, [track event lists]) with
+    events (tick, status, data bytes)."""
+    assert data[:4] == b'MThd' and int.from_bytes(data[4:8], 'big') == 6
+    fmt, ntrk, div = (int.from_bytes(data[8 + 2 * i:10 + 2 * i], 'big') for i in range(3))
+    pos, tracks = 14, []
+    for _ in range(ntrk):
+        assert data[pos:pos + 4] == b'MTrk'
+        n = int.from_bytes(data[pos + 4:pos + 8], 'big')
+        body, pos = data[pos + 8:pos + 8 + n], pos + 8 + n
+        i, tick, ev = 0, 0, []
+        while i < len(body):
+            delta = 0
+            while True:
+                delta = (delta << 7) | (body[i] & 0x7F)
+                i += 1
+                if not body[i - 1] & 0x80:
+                    break
+            tick += delta
+            st = body[i]
+            if st == 0xFF:
+                ln = body[i + 2]
+                ev.append((tick, 0xFF, bytes(body[i + 1:i + 3 + ln])))
+                i += 3 + ln
+            elif st & 0xF0 == 0xC0:
+                ev.append((tick, st, bytes(body[i + 1:i + 2])))
+                i += 2
+            else:
+                ev.append((tick, st, bytes(body[i + 1:i + 3])))
+                i += 3
+        tracks.append(ev)
+    assert pos == len(data)
+    return fmt, div, tracks
+
+
+def test_midi_export_round_trip(tmp_path):
+    from multinn_b200.multinn import default_config
+    from multinn_b200.utils import data as D
+    cfg = default_config()['data']
+    rng = np.random.default_rng(0)
+    x = (rng.random((2, 40, 84, 5)) < 0.06).astype(np.float32)
+    x[0, 38:40, 10, 1] = 1.0                                        # a note still sounding at the end of the song
+    music = D.pad_to_midi(x, cfg)
+    assert music.shape == (2, 40, 128, 5) and music[:, :, :24].sum() == 0 and music[:, :, 108:].sum() == 0
+    paths = D.save_music(music, 1, cfg, 'unit', save_dir=str(tmp_path), song_labels=['t3'])
+    assert [p.split('/')[-1] for p in paths] == ['unit_t3_0.mid', 'unit_t3_1.mid']          # data.py:196-200 names
+    for s, path in enumerate(paths):
+        fmt, div, tracks = _parse_smf(open(path, 'rb').read())
+        assert fmt == 1 and div == cfg['beat_resolution'] and len(tracks) == 6
+        assert tracks[0][0] == (0, 0xFF, b'\x51\x03' + (500000).to_bytes(3, 'big'))         # 120 bpm
+        for m, name in enumerate(cfg['instruments']):
+            ev = tracks[m + 1]
+            prog = [e for e in ev if e[1] & 0xF0 == 0xC0]
+            assert len(prog) == 1 and prog[0][2][0] == cfg['programs'][m]
+            ch = prog[0][1] & 0x0F
+            assert (ch == 9) == cfg['is_drums'][m]
+            roll = np.zeros((40, 128), bool)
+            sounding = {}
+            gain = D.TRACK_GAIN.get(name, 1.0)
+            for tick, st, d in ev:
+                if st & 0xF0 == 0x90:
+                    assert d[1] == int(round(100 * gain)) and d[0] not in sounding
+                    sounding[d[0]] = tick
+                elif st & 0xF0 == 0x80:
+                    roll[sounding.pop(d[0]):tick, d[0]] = True
+            assert not sounding
+            np.testing.assert_array_equal(roll, music[s, :, :, m] > 0)
+
+
+def test_evaluator_scores_bar_music():
+    """model.evaluator() (multinn_core.py:343-362) = reshape to bars + metric summary; needs no device."""
+    from multinn_b200.metrics import musical
+    from multinn_b200.modes.core import MultINNCore
+    from multinn_b200.multinn import default_config
+
+    class Stub:
+        _config = default_config()
+        tracks = list(_config['data']['instruments'])
+    x = (np.random.default_rng(1).random((2, 96, 84, 5)) < 0.05).astype(np.float32)
+    got = MultINNCore.evaluator(Stub())(x)
+    want = musical.metric_summary(x.reshape(2, 2, 48, 84, 5), Stub.tracks)
+    assert got == want and len(got) == 29
+    import torch
+    assert MultINNCore.evaluator(Stub())(torch.from_numpy(x)) == want
+
+
+def test_sample_songs_driver_with_stub_sampler(tmp_path):
+    """sample.py:40-115 after the checkpoint load, with a sampler stub on the host (device='cpu'): tiling of the intros,
+    intro + samples concatenation, 128-pitch padding, the saved ids / file names, and the metric table."""
+    import torch
+    from multinn_b200.multinn import default_config
+    cfg = default_config()
+    cfg['sampling'] = {'num_songs': 2, 'intro_beats': 2, 'sample_beats': 10, 'num_save': 2,
+                       'intro_ids': {'train': {'start': 0, 'end': 2}, 'valid': {'start': 1, 'end': 2}},
+                       'save_ids': {'train': [1], 'valid': [0]}}
+    rng = np.random.default_rng(4)
+    Xt = (rng.random((3, 30, 84, 5)) < 0.05).astype(np.float32)
+    Xv = (rng.random((2, 30, 84, 5)) < 0.05).astype(np.float32)
+    seen = {}
+
+    class Model:
+        def sampler(self, num_beats):
+            steps = num_beats * 12
+
+            def sample(x, u=None, seed=0):
+                seen['intro'] = tuple(x.shape)
+                g = torch.Generator().manual_seed(7)
+                return (torch.rand(x.shape[0], steps, 84, 5, generator=g) < 0.04).float()
+            return sample
+
+    out = U.sample_songs(Model(), Xt, Xv, cfg, epoch=3, samples_dir=str(tmp_path), eval_samples=True, device='cpu',
+                         name='unit')
+    assert seen['intro'] == (6, 24, 84, 5)                          # (2 train + 1 valid intros) x num_songs, 2 beats
+    assert out['samples'].shape == (6, 24 + 120, 128, 5)             # 3 bars of 48 steps
+    np.testing.assert_array_equal(out['samples'][:3, :24, 24:108], np.concatenate([Xt[:2, :24], Xv[1:2, :24]]))
+    assert [p.split('/')[-1] for p in out['paths']] == ['eval_unit_e3_t1_0.mid', 'eval_unit_e3_t1_1.mid',
+                                                          'eval_unit_e3_v0_0.mid', 'eval_unit_e3_v0_1.mid']
+    assert set(out['metrics']) == {'EB', 'UP', 'UPC', 'QN', 'PR', 'DP', 'TD'} and out['metrics']['TD'].shape == (4, 4)
+    assert out['table'].count('\n') >= 10 and 'Drums' in out['table']
