@@ -4,8 +4,9 @@ Bernoulli sampling contract (TFP 0.6.0, rbm.py:375-387): sample = float(u < p), 
 optional uniforms `u` (parity runs) and otherwise uses the in-kernel Philox generator keyed by (seed, offset).
 The k-step Gibbs chain runs as ONE launch of the fused kernel `mnn_rbm_gibbs` (W and its transpose in shared memory,
 bias + sigmoid + Bernoulli in registers, csrc/rbm.cu) when the shape fits (D, H <= 256, e.g. the 84 x 256 generator RBM
-and the 84/168 DBN layers); larger layers (the Joint encoder's 420 x 168) and single half-steps (`forward`,
-`reconstruct`) run a tensor-core GEMM followed by the fused bias + sigmoid + Bernoulli kernel.
+and the 84/168 DBN layers) and the batch is below the measured crossover (`ops.GIBBS_MODE = "auto"`: <= 32 768 rows,
+i.e. generation and small training batches); larger batches, larger layers (the Joint encoder's 420 x 168) and single
+half-steps (`forward`, `reconstruct`) run a tensor-core GEMM followed by the fused bias + sigmoid + Bernoulli kernel.
 """
 import torch
 
@@ -72,7 +73,7 @@ class RBM(Model):
         """rbm.py:192-231: k-step Gibbs chain from v. k=None -> self.k (quirk Q1: the docstring's intent).
         u = (uh[k,N,H], uv[k,N,D]) or None. Returns (p_v of the last step, v_k); k == 0 returns (v, v)."""
         k = self._k if k is None else k
-        if k > 0 and ops.GIBBS_MODE == 'fused':
+        if k > 0 and ops.gibbs_use_fused(v.shape[0]):
             bh_ = self.bh.data if bh is None else bh
             bv_ = self.bv.data if bv is None else bv
             if ops.rbm_gibbs_supported(v, self.W.data, bh_, bv_, u):

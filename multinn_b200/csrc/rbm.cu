@@ -74,8 +74,8 @@ __global__ void sigmoid_bwd_kernel(const float* __restrict__ y, long long ld_y, 
 //   * W[D][H] and its transpose Wt[H][D] are staged once per CTA in shared memory (2*D*H*4 bytes: 172 KB at 84 x 256),
 //     so both half-steps are the same "input element broadcast x weight row" loop with conflict-free 128-bit reads;
 //   * a warp owns 4 rows at a time; the binary states v_s / h_s live in a per-warp shared buffer laid out [dim][row] so
-//     that one 128-bit broadcast read feeds the 4 rows; input dims that are 0 in all 4 rows are skipped (exact: they add
-//     0), which is most of them for piano-roll-sparse visibles;
+//     that one 128-bit broadcast read feeds the 4 rows (a per-dim "all 4 rows are 0" skip was measured and dropped: it
+//     only pays in the first half-step and its branch kept the loop from being unrolled - 4.75 ms per C3 chain);
 //   * lane l owns output columns 4*l + 128*q: bias (per-row or broadcast) and the uniforms come in as 128-bit loads,
 //     sigmoid + strict `u < p` Bernoulli (TFP 0.6.0 contract) run in registers, FFMA2 on row pairs;
 //   * HBM traffic per row: v0, bh_t, bv_t in, p_v and v_k (and optionally h_k) out - nothing between the 2k half-steps.
@@ -100,7 +100,9 @@ struct GibbsArgs {
 constexpr int kGibbsThreads = 256;
 constexpr int kGibbsRows = 4;              // rows per warp
 
-// acc[q][c][0] = rows (0,1), acc[q][c][1] = rows (2,3) of output column 4*lane + 128*q + c
+// acc[q][c][0] = rows (0,1), acc[q][c][1] = rows (2,3) of output column 4*lane + 128*q + c.
+// Four input dims per trip (in_dim % 4 == 0): 4 broadcast reads of the rows' inputs and 4*NQ weight reads are in flight
+// before the 32*NQ FFMA2 that consume them; the CTA's second warp per scheduler covers the shared-memory latency.
 template <int NQ>
 __device__ __forceinline__ void gibbs_matvec(const float* __restrict__ wsm, int in_dim, int out_dim,
                                              const float* __restrict__ inbuf, int lane, float2 (&acc)[NQ][4][2]) {
@@ -108,23 +110,32 @@ __device__ __forceinline__ void gibbs_matvec(const float* __restrict__ wsm, int 
   for (int q = 0; q < NQ; ++q)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[q][c][0] = acc[q][c][1] = make_float2(0.f, 0.f);
-  for (int i = 0; i < in_dim; ++i) {
-    const float4 x = *reinterpret_cast<const float4*>(inbuf + 4 * i);    // the 4 rows' input i (broadcast read)
-    if (x.x == 0.f && x.y == 0.f && x.z == 0.f && x.w == 0.f) continue;  // warp-uniform
-    const float2 x01 = make_float2(x.x, x.y), x23 = make_float2(x.z, x.w);
+  bool act[NQ];
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const int col = 4 * lane + 128 * q;
-      if (col < out_dim) {
-        const float4 w = *reinterpret_cast<const float4*>(wsm + (size_t)i * out_dim + col);
-        acc[q][0][0] = ffma2(x01, make_float2(w.x, w.x), acc[q][0][0]);
-        acc[q][0][1] = ffma2(x23, make_float2(w.x, w.x), acc[q][0][1]);
-        acc[q][1][0] = ffma2(x01, make_float2(w.y, w.y), acc[q][1][0]);
-        acc[q][1][1] = ffma2(x23, make_float2(w.y, w.y), acc[q][1][1]);
-        acc[q][2][0] = ffma2(x01, make_float2(w.z, w.z), acc[q][2][0]);
-        acc[q][2][1] = ffma2(x23, make_float2(w.z, w.z), acc[q][2][1]);
-        acc[q][3][0] = ffma2(x01, make_float2(w.w, w.w), acc[q][3][0]);
-        acc[q][3][1] = ffma2(x23, make_float2(w.w, w.w), acc[q][3][1]);
+  for (int q = 0; q < NQ; ++q) act[q] = 4 * lane + 128 * q < out_dim;
+  for (int i0 = 0; i0 < in_dim; i0 += 4) {
+    float4 x[4], w[NQ][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) x[u] = *reinterpret_cast<const float4*>(inbuf + 4 * (i0 + u));   // 4 rows' input i0+u
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        w[q][u] = act[q] ? *reinterpret_cast<const float4*>(wsm + (size_t)(i0 + u) * out_dim + 4 * lane + 128 * q)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 x01 = make_float2(x[u].x, x[u].y), x23 = make_float2(x[u].z, x[u].w);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        acc[q][0][0] = ffma2(x01, make_float2(w[q][u].x, w[q][u].x), acc[q][0][0]);
+        acc[q][0][1] = ffma2(x23, make_float2(w[q][u].x, w[q][u].x), acc[q][0][1]);
+        acc[q][1][0] = ffma2(x01, make_float2(w[q][u].y, w[q][u].y), acc[q][1][0]);
+        acc[q][1][1] = ffma2(x23, make_float2(w[q][u].y, w[q][u].y), acc[q][1][1]);
+        acc[q][2][0] = ffma2(x01, make_float2(w[q][u].z, w[q][u].z), acc[q][2][0]);
+        acc[q][2][1] = ffma2(x23, make_float2(w[q][u].z, w[q][u].z), acc[q][2][1]);
+        acc[q][3][0] = ffma2(x01, make_float2(w[q][u].w, w[q][u].w), acc[q][3][0]);
+        acc[q][3][1] = ffma2(x23, make_float2(w[q][u].w, w[q][u].w), acc[q][3][1]);
       }
     }
   }

@@ -187,7 +187,16 @@ def bias_sigmoid_sample(pre, bias=None, u=None, p=None, s=None, use_philox=False
                                       _rowstride(s) if s is not None else 0, N, Cc, _stream()), "bias_sigmoid_sample")
 
 
-GIBBS_MODE = "fused"    # "fused": one launch per k-step chain (mnn_rbm_gibbs) where the shape fits; "gemm": 2k GEMM + half-step launches
+# k-step Gibbs chain: "fused" = one launch of mnn_rbm_gibbs where the shape fits; "gemm" = 2k tensor-core GEMM + half-step
+# launches; "auto" picks by the measured crossover (profiles/r1_gibbs_bench.log, 84 x 256, k = 10 on a B200: fused 0.21 ms
+# per wave of 4 736 rows, GEMM path 0.67 ms of launches + 0.026 ms per 1 000 rows -> fused wins below ~37 k rows: 3.1x at
+# the generation batch sizes, 0.83x at C3's 65 536 training rows).
+GIBBS_MODE = "auto"
+GIBBS_FUSED_MAX_ROWS = 32768
+
+
+def gibbs_use_fused(n_rows):
+    return GIBBS_MODE == "fused" or (GIBBS_MODE == "auto" and n_rows <= GIBBS_FUSED_MAX_ROWS)
 
 
 def _bias_ld(b, N):

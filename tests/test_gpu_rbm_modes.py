@@ -85,7 +85,7 @@ def test_rbm_gibbs_free_energy_and_cd():
 def test_fused_gibbs_chain_equals_oracle_and_half_step_path(N, D, H, k, rowbias):
     """mnn_rbm_gibbs (one launch per chain, W + W^T in shared memory) against the fp64 oracle chain (rbm.py:192-231) and
     against the GEMM + half-step path, same uniforms: samples bit-exact, last-step probabilities to 2e-5."""
-    from multinn_b200 import ops
+    from multinn_b200 import _lib, ops
     from multinn_b200.common.rbm import RBM
     from multinn_b200.params import ParamArena
     rng = np.random.default_rng(N * 1000 + D + H)
@@ -115,13 +115,17 @@ def test_fused_gibbs_chain_equals_oracle_and_half_step_path(N, D, H, k, rowbias)
     assert margin > 2e-6
     assert ops.rbm_gibbs_supported(cu(v), rbm.W.data, None, None, (cu(uh), cu(uv)))
     args = (cu(v), None if bh_t is None else cu(bh_t), None if bv_t is None else cu(bv_t))
-    assert ops.GIBBS_MODE == 'fused'
+    default = ops.GIBBS_MODE
+    assert default == 'auto' and ops.gibbs_use_fused(N) and not ops.gibbs_use_fused(ops.GIBBS_FUSED_MAX_ROWS + 1)
+    launches = _lib.lib.mnn_launch_count()
     p_f, v_f = rbm.sample(*args, u=(cu(uh), cu(uv)))
+    assert _lib.lib.mnn_launch_count() - launches == 1               # the whole chain was one kernel
     ops.GIBBS_MODE = 'gemm'
     try:
         p_g, v_g = rbm.sample(*args, u=(cu(uh), cu(uv)))
+        assert _lib.lib.mnn_launch_count() - launches >= 1 + 4 * k   # 2k GEMMs + 2k half-steps
     finally:
-        ops.GIBBS_MODE = 'fused'
+        ops.GIBBS_MODE = default
     rp, rv = O.rbm_gibbs(v.astype(f64), W, bh_o, bv_o, k, uh.astype(f64), uv.astype(f64))
     np.testing.assert_array_equal(v_f.cpu().numpy(), rv)
     np.testing.assert_array_equal(v_g.cpu().numpy(), rv)
