@@ -106,11 +106,9 @@ class MultINNCore(Model, abc.ABC):
         B, T, D, M = x.shape
         key = (B, T)
         st = self._stage.get(key)
-        if st is None:
-            st = self._stage = {key: {}}
-            st = st[key]
-        else:
-            pass
+        if st is None:                        # one shape at a time: a new (B, T) releases the previous staging buffers
+            st = {}
+            self._stage = {key: st}
         dev = x.device
         if stacked and 'xin' not in st:
             st['xin'] = torch.empty(T + 1, B, D * M, device=dev)
