@@ -154,7 +154,6 @@ def run_gpu(args):
     import torch.distributed as dist
     from multinn_b200 import _lib
     from multinn_b200.multinn import MultINN, default_config, default_params
-    from oracle import np_oracle as O   # synthetic data generator + cpu_baseline leg only
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))

@@ -16,7 +16,7 @@ from .. import ops
 from ..common.model import Model
 from ..encoders.pass_encoder import PassEncoder
 from ..params import ParamArena
-from ..training import AdamOptimizer, GradientApplier, GradientDescentOptimizer
+from ..training import AdamOptimizer, GradientApplier, GradientDescentOptimizer, rank_seed
 
 
 class MultINNCore(Model, abc.ABC):
@@ -155,7 +155,7 @@ class MultINNCore(Model, abc.ABC):
         def step(x, lengths=None, u_drop=None, seed=None, keep=None, **extra):
             x = self._check_x(x, lengths)
             self._applier.zero_grad()
-            s = counter[0] if seed is None else seed
+            s = rank_seed(counter[0]) if seed is None else seed      # an explicit seed is used as given on every rank
             counter[0] += 1
             if lengths is not None and self._supports_lengths:
                 extra['lengths'] = lengths
@@ -264,7 +264,7 @@ class MultINNCore(Model, abc.ABC):
         dc = self._config['data']
         pitch_span = dc['pitch_range']['highest'] - dc['pitch_range']['lowest']
         num_steps = num_beats * dc['beat_resolution'] * pitch_span // self.num_dims
-        return lambda x, u=None, seed=0: self.generate(x, num_steps, u=u, seed=seed)
+        return lambda x, u=None, seed=None: self.generate(x, num_steps, u=u, seed=rank_seed(0) if seed is None else seed)
 
     def evaluator(self):
         """multinn_core.py:343-362: returns `evaluate_music(x) -> {summary scope: value}`: x[B,T,num_dims,M] (device tensor

@@ -30,6 +30,14 @@ def world():
     return 0, 1
 
 
+def rank_seed(seed):
+    """Noise seed of this data-parallel rank: the Philox streams of dropout, DBN codes and sampling are indexed by the
+    LOCAL row, so every rank folds its rank into the seed - shards draw independent noise instead of G copies of the
+    same masks. Rank 0 (and single-GPU runs) keep `seed` unchanged."""
+    r, _ = world()
+    return int(seed) + r * 15485863
+
+
 def shard_batch(x, rank=None, world_size=None):
     """Data-parallel partition of a global batch along dim 0: rank r gets rows [r*B/G, (r+1)*B/G).
     Equal shards are required so that the mean of per-rank mean-loss gradients is the global-batch gradient."""

@@ -136,7 +136,7 @@ def collect_metrics(model, data, data_lengths, batch_size, piece_size, device='c
     return {'log_likelihood': float(total) / max(count, 1), 'perplexity': float(total_ppl) / max(count, 1), 'rows': count}
 
 
-def generate_music(model, sampler, intro_songs, num_songs=5, concat=True, device='cuda', u=None, seed=0):
+def generate_music(model, sampler, intro_songs, num_songs=5, concat=True, device='cuda', u=None, seed=None):
     """training.py:216-240: tile the intros `num_songs` times, sample, optionally prepend the intro."""
     intro = np.tile(intro_songs, (num_songs, 1, 1, 1))
     samples = sampler(_to_device(intro, device), u=u, seed=seed).cpu().numpy()
@@ -144,7 +144,7 @@ def generate_music(model, sampler, intro_songs, num_songs=5, concat=True, device
 
 
 def sample_songs(model, X_train, X_valid, config, epoch=0, samples_dir=None, eval_samples=False, device='cuda', u=None,
-                 seed=0, name='MultINN'):
+                 seed=None, name='MultINN'):
     """The sampling run of sample.py:40-115 after the checkpoint is loaded: intros from the train/valid splits ->
     `model.sampler(sample_beats)` -> generate_music (intro + samples) -> pad_to_midi -> MIDI files of the `save_ids`
     (when `samples_dir` is given) -> musical metrics of all samples (when `eval_samples`).
