@@ -88,3 +88,46 @@ def test_metric_summary_layout():
     assert 'sample_scores/intra-track/Drums/DP' in s and 'sample_scores/intra-track/Drums/QN' not in s
     assert s['sample_scores/intra-track/Piano/QN'] == float(GOLD['sparse48/QN'][1])
     assert s['sample_scores/inter-track/TD/Piano-Bass'] == pytest.approx(float(GOLD['sparse48/TD'][1][3]), rel=1e-12)
+
+
+@pytest.mark.skipif(not os.path.exists(gen.REF), reason='the reference checkout is not present on this machine')
+def test_golden_file_is_what_the_reference_produces_now(tmp_path, monkeypatch):
+    """Where /root/reference exists (the build container), re-run its musical.py and compare with the committed file."""
+    monkeypatch.setattr(gen, 'ROOT', str(tmp_path))
+    os.makedirs(tmp_path / 'tests' / 'golden')
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore', RuntimeWarning)
+        gen.main()
+    fresh = np.load(tmp_path / 'tests' / 'golden' / 'musical_metrics.npz')
+    assert sorted(fresh.files) == sorted(GOLD.files)
+    for k in GOLD.files:
+        np.testing.assert_array_equal(fresh[k], GOLD[k], err_msg=k)
+
+
+def test_metric_invariants_on_random_rolls():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.integers(0, 2 ** 31 - 1), st.sampled_from([16, 24, 32, 48]), st.sampled_from([12, 20, 84]),
+           st.floats(0.0, 0.6))
+    def check(seed, steps, pitches, density):
+        rng = np.random.default_rng(seed)
+        roll = rng.random((2, 2, steps, pitches, 3)) < density
+        chroma = MM.to_chroma(roll)
+        assert chroma.shape[-2] == 12 and chroma.sum() == roll.sum()                 # folding keeps every note
+        eb, up, pr = MM.empty_bar_rate(roll), MM.num_pitches_used(roll), MM.polyphonic_rate(roll)
+        assert np.all((eb >= 0) & (eb <= 1)) and np.all((pr >= 0) & (pr <= 1)) and np.all((up >= 0) & (up <= pitches))
+        assert np.all(MM.num_pitches_used(chroma) <= 12)
+        dp = MM.drum_in_pattern_rate(roll[..., 0])
+        assert 0.0 <= dp <= 1.0
+        td = MM.harmonicity(chroma)
+        finite = np.isfinite(td)
+        assert np.allclose(td[finite], td.T[finite]) and np.all(np.diag(td)[np.isfinite(np.diag(td))] == 0)
+        qn = MM.qualified_note_rate(roll, threshold=0)                               # every note lasts > 0 steps
+        ok = np.isfinite(qn)
+        assert np.all(qn[ok] >= 1.0)                                                 # == 1, or more with quirk M2
+        silent = np.zeros_like(roll)
+        assert np.all(MM.empty_bar_rate(silent) == 1) and np.all(np.isnan(MM.qualified_note_rate(silent)))
+
+    check()
