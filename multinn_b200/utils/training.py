@@ -119,21 +119,34 @@ def _to_device(songs, device):
     return torch.from_numpy(a).to(device, non_blocking=True)
 
 
-def collect_metrics(model, data, data_lengths, batch_size, piece_size, device='cuda'):
+def collect_metrics(model, data, data_lengths, batch_size, piece_size, device='cuda', distributed=None):
     """Streaming evaluation over a dataset (training.py:180-213 + metrics/statistical.py:22-34): the tf.metrics.mean
     accumulators become (sum, count) on the device. Returns {'log_likelihood': mean NLL over all evaluated rows and
-    tracks, 'perplexity': mean exp(NLL), 'rows': count}."""
+    tracks, 'perplexity': mean exp(NLL), 'rows': count}.
+    Data parallel (`distributed=None`: whenever torch.distributed is initialised with more than one rank): rank r
+    evaluates the batches b with b % world == r and the three accumulators are summed over the ranks with one
+    allreduce, so every rank returns the metrics of the WHOLE dataset."""
     import torch
-    total = torch.zeros((), dtype=torch.float64, device=device)
-    total_ppl = torch.zeros((), dtype=torch.float64, device=device)
-    count = 0
-    for songs, seq in evaluation_pieces(data, data_lengths, batch_size, piece_size):
+    import torch.distributed as dist
+    rank, world = 0, 1
+    if distributed is None:
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    if distributed:
+        rank, world = dist.get_rank(), dist.get_world_size()
+    acc = torch.zeros(3, dtype=torch.float64, device=device)            # sum NLL, sum exp(NLL), count
+    pieces_per_batch = len(range(0, data.shape[1], piece_size))
+    for idx, (songs, seq) in enumerate(evaluation_pieces(data, data_lengths, batch_size, piece_size)):
+        if (idx // pieces_per_batch) % world != rank:
+            continue
         out = model.evaluate(_to_device(songs, device), lengths=torch.as_tensor(np.asarray(seq)))
         nll = out['nll'].double()
-        total += nll.sum()
-        total_ppl += nll.exp().sum()
-        count += nll.numel()
-    return {'log_likelihood': float(total) / max(count, 1), 'perplexity': float(total_ppl) / max(count, 1), 'rows': count}
+        acc[0] += nll.sum()
+        acc[1] += nll.exp().sum()
+        acc[2] += nll.numel()
+    if distributed:
+        dist.all_reduce(acc)
+    total, total_ppl, count = (float(a) for a in acc)
+    return {'log_likelihood': total / max(count, 1), 'perplexity': total_ppl / max(count, 1), 'rows': int(count)}
 
 
 def generate_music(model, sampler, intro_songs, num_songs=5, concat=True, device='cuda', u=None, seed=None):
