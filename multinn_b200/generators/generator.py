@@ -30,3 +30,9 @@ class Generator(Model, abc.ABC):
     @abc.abstractmethod
     def generate(self, x, num_steps):
         ...
+
+    def pretrain(self, inputs_flat, lr, u=None, seed=None):
+        """generator.py:125-150: pre-training of a generator module on the flattened inputs [rows, num_dims]. The default
+        is the RNN-NADE behaviour (rnn_nade.py:320-326: nothing to pre-train, no update) and returns None."""
+        return None
+

@@ -85,6 +85,11 @@ class RnnRBM(RnnEstimator):
             sample = out
         return sample, cond_prob
 
+    def pretrain(self, inputs_flat, lr, u=None, seed=None):
+        """rnn_rbm.py:299-322: pre-trains the RBM module with one CD-k update on the flattened input frames (the LSTM,
+        Wuh and Wuv are untouched). u = dict(uh, uv, uh0, uhk) uniforms for parity runs. Returns (p_v, v_k) of the chain."""
+        return self._rbm.train(inputs_flat.contiguous(), lr, u=u, seed=seed)
+
     # ------------------------------------------------------------------ train / eval graph (rnn_rbm.py:94-119)
     def forward(self, inputs, targets, keep=1.0, u_drop=None, u_gibbs=None, seed=0):
         """inputs[T,B,I] (I == num_dims: the chain starts from the input frame), targets[T,B,D] time-major.

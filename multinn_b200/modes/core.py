@@ -167,6 +167,30 @@ class MultINNCore(Model, abc.ABC):
 
         return step
 
+    def _pretrain_rows(self, x, seed):
+        """(generator, flattened input rows) pairs for pretrain_generators; None rows for generators without a module to
+        pre-train (every NADE generator)."""
+        return [(g, None) for g in self._generators]
+
+    def pretrain_generators(self, optimizer=None, lr=0.01, separate_losses=False):
+        """multinn.py:232-250, multinn_composer.py:153-171, multinn_jamming.py:135-154, multinn_joint.py: returns
+        `step(x, lengths=None, u=None, seed=None) -> number of generators updated`. RNN-NADE generators have nothing to
+        pre-train (rnn_nade.py:320-326: empty update ops), an RNN-RBM generator gets one CD-k update of its RBM on the
+        flattened input frames (rnn_rbm.py:299-322; `RBM.train` applies it itself, the optimizer is unused there too)."""
+        counter = [0]
+
+        def step(x, lengths=None, u=None, seed=None):
+            x = self._check_x(x, lengths)
+            s = rank_seed(counter[0]) if seed is None else seed
+            counter[0] += 1
+            updated = 0
+            for gen, rows in self._pretrain_rows(x, s * 1000003):
+                if rows is not None and gen.pretrain(rows, lr, u=u, seed=s * 7919 + 13) is not None:
+                    updated += 1
+            return updated
+
+        return step
+
     # ------------------------------------------------------------------ encoder pre-training (train_encoders.py)
     def _encoder_rows(self, x, lengths=None):
         """Per-encoder training rows: the zero-padded inputs [B,T+1,..] flattened by flatten_maybe_padded_sequences

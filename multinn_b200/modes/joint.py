@@ -35,6 +35,14 @@ class MultINNJoint(MultINNCore):
         _, h = self._encoder.encode(flat, u=u_enc, seed=seed)
         return h.view(T + 1, B, -1)
 
+    def _pretrain_rows(self, x, seed):
+        """The generator's input frames: the codes of the zero-padded sequence without its last step, flattened."""
+        if not isinstance(self._generator, RnnRBM):
+            return [(self._generator, None)]
+        B, T, D, M = x.shape
+        codes = self._encode(x, None, seed)
+        return [(self._generator, codes[:T].reshape(T * B, -1))]
+
     def _forward_backward(self, x, keep, u_drop, seed, u_enc=None, u_gibbs=None):
         B, T, D, M = x.shape
         codes = self._encode(x, u_enc, seed)

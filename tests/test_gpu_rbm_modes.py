@@ -275,6 +275,26 @@ def test_joint_dbn_rnn_rbm_parity_and_gradients():
         assert torch.equal(before[n], after[n])
 
 
+def test_pretrain_generators_updates_only_the_rbm_module():
+    """multinn_joint.py / rnn_rbm.py:299-322: pre-training = CD-k on the generator's RBM over the flattened input codes;
+    RNN-NADE generators have nothing to pre-train (rnn_nade.py:320-326)."""
+    model = make('joint', encoder='DBN', encoder_hidden=[168, 84], generator='RBM', num_hidden=64, num_hidden_rnn=(32,))
+    x = cu(O.synthetic_pianoroll(3, 5, seed=2, density=0.1))
+    before = model._model.arena.state_dict()
+    step = model.pretrain_generators(None, 0.05)
+    assert step(x) == 1
+    after = model._model.arena.state_dict()
+    assert not torch.equal(before['generator/rbm/W'], after['generator/rbm/W'])
+    assert torch.isfinite(after['generator/rbm/W']).all()
+    for n in before:
+        if not n.startswith('generator/rbm/'):
+            assert torch.equal(before[n], after[n]), n
+    comp = make('composer', num_hidden=128, num_hidden_rnn=(32,))
+    b0 = comp._model.arena.flat.clone()
+    assert comp.pretrain_generators(None, 0.05)(x) == 0
+    assert torch.equal(b0, comp._model.arena.flat)
+
+
 def test_joint_generate_runs_and_is_binary():
     model = make('joint', encoder='DBN', encoder_hidden=[168, 84], generator='RBM', num_hidden=64, num_hidden_rnn=(32,))
     x = cu(O.synthetic_pianoroll(3, 5, seed=2))
