@@ -14,7 +14,8 @@ blocks i, c~, f, o and rows [x ; h] -- exactly the layout the kerne
 [in, units]; NADE w_enc [D,1,H] / w_dec [D,H,1] lose their singleton axis and are stacked over tracks; RBM W [D,H],
 bh [1,H], bv [1,D] are identical.
 
-Getting the variables out of a checkpoint (in an environment that has TensorFlow):
+Getting the variables out of a checkpoint: `utils/tf_checkpoint.read_checkpoint(ckpt_dir)` (pure Python), or in an
+environment that has TensorFlow:
     r = tf.train.load_checkpoint(ckpt_dir); np.savez('vars.npz', **{n: r.get_tensor(n) for n in r.get_variable_to_shape_map()})
 """
 import re

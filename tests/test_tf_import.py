@@ -71,3 +71,64 @@ def test_explicit_name_map_and_failures():
     with pytest.raises(ValueError, match='unused TF variables'):
         T.load_tf_variables(_composer(9), extra)
     T.load_tf_variables(_composer(9), extra, strict=False)
+
+
+# ----------------------------------------------------------------------------- checkpoint files without TensorFlow
+def test_checkpoint_file_round_trip_and_load(tmp_path):
+    """utils/tf_checkpoint.py: TF V2 checkpoint (tensor bundle) files written and read in pure Python: many small index
+    blocks (prefix-compressed keys, restart points), dtypes, scalars, the directory's `checkpoint` state file, and the
+    whole path file -> variables -> model parameters."""
+    from multinn_b200.utils import tf_checkpoint as C
+    src, dst = _composer(11), _composer(12)
+    tfv = {f'MultINN/generators/{n}': a for n, a in T.export_tf_variables(src).items()}
+    tfv['global_step'] = np.array(1234, np.int64)                               # scalar, ignored by the import
+    tfv['MultINN/generators/generator/dense/kernel/Adam'] = np.zeros((8, 1700), np.float32)    # optimiser slot, ignored
+    tfv['flags'] = np.array([True, False, True])
+    tfv['half'] = np.arange(6, dtype=np.float16).reshape(2, 3)
+    prefix = str(tmp_path / 'generators' / 'model-77')
+    C.write_checkpoint(prefix, tfv, block_size=200)                              # forces many data blocks
+    assert sorted(f.name for f in (tmp_path / 'generators').iterdir()) == ['checkpoint', 'model-77.data-00000-of-00001',
+                                                                           'model-77.index']
+    for where in (prefix, prefix + '.index', str(tmp_path / 'generators')):
+        got = C.read_checkpoint(where, verify_data=True)
+        assert sorted(got) == sorted(tfv)
+        for n in tfv:
+            assert got[n].dtype == tfv[n].dtype and got[n].shape == tfv[n].shape and np.array_equal(got[n], tfv[n]), n
+    only = C.read_checkpoint(prefix, names=lambda n: n.endswith('w_enc'))
+    assert len(only) == 5
+    T.load_tf_variables(dst, C.read_checkpoint(prefix), strict=False)
+    assert _same(src.arena, dst.arena)
+
+
+def test_checkpoint_reader_rejects_damage(tmp_path):
+    from multinn_b200.utils import tf_checkpoint as C
+    prefix = str(tmp_path / 'm')
+    C.write_checkpoint(prefix, {'a/b': np.arange(12, dtype=np.float32).reshape(3, 4), 'a/c': np.ones(5, np.int32)})
+    idx = bytearray(open(prefix + '.index', 'rb').read())
+    bad = bytearray(idx)
+    bad[3] ^= 0x40
+    open(prefix + '.index', 'wb').write(bad)
+    with pytest.raises(C.CheckpointFormatError, match='checksum|corrupt|truncated|varint'):
+        C.read_checkpoint(prefix)
+    bad = bytearray(idx)
+    bad[-1] ^= 0xFF
+    open(prefix + '.index', 'wb').write(bad)
+    with pytest.raises(C.CheckpointFormatError, match='magic'):
+        C.read_checkpoint(prefix)
+    open(prefix + '.index', 'wb').write(idx)
+    data = bytearray(open(prefix + '.data-00000-of-00001', 'rb').read())
+    data[5] ^= 1
+    open(prefix + '.data-00000-of-00001', 'wb').write(data)
+    assert C.read_checkpoint(prefix)['a/c'].sum() == 5                           # not verified by default
+    with pytest.raises(C.CheckpointFormatError, match='tensor checksum'):
+        C.read_checkpoint(prefix, verify_data=True)
+    with pytest.raises(FileNotFoundError):
+        C.read_checkpoint(str(tmp_path / 'missing'))
+
+
+def test_crc32c_known_answers():
+    from multinn_b200.utils.tf_checkpoint import crc32c, mask_crc
+    assert crc32c(b'123456789') == 0xE3069283                                    # CRC-32C check value
+    assert crc32c(bytes(32)) == 0x8a9136aa and crc32c(bytes([0xFF] * 32)) == 0x62a8ab43      # RFC 3720 B.4 vectors
+    assert crc32c(b'world', crc32c(b'hello ')) == crc32c(b'hello world')
+    assert mask_crc(crc32c(b'foo')) != crc32c(b'foo')
