@@ -318,3 +318,17 @@ class MultINNCore(Model, abc.ABC):
 
     def load(self, path):
         self.load_state_dict(torch.load(path, map_location='cpu'))
+
+    def load_tf(self, path, which='generators', name_map=None, strict=False):
+        """Restores the generator (or encoder) parameters from a TensorFlow Saver checkpoint of the reference
+        (common/model.py:216-234, core/multinn_core.py:425-448: `path` = its directory or prefix), read in pure Python.
+        strict=False by default: a Saver file may also hold optimiser slots and counters. Returns the applied mapping."""
+        from ..utils import tf_checkpoint, tf_import
+        return tf_import.load_tf_variables(self, tf_checkpoint.read_checkpoint(path), which=which, name_map=name_map,
+                                           strict=strict)
+
+    def save_tf(self, prefix, which='generators'):
+        """Writes the generator (or encoder) parameters as a TF V2 checkpoint (`<prefix>.index`, `.data-00000-of-00001`,
+        `checkpoint`) with TF-shaped tensors, the files common/model.py:180-214 writes."""
+        from ..utils import tf_checkpoint, tf_import
+        tf_checkpoint.write_checkpoint(prefix, tf_import.export_tf_variables(self, which))

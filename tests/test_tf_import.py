@@ -132,3 +132,15 @@ def test_crc32c_known_answers():
     assert crc32c(bytes(32)) == 0x8a9136aa and crc32c(bytes([0xFF] * 32)) == 0x62a8ab43      # RFC 3720 B.4 vectors
     assert crc32c(b'world', crc32c(b'hello ')) == crc32c(b'hello world')
     assert mask_crc(crc32c(b'foo')) != crc32c(b'foo')
+
+
+def test_model_save_tf_load_tf(tmp_path):
+    mk = lambda s: MultINN(default_config(), default_params(mode='joint', encoder='DBN', encoder_hidden=[24, 12], generator='RBM',
+                                                            num_hidden=16, num_hidden_rnn=(8,)), 'joint', device='cpu', seed=s)
+    src, dst = mk(21), mk(22)
+    src.save_tf(str(tmp_path / 'generators' / 'model'))
+    src.save_tf(str(tmp_path / 'encoders' / 'model'), which='encoders')
+    applied = dst.load_tf(str(tmp_path / 'generators'))
+    dst.load_tf(str(tmp_path / 'encoders'), which='encoders', strict=True)
+    assert _same(src.arena, dst.arena) and _same(src.encoder_arena, dst.encoder_arena)
+    assert applied['generator/rbm/W'] == 'generator/rbm/W'
