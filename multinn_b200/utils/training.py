@@ -119,34 +119,46 @@ def _to_device(songs, device):
     return torch.from_numpy(a).to(device, non_blocking=True)
 
 
-def collect_metrics(model, data, data_lengths, batch_size, piece_size, device='cuda', distributed=None):
-    """Streaming evaluation over a dataset (training.py:180-213 + metrics/statistical.py:22-34): the tf.metrics.mean
-    accumulators become (sum, count) on the device. Returns {'log_likelihood': mean NLL over all evaluated rows and
-    tracks, 'perplexity': mean exp(NLL), 'rows': count}.
+def collect_metrics(model, data, data_lengths, batch_size, piece_size, device='cuda', distributed=None,
+                    classification=False):
+    """Streaming evaluation over a dataset (training.py:180-213 + metrics/statistical.py:22-34): the tf.metrics
+    accumulators become counters on the device (metrics/statistical.py::BaseMetrics). Returns {'log_likelihood': mean
+    NLL over all evaluated rows and tracks, 'perplexity': mean exp(NLL), 'rows': count}; with `classification=True`
+    (models whose evaluate() takes `cond_probs=True`) also accuracy / precision / recall / f1_score of the thresholded
+    conditional probabilities (predictions = p >= .5, rnn_multinade.py:139-143) against the targets.
     Data parallel (`distributed=None`: whenever torch.distributed is initialised with more than one rank): rank r
-    evaluates the batches b with b % world == r and the three accumulators are summed over the ranks with one
-    allreduce, so every rank returns the metrics of the WHOLE dataset."""
+    evaluates the batches b with b % world == r and the accumulators are summed over the ranks with one allreduce, so
+    every rank returns the metrics of the WHOLE dataset."""
     import torch
     import torch.distributed as dist
+    from ..metrics.statistical import BaseMetrics
     rank, world = 0, 1
     if distributed is None:
         distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     if distributed:
         rank, world = dist.get_rank(), dist.get_world_size()
-    acc = torch.zeros(3, dtype=torch.float64, device=device)            # sum NLL, sum exp(NLL), count
+    acc = BaseMetrics(device)
     pieces_per_batch = len(range(0, data.shape[1], piece_size))
     for idx, (songs, seq) in enumerate(evaluation_pieces(data, data_lengths, batch_size, piece_size)):
         if (idx // pieces_per_batch) % world != rank:
             continue
-        out = model.evaluate(_to_device(songs, device), lengths=torch.as_tensor(np.asarray(seq)))
-        nll = out['nll'].double()
-        acc[0] += nll.sum()
-        acc[1] += nll.exp().sum()
-        acc[2] += nll.numel()
+        x = _to_device(songs, device)
+        lengths = torch.as_tensor(np.asarray(seq))
+        if not classification:
+            acc.update(model.evaluate(x, lengths=lengths)['nll'])
+            continue
+        out = model.evaluate(x, lengths=lengths, cond_probs=True)
+        B, T = x.shape[0], x.shape[1]
+        targets = x.reshape(B * T, *x.shape[2:])                       # rows n = b*T + t, like the per-row results
+        if out['cond_probs'].shape[0] != B * T:                        # padded rows were dropped (utils/sequences.py:29-37)
+            keep = (torch.arange(T)[None, :] < lengths[:, None]).reshape(-1).nonzero().squeeze(1).to(x.device)
+            targets = targets[keep]
+        acc.update(out['nll'], targets, out['cond_probs'] >= 0.5)
     if distributed:
-        dist.all_reduce(acc)
-    total, total_ppl, count = (float(a) for a in acc)
-    return {'log_likelihood': total / max(count, 1), 'perplexity': total_ppl / max(count, 1), 'rows': int(count)}
+        acc.allreduce()
+    res = acc.result()
+    res.pop('loss')
+    return res
 
 
 def generate_music(model, sampler, intro_songs, num_songs=5, concat=True, device='cuda', u=None, seed=None):
