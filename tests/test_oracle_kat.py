@@ -217,3 +217,64 @@ def test_variable_lengths_drop_padded_rows():
     loss, nll = R.composer_loss(torch.tensor(x), tp, lengths=lengths)
     np.testing.assert_allclose(float(loss), out['loss'], rtol=1e-12)
     np.testing.assert_allclose(nll.numpy(), out['nll'], rtol=1e-12)
+
+
+# ----------------------------------------------------------------------------- pins against INDEPENDENT implementations
+class _FixedUniforms:
+    """Stands in for the numpy RandomState scikit-learn's RBM draws from: hands out the supplied uniform tensors."""
+
+    def __init__(self, tensors):
+        self.tensors = list(tensors)
+
+    def uniform(self, size=None):
+        u = self.tensors.pop(0)
+        assert u.shape == tuple(size)
+        return u
+
+
+def test_rbm_oracle_equals_scikit_learn_bernoulli_rbm():
+    """The oracle's RBM conditionals, strict-`<` Bernoulli sampling, k-step Gibbs chain and free energy (common/rbm.py:148-263,
+    337-387) against scikit-learn's BernoulliRBM, an implementation that shares no code with the oracle."""
+    from sklearn.neural_network import BernoulliRBM
+    rng = np.random.default_rng(42)
+    N, D, H, k = 13, 20, 9, 4
+    W, bh, bv = rng.standard_normal((D, H)) * 0.7, rng.standard_normal((1, H)) * 0.4, rng.standard_normal((1, D)) * 0.4
+    v0 = (rng.random((N, D)) < 0.3).astype(np.float64)
+    uh, uv = rng.random((k, N, H)), rng.random((k, N, D))
+    sk = BernoulliRBM(n_components=H)
+    sk.components_, sk.intercept_hidden_, sk.intercept_visible_ = W.T.copy(), bh[0].copy(), bv[0].copy()
+    np.testing.assert_allclose(O.rbm_cond_prob_h(v0, W, bh), sk._mean_hiddens(v0), rtol=1e-13)
+    np.testing.assert_allclose(O.rbm_free_energy(v0, W, bh, bv), sk._free_energy(v0), rtol=1e-13)
+    feed = _FixedUniforms([t for s in range(k) for t in (uh[s], uv[s])])
+    v = v0
+    for _ in range(k):
+        h = sk._sample_hiddens(v, feed)
+        v = sk._sample_visibles(h.astype(np.float64), feed).astype(np.float64)
+    p_v, v_k = O.rbm_gibbs(v0, W, bh, bv, k, uh, uv)
+    np.testing.assert_array_equal(v_k, v)
+    assert not feed.tensors
+
+
+def test_tf_adam_and_clip_equal_torch_optim_after_reparametrisation():
+    """TF's Adam (epsilon added to the UNCORRECTED sqrt(v), train.py:64) is torch.optim.Adam with eps_t = eps / sqrt(1 -
+    beta2^t); tf.clip_by_global_norm(5.) is torch's clip_grad_norm_ up to its 1e-6 guard. Ten steps on a quadratic."""
+    import torch
+    rng = np.random.default_rng(7)
+    p0 = rng.standard_normal(50)
+    A = rng.standard_normal((50, 50)) * 3
+    grad = lambda p: A.T @ (A @ p)                                   # large gradients: the clip is active
+    p, m, v = p0.copy(), np.zeros(50), np.zeros(50)
+    tp = torch.tensor(p0, dtype=torch.float64, requires_grad=True)
+    opt = torch.optim.Adam([tp], lr=0.01, betas=(0.9, 0.999), eps=1e-4)
+    clipped = 0
+    for t in range(1, 11):
+        g = grad(p)
+        (gc,), gn = O.clip_by_global_norm([g], 5.0)
+        clipped += gn > 5.0
+        p, m, v = O.tf_adam_step(p, gc, m, v, t)
+        tp.grad = torch.tensor(grad(tp.detach().numpy()))
+        torch.nn.utils.clip_grad_norm_([tp], 5.0)
+        opt.param_groups[0]['eps'] = 1e-4 / np.sqrt(1 - 0.999 ** t)
+        opt.step()
+        np.testing.assert_allclose(p, tp.detach().numpy(), rtol=1e-6, atol=1e-9)
+    assert clipped == 10
