@@ -144,3 +144,25 @@ def test_model_save_tf_load_tf(tmp_path):
     dst.load_tf(str(tmp_path / 'encoders'), which='encoders', strict=True)
     assert _same(src.arena, dst.arena) and _same(src.encoder_arena, dst.encoder_arena)
     assert applied['generator/rbm/W'] == 'generator/rbm/W'
+
+
+def test_checkpoint_table_round_trip_property(tmp_path_factory):
+    """Random variable names with long shared prefixes, random block sizes (1 entry per block .. everything in one block),
+    restart points every 16 keys: the table writer / reader pair keeps every key, value and order."""
+    from hypothesis import given, settings, strategies as st
+    from multinn_b200.utils import tf_checkpoint as C
+    root = tmp_path_factory.mktemp('tables')
+    counter = [0]
+
+    @settings(max_examples=30, deadline=None)
+    @given(st.sets(st.text(alphabet='abc/_0', min_size=1, max_size=24), min_size=1, max_size=60),
+           st.integers(1, 3000), st.integers(0, 2 ** 31 - 1))
+    def check(names, block_size, seed):
+        rng = np.random.default_rng(seed)
+        items = [(n.encode(), rng.bytes(int(rng.integers(0, 40)))) for n in names]
+        path = str(root / f't{counter[0]}')
+        counter[0] += 1
+        C.write_table(path, items, block_size=block_size)
+        assert C.read_table(path) == sorted(items)
+
+    check()
