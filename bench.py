@@ -248,6 +248,21 @@ def run_gpu(args):
                     'generated_time_steps_per_s': world * Bl / (us * 1e-6),
                     'note': 'random-init weights sample ~50 % dense frames: the worst case for the segment-form sampler'}
 
+    # ---- size-independent property at the FULL bench size (after every timed region; never fatal): a sequence's per-row
+    # NLL does not depend on what else is in the batch, although B = 2048 runs the pair kernels and B = 8 the 1-CTA ones
+    fullsize = None
+    if rank == 0 and world == 1:
+        try:
+            sub = 8
+            full = model.evaluate(xdev[0])['nll'][:sub * T].clone()
+            part = model.evaluate(xdev[0][:sub].contiguous())['nll']
+            rel = float(((full - part).abs() / part.abs().clamp_min(1e-6)).max())
+            fullsize = {'property': f'per-row NLL of the first {sub} sequences inside the [{Bl},{T},84,5] batch equals the '
+                                    'same sequences evaluated alone (rows n = b*T + t)', 'rows': sub * T,
+                        'max_rel_diff': rel, 'tolerance': 1e-4, 'ok': bool(rel < 1e-4)}
+        except Exception as e:          # noqa: BLE001 - a diagnostic must not cost the bench line
+            fullsize = {'error': repr(e)[:300]}
+
     if rank == 0:
         pk = peaks()
         tps = B * T / (ms * 1e-3)
@@ -280,6 +295,7 @@ def run_gpu(args):
             'kernels': kernel_table(phases, n_rows, pk),
             'sampling': sampling,
             'final_loss': final_loss,
+            'fullsize_check': fullsize,
         }
         if world == 1 and not args.no_cpu:
             v, cores, _, sec = cpu_port_run(args.cpu_batch, T, 3, 1)
