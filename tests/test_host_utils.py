@@ -262,3 +262,20 @@ def test_sample_songs_driver_with_stub_sampler(tmp_path):
                                                           'eval_unit_e3_v0_0.mid', 'eval_unit_e3_v0_1.mid']
     assert set(out['metrics']) == {'EB', 'UP', 'UPC', 'QN', 'PR', 'DP', 'TD'} and out['metrics']['TD'].shape == (4, 4)
     assert out['table'].count('\n') >= 10 and 'Drums' in out['table']
+
+
+def test_recurrence_schedule_dispatch_for_the_baseline_shards():
+    """Which schedule common/rnn.py picks for the per-GPU batches of the C5 scaling sweep (T = 256): full time-chunk
+    pipeline at 256 / 512 (8 and 4 GPUs), forward-only pipeline at 1024 (2 GPUs), tail pipeline at 2048 (1 GPU), plain
+    phase-by-phase for short or ragged time axes. Pure host logic: runs on a CPU arena."""
+    from multinn_b200.multinn import MultINN, default_config, default_params
+    model = MultINN(default_config(), default_params(mode='composer', num_hidden=128, num_hidden_rnn=(16, 8)), 'composer',
+                    device='cpu')
+    rnn = model.generators[0].rnn
+    T = 256
+    for B in (256, 512):
+        assert rnn.use_pipeline(T, B) and rnn.use_any_pipeline(T, B) and rnn.use_fwd_pipeline(T, B)
+    assert not rnn.use_pipeline(T, 1024) and rnn.use_fwd_pipeline(T, 1024)
+    assert not rnn.use_pipeline(T, 2048) and not rnn.use_fwd_pipeline(T, 2048) and rnn.use_any_pipeline(T, 2048)
+    for t, b in ((48, 256), (40, 256), (250, 2048)):            # T < 2 chunks, or not a multiple of the 32-step chunk
+        assert not rnn.use_any_pipeline(t, b), (t, b)
