@@ -175,6 +175,57 @@ def test_fused_gibbs_philox_statistics_and_determinism():
     assert torch.equal(vk, outs[0][0][100:200])
 
 
+_NOT_RUN_YET = pytest.mark.xfail(strict=False, reason='written after round 1\'s GPU budget was spent: not yet run on a '
+                                'B200 (the CPU Philox is pinned by the Random123 vectors); promote once it has passed')
+
+
+@_NOT_RUN_YET
+def test_fused_gibbs_philox_stream_equals_cpu_philox():
+    """The in-kernel generator of mnn_rbm_gibbs, not only its statistics: the CPU Philox4x32-10 with the kernel's counter
+    layout (oracle/philox.py) reproduces the uniforms, so the Philox-mode chain must equal the oracle chain bit for bit."""
+    from multinn_b200 import ops
+    from oracle.philox import gibbs_chain_uniforms
+    rng = np.random.default_rng(17)
+    N, D, H, k, offset = 37, 84, 256, 3, 1000
+    W = (rng.standard_normal((D, H)) * 0.1).astype(np.float32)
+    bh = (rng.standard_normal((N, H)) * 0.3).astype(np.float32)
+    bv = (rng.standard_normal((N, D)) * 0.3).astype(np.float32)
+    v0 = (rng.random((N, D)) < 0.2).astype(np.float32)
+    for seed in range(100, 400):                      # a seed whose every comparison has a margin fp32 cannot cross
+        uh, uv = gibbs_chain_uniforms(seed, offset, N, D, H, k)
+        vv, margin = v0.astype(f64), 1.0
+        for s_ in range(k):
+            ph = O.rbm_cond_prob_h(vv, W.astype(f64), bh.astype(f64))
+            hh = (uh[s_] < ph).astype(f64)
+            pv = O.rbm_cond_prob_v(hh, W.astype(f64), bv.astype(f64))
+            vv = (uv[s_] < pv).astype(f64)
+            margin = min(margin, float(np.abs(uh[s_] - ph).min()), float(np.abs(uv[s_] - pv).min()))
+        if margin > 2e-6:
+            break
+    assert margin > 2e-6
+    v_k, h_k = torch.empty(N, D, device='cuda'), torch.empty(N, H, device='cuda')
+    ops.rbm_gibbs(cu(v0), cu(W), cu(bh), cu(bv), k, v_k=v_k, h_k=h_k, seed=seed, offset=offset)
+    np.testing.assert_array_equal(v_k.cpu().numpy(), vv)
+    np.testing.assert_array_equal(h_k.cpu().numpy(), hh)
+
+
+@_NOT_RUN_YET
+def test_half_step_philox_stream_equals_cpu_philox():
+    from multinn_b200 import ops
+    from oracle.philox import half_step_uniforms
+    rng = np.random.default_rng(18)
+    N, C, offset = 29, 168, 12345
+    pre = (rng.standard_normal((N, C))).astype(np.float32)
+    p_ref = O.sigmoid(pre.astype(f64))
+    for seed in range(7, 200):
+        u = half_step_uniforms(seed, offset, N, C)
+        if float(np.abs(u - p_ref).min()) > 2e-6:
+            break
+    s = torch.empty(N, C, device='cuda')
+    ops.bias_sigmoid_sample(cu(pre), s=s, use_philox=True, seed=seed, offset=offset)
+    np.testing.assert_array_equal(s.cpu().numpy(), (u < p_ref).astype(np.float32))
+
+
 def test_rbm_philox_half_step_statistics():
     from multinn_b200.common.rbm import RBM
     from multinn_b200.params import ParamArena

@@ -278,3 +278,25 @@ def test_tf_adam_and_clip_equal_torch_optim_after_reparametrisation():
         opt.step()
         np.testing.assert_allclose(p, tp.detach().numpy(), rtol=1e-6, atol=1e-9)
     assert clipped == 10
+
+
+def test_cpu_philox_known_answers_and_counter_layouts():
+    """oracle/philox.py against the Random123 known-answer vectors of Philox4x32-10, and the shapes / ranges / keying of
+    the two counter layouts the kernels use."""
+    from oracle.philox import gibbs_chain_uniforms, half_step_uniforms, philox4x32_10
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = philox4x32_10(np.array(ctr, np.uint32), np.array(key, np.uint32))
+        assert tuple(int(x) for x in got) == want
+    uh, uv = gibbs_chain_uniforms(11, 5, 6, 84, 256, 2)
+    assert uh.shape == (2, 6, 256) and uv.shape == (2, 6, 84) and uh.dtype == np.float32
+    assert 0.0 <= uh.min() and uh.max() < 1.0 and abs(float(uh.mean()) - 0.5) < 0.03
+    # keyed by the global row: rows 2.. of a chain at offset 5 are rows 0.. of a chain at offset 7
+    uh2, uv2 = gibbs_chain_uniforms(11, 7, 4, 84, 256, 2)
+    assert np.array_equal(uh[:, 2:], uh2) and np.array_equal(uv[:, 2:], uv2)
+    assert not np.array_equal(uh[0], uh[1]) and not np.array_equal(gibbs_chain_uniforms(12, 5, 6, 84, 256, 2)[0], uh)
+    a = half_step_uniforms(3, 100, 4, 8)
+    assert np.array_equal(a.reshape(-1)[8:], half_step_uniforms(3, 108, 3, 8).reshape(-1))     # offset = element index
