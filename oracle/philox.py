@@ -62,3 +62,14 @@ def gibbs_chain_uniforms(seed, offset, N, D, H, k):
     uh = np.stack([draw(2 * s, H) for s in range(k)])
     uv = np.stack([draw(2 * s + 1, D) for s in range(k)])
     return uh, uv
+
+
+def nade_sample_uniforms(seed, offset, M, N, D):
+    """csrc/nade.cu::nade_sample_kernel in Philox mode: (track m, row n, dim i) draws word 0 of
+    Philox(ctr = ((m*N + n)*D + i as 64 bits, offset as 64 bits), key = seed). Returns float32 [M, N, D]
+    (`offset` is the generated step index in RnnEstimator.generate)."""
+    lo, hi = _split64(np.arange(M * N * D, dtype=np.uint64))
+    olo, ohi = _split64(np.uint64(offset))
+    klo, khi = _split64(np.uint64(seed))
+    ctr = np.stack(np.broadcast_arrays(lo, hi, olo, ohi), -1)
+    return u01(philox4x32_10(ctr, np.stack([klo, khi], -1)[None, :])[:, 0]).reshape(M, N, D)

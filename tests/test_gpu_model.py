@@ -137,6 +137,23 @@ def test_composer_generate_bit_exact():
     assert set(np.unique(thr.cpu().numpy())) <= {0.0, 1.0}
 
 
+@pytest.mark.xfail(strict=False, reason='written after round 1\'s GPU budget was spent: not yet run on a B200 (the CPU '
+                                        'Philox is pinned by the Random123 vectors); promote once it has passed')
+def test_composer_generate_philox_stream_equals_cpu_philox():
+    """Default generation path (no uniforms supplied): the sampler's in-kernel Philox stream is reproduced on the CPU
+    (oracle/philox.py::nade_sample_uniforms, step index as the counter's high half), so the generated piano-rolls must
+    equal the oracle's ancestral sampling bit for bit."""
+    from oracle.philox import nade_sample_uniforms
+    B, Ti, S, seed = 4, 5, 6, 77
+    model = make('composer', H=128, Rnn=(64, 32))
+    p = arena_to_params(model, 'generator', 2, True)
+    x = O.synthetic_pianoroll(B, Ti, seed=10, density=0.1)
+    u = np.stack([nade_sample_uniforms(seed, s, 5, B, 84) for s in range(S)])          # [S, M, B, D]
+    got = model.generate(torch.from_numpy(x).cuda(), S, u=None, seed=seed).cpu().numpy()
+    ref = O.composer_generate(x.astype(np.float64), O.cast_params(p, np.float64), S, u.astype(np.float64))
+    np.testing.assert_array_equal(got, ref)
+
+
 def test_jamming_parity_and_training():
     """Config C1 = Jamming LSTM-NADE: NLL parity + joint clip/Adam over the union of the 5 generators."""
     B, T, H, Rn = 4, 9, 128, (48, 32)

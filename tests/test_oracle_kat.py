@@ -300,3 +300,13 @@ def test_cpu_philox_known_answers_and_counter_layouts():
     assert not np.array_equal(uh[0], uh[1]) and not np.array_equal(gibbs_chain_uniforms(12, 5, 6, 84, 256, 2)[0], uh)
     a = half_step_uniforms(3, 100, 4, 8)
     assert np.array_equal(a.reshape(-1)[8:], half_step_uniforms(3, 108, 3, 8).reshape(-1))     # offset = element index
+
+
+def test_cpu_philox_nade_sampler_layout():
+    from oracle.philox import nade_sample_uniforms, philox4x32_10
+    u = nade_sample_uniforms(77, 3, 5, 4, 84)
+    assert u.shape == (5, 4, 84) and u.dtype == np.float32 and 0 <= u.min() and u.max() < 1
+    idx = (2 * 4 + 1) * 84 + 7                                             # track 2, row 1, dim 7
+    w = philox4x32_10(np.array([idx, 0, 3, 0], np.uint32), np.array([77, 0], np.uint32))
+    assert u[2, 1, 7] == np.float32(int(w[0]) >> 8) * np.float32(2.0 ** -24)
+    assert not np.array_equal(u, nade_sample_uniforms(77, 4, 5, 4, 84))   # a new step draws new noise
