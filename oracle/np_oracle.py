@@ -336,6 +336,41 @@ def rnn_rbm_forward(inp, tgt, params, k, uh, uv, keep=1.0, u_drop=None):
     return dict(cond_p=p_v, sample=v_s, loss=loss, bh_t=bh_t, bv_t=bv_t)
 
 
+def rnn_rbm_generate(codes, params, k, num_steps, us):
+    """RnnEstimator.generate for an RNN-RBM (generators/rnn_estimator.py:271-323, rnn_rbm.py:261-297): scan the intro
+    codes[B,Ti,E] (dropout off) -> last-step biases and RNN state; then `num_steps` times: k-step Gibbs chain STARTED FROM
+    THE PREVIOUS FRAME (the last intro frame first, rnn_rbm.py:295) with the state's biases, one LSTM step on the sample,
+    new biases. us[s] = (uh[k,B,H], uv[k,B,E]). Returns samples[B,num_steps,E]."""
+    W, bh, bv = params['rbm']
+    outs, state = rnn_scan(codes, params['lstm'])
+    o = outs[:, -1]
+    prev = codes[:, -1]
+    B, E = prev.shape
+    out = np.zeros((B, num_steps, E), codes.dtype)
+    for s in range(num_steps):
+        bh_t = bh + o @ params['Wuh']                                # rnn_rbm.py:252-257 (internal_bias=True)
+        bv_t = bv + o @ params['Wuv']
+        _, prev = rbm_gibbs(prev, W, bh_t, bv_t, k, us[s][0], us[s][1])
+        out[:, s] = prev
+        o, state = multi_rnn_step(prev, state, params['lstm'])
+    return out
+
+
+def joint_generate(x_intro, enc_rbms, gen_params, k, num_steps, u_enc, us, u_dec):
+    """multinn_joint.py:188-215: encode the zero-padded stacked intro with the DBN (sampled codes, quirk Q12), generate
+    codes with the RNN-RBM, decode them through the DBN (sampled visibles). Rows of the encoder / decoder uniforms are
+    TIME-MAJOR (t*B + b) resp. (b*S + s), as the device code lays them out. Returns [B,S,D,M]."""
+    B, Ti, D, M = x_intro.shape
+    inp, _ = composer_inputs_targets(x_intro)
+    pad = np.concatenate([inp, x_intro.reshape(B, Ti, -1)[:, -1:]], axis=1)           # [B,Ti+1,D*M]
+    flat_tm = pad.transpose(1, 0, 2).reshape((Ti + 1) * B, -1)
+    _, codes = dbn_forward(flat_tm, enc_rbms, u_enc)
+    codes = codes.reshape(Ti + 1, B, -1).transpose(1, 0, 2)
+    samples_h = rnn_rbm_generate(codes, gen_params, k, num_steps, us)                 # [B,S,E]
+    _, v = dbn_reconstruct(samples_h.reshape(B * num_steps, -1), enc_rbms, u_dec)
+    return v.reshape(B, num_steps, D, M)
+
+
 # ----------------------------------------------------------------------------- optimiser
 def clip_by_global_norm(grads, clip=5.0):
     """tf.clip_by_global_norm at utils/training.py:166: g * clip / max(gn, clip)."""

@@ -310,3 +310,24 @@ def test_cpu_philox_nade_sampler_layout():
     w = philox4x32_10(np.array([idx, 0, 3, 0], np.uint32), np.array([77, 0], np.uint32))
     assert u[2, 1, 7] == np.float32(int(w[0]) >> 8) * np.float32(2.0 ** -24)
     assert not np.array_equal(u, nade_sample_uniforms(77, 4, 5, 4, 84))   # a new step draws new noise
+
+
+def test_rnn_rbm_generate_is_the_composition_of_its_steps():
+    """oracle rnn_rbm_generate (rnn_estimator.py:271-323 for an RNN-RBM): the first generated frame is a k-step chain from
+    the LAST INTRO FRAME under the biases of the intro's last LSTM output; later frames chain from the previous sample."""
+    rng = np.random.default_rng(31)
+    B, Ti, E, H, k, S = 3, 4, 12, 7, 2, 3
+    p = O.init_rnn_rbm_params(I=E, D=E, H=H, R=(6, 5), seed=3)
+    p = O.cast_params(p, np.float64)
+    codes = (rng.random((B, Ti, E)) < 0.4).astype(np.float64)
+    us = [(rng.random((k, B, H)), rng.random((k, B, E))) for _ in range(S)]
+    out = O.rnn_rbm_generate(codes, p, k, S, us)
+    assert out.shape == (B, S, E) and set(np.unique(out)) <= {0.0, 1.0}
+    W, bh, bv = p['rbm']
+    outs, state = O.rnn_scan(codes, p['lstm'])
+    _, first = O.rbm_gibbs(codes[:, -1], W, bh + outs[:, -1] @ p['Wuh'], bv + outs[:, -1] @ p['Wuv'], k, *us[0])
+    np.testing.assert_array_equal(out[:, 0], first)
+    o, state = O.multi_rnn_step(first, state, p['lstm'])
+    _, second = O.rbm_gibbs(first, W, bh + o @ p['Wuh'], bv + o @ p['Wuv'], k, *us[1])
+    np.testing.assert_array_equal(out[:, 1], second)
+    np.testing.assert_array_equal(out, O.rnn_rbm_generate(codes, p, k, S, us))          # pure function of the uniforms
