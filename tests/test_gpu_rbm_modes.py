@@ -347,6 +347,29 @@ def test_pretrain_generators_updates_only_the_rbm_module():
 
 
 @_NOT_RUN_YET
+def test_joint_with_nade_generator_nll_parity():
+    """Joint mode with an RNN-NADE generator over the DBN codes (one "track" of 84 code bits): per-row NLL against the
+    oracle on the same sampled codes; `batch/loss` is the mean NLL divided by the number of tracks (multinn_joint.py:182-184)."""
+    B, T = 5, 6
+    model = make('joint', encoder='DBN', encoder_hidden=[168, 84], generator='NADE', num_hidden=128, num_hidden_rnn=(48, 32))
+    core = model._model
+    rng = np.random.default_rng(33)
+    sd, esd = sd_np(core.arena), sd_np(core.encoder_arena)
+    x = O.synthetic_pianoroll(B, T, seed=14, density=0.1)
+    N1 = (T + 1) * B
+    u_enc = [rng.random((N1, 168), dtype=np.float32), rng.random((N1, 84), dtype=np.float32)]
+    out = model.evaluate(cu(x), u_enc=[cu(a) for a in u_enc])
+    rbms = [tuple(a.astype(f64) for a in r) for r in dbn_params(esd, 'encoder/all', 2)]
+    inp, _ = O.composer_inputs_targets(x)
+    pad = np.concatenate([inp, x.reshape(B, T, -1)[:, -1:]], axis=1)
+    _, codes = O.dbn_forward(pad.transpose(1, 0, 2).reshape(N1, -1).astype(f64), rbms, [a.astype(f64) for a in u_enc])
+    codes = codes.reshape(T + 1, B, -1).transpose(1, 0, 2)                                   # [B,T+1,84]
+    ref = O.rnn_nade_forward(codes[:, :-1], codes[:, 1:], O.cast_params(rnn_nade_params(sd, 'generator', 2), f64))
+    np.testing.assert_allclose(out['nll'].cpu().numpy()[:, 0], ref['nll'], rtol=1e-4)
+    assert abs(float(out['batch/loss']) - ref['nll'].mean() / 5) < 1e-4 * ref['nll'].mean()
+
+
+@_NOT_RUN_YET
 def test_joint_generate_bit_exact_against_oracle():
     """multinn_joint.py:188-215 end to end with supplied uniforms: DBN-encode the intro, RNN-RBM generation (k-step chain
     from the previous frame, LSTM step, new biases), DBN-decode: the generated piano-rolls equal the oracle's bit for bit."""
