@@ -88,3 +88,29 @@ def test_argument_errors_are_codes_not_crashes():
     import pytest
     with pytest.raises(_lib.MultinnLibraryError):
         _lib.check(ERR_ARG, 'unit test')
+
+
+def test_plain_c_program_compiles_against_the_header_and_links():
+    """include/multinn_b200.h is the boundary: it must be valid C (not only C++), and a C program must link against the
+    library and reach its argument checks. gcc -std=c99 -Wall -Werror; no GPU needed."""
+    import shutil
+    import subprocess
+    import tempfile
+    if shutil.which('gcc') is None:
+        import pytest
+        pytest.skip('gcc not available')
+    import __graft_entry__ as g
+    libdir = os.path.join(ROOT, 'multinn_b200')
+    if not os.path.exists(os.path.join(libdir, 'libmultinn_sm100.so')):
+        g.build()
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, 'abi_smoke')
+        cuda_lib = '/usr/local/cuda/lib64'
+        cmd = ['gcc', '-std=c99', '-Wall', '-Wextra', '-Werror', '-pedantic', '-I', os.path.join(ROOT, 'include'),
+               os.path.join(ROOT, 'tests', 'abi_smoke.c'), '-o', exe, '-L', libdir, '-l:libmultinn_sm100.so',
+               f'-Wl,-rpath,{libdir}', f'-Wl,-rpath-link,{cuda_lib}', '-Wl,--allow-shlib-undefined']
+        subprocess.check_call(cmd)
+        env = dict(os.environ, LD_LIBRARY_PATH=f'{libdir}:{cuda_lib}:' + os.environ.get('LD_LIBRARY_PATH', ''))
+        out = subprocess.run([exe], env=env, capture_output=True, text=True)
+        assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+        assert 'abi smoke ok' in out.stdout
