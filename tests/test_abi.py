@@ -114,3 +114,47 @@ def test_plain_c_program_compiles_against_the_header_and_links():
         out = subprocess.run([exe], env=env, capture_output=True, text=True)
         assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
         assert 'abi smoke ok' in out.stdout
+
+
+def _header_prototypes():
+    """{name: (return type, [parameter types])} parsed from the header's declarations."""
+    src = open(os.path.join(ROOT, 'include', 'multinn_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r'([A-Za-z_][\w\s\*]*?)\b(mnn_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;', src):
+        ret, name, params = m.group(1).strip(), m.group(2), m.group(3).strip()
+        types = []
+        if params and params != 'void':
+            for p in params.split(','):
+                p = ' '.join(p.split())
+                p = re.sub(r'\b[A-Za-z_]\w*$', '', p).strip() if not p.endswith('*') else p      # drop the parameter name
+                types.append(p.replace(' *', '*'))
+        protos[name] = (ret, types)
+    return protos
+
+
+def _ctype_of(ctype_str):
+    import ctypes as C
+    t = ctype_str.replace('const ', '').strip()
+    if t.endswith('*') or t == 'mnn_stream_t':
+        return C.c_char_p if ctype_str.strip() == 'const char*' else C.c_void_p
+    return {'int': C.c_int, 'long long': C.c_longlong, 'float': C.c_float, 'unsigned long long': C.c_ulonglong,
+            'size_t': C.c_size_t, 'uint32_t': C.c_uint32}[t]
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every argtypes / restype entry of multinn_b200/_lib.py against the C prototype in the header: arity, integer widths
+    (int vs long long vs size_t), floats, pointers. A mismatch here corrupts arguments silently at call time."""
+    import ctypes as C
+    from multinn_b200 import _lib
+    protos = _header_prototypes()
+    assert sorted(protos) == sorted(_lib.SIGNATURES)
+    for name, (ret, params) in protos.items():
+        want = [_ctype_of(p) for p in params]
+        got = list(_lib.SIGNATURES[name])
+        assert len(got) == len(want), f'{name}: {len(got)} ctypes arguments for {len(want)} C parameters'
+        for i, (g, w) in enumerate(zip(got, want)):
+            assert g is w, f'{name}: argument {i} is {g.__name__} in _lib.py but `{params[i]}` in the header'
+        want_ret = _ctype_of(ret)
+        got_ret = _lib._RESTYPES.get(name, C.c_int)
+        assert got_ret is want_ret, f'{name}: restype {got_ret.__name__} but the header returns `{ret}`'
