@@ -110,6 +110,91 @@ def pack_tiles(V, tile_rows=128):
     return np.asarray(starts), total / ((len(starts) - 1) * tile_rows)
 
 
+def forward_backward_tiled(V, b_enc, b_dec, w_enc, w_dec, dnll, tile_rows=128, kblock=32, flush_every=16, eps=1e-6):
+    """The same computation in the ORDER the planned kernels do it, tile by tile (one tile = `tile_rows` segment rows =
+    the TMEM lanes of one accumulator, whole source rows only):
+      producer   per k-block of `kblock` hidden units: walk each source row's set bits with a `kblock`-wide slice of `a`
+                 and emit one H row per segment (what the producer warps write into the A-operand stage);
+      MMA 1      Lt += H[:, kb] @ W_dec[:, kb]^T over the k-blocks                      [tile_rows, D]
+      epilogue   lane r owns dims lo(r)..hi(r): logits, probabilities, NLL partials, g; per-source-row NLL = sum of its
+                 lanes' partials (stays inside the tile because rows never straddle);
+      backward   Gt (masked g) -> MMA 3: dH = Gt @ W_dec; dA = dH*H*(1-H); suffix sums inside the tile -> d b_enc, S;
+                 MMA 2 / 4: dW_dec += Gt^T @ H, dW_enc += Vt^T @ S into PERSISTENT accumulators that are flushed (added
+                 into the global result) every `flush_every` tiles - the TMEM-resident accumulators of the CTA.
+    Returns (nll, cond_p, grads) equal to forward() / backward()."""
+    N, D = V.shape
+    Hdim = w_enc.shape[1]
+    assert Hdim % kblock == 0
+    starts, _ = pack_tiles(V, tile_rows)
+    nll = np.zeros(N, V.dtype)
+    P = np.zeros((N, D), V.dtype)
+    g_b_enc, g_b_dec = np.zeros((N, Hdim), V.dtype), np.zeros((N, D), V.dtype)
+    g_w_enc, g_w_dec = np.zeros_like(w_enc), np.zeros_like(w_dec)
+    acc_enc, acc_dec, pending = np.zeros_like(w_enc), np.zeros_like(w_dec), 0
+    cols = np.arange(D)[None, :]
+    for a, b in zip(starts[:-1], starts[1:]):
+        rows = np.arange(a, b)
+        bits = [np.flatnonzero(V[n, :D - 1]) for n in rows]
+        r_of, lo, hi, opener, first_lane = [], [], [], [], {}
+        for j, n in enumerate(rows):                                  # lane table of the tile (built once per tile)
+            first_lane[n] = len(r_of)
+            for k in range(len(bits[j]) + 1):
+                r_of.append(n)
+                lo.append(0 if k == 0 else bits[j][k - 1] + 1)
+                hi.append(bits[j][k] if k < len(bits[j]) else D - 1)
+                opener.append(-1 if k == 0 else bits[j][k - 1])
+        R = len(r_of)
+        assert R <= tile_rows
+        r_of, lo, hi, opener = (np.asarray(x) for x in (r_of, lo, hi, opener))
+        # ---- producer + MMA 1, k-block by k-block
+        Htile = np.zeros((R, Hdim), V.dtype)
+        Lt = np.zeros((R, D), V.dtype)
+        for kb in range(0, Hdim, kblock):
+            sl = slice(kb, kb + kblock)
+            for j, n in enumerate(rows):
+                avec = b_enc[n, sl].copy()
+                r = first_lane[n]
+                Htile[r, sl] = sigmoid(avec)
+                for bit in bits[j]:
+                    avec = avec + w_enc[bit, sl]
+                    r += 1
+                    Htile[r, sl] = sigmoid(avec)
+            Lt += Htile[:, sl] @ w_dec[:, sl].T
+        # ---- epilogue: lane r walks its own dims only
+        own = (cols >= lo[:, None]) & (cols <= hi[:, None])
+        L = b_dec[r_of] + Lt
+        Pt = sigmoid(L)
+        Vr = V[r_of]
+        part = -np.where(own, Vr * np.log(eps + Pt) + (1 - Vr) * np.log(eps + 1 - Pt), 0.0).sum(1)
+        Gt = np.where(own, -(Vr / (eps + Pt) - (1 - Vr) / (eps + 1 - Pt)) * Pt * (1 - Pt) * dnll[r_of][:, None], 0.0)
+        for n in rows:                                                # the lane with k == 0 sums its row's partials
+            lanes = np.flatnonzero(r_of == n)
+            nll[n] = part[lanes].sum()
+            P[n] = (Pt[lanes] * own[lanes]).sum(0)                    # each dim is owned by exactly one lane
+            g_b_dec[n] = Gt[lanes].sum(0)
+        # ---- backward
+        dH = Gt @ w_dec                                               # MMA 3
+        S = dH * Htile * (1 - Htile)
+        for r in range(R - 2, -1, -1):
+            if r_of[r + 1] == r_of[r]:
+                S[r] += S[r + 1]
+        for n in rows:
+            g_b_enc[n] = S[first_lane[n]]
+        Vt = np.zeros((R, D), V.dtype)
+        opened = opener >= 0
+        Vt[np.flatnonzero(opened), opener[opened]] = 1.0
+        acc_dec += Gt.T @ Htile                                       # MMA 2 (persistent accumulator)
+        acc_enc += Vt.T @ S                                           # MMA 4
+        pending += 1
+        if pending == flush_every:                                    # cp.reduce.async.bulk add into global memory
+            g_w_dec += acc_dec
+            g_w_enc += acc_enc
+            acc_dec[:], acc_enc[:], pending = 0.0, 0.0, 0
+    g_w_dec += acc_dec
+    g_w_enc += acc_enc
+    return nll, P, dict(b_enc=g_b_enc, b_dec=g_b_dec, w_enc=g_w_enc, w_dec=g_w_dec)
+
+
 def flops(N, D, H, K_mean, tracks=1):
     R = (K_mean + 1) * N * tracks
     return dict(segment_rows=R, gemm_flops=4 * 2 * R * D * H, dense_triangular_flops=3 * tracks * N * D * (D - 1) * H)
