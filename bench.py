@@ -263,6 +263,22 @@ def run_gpu(args):
         except Exception as e:          # noqa: BLE001 - a diagnostic must not cost the bench line
             fullsize = {'error': repr(e)[:300]}
 
+    # ---- RBM Gibbs chain of config C3's generator (84 x 256, k = 10): fused one-launch kernel vs the GEMM + half-step
+    # path at generation and training row counts (tools/gibbs_bench.py; after every timed region; never fatal)
+    gibbs = None
+    if rank == 0 and world == 1 and not args.no_sampling:
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location('gibbs_bench', os.path.join(ROOT, 'tools', 'gibbs_bench.py'))
+            gb = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(gb)
+            import contextlib
+            import io
+            with contextlib.redirect_stdout(io.StringIO()):
+                gibbs = gb.main()
+        except Exception as e:          # noqa: BLE001
+            gibbs = {'error': repr(e)[:300]}
+
     if rank == 0:
         pk = peaks()
         tps = B * T / (ms * 1e-3)
@@ -296,6 +312,7 @@ def run_gpu(args):
             'sampling': sampling,
             'final_loss': final_loss,
             'fullsize_check': fullsize,
+            'rbm_gibbs_chain_84x256_k10': gibbs,
         }
         if world == 1 and not args.no_cpu:
             v, cores, _, sec = cpu_port_run(args.cpu_batch, T, 3, 1)
