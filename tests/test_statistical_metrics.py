@@ -60,3 +60,28 @@ def test_collect_metrics_classification_with_variable_lengths():
     assert got['precision'] == 1.0 and abs(got['recall'] - tp / (tp + fn)) < 1e-12 and fp == 0
     plain = U.collect_metrics(_Stub(), X, lengths, batch_size=2, piece_size=8, device='cpu')
     assert plain['log_likelihood'] == got['log_likelihood'] and 'accuracy' not in plain
+
+
+def test_streaming_result_does_not_depend_on_the_batching():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=30, deadline=None)
+    @given(st.integers(0, 2 ** 31 - 1), st.lists(st.integers(1, 7), min_size=1, max_size=6))
+    def check(seed, sizes):
+        rng = np.random.default_rng(seed)
+        n = sum(sizes)
+        t = torch.from_numpy(rng.random((n, 5)) < 0.4)
+        p = torch.from_numpy(rng.random((n, 5)) < 0.5)
+        lp = torch.from_numpy(rng.random(n) * 3)
+        whole = BaseMetrics()
+        whole.update(lp, t, p)
+        parts, a = BaseMetrics(), 0
+        for s in sizes:
+            parts.update(lp[a:a + s], t[a:a + s], p[a:a + s])
+            a += s
+        rw, rp = whole.result(), parts.result()
+        assert rw.keys() == rp.keys()
+        for k in rw:
+            assert abs(rw[k] - rp[k]) < 1e-12, k
+
+    check()
