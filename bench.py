@@ -131,8 +131,9 @@ def run_reference(args):
     wl = WORKLOADS[args.workload]
     sB, sT = args.cpu_batch, wl['T']
     steps = max(1, args.steps)
-    # bounded sample: keep the whole run within a few minutes whatever --steps asks for (calibrated on 8 rows)
-    v0, _, _, _ = cpu_port_run(8, sT, 1, 0)
+    # bounded sample: keep the whole run within a few minutes whatever --steps asks for. Calibrated on 32 rows (8 rows
+    # would under-use the cores and shrink the sample - and with it the reference's throughput - more than needed)
+    v0, _, _, _ = cpu_port_run(min(32, sB), sT, 1, 0)
     cap = int(args.cpu_seconds * v0 / (steps * sT)) // 8 * 8
     sB = max(8, min(sB, cap))
     v, cores, loss, sec = cpu_port_run(sB, sT, steps, min(args.warmup, 1))
