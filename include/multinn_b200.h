@@ -64,6 +64,19 @@ int mnn_gemm_tc(const float* A, long long lda, int transA, const float* B, long 
  * per-GPU batches) instead of queueing CTAs behind them. Host-side, thread-local; no reference counterpart. */
 int mnn_set_sm_budget(int sms);
 
+/* Data-parallel noise keying (no reference counterpart: the reference is single-device; SURVEY 8(e) asks that results
+ * do not depend on the GPU count). Every entry point that can draw Philox noise (dropout in mnn_lstm_*_fwd*, the
+ * Bernoulli draws of mnn_bias_sigmoid_sample, mnn_rbm_gibbs, mnn_nade_sample, mnn_sample_steps) keys the counter by the
+ * GLOBAL row of its local row r:  (r / rows_local) * rows_global + row_base + r % rows_local  -- for a time-major
+ * [T, B_local, .] tensor of a rank that owns sequences [row_base, row_base + B_local) of a global batch B_global:
+ * rows_local = B_local, rows_global = B_global. Thread-local, applies to the calling thread's following launches;
+ * (0, 0, 0) restores the identity. Supplied uniforms are unaffected. */
+int mnn_set_row_map(long long rows_local, long long rows_global, long long row_base);
+/* Index of the first time step of the calling thread's following mnn_lstm_* launches inside the whole sequence: the
+ * dropout counter is (global batch row, unit, GLOBAL time step), so a sequence run in time chunks (the small-batch
+ * pipelines) draws the same masks as one launch over all T steps. 0 by default. */
+int mnn_set_time_base(long long t_base);
+
 /* K2 -- LSTM temporal unit. common/rnn.py:104-145 (CudnnCompatibleLSTMCell, gate blocks i,j,f,o, forget_bias 0;
  * DropoutWrapper output_keep_prob; MultiRNNCell), driven like dynamic_decode at generators/rnn_nade.py:204-218.
  * One cell step: gates[B,4R] in = pre-activations, out = activations; out = h/keep*floor(keep+u). */

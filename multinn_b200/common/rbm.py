@@ -8,6 +8,8 @@ and the 84/168 DBN layers) and the batch is below the measured crossover (`ops.G
 i.e. generation and small training batches); larger batches, larger layers (the Joint encoder's 420 x 168) and single
 half-steps (`forward`, `reconstruct`) run a tensor-core GEMM followed by the fused bias + sigmoid + Bernoulli kernel.
 """
+import zlib
+
 import torch
 
 from .. import ops
@@ -24,6 +26,11 @@ class RBM(Model):
         self.bv = arena.add(f'{name}/bv', (1, num_dims), zeros())                                        # :53-58
         self._seed = 0
         self._calls = 0
+        # Every RBM draws from its own Philox stream: the reference's Bernoulli draws of distinct RBMs (DBN layers, the
+        # per-track encoders, the generator's RBM) are independent (tfp Bernoulli.sample at rbm.py:375-387 has one op-level
+        # seed per graph node), so the kernels' key = seed is mixed with a stream id derived from the variable scope name,
+        # and with a domain tag that separates the fused chain (counter = row) from the half-step kernels (counter = element).
+        self._stream = zlib.crc32(name.encode())
 
     num_dims = property(lambda s: s._num_dims)
     num_hidden = property(lambda s: s._num_hidden)
@@ -33,9 +40,16 @@ class RBM(Model):
     def trainable_params(self):
         return [self.W, self.bh, self.bv]
 
+    def _key(self, seed, domain=0):
+        """64-bit Philox key of this RBM for a user seed: splitmix-style mix of (seed, stream id, domain)."""
+        z = ((self._seed if seed is None else int(seed)) + 0x9E3779B97F4A7C15 * (2 * self._stream + domain + 1)) % (1 << 64)
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) % (1 << 64)
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) % (1 << 64)
+        return z ^ (z >> 31)
+
     def _next_offset(self, n):
         o = self._calls
-        self._calls += n
+        self._calls += n * ops.row_scale()      # counters advance by GLOBAL element counts (ops.row_map)
         return o
 
     # ------------------------------------------------------------------ conditionals (rbm.py:337-373)
@@ -57,7 +71,7 @@ class RBM(Model):
         p = torch.empty_like(pre)
         h = torch.empty_like(pre) if sample else None
         ops.bias_sigmoid_sample(pre, bias=bh, u=u, p=p, s=h, use_philox=sample and u is None,
-                                seed=self._seed if seed is None else seed, offset=self._next_offset(pre.numel()))
+                                seed=self._key(seed), offset=self._next_offset(pre.numel()))
         return p, h
 
     def reconstruct(self, h, bv=None, u=None, seed=None, sample=True):
@@ -66,7 +80,7 @@ class RBM(Model):
         p = torch.empty_like(pre)
         v = torch.empty_like(pre) if sample else None
         ops.bias_sigmoid_sample(pre, bias=bv, u=u, p=p, s=v, use_philox=sample and u is None,
-                                seed=self._seed if seed is None else seed, offset=self._next_offset(pre.numel()))
+                                seed=self._key(seed), offset=self._next_offset(pre.numel()))
         return p, v
 
     def sample(self, v, bh=None, bv=None, k=None, u=None, seed=None):
@@ -83,7 +97,7 @@ class RBM(Model):
                 uu = None if u is None else (u[0][:k], u[1][:k])
                 # Philox: the chain's stream is keyed by the row, so only one offset unit per call is consumed per row
                 ops.rbm_gibbs(v, self.W.data, bh_, bv_, k, p_v=p_v, v_k=vk, u=uu,
-                              seed=self._seed if seed is None else seed, offset=self._next_offset(N))
+                              seed=self._key(seed, domain=1), offset=self._next_offset(N))
                 return p_v, vk
         p_v, vk = v, v
         for s in range(k):

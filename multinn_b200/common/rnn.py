@@ -263,7 +263,7 @@ class RNN:
                     ops.lstm_seq_fwd(w['gates'][t0:t1], wh, w['hbuf'][t0:t1 + 1], w['cbuf'][t0:t1 + 1],
                                      out=w['out'][t0:t1] if dropout else None,
                                      dscale=w['dscale'][t0:t1] if dropout else None,
-                                     u=None if u is None else u[l][t0:t1], keep=keep, seed=seed + 7919 * l + 104729 * c)
+                                     u=None if u is None else u[l][t0:t1], keep=keep, seed=seed + 7919 * l, t_base=t0)
                 finally:
                     ops.set_sm_budget(0)
                 done = self._event(f'fwd top chunk {c}')
@@ -328,7 +328,7 @@ class RNN:
                                          out=w['out'][t0:t1] if dropout else None,
                                          dscale=w['dscale'][t0:t1] if dropout else None,
                                          u=None if u is None else u[l][t0:t1], keep=keep,
-                                         seed=seed + 7919 * l + 104729 * c)
+                                         seed=seed + 7919 * l, t_base=t0)
                     finally:
                         ops.set_sm_budget(0)
                     done[l][c].record(streams[l])

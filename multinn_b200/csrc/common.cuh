@@ -21,6 +21,22 @@ int mnn_check_launch(const char* what, int kernels = 1);  // also counts kernel 
 
 namespace mnn {
 
+// Data-parallel row keying of the in-kernel Philox streams: a kernel that draws noise for its LOCAL row r
+// keys the counter by the GLOBAL row  (r / rows_local) * rows_global + row_base + r % rows_local  -- local rows come in
+// groups of rows_local (the per-GPU batch of one time step of a time-major tensor) that sit rows_global apart in the
+// global tensor, this rank's group starting at row_base. rows_local == 0: identity. Set per host thread with
+// mnn_set_row_map(); every Philox-capable launch copies the calling thread's map into its kernel arguments.
+struct RowMap {
+  long long rows_local, rows_global, row_base;
+  long long t_base;   // index of a sequence launch's first time step inside the whole sequence (chunked launches)
+};
+__host__ __device__ __forceinline__ unsigned long long global_row(const RowMap& m, unsigned long long r) {
+  if (m.rows_local <= 0) return r;
+  const unsigned long long g = r / (unsigned long long)m.rows_local;
+  return g * (unsigned long long)m.rows_global + (unsigned long long)m.row_base + (r - g * (unsigned long long)m.rows_local);
+}
+RowMap current_row_map();   // host: the calling thread's map (util.cu)
+
 constexpr float kSafeLogEps = 1e-6f;  // reference utils/auxiliary.py:11
 
 __device__ __forceinline__ float sigmoid_fast(float x) {
@@ -88,6 +104,14 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
     key.y += W1;
   }
   return ctr;
+}
+// Dropout noise of the LSTM kernels (SIMT cell, tcgen05 sequence kernels, any chunking, any GPU count draw the SAME mask):
+// the 4 uniforms of units [4q, 4q+4) of batch row b at time step t are the 4 words of
+// Philox(ctr = ((global b) * R/4 + q as 64 bits, global t, 0), key = seed).
+__device__ __forceinline__ uint4 dropout_bits4(unsigned long long seed, const RowMap& m, int b, int unit4, int R, int t) {
+  const unsigned long long e = global_row(m, (unsigned long long)b) * (unsigned long long)(R >> 2) + (unsigned)(unit4 >> 2);
+  return philox4x32_10(make_uint4((uint32_t)e, (uint32_t)(e >> 32), (uint32_t)(t + (int)m.t_base), 0u),
+                       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
 }
 // 24-bit uniform in [0,1): exactly representable in fp32, strict-< comparisons behave like TF's.
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }

@@ -19,6 +19,7 @@ struct CellFwdArgs {
   float keep;
   unsigned long long seed, offset;  // philox when u == null and keep < 1
   int B, R;
+  RowMap rmap;                      // global-row keying of the Philox counter (offset must be a multiple of R)
 };
 
 __global__ void lstm_cell_fwd_kernel(CellFwdArgs a) {
@@ -41,10 +42,11 @@ __global__ void lstm_cell_fwd_kernel(CellFwdArgs a) {
       float uu;
       if (a.u) uu = a.u[idx];
       else {
-        const unsigned long long e = a.offset + (unsigned long long)idx;
-        const uint4 r4 = philox4x32_10(make_uint4((uint32_t)e, (uint32_t)(e >> 32), 0u, 0u),
-                                       make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
-        uu = u01(r4.x);
+        // offset = t * B * R of the sequence loop (mnn_lstm_seq_fwd); the word of unit r is r % 4 of its group of 4
+        const int t = (int)(a.offset / ((unsigned long long)a.B * a.R));
+        const uint4 r4 = dropout_bits4(a.seed, a.rmap, b, r & ~3, a.R, t);
+        const uint32_t w4[4] = {r4.x, r4.y, r4.z, r4.w};
+        uu = u01(w4[r & 3]);
       }
       // tf.nn.dropout: x / keep * floor(keep + u)
       const float keepmask = floorf(a.keep + uu);
@@ -124,7 +126,7 @@ extern "C" int mnn_lstm_cell_fwd(float* gates, const float* c_prev, float* c, fl
   MNN_REQUIRE(gates && c_prev && c && h, MNN_ERR_ARG, "lstm_cell_fwd: null pointer");
   MNN_REQUIRE(B > 0 && R > 0, MNN_ERR_ARG, "lstm_cell_fwd: non-positive size");
   MNN_REQUIRE(!(out && keep < 1.f && !dscale), MNN_ERR_ARG, "lstm_cell_fwd: dscale required when keep < 1");
-  CellFwdArgs a{gates, c_prev, c, h, out, dscale, u, keep, seed, offset, B, R};
+  CellFwdArgs a{gates, c_prev, c, h, out, dscale, u, keep, seed, offset, B, R, current_row_map()};
   const int n = B * R;
   lstm_cell_fwd_kernel<<<(n + 255) / 256, 256, 0, stream>>>(a);
   return mnn_check_launch("lstm_cell_fwd");

@@ -43,6 +43,7 @@ struct LstmParams {
   float* dc;            // [B][R] carry (bwd)
   float keep;
   unsigned long long seed;
+  RowMap rmap;          // global-row / global-time keying of the dropout Philox counter
   int T, B, R;
   int t0, t1;           // fwd: steps t0..t1-1 ascending; bwd: steps t1-1..t0 descending
   int slabs, blocks;    // work items per step
@@ -323,9 +324,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                   } else {
 #pragma unroll
                     for (int h4 = 0; h4 < 2; ++h4) {
-                      const unsigned long long ctr = (unsigned long long)(e >> 2) + h4;
-                      const uint4 r4 = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u),
-                                                     make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+                      const uint4 r4 = dropout_bits4(p.seed, p.rmap, b, unit + 4 * h4, R, t);
                       uu[4 * h4] = u01(r4.x); uu[4 * h4 + 1] = u01(r4.y);
                       uu[4 * h4 + 2] = u01(r4.z); uu[4 * h4 + 3] = u01(r4.w);
                     }
@@ -580,9 +579,7 @@ lstm_tc2_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           } else {
 #pragma unroll
             for (int h4 = 0; h4 < 2; ++h4) {
-              const unsigned long long ctr = (unsigned long long)(e >> 2) + h4;
-              const uint4 r4 = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u),
-                                             make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+              const uint4 r4 = dropout_bits4(p.seed, p.rmap, b, unit0 + ug * 8 + 4 * h4, R, t);
               uu[4 * h4] = u01(r4.x); uu[4 * h4 + 1] = u01(r4.y);
               uu[4 * h4 + 2] = u01(r4.z); uu[4 * h4 + 3] = u01(r4.w);
             }
@@ -1421,7 +1418,7 @@ extern "C" int mnn_lstm_seq_fwd_tc(float* gates, const float* wh, float* hbuf, f
   if (rc) return rc;
   if (pair) {
     LstmParams p{};
-    p.gates = gates; p.hbuf = hbuf; p.cbuf = cbuf; p.out = out; p.dscale = dscale; p.u = u; p.keep = keep; p.seed = seed;
+    p.gates = gates; p.hbuf = hbuf; p.cbuf = cbuf; p.out = out; p.dscale = dscale; p.u = u; p.keep = keep; p.seed = seed; p.rmap = current_row_map();
     p.T = T; p.B = B; p.R = R; p.t0 = 0; p.t1 = T;
     p.slabs = (B + 2 * BM - 1) / (2 * BM); p.blocks = blocks; p.kb_total = (R + BK - 1) / BK; p.flags = flags;
     static const char* bf16x_env = getenv("MNN_LSTM_BF16X");   // "0": 3xTF32
@@ -1480,7 +1477,7 @@ extern "C" int mnn_lstm_seq_fwd_tc(float* gates, const float* wh, float* hbuf, f
   }
 
   LstmParams p{};
-  p.gates = gates; p.hbuf = hbuf; p.cbuf = cbuf; p.out = out; p.dscale = dscale; p.u = u; p.keep = keep; p.seed = seed;
+  p.gates = gates; p.hbuf = hbuf; p.cbuf = cbuf; p.out = out; p.dscale = dscale; p.u = u; p.keep = keep; p.seed = seed; p.rmap = current_row_map();
   p.T = T; p.B = B; p.R = R; p.t0 = 0; p.t1 = T;
   p.slabs = (B + BM - 1) / BM; p.blocks = blocks; p.kb_total = (R + BK - 1) / BK; p.flags = flags;
   CUtensorMap ma, mb;

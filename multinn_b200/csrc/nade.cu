@@ -498,6 +498,7 @@ struct NadeSampleArgs {
   float* nll;                              // [M][N] or null
   int N, M, D;
   unsigned long long seed, offset; int use_philox;
+  RowMap rmap;   // Philox counter = ((global_row(row) * M + m) * D + i, offset)
 };
 
 // 1024 threads: every dim of a row is a dependent chain (dot -> reduce -> sigmoid -> compare -> maybe 8 more sigmoids), so
@@ -541,7 +542,7 @@ __global__ void __launch_bounds__(kSampleThreads, 1) nade_sample_kernel(NadeSamp
       if (i < D) {
         if (p.u) uu = __ldg(p.u + ((size_t)m * p.N + row) * D + i);
         else if (p.use_philox) {
-          const unsigned long long idx = ((unsigned long long)m * p.N + row) * D + i;
+          const unsigned long long idx = (global_row(p.rmap, (unsigned long long)row) * p.M + m) * D + i;
           const uint4 r4 = philox4x32_10(make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)p.offset,
                                                     (uint32_t)(p.offset >> 32)),
                                          make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
@@ -687,7 +688,7 @@ extern "C" int mnn_nade_sample(const float* fc, long long ld, int enc_col0, int 
   int rc = check_nade_common(N, M, D, H, ld, enc_col0, dec_col0);
   if (rc) return rc;
   NadeSampleArgs a{fc, ld, enc_col0, dec_col0, w_enc, w_dec, u, out, out_ld, out_dim_stride, out_track_stride,
-                   nll, N, M, D, seed, offset, use_philox};
+                   nll, N, M, D, seed, offset, use_philox, current_row_map()};
   const size_t smem = (size_t)2 * D * H * sizeof(float);
   int grid = num_sms();
   const int wpc = kSampleThreads / 32;

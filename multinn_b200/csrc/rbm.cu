@@ -15,6 +15,7 @@ struct SigSampleArgs {
   int N, C;
   int mode;                               // 0: no sampling, 1: u supplied, 2: philox
   unsigned long long seed, offset;
+  RowMap rmap;                            // Philox counter = offset + global_row(r) * C + c
 };
 
 __global__ void bias_sigmoid_sample_kernel(SigSampleArgs a) {
@@ -29,7 +30,7 @@ __global__ void bias_sigmoid_sample_kernel(SigSampleArgs a) {
     float uu = 0.f;
     if (a.mode == 1) uu = a.u[(size_t)r * a.ld_u + c];
     else if (a.mode == 2) {
-      const unsigned long long e = a.offset + idx;
+      const unsigned long long e = a.offset + global_row(a.rmap, (unsigned long long)r) * a.C + c;
       const uint4 r4 = philox4x32_10(make_uint4((uint32_t)e, (uint32_t)(e >> 32), 0u, 0u),
                                      make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
       uu = u01(r4.x);
@@ -95,6 +96,7 @@ struct GibbsArgs {
   int N, D, H, k;
   int philox;
   unsigned long long seed, offset;
+  RowMap rmap;                             // Philox counter row = offset + global_row(row)
 };
 
 constexpr int kGibbsThreads = 256;
@@ -148,7 +150,7 @@ __device__ __forceinline__ void gibbs_epilogue(float2 (&acc)[NQ][4][2], int out_
                                                const float* __restrict__ bias, long long ld_bias,
                                                const float* __restrict__ u /* [N][out_dim] of this half-step or null */,
                                                int philox, unsigned long long seed, unsigned long long offset,
-                                               unsigned half_step, float* __restrict__ outbuf, float* __restrict__ p_out,
+                                               const RowMap& rmap, unsigned half_step, float* __restrict__ outbuf, float* __restrict__ p_out,
                                                long long ld_p, float* __restrict__ s_out, long long ld_s) {
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
@@ -173,7 +175,7 @@ __device__ __forceinline__ void gibbs_epilogue(float2 (&acc)[NQ][4][2], int out_
         if (u) {
           uu = *reinterpret_cast<const float4*>(u + (size_t)row * out_dim + col);
         } else if (philox) {
-          const unsigned long long e = offset + (unsigned long long)row;
+          const unsigned long long e = offset + global_row(rmap, (unsigned long long)row);
           const uint4 r4 = philox4x32_10(make_uint4((uint32_t)e, (uint32_t)(e >> 32), half_step, (uint32_t)(col >> 2)),
                                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
           uu = make_float4(u01(r4.x), u01(r4.y), u01(r4.z), u01(r4.w));
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(kGibbsThreads, 1) rbm_gibbs_kernel(GibbsArgs a
         float2 acc[NQH][4][2];
         gibbs_matvec<NQH>(wsm, D, H, vbuf, lane, acc);
         gibbs_epilogue<NQH>(acc, H, lane, row0, a.N, a.bh, a.ld_bh,
-                            a.uh ? a.uh + (size_t)s * a.N * H : nullptr, a.philox, a.seed, a.offset, 2u * s, hbuf,
+                            a.uh ? a.uh + (size_t)s * a.N * H : nullptr, a.philox, a.seed, a.offset, a.rmap, 2u * s, hbuf,
                             nullptr, 0, last ? a.h_k : nullptr, a.ld_hk);
       }
       __syncwarp();
@@ -244,7 +246,7 @@ __global__ void __launch_bounds__(kGibbsThreads, 1) rbm_gibbs_kernel(GibbsArgs a
         gibbs_matvec<NQD>(wtsm, H, D, hbuf, lane, acc);
         __syncwarp();   // every lane has read vbuf's predecessor state before it is overwritten (it was: matvec above)
         gibbs_epilogue<NQD>(acc, D, lane, row0, a.N, a.bv, a.ld_bv,
-                            a.uv ? a.uv + (size_t)s * a.N * D : nullptr, a.philox, a.seed, a.offset, 2u * s + 1u, vbuf,
+                            a.uv ? a.uv + (size_t)s * a.N * D : nullptr, a.philox, a.seed, a.offset, a.rmap, 2u * s + 1u, vbuf,
                             last ? a.p_v : nullptr, a.ld_p, last ? a.v_k : nullptr, a.ld_vk);
       }
       __syncwarp();
@@ -270,7 +272,7 @@ extern "C" int mnn_bias_sigmoid_sample(const float* pre, long long ld_pre, const
                                        int N, int C, cudaStream_t stream) {
   MNN_REQUIRE(pre && (p || s) && N > 0 && C > 0, MNN_ERR_ARG, "bias_sigmoid_sample: bad argument");
   MNN_REQUIRE(!(s && !u && !use_philox), MNN_ERR_ARG, "bias_sigmoid_sample: sampling needs uniforms or philox");
-  SigSampleArgs a{pre, ld_pre, bias, ld_bias, u, ld_u, p, ld_p, s, ld_s, N, C, u ? 1 : (use_philox ? 2 : 0), seed, offset};
+  SigSampleArgs a{pre, ld_pre, bias, ld_bias, u, ld_u, p, ld_p, s, ld_s, N, C, u ? 1 : (use_philox ? 2 : 0), seed, offset, current_row_map()};
   const size_t n = (size_t)N * C;
   bias_sigmoid_sample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a);
   return mnn_check_launch("bias_sigmoid_sample");
@@ -308,7 +310,7 @@ extern "C" int mnn_rbm_gibbs(const float* v0, long long ld_v, const float* W, co
                   ld_vk % 4 == 0 && ld_hk % 4 == 0,
               MNN_ERR_ARG, "rbm_gibbs: pointers must be 16-byte aligned and row strides multiples of 4 floats");
   GibbsArgs a{v0, ld_v, W, bh, ld_bh, bv, ld_bv, uh, uv, p_v, ld_p, v_k, ld_vk, h_k, ld_hk, N, D, H, k,
-              use_philox ? 1 : 0, seed, offset};
+              use_philox ? 1 : 0, seed, offset, current_row_map()};
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -29,3 +29,19 @@ int mnn_check_launch(const char* what, int kernels) {
 extern "C" int mnn_version(void) { return 100; }
 extern "C" unsigned long long mnn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" const char* mnn_last_error_string(void) { return g_err; }
+
+static thread_local mnn::RowMap g_row_map{0, 0, 0, 0};
+mnn::RowMap mnn::current_row_map() { return g_row_map; }
+extern "C" int mnn_set_row_map(long long rows_local, long long rows_global, long long row_base) {
+  MNN_REQUIRE(rows_local >= 0 && row_base >= 0, MNN_ERR_ARG, "set_row_map: negative sizes");
+  MNN_REQUIRE(rows_local == 0 || rows_global >= rows_local + 0, MNN_ERR_ARG, "set_row_map: rows_global < rows_local");
+  MNN_REQUIRE(rows_local == 0 || row_base + rows_local <= rows_global, MNN_ERR_ARG,
+              "set_row_map: the local group does not fit into the global one");
+  g_row_map = mnn::RowMap{rows_local, rows_global, row_base, g_row_map.t_base};
+  return MNN_OK;
+}
+extern "C" int mnn_set_time_base(long long t_base) {
+  MNN_REQUIRE(t_base >= 0, MNN_ERR_ARG, "set_time_base: negative");
+  g_row_map.t_base = t_base;
+  return MNN_OK;
+}

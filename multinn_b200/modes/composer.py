@@ -32,13 +32,13 @@ class MultINNComposer(MultINNCore):
         if self.encoder_type != 'Pass':
             raise NotImplementedError('Composer with DBN encoders: use feedback/joint modes or Pass encoders')
 
-    def _forward_backward(self, x, keep, u_drop, seed, lengths=None, **extra):
+    def _forward_backward(self, x, keep, u_drop, seed, lengths=None, loss_scale=1.0, **extra):
         self._require_pass()
         B, T, D, M = x.shape
         st = self._stage_inputs(x, stacked=True, bits=True)
         # inputs = slots 0..T-1 ([0, x_0..x_{T-2}]), targets = slots 1..T (multinn_composer.py:82-86)
         loss, nll, _ = self._generator.forward_backward(st['xin'][:T], st['bits'], keep=keep, u_drop=u_drop, seed=seed,
-                                                        lengths=lengths)
+                                                        lengths=lengths, loss_scale=loss_scale)
         self._last_nll = (nll, T, B)
         return loss
 

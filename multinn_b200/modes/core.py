@@ -16,7 +16,7 @@ from .. import ops
 from ..common.model import Model
 from ..encoders.pass_encoder import PassEncoder
 from ..params import ParamArena
-from ..training import AdamOptimizer, GradientApplier, GradientDescentOptimizer, rank_seed
+from ..training import AdamOptimizer, GradientApplier, GradientDescentOptimizer, dp_row_map
 
 
 class MultINNCore(Model, abc.ABC):
@@ -152,15 +152,16 @@ class MultINNCore(Model, abc.ABC):
         self._applier = GradientApplier(self._arena, opt, lr=lr)
         counter = [0]
 
-        def step(x, lengths=None, u_drop=None, seed=None, keep=None, **extra):
+        def step(x, lengths=None, u_drop=None, seed=None, keep=None, row_base=None, global_batch=None, **extra):
             x = self._check_x(x, lengths)
             self._applier.zero_grad()
-            s = rank_seed(counter[0]) if seed is None else seed      # an explicit seed is used as given on every rank
+            s = counter[0] if seed is None else seed      # the same seed on every rank: noise is keyed by the global row
             counter[0] += 1
             if lengths is not None and self._supports_lengths:
                 extra['lengths'] = lengths
-            loss = self._forward_backward(x, keep=self._keep_prob if keep is None else keep, u_drop=u_drop,
-                                          seed=s * 1000003, **extra)
+            with ops.row_map(*dp_row_map(x.shape[0], row_base, global_batch)):
+                loss = self._forward_backward(x, keep=self._keep_prob if keep is None else keep, u_drop=u_drop,
+                                              seed=s * 1000003, **extra)
             self._applier.apply()
             self._metrics['batch/loss'] = loss
             return loss
@@ -179,14 +180,15 @@ class MultINNCore(Model, abc.ABC):
         flattened input frames (rnn_rbm.py:299-322; `RBM.train` applies it itself, the optimizer is unused there too)."""
         counter = [0]
 
-        def step(x, lengths=None, u=None, seed=None):
+        def step(x, lengths=None, u=None, seed=None, row_base=None, global_batch=None):
             x = self._check_x(x, lengths)
-            s = rank_seed(counter[0]) if seed is None else seed
+            s = counter[0] if seed is None else seed
             counter[0] += 1
             updated = 0
-            for gen, rows in self._pretrain_rows(x, s * 1000003):
-                if rows is not None and gen.pretrain(rows, lr, u=u, seed=s * 7919 + 13) is not None:
-                    updated += 1
+            with ops.row_map(*dp_row_map(x.shape[0], row_base, global_batch)):
+                for gen, rows in self._pretrain_rows(x, s * 1000003):
+                    if rows is not None and gen.pretrain(rows, lr, u=u, seed=s * 7919 + 13) is not None:
+                        updated += 1
             return updated
 
         return step
@@ -238,8 +240,9 @@ class MultINNCore(Model, abc.ABC):
                 if enc not in trainable:
                     continue
                 um = None if u is None else u[m]
-                met = enc.layer_metrics(rows, layer, u=None if um is None else um['metrics'], seed=s * 7919 + 31 * m)
-                enc.train(rows, lr, layer=layer, u=None if um is None else um['train'], seed=s * 7919 + 31 * m + 1)
+                with ops.row_map(*dp_row_map(x.shape[0])):
+                    met = enc.layer_metrics(rows, layer, u=None if um is None else um['metrics'], seed=s * 7919 + 31 * m)
+                    enc.train(rows, lr, layer=layer, u=None if um is None else um['train'], seed=s * 7919 + 31 * m + 1)
                 for k in out:
                     out[k] = out[k] + met[k].reshape(()) / max(len(trainable), 1)
             self._metrics.update({f'encoders/{k}': v for k, v in out.items()})
@@ -288,7 +291,10 @@ class MultINNCore(Model, abc.ABC):
         dc = self._config['data']
         pitch_span = dc['pitch_range']['highest'] - dc['pitch_range']['lowest']
         num_steps = num_beats * dc['beat_resolution'] * pitch_span // self.num_dims
-        return lambda x, u=None, seed=None: self.generate(x, num_steps, u=u, seed=rank_seed(0) if seed is None else seed)
+        def sample(x, u=None, seed=None, row_base=None, global_batch=None):
+            with ops.row_map(*dp_row_map(x.shape[0], row_base, global_batch)):
+                return self.generate(x, num_steps, u=u, seed=0 if seed is None else seed)
+        return sample
 
     def evaluator(self):
         """multinn_core.py:343-362: returns `evaluate_music(x) -> {summary scope: value}`: x[B,T,num_dims,M] (device tensor

@@ -78,7 +78,7 @@ class MultINNFeedback(MultINNCore):
     _supports_lengths = True      # the generators take `lengths` (multinn_feedback.py:93-94); the feedback module runs
                                   # over every padded step in training (:76-80 passes no lengths)
 
-    def _forward_backward(self, x, keep, u_drop, seed, u_enc=None, u_fb=None, lengths=None, **extra):
+    def _forward_backward(self, x, keep, u_drop, seed, u_enc=None, u_fb=None, lengths=None, loss_scale=1.0, **extra):
         B, T, D, M = x.shape
         xe, stack, bits = self._encode(x, u_enc, seed)
         fb = self._apply_feedback(stack, keep=keep, u_fb=u_fb, seed=seed + 17)
@@ -89,7 +89,7 @@ class MultINNFeedback(MultINNCore):
             inp = torch.cat([xe[m][:T], fb[:T]], dim=2)                       # multinn_feedback.py:86-88
             loss, nll, dx = gen.forward_backward(inp, bits[m:m + 1], keep=keep,
                                                  u_drop=None if u_drop is None else u_drop[m],
-                                                 seed=seed + 104729 * m, loss_scale=1.0 / M, need_dx=True,
+                                                 seed=seed + 104729 * m, loss_scale=loss_scale / M, need_dx=True,
                                                  lengths=lengths)
             total += loss
             dfb[:T] += dx[:, :, E:]
@@ -144,8 +144,10 @@ class MultINNFeedback(MultINNCore):
                       for m, gen in enumerate(self._generators)]
             prev = cur
         music = torch.empty(B, num_steps, D, M, device=x.device)
-        for m, enc in enumerate(self._encoders):
-            _, v = enc.decode(samples_h[..., m].reshape(B * num_steps, E), u=None if u_dec is None else u_dec[m],
-                              seed=seed + 977 * m) if enc.stochastic else enc.decode(samples_h[..., m].reshape(B * num_steps, E))
-            music[..., m] = v.view(B, num_steps, D)
+        with ops.row_map_scaled(num_steps):            # decode rows are b-major (b*S + s)
+            for m, enc in enumerate(self._encoders):
+                h_m = samples_h[..., m].reshape(B * num_steps, E).contiguous()     # the track slice is a strided view
+                _, v = enc.decode(h_m, u=None if u_dec is None else u_dec[m],
+                                  seed=seed + 977 * m) if enc.stochastic else enc.decode(h_m)
+                music[..., m] = v.view(B, num_steps, D)
         return music

@@ -30,7 +30,7 @@ class MultINNJamming(MultINNCore):
         if self.encoder_type != 'Pass':
             raise NotImplementedError('Jamming with DBN encoders is not wired yet')
 
-    def _forward_backward(self, x, keep, u_drop, seed, lengths=None, **extra):
+    def _forward_backward(self, x, keep, u_drop, seed, lengths=None, loss_scale=1.0, **extra):
         self._require_pass()
         B, T, D, M = x.shape
         st = self._stage_inputs(x, per_track=True, bits=True)
@@ -39,7 +39,7 @@ class MultINNJamming(MultINNCore):
         for m, gen in enumerate(self._generators):
             loss, nll, _ = gen.forward_backward(st['xtr'][m, :T], st['bits'][m:m + 1], keep=keep,
                                                 u_drop=None if u_drop is None else u_drop[m],
-                                                seed=seed + 104729 * m, loss_scale=1.0 / M, lengths=lengths)
+                                                seed=seed + 104729 * m, loss_scale=loss_scale / M, lengths=lengths)
             total += loss
             nlls.append(nll)
         return total

@@ -47,32 +47,39 @@ class MultINNJoint(MultINNCore):
         B, T, D, M = x.shape
         codes = self._encode(x, u_enc, seed)
         if isinstance(self._generator, RnnRBM):
+            # train_generators (:263-288) optimises the GENERATOR's own batch/loss (generator.py:196-201): no 1/M;
+            # :182-184 divides only the model-level (encoder `global`) metrics by M.
             loss, out = self._generator.forward_backward(codes[:T], codes[1:], keep=keep, u_drop=u_drop, u_gibbs=u_gibbs,
-                                                         seed=seed, loss_scale=1.0 / M)          # :182-184 divides by M
+                                                         seed=seed)
             return loss
         bits = torch.empty(1, T * B, 4, dtype=torch.int32, device=x.device)
         from .. import ops
         ops.pack_rows(codes[1:].reshape(T * B, -1), bits[0])
-        loss, nll, _ = self._generator.forward_backward(codes[:T], bits, keep=keep, u_drop=u_drop, seed=seed,
-                                                        loss_scale=1.0 / M)
+        loss, nll, _ = self._generator.forward_backward(codes[:T], bits, keep=keep, u_drop=u_drop, seed=seed)
         return loss
 
     def evaluate(self, x, lengths=None, u_enc=None, u_gibbs=None, seed=0):
-        """is_train=False forward. RBM generator: `batch/loss` = mean free-energy cost / M, `sample` = chain samples."""
+        """is_train=False forward: the generator's own metrics (what train.py:75-76 monitors). RBM generator:
+        `batch/loss` = mean free-energy cost, `nll` = per-row sum of tf.losses.log_loss(targets, cond_probs) (eps 1e-7,
+        common/rbm.py:121-129) in the reference's row order, `sample` = chain samples."""
         x = self._check_x(x, lengths)
         B, T, D, M = x.shape
         codes = self._encode(x, u_enc, seed)
         if isinstance(self._generator, RnnRBM):
             out = self._generator.forward(codes[:T], codes[1:], u_gibbs=u_gibbs, seed=seed)
-            res = {'batch/loss': out['loss'] / M, 'free_energy': out['free_energy'], 'codes': codes,
-                   'sample': out['sample'], 'cond_probs': out['cond_probs']}
+            t, p = codes[1:].reshape(T * B, -1), out['cond_probs']
+            nll = -(t * torch.log(p + 1e-7) + (1 - t) * torch.log(1 - p + 1e-7)).sum(1)
+            nll_ref = self.rows_to_reference_order(nll.view(1, -1), T, B)
+            res = {'nll': nll_ref, 'log_likelihood': nll_ref.mean(), 'batch/loss': out['loss'],
+                   'free_energy': out['free_energy'], 'codes': codes, 'sample': out['sample'],
+                   'cond_probs': out['cond_probs']}
         else:
             from .. import ops
             bits = torch.empty(1, T * B, 4, dtype=torch.int32, device=x.device)
             ops.pack_rows(codes[1:].reshape(T * B, -1), bits[0])
             nll, _ = self._generator.log_prob(codes[:T], bits)
             nll_ref = self.rows_to_reference_order(nll, T, B)
-            res = {'nll': nll_ref, 'batch/loss': nll_ref.mean() / M, 'codes': codes}
+            res = {'nll': nll_ref, 'log_likelihood': nll_ref.mean(), 'batch/loss': nll_ref.mean(), 'codes': codes}
         self._metrics.update(res)
         return res
 
@@ -83,5 +90,7 @@ class MultINNJoint(MultINNCore):
         B, T, D, M = x.shape
         codes = self._encode(x, u_enc, seed)
         samples_h = self._generator.generate(codes, num_steps, u=u, seed=seed)          # [B,S,E]
-        _, v = self._encoder.decode(samples_h.reshape(B * num_steps, -1), u=u_dec, seed=seed + 1)
+        from .. import ops
+        with ops.row_map_scaled(num_steps):            # decode rows are b-major (b*S + s)
+            _, v = self._encoder.decode(samples_h.reshape(B * num_steps, -1), u=u_dec, seed=seed + 1)
         return v.view(B, num_steps, D, M)

@@ -94,6 +94,41 @@ def colsum(A, out, accumulate=False):
           "colsum")
 
 
+# ----------------------------------------------------------------------------- data-parallel noise keying
+_row_map = (0, 0, 0)
+
+
+class row_map:
+    """Context manager around launches that may draw Philox noise: local row r of the calling rank is keyed as global
+    row (r // rows_local) * rows_global + row_base + r % rows_local (mnn_set_row_map), so dropout masks, Bernoulli codes
+    and samples do not depend on how the batch is sharded over GPUs. Nests; restores the previous map on exit."""
+
+    def __init__(self, rows_local, rows_global, row_base):
+        self.new = (int(rows_local), int(rows_global), int(row_base))
+
+    def __enter__(self):
+        global _row_map
+        self.old, _row_map = _row_map, self.new
+        check(lib.mnn_set_row_map(*self.new), "set_row_map")
+        return self
+
+    def __exit__(self, *exc):
+        global _row_map
+        _row_map = self.old
+        check(lib.mnn_set_row_map(*self.old), "set_row_map")
+        return False
+
+
+def row_map_scaled(k):
+    """The active map with every size multiplied by k: for b-major [B*k, .] row blocks (k generated steps per sequence)."""
+    return row_map(_row_map[0] * k, _row_map[1] * k, _row_map[2] * k)
+
+
+def row_scale():
+    """rows_global / rows_local of the active row map (1 without one): per-call Philox offsets advance by GLOBAL counts."""
+    return _row_map[1] // _row_map[0] if _row_map[0] else 1
+
+
 def lstm_cell_fwd(gates, c_prev, c, h, out=None, dscale=None, u=None, keep=1.0, seed=0, offset=0):
     B, R4 = gates.shape
     check(lib.mnn_lstm_cell_fwd(_ptr(gates), _ptr(c_prev), _ptr(c), _ptr(h), _ptr(out), _ptr(dscale), _ptr(u),
@@ -113,19 +148,29 @@ def _lstm_workspace(B, R, device):
     return ws
 
 
-def lstm_seq_fwd(gates, wh, hbuf, cbuf, out=None, dscale=None, u=None, keep=1.0, seed=0, mode=None, persistent=None):
+def lstm_seq_fwd(gates, wh, hbuf, cbuf, out=None, dscale=None, u=None, keep=1.0, seed=0, mode=None, persistent=None,
+                 t_base=0):
+    """t_base: index of gates[0]'s time step inside the whole sequence (chunked launches): the Philox dropout counter is
+    (global batch row, unit, t_base + t), so every chunking, kernel variant and GPU count draws the same masks."""
     T, B, R4 = gates.shape
     assert gates.is_contiguous() and hbuf.is_contiguous() and cbuf.is_contiguous()
     assert wh.stride(1) == 1 and wh.stride(0) == R4
     mode = mode or LSTM_MODE
-    if mode == "tc" and lib.mnn_lstm_tc_supported(B, R4 // 4):
-        pers = LSTM_PERSISTENT if persistent is None else persistent
-        check(lib.mnn_lstm_seq_fwd_tc(_ptr(gates), _ptr(wh), _ptr(hbuf), _ptr(cbuf), _ptr(out), _ptr(dscale), _ptr(u),
-                                      float(keep), seed, T, B, R4 // 4, _ptr(_lstm_workspace(B, R4 // 4, gates.device)),
-                                      int(pers), _stream()), "lstm_seq_fwd_tc")
-        return
-    check(lib.mnn_lstm_seq_fwd(_ptr(gates), _ptr(wh), _ptr(hbuf), _ptr(cbuf), _ptr(out), _ptr(dscale), _ptr(u),
-                               float(keep), seed, T, B, R4 // 4, _stream()), "lstm_seq_fwd")
+    if t_base:
+        check(lib.mnn_set_time_base(int(t_base)), "set_time_base")
+    try:
+        if mode == "tc" and lib.mnn_lstm_tc_supported(B, R4 // 4):
+            pers = LSTM_PERSISTENT if persistent is None else persistent
+            check(lib.mnn_lstm_seq_fwd_tc(_ptr(gates), _ptr(wh), _ptr(hbuf), _ptr(cbuf), _ptr(out), _ptr(dscale), _ptr(u),
+                                          float(keep), seed, T, B, R4 // 4,
+                                          _ptr(_lstm_workspace(B, R4 // 4, gates.device)), int(pers), _stream()),
+                  "lstm_seq_fwd_tc")
+            return
+        check(lib.mnn_lstm_seq_fwd(_ptr(gates), _ptr(wh), _ptr(hbuf), _ptr(cbuf), _ptr(out), _ptr(dscale), _ptr(u),
+                                   float(keep), seed, T, B, R4 // 4, _stream()), "lstm_seq_fwd")
+    finally:
+        if t_base:
+            check(lib.mnn_set_time_base(0), "set_time_base")
 
 
 def lstm_seq_bwd(gates, wh, cbuf, dout, dscale, dh_work, dc_work, mode=None, persistent=None, has_next=False):

@@ -30,12 +30,14 @@ def world():
     return 0, 1
 
 
-def rank_seed(seed):
-    """Noise seed of this data-parallel rank: the Philox streams of dropout, DBN codes and sampling are indexed by the
-    LOCAL row, so every rank folds its rank into the seed - shards draw independent noise instead of G copies of the
-    same masks. Rank 0 (and single-GPU runs) keep `seed` unchanged."""
-    r, _ = world()
-    return int(seed) + r * 15485863
+def dp_row_map(batch_local, row_base=None, global_batch=None):
+    """ops.row_map arguments of a data-parallel shard: this rank holds sequences [row_base, row_base + batch_local) of a
+    global batch (defaults: equal shards in rank order). The kernels key their Philox streams (dropout, DBN
+    codes, Gibbs chains, NADE sampling) by the GLOBAL sequence index, so every rank uses the SAME seed and the noise --
+    hence the loss and the samples -- does not depend on the number of GPUs."""
+    r, ws = world()
+    return (batch_local, batch_local * ws if global_batch is None else global_batch,
+            r * batch_local if row_base is None else row_base)
 
 
 def shard_batch(x, rank=None, world_size=None):

@@ -22,47 +22,41 @@ def reshape_songs(songs, step_size=1):
 
 
 def load_data(data_config, step_size=1):
-    """data.py:36-94: `<filename>.npy` piano-rolls [songs, time, pitches, tracks] (bool/uint8 as prepare_data.py stores
-    them, or float32), optional lengths file, split into (train, valid, test) pairs of (data, lengths)."""
-    path = data_config['filename']
-    num_train = data_config['split']['num_train']
-    num_valid = data_config['split']['num_valid']
-    num_test = data_config['split']['num_test']
+    """Loads the `.npy` piano-roll dataset the way reference utils/data.py:36-94 does and returns three (songs, lengths)
+    pairs: train = the first `num_train` songs, valid = the next `num_valid`, test = the LAST `num_test` of the songs
+    kept. Only the first num_train + num_valid + num_test songs of the file are used; `step_size` pixels are folded into
+    the feature axis (reshape_songs); without a `sequence_lengths` file every song has the full (folded) length."""
     if data_config['source'] != 'npy':
-        raise ValueError('Not supported data format :(')
-    songs = np.load(f'{path}.npy')[:num_train + num_valid + num_test]
-    if len(songs.shape) != 4:
-        raise ValueError("Dataset must have 4 dimensions.")
-    if songs.shape[-1] != len(data_config['instruments']):
-        raise ValueError(f"Dataset must have {len(data_config['instruments'])} tracks.")
+        raise ValueError(f"data source {data_config['source']!r} is not supported (only 'npy')")
+    counts = [data_config['split'][k] for k in ('num_train', 'num_valid', 'num_test')]
+    used = sum(counts)
+    songs = np.load(data_config['filename'] + '.npy')[:used]
+    if songs.ndim == 4 and songs.shape[3] != len(data_config['instruments']):
+        raise ValueError(f"the dataset has {songs.shape[3]} tracks, the config names {len(data_config['instruments'])}")
     songs = reshape_songs(songs, step_size)
-    if data_config.get('sequence_lengths'):
-        lengths = np.load(data_config['sequence_lengths'])[:num_train + num_valid + num_test]
-    else:
-        lengths = np.full(songs.shape[0], songs.shape[1])
-    train = (songs[:num_train], lengths[:num_train])
-    valid = (songs[num_train:num_train + num_valid], lengths[num_train:num_train + num_valid])
-    test = (songs[-num_test:], lengths[-num_test:])
-    return train, valid, test
+    lengths_file = data_config.get('sequence_lengths')
+    lengths = np.load(lengths_file)[:used] if lengths_file else np.full(len(songs), songs.shape[1])
+    n_tr, n_va, n_te = counts
+    cut = lambda sl: (songs[sl], lengths[sl])
+    return cut(slice(0, n_tr)), cut(slice(n_tr, n_tr + n_va)), cut(slice(len(songs) - n_te, len(songs)))
 
 
 def prepare_sampling_inputs(X_train, X_valid, sampling_config, beat_size):
-    """data.py:97-139: intro songs for sampling, the ids of the samples to save and their labels."""
-    intro_steps = int(sampling_config['intro_beats'] * beat_size)
-    intro_ids = sampling_config['intro_ids']
-    intro_train = X_train[intro_ids['train']['start']:intro_ids['train']['end'], :intro_steps, :]
-    intro_valid = X_valid[intro_ids['valid']['start']:intro_ids['valid']['end'], :intro_steps, :]
-    intro_songs = np.concatenate([intro_train, intro_valid], axis=0)
-    save_ids = sampling_config['save_ids']
-    save_train = np.array(save_ids['train'])
-    save_valid = np.array(save_ids['valid'])
-    song_labels = [f't{i}' for i in save_train] + [f'v{i}' for i in save_valid]
-    save_valid = save_valid + (intro_ids['train']['end'] - intro_ids['train']['start'])
-    save_ids = np.concatenate([save_train, save_valid], axis=0)
-    next_ids = save_ids
-    for _ in range(1, sampling_config['num_save']):
-        next_ids = next_ids + len(intro_songs)
-        save_ids = np.concatenate([save_ids, next_ids], axis=0)
+    """Picks the intro songs of a sampling run (role of reference utils/data.py:97-138). Returns
+    (intro_songs, save_ids, song_labels): the first `intro_beats` beats of the configured train and valid song ranges,
+    concatenated; the rows of the TILED sample batch (generate_music repeats the intros `num_songs` times) that are
+    written to disk -- `num_save` repeats of the chosen train ids and (shifted past the train intros) valid ids; and the
+    labels 't<i>' / 'v<i>' of those songs."""
+    steps = int(sampling_config['intro_beats'] * beat_size)
+    ranges, chosen = sampling_config['intro_ids'], sampling_config['save_ids']
+    take = lambda X, r: X[r['start']:r['end'], :steps]
+    intro_songs = np.concatenate([take(X_train, ranges['train']), take(X_valid, ranges['valid'])], axis=0)
+    n_train_intros = ranges['train']['end'] - ranges['train']['start']
+    first = np.concatenate([np.asarray(chosen['train'], dtype=np.int64),
+                            np.asarray(chosen['valid'], dtype=np.int64) + n_train_intros])
+    repeats = np.arange(sampling_config['num_save'])[:, None] * len(intro_songs)
+    save_ids = (first[None, :] + repeats).reshape(-1)
+    song_labels = [f't{i}' for i in chosen['train']] + [f'v{i}' for i in chosen['valid']]
     return intro_songs, save_ids, song_labels
 
 

@@ -8,79 +8,90 @@ import numpy as np
 
 
 class TrainingStats:
-    """training.py:8-88: counters + best monitored metric; `save`/`load` keep the reference's pickle of a 4-tuple."""
+    """Progress counters of a training run (role of reference utils/training.py:8-95): optimisation steps, epochs, runs
+    (how often training was (re)started), the best monitored metric so far and the epochs since it last improved.
+    On disk: the reference's pickle of the 4-tuple (steps, epoch, run, metric_best), so stats files interchange."""
+    _PERSISTED = ('steps', 'epoch', 'run', 'metric_best')
 
     def __init__(self, steps=0, epoch=0, run=0, metric_best=1e3):
-        self._steps, self._epoch, self._run, self._metric_best = steps, epoch, run, metric_best
-        self._idle_epochs = 0
+        self._c = dict(steps=steps, epoch=epoch, run=run, metric_best=metric_best, idle_epochs=0)
 
-    steps = property(lambda s: s._steps)
-    epoch = property(lambda s: s._epoch)
-    run = property(lambda s: s._run)
-    metric_best = property(lambda s: s._metric_best)
-    idle_epochs = property(lambda s: s._idle_epochs)
+    def __getattr__(self, name):
+        c = self.__dict__.get('_c', {})
+        if name in c:
+            return c[name]
+        raise AttributeError(name)
 
-    def new_epoch(self):
-        self._epoch += 1
+    def _bump(self, key):
+        self._c[key] += 1
 
     def new_step(self):
-        self._steps += 1
+        self._bump('steps')
+
+    def new_epoch(self):
+        self._bump('epoch')
 
     def new_run(self):
-        self._run += 1
-
-    def update_metric_best(self, val):
-        self._metric_best = val
+        self._bump('run')
 
     def new_idle_epoch(self):
-        self._idle_epochs += 1
+        self._bump('idle_epochs')
 
     def reset_idle_epochs(self):
-        self._idle_epochs = 0
+        self._c['idle_epochs'] = 0
 
-    def load(self, filename):
-        with open(filename, 'rb') as f:
-            self._steps, self._epoch, self._run, self._metric_best = pickle.load(f)
+    def update_metric_best(self, val):
+        self._c['metric_best'] = val
 
     def save(self, filename):
-        with open(filename, 'wb') as f:
-            pickle.dump((self.steps, self.epoch, self.run, self.metric_best), f)
+        with open(filename, 'wb') as fh:
+            pickle.dump(tuple(self._c[k] for k in self._PERSISTED), fh)
+
+    def load(self, filename):
+        with open(filename, 'rb') as fh:
+            self._c.update(zip(self._PERSISTED, pickle.load(fh)))
 
 
 class LossAccumulator:
-    """training.py:91-148: mean training loss that skips NaN / +-inf values and counts them."""
+    """Running mean of the per-step training losses that leaves non-finite values out of the mean and tallies them by
+    kind (role of reference utils/training.py:98-148; train.py:192 feeds it, train.py:199 prints it)."""
+    _KINDS = ('nan', '+inf', '-inf')
 
     def __init__(self):
-        self._sum_loss, self._num_loss = 0., 0
-        self._num_nan = self._num_posinf = self._num_neginf = self._num_total = 0
+        self.clear()
 
     def clear(self):
-        self.__init__()
+        self._total, self._finite = 0.0, 0
+        self._bad = dict.fromkeys(self._KINDS, 0)
+
+    @staticmethod
+    def _kind(x):
+        if x != x:
+            return 'nan'
+        if x in (float('inf'), float('-inf')):
+            return '+inf' if x > 0 else '-inf'
+        return None
 
     def update(self, loss):
-        self._num_total += 1
-        if np.isnan(loss):
-            self._num_nan += 1
-        elif np.isposinf(loss):
-            self._num_posinf += 1
-        elif np.isneginf(loss):
-            self._num_neginf += 1
+        kind = self._kind(float(loss))
+        if kind is None:
+            self._total += float(loss)
+            self._finite += 1
         else:
-            self._num_loss += 1
-            self._sum_loss += loss
+            self._bad[kind] += 1
 
     def loss(self):
-        return self._sum_loss / self._num_loss if self._num_loss > 0 else np.nan
+        return self._total / self._finite if self._finite else float('nan')
 
     def num_bad(self):
-        return self._num_nan + self._num_posinf + self._num_neginf
+        return sum(self._bad.values())
 
     def ratio_bad(self):
-        return self.num_bad() / self._num_total
+        return self.num_bad() / (self._finite + self.num_bad())
 
     def __str__(self):
-        return (f' - loss: {self.loss():7.3f} (nan: {self._num_nan}, +inf: {self._num_posinf}, -inf: {self._num_neginf}, '
-                f'bad: {100. * self.ratio_bad():.2f}%)')
+        tally = ', '.join(f'{k}: {self._bad[k]}' for k in self._KINDS)
+        return f' - loss: {self.loss():7.3f} ({tally}, bad: {100. * self.ratio_bad():.2f}%)'
 
 
 def training_pieces(X, lengths, ids, batch_size, piece_size):
@@ -193,25 +204,51 @@ def sample_songs(model, X_train, X_valid, config, epoch=0, samples_dir=None, eva
     return out
 
 
+def _dp_world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
 def train_epoch(step, X_train, len_train, batch_size, piece_size, epoch, stats, loss_accum=None, device='cuda',
-                fetch_every=1):
+                fetch_every=1, ids=None):
     """One epoch of train.py:153-200: np.random.seed(epoch), shuffle the song ids, feed every batch piece to `step`
-    (= model.train_generators(...)), advance the step counter once per batch. The reference fetches the loss after
-    every sess.run; `fetch_every` > 1 reads it back less often so that the host does not stall the device."""
+    (= model.train_generators(...)), advance the step counter once per batch. `ids` is the PERSISTENT id array of the run
+    (train.py:142 creates it once, :160 shuffles it in place every epoch, so the order is cumulative over epochs); None
+    starts from arange (a single-epoch call). The reference fetches the loss after every sess.run; `fetch_every` > 1
+    reads it back less often so that the host does not stall the device.
+    Data parallel (torch.distributed initialised, world G > 1): every rank walks the same pieces and takes rows
+    [r*b/G, (r+1)*b/G) of each piece whose row count b divides by G (other pieces are trained replicated, every rank on
+    all rows: same gradient on every rank, nothing lost); the noise seed is the same on every rank because the kernels key
+    their Philox streams by the GLOBAL row (`row_base`); with ragged lengths the shard's mean is re-weighted by
+    (valid rows of the shard * G / valid rows of the piece) so that the allreduced gradient is the piece's."""
     import torch
     loss_accum = LossAccumulator() if loss_accum is None else loss_accum
     stats.new_epoch()
     np.random.seed(epoch)
-    ids = np.arange(X_train.shape[0])
+    if ids is None:
+        ids = np.arange(X_train.shape[0])
     np.random.shuffle(ids)
     loss_accum.clear()
     pending = []
     steps0 = stats.steps
     n_batches = (X_train.shape[0] + batch_size - 1) // batch_size
+    rank, world = _dp_world()
     for bi, songs, len_batch in training_pieces(X_train, len_train, ids, batch_size, piece_size):
         while stats.steps < steps0 + bi:          # stats.new_step() once per finished batch (train.py:194, quirk Q11)
             stats.new_step()
-        loss = step(_to_device(songs, device), lengths=torch.as_tensor(np.asarray(len_batch)), seed=stats.steps * 131 + epoch)
+        kw = {}
+        len_batch = np.asarray(len_batch)
+        if world > 1 and songs.shape[0] % world == 0:
+            per = songs.shape[0] // world
+            valid_all = float(np.minimum(len_batch, songs.shape[1]).sum())
+            songs, len_batch = songs[rank * per:(rank + 1) * per], len_batch[rank * per:(rank + 1) * per]
+            kw = {'row_base': rank * per, 'global_batch': per * world,
+                  'loss_scale': float(np.minimum(len_batch, songs.shape[1]).sum()) * world / valid_all}
+        elif world > 1:
+            kw = {'row_base': 0, 'global_batch': songs.shape[0]}           # replicated piece: identical work on every rank
+        loss = step(_to_device(songs, device), lengths=torch.as_tensor(len_batch), seed=stats.steps * 131 + epoch, **kw)
         pending.append(loss.detach().clone())
         if len(pending) >= fetch_every:
             for v in torch.stack(pending).flatten().cpu().tolist():
@@ -229,7 +266,8 @@ def fit(model, train, valid, training_config, stats=None, optimizer='adam', chec
         beat_size=None, device='cuda', log=None):
     """The epoch loop of train.py:153-282 without its logging / sampling side effects: train, evaluate on the
     validation set, keep the best checkpoint (`loglik_val < stats.metric_best`, :243-257), stop after
-    `early_stopping` epochs without improvement (:258-270). Returns (stats, history)."""
+    `early_stopping` epochs without improvement (:258-270). Returns (stats, history). Under data parallelism every rank
+    runs the loop (train_epoch shards the pieces, collect_metrics the evaluation batches); rank 0 alone writes files."""
     X_train, len_train = train
     X_valid, len_valid = valid
     stats = TrainingStats() if stats is None else stats
@@ -243,8 +281,10 @@ def fit(model, train, valid, training_config, stats=None, optimizer='adam', chec
     history = []
     past_epochs = stats.epoch
     loglik_val = float('inf')
+    ids = np.arange(X_train.shape[0])                                    # train.py:142: one array for the whole run
+    writer = _dp_world()[0] == 0
     for epoch in range(past_epochs + 1, past_epochs + training_config['epochs'] + 1):
-        train_epoch(step, X_train, len_train, batch_size, piece_size, epoch, stats, loss_accum, device)
+        train_epoch(step, X_train, len_train, batch_size, piece_size, epoch, stats, loss_accum, device, ids=ids)
         rec = {'epoch': epoch, 'steps': stats.steps, 'loss': loss_accum.loss(), 'bad': loss_accum.num_bad()}
         if evaluate_epochs > 0 and epoch % evaluate_epochs == 0:
             m = collect_metrics(model, X_valid, len_valid, batch_size * 2, piece_size, device)
@@ -256,7 +296,7 @@ def fit(model, train, valid, training_config, stats=None, optimizer='adam', chec
         if loglik_val < stats.metric_best:
             stats.update_metric_best(loglik_val)
             stats.reset_idle_epochs()
-            if checkpoint_path is not None:
+            if checkpoint_path is not None and writer:
                 model.save(checkpoint_path)
                 stats.save(checkpoint_path + '.stats')
         else:

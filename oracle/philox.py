@@ -36,10 +36,20 @@ def _split64(x):
     return (x & MASK).astype(np.uint32), (x >> np.uint64(32)).astype(np.uint32)
 
 
-def half_step_uniforms(seed, offset, N, C):
+def _global_rows(n, row_map):
+    """common.cuh::global_row for local rows 0..n-1; row_map = (rows_local, rows_global, row_base) or None."""
+    r = np.arange(n, dtype=np.uint64)
+    if not row_map or not row_map[0]:
+        return r
+    rl, rg, rb = (np.uint64(v) for v in row_map)
+    return (r // rl) * rg + rb + r % rl
+
+
+def half_step_uniforms(seed, offset, N, C, row_map=None):
     """csrc/rbm.cu::bias_sigmoid_sample_kernel in Philox mode: element (r, c) draws word 0 of
-    Philox(ctr = (offset + r*C + c as 64 bits, 0, 0), key = seed as 64 bits). Returns float32 [N, C]."""
-    e = np.uint64(offset) + np.arange(N * C, dtype=np.uint64)
+    Philox(ctr = (offset + global_row(r)*C + c as 64 bits, 0, 0), key = seed as 64 bits). Returns float32 [N, C]."""
+    g = _global_rows(N, row_map)
+    e = np.uint64(offset) + (g[:, None] * np.uint64(C) + np.arange(C, dtype=np.uint64)[None, :]).reshape(-1)
     lo, hi = _split64(e)
     klo, khi = _split64(np.uint64(seed))
     z = np.zeros_like(lo)
@@ -47,14 +57,14 @@ def half_step_uniforms(seed, offset, N, C):
     return u01(out[:, 0]).reshape(N, C)
 
 
-def gibbs_chain_uniforms(seed, offset, N, D, H, k):
+def gibbs_chain_uniforms(seed, offset, N, D, H, k, row_map=None):
     """csrc/rbm.cu::rbm_gibbs_kernel in Philox mode: row r, half-step hs = 2*s (hidden) or 2*s + 1 (visible), column c
     draws word c % 4 of Philox(ctr = (offset + r as 64 bits, hs, c // 4), key = seed). Returns (uh[k,N,H], uv[k,N,D])."""
     klo, khi = _split64(np.uint64(seed))
     key = np.stack([klo, khi], -1)
 
     def draw(hs, C):
-        lo, hi = _split64(np.uint64(offset) + np.arange(N, dtype=np.uint64))
+        lo, hi = _split64(np.uint64(offset) + _global_rows(N, row_map))
         g = np.arange(C // 4, dtype=np.uint32)
         ctr = np.stack(np.broadcast_arrays(lo[:, None], hi[:, None], np.uint32(hs), g[None, :]), -1)      # [N, C/4, 4]
         return u01(philox4x32_10(ctr, key)).reshape(N, C)
@@ -64,12 +74,31 @@ def gibbs_chain_uniforms(seed, offset, N, D, H, k):
     return uh, uv
 
 
-def nade_sample_uniforms(seed, offset, M, N, D):
-    """csrc/nade.cu::nade_sample_kernel in Philox mode: (track m, row n, dim i) draws word 0 of
-    Philox(ctr = ((m*N + n)*D + i as 64 bits, offset as 64 bits), key = seed). Returns float32 [M, N, D]
+def nade_sample_uniforms(seed, offset, M, N, D, row_map=None):
+    """csrc/nade.cu::nade_sample_kernel (and csrc/sample.cu) in Philox mode: (track m, row n, dim i) draws word 0 of
+    Philox(ctr = ((global_row(n)*M + m)*D + i as 64 bits, offset as 64 bits), key = seed). Returns float32 [M, N, D]
     (`offset` is the generated step index in RnnEstimator.generate)."""
-    lo, hi = _split64(np.arange(M * N * D, dtype=np.uint64))
+    g = _global_rows(N, row_map)
+    idx = ((g[None, :, None] * np.uint64(M) + np.arange(M, dtype=np.uint64)[:, None, None]) * np.uint64(D)
+           + np.arange(D, dtype=np.uint64)[None, None, :]).reshape(-1)
+    lo, hi = _split64(idx)
     olo, ohi = _split64(np.uint64(offset))
     klo, khi = _split64(np.uint64(seed))
     ctr = np.stack(np.broadcast_arrays(lo, hi, olo, ohi), -1)
     return u01(philox4x32_10(ctr, np.stack([klo, khi], -1)[None, :])[:, 0]).reshape(M, N, D)
+
+
+def dropout_uniforms(seed, T, B, R, row_map=None, t_base=0):
+    """csrc/common.cuh::dropout_bits4 -- the dropout noise of every LSTM kernel (SIMT cell, tcgen05 sequence kernels, any
+    chunking): units [4q, 4q+4) of batch row b at step t are the 4 words of
+    Philox(ctr = (global_row(b) * R/4 + q as 64 bits, t_base + t, 0), key = seed). Returns float32 [T, B, R]."""
+    g = _global_rows(B, row_map)
+    e = (g[:, None] * np.uint64(R // 4) + np.arange(R // 4, dtype=np.uint64)[None, :]).reshape(-1)         # [B*R/4]
+    lo, hi = _split64(e)
+    klo, khi = _split64(np.uint64(seed))
+    key = np.stack([klo, khi], -1)[None, :]
+    out = np.empty((T, B, R), np.float32)
+    for t in range(T):
+        ctr = np.stack(np.broadcast_arrays(lo, hi, np.uint32(t_base + t), np.uint32(0)), -1)
+        out[t] = u01(philox4x32_10(ctr, key)).reshape(B, R)
+    return out

@@ -20,9 +20,9 @@ def _free_port():
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group('gloo', rank=rank, world_size=world)
-    from multinn_b200.training import allreduce_sum_, rank_seed, shard_batch, world as w
+    from multinn_b200.training import allreduce_sum_, dp_row_map, shard_batch, world as w
     assert w() == (rank, world)
-    assert rank_seed(5) == 5 + rank * 15485863          # shards draw independent dropout / sampling noise; rank 0 unchanged
+    assert dp_row_map(4) == (4, 4 * world, 4 * rank)      # noise is keyed by the GLOBAL sequence index, same seed everywhere
     x = torch.arange(8 * 3, dtype=torch.float32).view(8, 3)
     shard = shard_batch(x)
     assert shard.shape[0] == 4 and float(shard[0, 0]) == rank * 12

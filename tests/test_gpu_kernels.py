@@ -276,6 +276,65 @@ def test_lstm_sequence_fwd_bwd(T, B, I, Rn, keep, mode, persistent):
     assert rel_err(db.cpu().numpy(), b_t.grad.numpy()) < 2e-5
 
 
+@pytest.mark.parametrize("T,B,Rn", [(6, 8, 64), (5, 260, 512), (4, 512, 256)])
+def test_lstm_dropout_philox_stream_is_global_row_keyed(T, B, Rn):
+    """the dropout noise is a function of (global batch row, unit, global time step, seed) only. The SIMT
+    cell, the 1-CTA and pair tcgen05 kernels draw the SAME masks, equal to the CPU Philox (oracle/philox.py::dropout_uniforms);
+    a batch shard run under ops.row_map and a time chunk run with t_base reproduce the slices of the whole run."""
+    from oracle.philox import dropout_uniforms
+    ops = _ops()
+    keep, seed = 0.8, 4242
+    rng = np.random.default_rng(B)
+    gates0 = dev(rng.standard_normal((T, B, 4 * Rn)).astype(np.float32))
+    wh = dev((rng.standard_normal((Rn, 4 * Rn)) * 0.05).astype(np.float32))
+    ref = np.floor(np.float32(keep) + dropout_uniforms(seed, T, B, Rn)) / np.float32(keep)
+
+    def run(g, mode, persistent, t_base=0):
+        Tn, Bn = g.shape[0], g.shape[1]
+        g = g.clone()
+        hbuf, cbuf = torch.zeros(Tn + 1, Bn, Rn, device='cuda'), torch.zeros(Tn + 1, Bn, Rn, device='cuda')
+        out, dscale = torch.empty(Tn, Bn, Rn, device='cuda'), torch.empty(Tn, Bn, Rn, device='cuda')
+        ops.lstm_seq_fwd(g, wh, hbuf, cbuf, out=out, dscale=dscale, keep=keep, seed=seed, mode=mode,
+                         persistent=persistent, t_base=t_base)
+        return dscale.cpu().numpy()
+
+    for mode, persistent in (("simt", False), ("tc", False), ("tc", True)):
+        np.testing.assert_array_equal(run(gates0, mode, persistent), ref, err_msg=f'{mode} {persistent}')
+    half = B // 2
+    with ops.row_map(half, B, half):                                   # second shard of a 2-way data-parallel split
+        np.testing.assert_array_equal(run(gates0[:, half:].contiguous(), "tc", True), ref[:, half:])
+    np.testing.assert_array_equal(run(gates0[2:].contiguous(), "tc", True, t_base=2), ref[2:])   # a later time chunk
+    np.testing.assert_array_equal(run(gates0, "tc", True), ref)        # the map was restored
+
+
+def test_half_step_and_gibbs_row_map_reproduce_global_run():
+    """Philox Bernoulli draws of a row shard under ops.row_map equal the same rows of the unsharded call
+    (time-major groups: local rows t*Bl + b <-> global rows t*Bg + base + b)."""
+    ops = _ops()
+    rng = np.random.default_rng(3)
+    Tn, Bg, Bl, C = 3, 8, 4, 84
+    pre = dev(rng.standard_normal((Tn * Bg, C)).astype(np.float32))
+    s_all = torch.empty(Tn * Bg, C, device='cuda')
+    ops.bias_sigmoid_sample(pre, s=s_all, use_philox=True, seed=5, offset=1000)
+    for base in (0, 4):
+        loc = pre.view(Tn, Bg, C)[:, base:base + Bl].reshape(Tn * Bl, C).contiguous()
+        s_loc = torch.empty(Tn * Bl, C, device='cuda')
+        with ops.row_map(Bl, Bg, base):
+            ops.bias_sigmoid_sample(loc, s=s_loc, use_philox=True, seed=5, offset=1000)
+        assert torch.equal(s_loc.view(Tn, Bl, C), s_all.view(Tn, Bg, C)[:, base:base + Bl])
+    D, H, k = 84, 64, 2
+    W = dev(O._glorot(rng, D, H))
+    v0 = dev((rng.random((Tn * Bg, D)) < 0.2).astype(np.float32))
+    bh, bv = torch.zeros(1, H, device='cuda'), torch.zeros(1, D, device='cuda')
+    vk_all = torch.empty(Tn * Bg, D, device='cuda')
+    ops.rbm_gibbs(v0, W, bh, bv, k, v_k=vk_all, seed=9, offset=77)
+    loc = v0.view(Tn, Bg, D)[:, 4:].reshape(Tn * Bl, D).contiguous()
+    vk_loc = torch.empty(Tn * Bl, D, device='cuda')
+    with ops.row_map(Bl, Bg, 4):
+        ops.rbm_gibbs(loc, W, bh, bv, k, v_k=vk_loc, seed=9, offset=77)
+    assert torch.equal(vk_loc.view(Tn, Bl, D), vk_all.view(Tn, Bg, D)[:, 4:])
+
+
 # ----------------------------------------------------------------------------- RBM half-steps, free energy
 def test_bias_sigmoid_sample_and_free_energy():
     ops = _ops()

@@ -137,8 +137,6 @@ def test_composer_generate_bit_exact():
     assert set(np.unique(thr.cpu().numpy())) <= {0.0, 1.0}
 
 
-@pytest.mark.xfail(strict=False, reason='written after round 1\'s GPU budget was spent: not yet run on a B200 (the CPU '
-                                        'Philox is pinned by the Random123 vectors); promote once it has passed')
 def test_composer_generate_philox_stream_equals_cpu_philox():
     """Default generation path (no uniforms supplied): the sampler's in-kernel Philox stream is reproduced on the CPU
     (oracle/philox.py::nade_sample_uniforms, step index as the counter's high half), so the generated piano-rolls must

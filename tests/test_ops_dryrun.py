@@ -88,6 +88,12 @@ def test_every_wrapper_matches_the_abi_signature(dry):
     ops.clip_sgd(f(100), f(100), f(1), 0.01)
     ops.scale_rows(f(N, 12), f(N))
     ops.axpy(f(100), f(100), -0.5)
+    with ops.row_map(B, 4 * B, B):
+        assert ops.row_scale() == 4
+        with ops.row_map_scaled(3):
+            assert ops.row_scale() == 4
+        ops.lstm_seq_fwd(gates, wh, hb, cb, out=f(T, B, R), dscale=f(T, B, R), keep=0.9, seed=5, t_base=32)
+    assert ops.row_scale() == 1
     called = set(dry.calls)
     never = set(_lib.SIGNATURES) - called - {'mnn_version', 'mnn_last_error_string', 'mnn_launch_count',
                                              'mnn_lstm_seq_bwd_tc'}      # superseded by the _chunk entry point

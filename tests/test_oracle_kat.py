@@ -306,10 +306,21 @@ def test_cpu_philox_nade_sampler_layout():
     from oracle.philox import nade_sample_uniforms, philox4x32_10
     u = nade_sample_uniforms(77, 3, 5, 4, 84)
     assert u.shape == (5, 4, 84) and u.dtype == np.float32 and 0 <= u.min() and u.max() < 1
-    idx = (2 * 4 + 1) * 84 + 7                                             # track 2, row 1, dim 7
+    idx = (1 * 5 + 2) * 84 + 7                                             # row 1, track 2, dim 7 (row-major over tracks)
     w = philox4x32_10(np.array([idx, 0, 3, 0], np.uint32), np.array([77, 0], np.uint32))
     assert u[2, 1, 7] == np.float32(int(w[0]) >> 8) * np.float32(2.0 ** -24)
     assert not np.array_equal(u, nade_sample_uniforms(77, 4, 5, 4, 84))   # a new step draws new noise
+    # a data-parallel shard (rows 2..3 of the global batch of 4) draws the global rows' noise
+    assert np.array_equal(nade_sample_uniforms(77, 3, 5, 2, 84, row_map=(2, 4, 2)), u[:, 2:])
+
+
+def test_cpu_philox_dropout_layout_is_shard_and_chunk_invariant():
+    from oracle.philox import dropout_uniforms, philox4x32_10
+    u = dropout_uniforms(9, 3, 6, 16)
+    w = philox4x32_10(np.array([4 * 4 + 2, 0, 1, 0], np.uint32), np.array([9, 0], np.uint32))   # row 4, units 8..11, t=1
+    assert u[1, 4, 9] == np.float32(int(w[1]) >> 8) * np.float32(2.0 ** -24)
+    assert np.array_equal(dropout_uniforms(9, 3, 3, 16, row_map=(3, 6, 3)), u[:, 3:])
+    assert np.array_equal(dropout_uniforms(9, 2, 6, 16, t_base=1), u[1:])
 
 
 def test_rnn_rbm_generate_is_the_composition_of_its_steps():

@@ -44,7 +44,7 @@ def run(name, steps, full_c4):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
-    dev_losses = [step(x) for _ in range(steps)]
+    dev_losses = [step(x).clone() for _ in range(steps)]       # the step returns a view of a reused device buffer
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
@@ -78,7 +78,9 @@ def main():
             ok &= r['finite'] and r['generated_binary']
         except Exception as e:      # noqa: BLE001 - report and go on to the next configuration
             ok = False
-            print(json.dumps({'config': name, 'error': repr(e)[:400]}), flush=True)
+            import traceback
+            print(json.dumps({'config': name, 'error': repr(e)[:400], 'traceback': traceback.format_exc()[-1500:]}),
+                  flush=True)
     sys.exit(0 if ok else 1)
 
 
