@@ -14,6 +14,7 @@ supports assign / assign_add, `tf.metrics.*` return (value of this batch, the sa
 `tf.while_loop` / `tf.cond` run as Python control flow. Randomness: initialisers draw from a module-level Generator
 (`set_random_seed`); Bernoulli sampling lives in the tensorflow_probability stub and consumes an injected uniform stream.
 """
+import builtins
 import contextlib
 import types
 
@@ -331,7 +332,7 @@ def equal(x, y, name=None):
 
 
 def _reduce(fn, x, axis, keepdims):
-    return _t(fn(np.asarray(x), axis=None if axis is None else tuple(np.atleast_1d(axis)), keepdims=bool(keepdims)))
+    return _t(fn(np.asarray(x), axis=None if axis is None else tuple(np.atleast_1d(axis)), keepdims=builtins.bool(keepdims)))
 
 
 def reduce_sum(x, axis=None, keepdims=False, name=None, keep_dims=None):
