@@ -129,6 +129,11 @@ int mnn_colsum(const float* A, long long ld, int rows, int cols, float* out, int
 int mnn_nade_logprob_fwd(const uint32_t* bits, const float* fc, long long ld, int enc_col0, int dec_col0,
                          const float* w_enc, const float* w_dec, float* nll, float* cond_p, float* dfc, float gscale,
                          int N, int M, int D, int H, long long track_stride, mnn_stream_t stream);
+/* Which forward kernel mnn_nade_logprob_fwd runs: 0 = the tcgen05 segment-row kernel (nade_tc.cu: H rows synthesised
+ * from the bit masks as bf16 hi/lo tiles, W_dec split and resident in shared memory, logits in TMEM) where the shape
+ * fits (H in {128, 256}, D <= 96), 1 (default: the faster one today) = the SIMT segment kernel always. Process-wide;
+ * the environment variable MNN_NADE_MODE=0 makes the tensor-core kernel the default. */
+int mnn_set_nade_mode(int mode);
 /* K5 -- its backward (what tf.gradients builds through nade.py:199-226). Needs the d b_dec columns written by
  * the forward; writes the d b_enc columns of dfc and ACCUMULATES into dw_enc/dw_dec[M,D,H]. */
 int mnn_nade_logprob_bwd(const uint32_t* bits, const float* fc, long long ld, int enc_col0, int dec_col0,

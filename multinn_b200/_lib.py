@@ -53,6 +53,7 @@ SIGNATURES = {
     "mnn_colsum_workspace_bytes": [_i],
     "mnn_colsum": [_p, _ll, _i, _i, _p, _i, _p, _p],
     "mnn_nade_logprob_fwd": [_p, _p, _ll, _i, _i, _p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _ll, _p],
+    "mnn_set_nade_mode": [_i],
     "mnn_nade_logprob_bwd": [_p, _p, _ll, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _ll, _p],
     "mnn_nade_sample": [_p, _ll, _i, _i, _p, _p, _p, _i, _u64, _u64, _p, _ll, _i, _i, _p, _i, _i, _i, _i, _p],
     "mnn_bias_sigmoid_sample": [_p, _ll, _p, _ll, _p, _ll, _i, _u64, _u64, _p, _ll, _p, _ll, _i, _i, _p],

@@ -698,6 +698,26 @@ static int make_map_plain(const float* ptr, long long ld, long long inner, long 
   return MNN_OK;
 }
 
+// 2-D bf16 tensor map over a row-major matrix [outer][inner], box {32, box_outer}, SWIZZLE_64B: a box lands in shared memory
+// in the UMMA canonical K-major SWIZZLE_64B layout (64-byte rows, 8-row atoms) that kind::f16 descriptors (layout 4) read
+static int make_map_bf16(const void* ptr, long long ld_elems, long long inner, long long outer, int box_outer,
+                         CUtensorMap* out) {
+  EncodeTiledFn enc = get_encode();
+  MNN_REQUIRE(enc != nullptr, MNN_ERR_UNSUPPORTED, "tensor map: cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 2};
+  const cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mnn_set_error("tensor map (bf16): cuTensorMapEncodeTiled failed");
+    return MNN_ERR_ARG;
+  }
+  return MNN_OK;
+}
+
 static int device_sms() {
   static int n = 0;
   if (!n) {
@@ -787,6 +807,10 @@ int mnn_tc_make_map(const float* ptr, long long ld, long long inner, long long o
 int mnn_tc_make_map_plain(const float* ptr, long long ld, long long inner, long long outer, int box_inner, int box_outer,
                            CUtensorMap* out) {
   return mnn::tc::make_map_plain(ptr, ld, inner, outer, box_inner, box_outer, out);
+}
+int mnn_tc_make_map_bf16(const void* ptr, long long ld_elems, long long inner, long long outer, int box_outer,
+                         CUtensorMap* out) {
+  return mnn::tc::make_map_bf16(ptr, ld_elems, inner, outer, box_outer, out);
 }
 int mnn_tc_num_sms() { return mnn::tc::device_sms(); }
 

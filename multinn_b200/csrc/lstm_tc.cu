@@ -17,6 +17,13 @@
 #include "multinn_b200.h"
 #include "tc_common.cuh"
 
+// lstm_res.cu: weight-resident persistent forward kernel for small per-GPU batches
+int mnn_lstm_res_ctas(int T, int B, int R, int sms);
+size_t mnn_lstm_res_workspace_bytes(int B, int R);
+int mnn_lstm_res_fwd(float* gates, const float* wh, float* hbuf, float* cbuf, float* out, float* dscale, const float* u,
+                     float keep, unsigned long long seed, int T, int B, int R, void* hs, unsigned int* flags, int sms,
+                     cudaStream_t stream);
+
 namespace mnn {
 namespace tc {
 
@@ -1299,8 +1306,17 @@ static size_t whp_region_bytes(int R) {
 
 // workspace: [permuted weights | 4 KB of counters: flags @0, cntA @1024, cntB @2048 | dh_acc[B,R]]
 constexpr size_t kCounterBytes = 4096;
+// SMs the weight-resident forward kernel may occupy: the calling thread's SM budget (wavefront / chunk pipeline) or all
+static int res_sms() {
+  const int n = mnn_tc_num_sms(), b = mnn_tc_sm_budget();
+  return (b > 0 && b < n) ? b : n;
+}
+// ... | split h double buffer of the weight-resident forward kernel (lstm_res.cu)]
+static size_t res_region_offset(int B, int R) {
+  return (whp_region_bytes(R) + kCounterBytes + (size_t)B * R * sizeof(float) + 255) / 256 * 256;
+}
 extern "C" size_t mnn_lstm_workspace_bytes(int B, int R) {
-  return whp_region_bytes(R) + kCounterBytes + (size_t)B * R * sizeof(float);
+  return res_region_offset(B, R) + mnn_lstm_res_workspace_bytes(B, R);
 }
 
 static int pair_bwd_clusters() {
@@ -1378,6 +1394,7 @@ extern "C" int mnn_lstm_tc_supported(int B, int R) { return R % 8 == 0 && R >= 8
 extern "C" int mnn_lstm_seq_fwd_ctas(int T, int B, int R) {
   if (!mnn_lstm_tc_supported(B, R)) return 0;
   const int sms = mnn_tc_num_sms();
+  if (const int n = mnn_lstm_res_ctas(T, B, R, res_sms())) return n;
   if (use_pair_fwd(B, R, T, 1)) {
     const int items = (B / (2 * BM)) * (R / kL2UB);
     return 2 * (items < pair_fwd_clusters() ? items : pair_fwd_clusters());
@@ -1408,6 +1425,11 @@ extern "C" int mnn_lstm_seq_fwd_tc(float* gates, const float* wh, float* hbuf, f
   MNN_REQUIRE(gates && wh && hbuf && cbuf && ws, MNN_ERR_ARG, "lstm_seq_fwd_tc: null pointer");
   MNN_REQUIRE(T > 0 && mnn_lstm_tc_supported(B, R), MNN_ERR_UNSUPPORTED, "lstm_seq_fwd_tc: needs num_units % 8 == 0");
   MNN_REQUIRE(!(out && keep < 1.f && !dscale), MNN_ERR_ARG, "lstm_seq_fwd_tc: dscale required when keep < 1");
+  if (persistent && mnn_lstm_res_ctas(T, B, R, res_sms())) {
+    uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+    return mnn_lstm_res_fwd(gates, wh, hbuf, cbuf, out, dscale, u, keep, seed, T, B, R, w8 + res_region_offset(B, R),
+                            reinterpret_cast<unsigned int*>(w8 + whp_region_bytes(R)), res_sms(), stream);
+  }
   const bool pair = use_pair_fwd(B, R, T, persistent);
   const int UB = pair ? kL2UB : fwd_unit_block(B, R);
   const int blocks = (R + UB - 1) / UB;

@@ -11,6 +11,12 @@
 #include "multinn_b200.h"
 
 int mnn_tc_sm_budget();   // gemm_tc.cu: mnn_set_sm_budget of the calling thread (0 = whole device)
+// nade_tc.cu: the same forward pass on the tcgen05 tensor cores (segment-row GEMM); nade_fwd_kernel below stays as the
+// path for shapes it does not take and as the checker (mnn_set_nade_mode(1))
+int mnn_nade_tc_wanted(int D, int H, long long ld, const float* w_enc);
+int mnn_nade_tc_fwd(const uint32_t* bits, const float* fc, long long ld, int enc_col0, int dec_col0, const float* w_enc,
+                    const float* w_dec, float* nll, float* cond_p, float* dfc, float gscale, int N, int M, int D, int H,
+                    long long tstride, int sms, cudaStream_t stream);
 
 namespace mnn {
 
@@ -633,6 +639,9 @@ extern "C" int mnn_nade_logprob_fwd(const uint32_t* bits, const float* fc, long 
   int rc = check_nade_common(N, M, D, H, ld, enc_col0, dec_col0);
   if (rc) return rc;
   MNN_REQUIRE(track_stride == 0 || track_stride >= N, MNN_ERR_ARG, "nade_logprob_fwd: track_stride < N");
+  if (mnn_nade_tc_wanted(D, H, ld, w_enc))
+    return mnn_nade_tc_fwd(bits, fc, ld, enc_col0, dec_col0, w_enc, w_dec, nll, cond_p, dfc, gscale, N, M, D, H,
+                           track_stride ? track_stride : N, num_sms(), stream);
   NadeArgs a{bits, fc, ld, enc_col0, dec_col0, w_enc, w_dec, nll, cond_p, dfc, nullptr, nullptr, gscale, N, M, D,
              track_stride ? track_stride : N};
   const size_t smem = (size_t)2 * D * H * sizeof(float);

@@ -189,6 +189,12 @@ def lstm_seq_bwd(gates, wh, cbuf, dout, dscale, dh_work, dc_work, mode=None, per
                                _ptr(dc_work), T, B, R4 // 4, _stream()), "lstm_seq_bwd")
 
 
+def set_nade_mode(mode):
+    """'simt' (default): the CUDA-core segment kernel; 'tc': the tcgen05 segment-row forward kernel where the shape fits
+    (parity-tested, slower today: DESIGN.md section 9)."""
+    check(lib.mnn_set_nade_mode({'tc': 0, 'simt': 1}[mode]), "set_nade_mode")
+
+
 def nade_logprob_fwd(bits, fc, enc_col0, dec_col0, w_enc, w_dec, nll, cond_p=None, dfc=None, gscale=0.0):
     """bits[M,N,4], nll[M,N], cond_p[M,N,D] may be row slices ([:, r0:r1]) of longer buffers; fc/dfc the same rows."""
     M, D, H = w_enc.shape

@@ -102,9 +102,19 @@ def _bits_of(x_m):
     return bits
 
 
+@pytest.fixture(params=['simt', 'tc'])
+def nade_mode(request):
+    """Both forward kernels behind mnn_nade_logprob_fwd: the SIMT segment kernel (nade.cu, default) and the tcgen05
+    segment-row kernel (nade_tc.cu); same tolerances."""
+    ops = _ops()
+    ops.set_nade_mode(request.param)
+    yield request.param
+    ops.set_nade_mode('simt')
+
+
 @pytest.mark.parametrize("N,D,H,M,density", [(301, 84, 256, 5, 0.05), (64, 84, 256, 1, 0.5), (130, 84, 128, 2, 1.0),
-                                             (33, 20, 128, 3, 0.0), (1000, 84, 256, 5, 0.2)])
-def test_nade_logprob_fwd(N, D, H, M, density):
+                                             (33, 20, 128, 3, 0.0), (1000, 84, 256, 5, 0.2), (4000, 84, 256, 5, 0.01)])
+def test_nade_logprob_fwd(N, D, H, M, density, nade_mode):
     ops = _ops()
     x, fc, we, wd = _nade_case(N, D, H, M, seed=N + D, density=density)
     bits = _bits_of(x)
@@ -121,7 +131,7 @@ def test_nade_logprob_fwd(N, D, H, M, density):
 
 
 @pytest.mark.parametrize("N,D,H,M,density", [(257, 84, 256, 5, 0.05), (50, 84, 128, 2, 0.6), (40, 20, 128, 3, 0.3)])
-def test_nade_logprob_bwd(N, D, H, M, density):
+def test_nade_logprob_bwd(N, D, H, M, density, nade_mode):
     ops = _ops()
     x, fc, we, wd = _nade_case(N, D, H, M, seed=N * 3 + H, density=density)
     bits = _bits_of(x)
@@ -147,7 +157,7 @@ def test_nade_logprob_bwd(N, D, H, M, density):
 
 
 @pytest.mark.parametrize("budget", [0, 20])
-def test_nade_row_chunks_and_sm_budget_equal_whole_call(budget):
+def test_nade_row_chunks_and_sm_budget_equal_whole_call(budget, nade_mode):
     """The chunk pipeline calls the NADE kernels on row slices of the [M,N,..] buffers (track_stride > rows) under an SM
     budget: forward results are bit-identical to one whole call, accumulated weight gradients equal within fp32 order."""
     ops = _ops()

@@ -140,15 +140,23 @@ def _bits(x):
     return bits
 
 
+@pytest.fixture(params=['simt', 'tc'])
+def nade_mode(request):
+    from multinn_b200 import ops
+    ops.set_nade_mode(request.param)
+    yield request.param
+    ops.set_nade_mode('simt')
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize('name', NADE_CASES)
-def test_gpu_nade_matches_reference_code(name):
+def test_gpu_nade_matches_reference_code(name, nade_mode):
     from multinn_b200 import ops
     c = case(f'nade/{name}')
     N, D = c['x'].shape
     H = c['b_enc'].shape[1]
-    if H % 32 or D > 128:
-        pytest.skip('shape outside the kernels\' instantiations')
+    if H not in (128, 256) or D > 128:
+        pytest.skip('shape outside the kernels\' instantiations (num_hidden 128 or 256)')
     fc = dev(np.concatenate([c['b_enc'], c['b_dec']], 1))
     we, wd = dev(c['w_enc'][None]), dev(c['w_dec'][None])
     nll = torch.empty(1, N, device='cuda')
@@ -166,7 +174,7 @@ def test_gpu_nade_matches_reference_code(name):
 
 
 @pytest.mark.gpu
-def test_gpu_multinade_matches_reference_code():
+def test_gpu_multinade_matches_reference_code(nade_mode):
     """Bias split read in place from the Dense output, 5 tracks in one launch, loss = mean of track means, sampler output
     layout d*M + m."""
     from multinn_b200 import ops

@@ -59,8 +59,8 @@ def put(prefix, **kw):
 
 def nade_cases():
     """NADE.log_prob (nade.py:155-229) and NADE.sample (:231-308): external biases, the shapes the generators use."""
-    for name, (N, D, H, density, seed) in {'d05': (24, 84, 64, 0.05, 1), 'd50': (16, 84, 256, 0.5, 2),
-                                           'd100': (5, 84, 32, 1.0, 3), 'd0': (4, 84, 32, 0.0, 4),
+    for name, (N, D, H, density, seed) in {'d05': (24, 84, 128, 0.05, 1), 'd50': (16, 84, 256, 0.5, 2),
+                                           'd100': (5, 84, 128, 1.0, 3), 'd0': (4, 84, 128, 0.0, 4),
                                            'small': (9, 20, 12, 0.3, 5)}.items():
         rng = _R32(seed)
         nade = NADE(D, H, internal_bias=False, name=f'nade_{name}')
@@ -180,7 +180,7 @@ def multinade_cases():
     from models.generators.rnn_multinade import RnnMultiNADE
     from models.generators.rnn_estimator import RnnEstimatorStateTuple
     rng = _R32(41)
-    M, D, H, N = 5, 84, 32, 11
+    M, D, H, N = 5, 84, 128, 11
     tracks = ['Drums', 'Piano', 'Guitar', 'Bass', 'Strings']
     g = object.__new__(RnnMultiNADE)
     g._name, g._tracks, g._num_dims, g._num_hidden, g._internal_bias = 'rnn-multinade', tracks, D, [H], False
