@@ -264,7 +264,8 @@ lstm_res_fwd_kernel(const __grid_constant__ CUtensorMap map_h1, const __grid_con
         *reinterpret_cast<uint4*>(p.hs1 + so) = make_uint4(hi0.x, hi0.y, hi1.x, hi1.y);
         *reinterpret_cast<uint4*>(p.hs2 + so) = make_uint4(lo0.x, lo0.y, lo1.x, lo1.y);
       }
-      __threadfence();
+      // bar.sync orders every epilogue thread's h stores before thread 0's release (cumulative at gpu scope): no
+      // per-thread __threadfence on the critical path
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
       if (we == 0 && lane == 0)
         asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.flags + m_blk), "r"(1u) : "memory");
@@ -338,7 +339,8 @@ int mnn_lstm_res_ctas(int T, int B, int R, int sms) {
   return UB ? ((B + tc::BM - 1) / tc::BM) * (R / UB) : 0;
 }
 
-size_t mnn_lstm_res_workspace_bytes(int B, int R) { return (size_t)8 * B * R + 256; }
+// forward: split h double buffer (8 B R bytes); BPTT: split dG double buffer (32 B R bytes); never live at the same time
+size_t mnn_lstm_res_workspace_bytes(int B, int R) { return (size_t)32 * B * R + 256; }
 
 // hs: mnn_lstm_res_workspace_bytes(B, R) bytes, 256-byte aligned; flags: >= slabs counters
 int mnn_lstm_res_fwd(float* gates, const float* wh, float* hbuf, float* cbuf, float* out, float* dscale, const float* u,
@@ -388,4 +390,374 @@ int mnn_lstm_res_fwd(float* gates, const float* wh, float* hbuf, float* cbuf, fl
     return (int)e;
   }
   return mnn_check_launch("lstm_seq_fwd(resident)");
+}
+
+// ================================================================================================ BPTT
+// Weight-resident persistent BPTT for the same small-batch regime. dh_t = dG_{t+1} . Wh^T has K = 4R: a CTA that owned
+// whole K would stream 1 MB of dG per step. Instead a CLUSTER OF 4 CTAs owns (128-row slab, 32 units): CTA kq keeps the
+// K-slice Wh[32 units][kq R .. (kq+1) R) resident (bf16 w1 + w2, 64 KB at R = 512), streams only its quarter of the slab's
+// dG_{t+1} (published pre-split in bf16 by the step before, like h in the forward kernel) and produces a PARTIAL
+// dh[128 x 32] in TMEM; the partials are exchanged through distributed shared memory (st.shared::cluster + a remote
+// mbarrier arrive with release.cluster): CTA d receives the 8 unit columns it owns from its three peers, adds its own,
+// and runs the cell backward for (row, 8 units) with the cell-gradient carry dc in REGISTERS across steps.
+namespace mnn {
+namespace res {
+
+struct BParams {
+  float* gates; const float* cbuf; const float* dout; const float* dscale; float* dc;
+  const float* wh;
+  __nv_bfloat16* gs1; __nv_bfloat16* gs2;   // [2][B][4R] split dG, slot s & 1 = dG_{t+1} of local step s
+  int B, R, t_top, n_steps, slabs, blocks, kb_local, stages;
+  unsigned int* flags;
+};
+
+constexpr int kSplit = 4;                  // cluster size = K split
+constexpr int kBU = 32;                    // units per cluster = MMA N
+constexpr int XBUF = 3 * 128 * 32;         // one parity: [3 peers][128 rows][8 floats]
+
+__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+__global__ void split_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ x1, __nv_bfloat16* __restrict__ x2,
+                                  size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    uint2 hi, lo;
+    split_bf16x4(v.x, v.y, v.z, v.w, hi, lo);
+    reinterpret_cast<uint2*>(x1)[i] = hi;
+    reinterpret_cast<uint2*>(x2)[i] = lo;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+lstm_res_bwd_kernel(const __grid_constant__ CUtensorMap map_g1, const __grid_constant__ CUtensorMap map_g2, const BParams p) {
+  constexpr int BN = kBU, B_TILE = BN * 64, TMEM_COLS = 64;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 3];
+  __shared__ uint32_t tmem_base_s;
+
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem0 - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int R = p.R, B = p.B, KB = p.kb_local, STAGES = p.stages, KS = R;   // K-slice of this CTA: [kq R, (kq+1) R)
+  const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = bar_full + 8 * kMaxStages;
+  const uint32_t bar_tfull = bar_empty + 8 * kMaxStages, bar_tempty = bar_tfull + 8, bar_x = bar_tempty + 8;
+  const uint32_t off_b2 = (uint32_t)KB * B_TILE, off_x = 2u * KB * B_TILE, off_a = off_x + 2 * XBUF * 4;
+
+  const int kq = (int)cluster_ctarank();
+  const int cid = blockIdx.x / kSplit;
+  const int n_blk = cid % p.blocks, m_blk = cid / p.blocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_tfull, 1);
+    mbar_init(bar_tempty, 4);
+    mbar_init(bar_x, 3 * 4);                 // 3 peers x 4 epilogue warps
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // resident B operand: element (n, k) = Wh[n_blk 32 + n][kq R + k]
+  for (int idx = threadIdx.x; idx < BN * (KS / 4); idx += kThreads) {
+    const int n = idx / (KS / 4), k0 = (idx - n * (KS / 4)) * 4;
+    const float4 w = __ldg(reinterpret_cast<const float4*>(p.wh + (size_t)(n_blk * kBU + n) * 4 * R + (size_t)kq * KS + k0));
+    uint2 hi, lo;
+    split_bf16x4(w.x, w.y, w.z, w.w, hi, lo);
+    const uint32_t off = (uint32_t)((k0 >> 5) * B_TILE) + sw64_off(n, k0 & 31);
+    *reinterpret_cast<uint2*>(smem + off) = hi;
+    *reinterpret_cast<uint2*>(smem + off_b2 + off) = lo;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  cluster_sync_all();                          // every CTA's barriers exist before a peer arrives on them
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const unsigned int per_step = (unsigned int)p.blocks * kSplit;   // CTAs of a slab
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int s = 0; s < p.n_steps; ++s) {
+        if (s > 0) {
+          while (ld_acquire_u32(p.flags + m_blk) < (unsigned int)s * per_step) __nanosleep(20);
+          asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        const int row0 = (s & 1) * B + m_blk * BM;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t full = bar_full + 8 * stage;
+          mbar_expect_tx(full, A_STAGE);
+          const uint32_t dst = smem0 + off_a + stage * A_STAGE;
+          tma_load_2d(dst, &map_g1, full, kq * KS + kb * 32, row0);
+          tma_load_2d(dst + A_STAGE / 2, &map_g2, full, kq * KS + kb * 32, row0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(BN, false, false, 128);
+      const uint32_t d_main = tmem_base, d_aux = tmem_base + BN;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int s = 0; s < p.n_steps; ++s) {
+        if (s > 0) {
+          mbar_wait(bar_tempty, (uint32_t)(s - 1) & 1u);
+          tc_fence_after();
+        }
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t a1 = smem0 + off_a + stage * A_STAGE, a2 = a1 + A_STAGE / 2;
+          const uint32_t b1 = smem0 + kb * B_TILE, b2 = smem0 + off_b2 + kb * B_TILE;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint64_t da1 = smem_desc(a1 + j * 32, 16, 512, 4), da2 = smem_desc(a2 + j * 32, 16, 512, 4);
+            const uint64_t db1 = smem_desc(b1 + j * 32, 16, 512, 4), db2 = smem_desc(b2 + j * 32, 16, 512, 4);
+            const uint32_t first = (kb > 0 || j > 0) ? 1u : 0u;
+            umma_bf16(d_main, da1, db1, idesc, first);
+            umma_bf16(d_aux, da1, db2, idesc, first);
+            umma_bf16(d_aux, da2, db1, idesc, 1u);
+          }
+          umma_commit(bar_empty + 8 * stage);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar_tfull);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ exchange + cell backward: thread = (row, 8 units)
+    const int q = warp - 4, r = q * 32 + lane;
+    const int b = m_blk * BM + r;
+    const bool row_ok = b < B;
+    const int unit = n_blk * kBU + kq * 8;
+    const size_t BR = (size_t)B * R;
+    const size_t ridx = (size_t)(row_ok ? b : 0) * R + unit;
+    const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t xlocal = smem0 + off_x;
+    uint32_t xremote[4], xbar_remote[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) { xremote[d] = mapa_cluster(xlocal, (uint32_t)d); xbar_remote[d] = mapa_cluster(bar_x, (uint32_t)d); }
+    auto ld8 = [](const float* ptr, float (&v)[8]) {
+      const float4 a = *reinterpret_cast<const float4*>(ptr), c = *reinterpret_cast<const float4*>(ptr + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+    };
+    auto st8 = [](float* ptr, const float (&v)[8]) {
+      *reinterpret_cast<float4*>(ptr) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(ptr + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    };
+    float dc[8];
+    ld8(p.dc + ridx, dc);
+    for (int s = 0; s < p.n_steps; ++s) {
+      const int t = p.t_top - s;
+      float* gp = p.gates + ((size_t)t * B + (row_ok ? b : 0)) * 4 * R + unit;
+      // operands of the cell backward that do not depend on dh: in flight while the mainloop runs
+      float gi[8], gj[8], gf[8], go[8], cp[8], cn[8], dh[8];
+      ld8(gp, gi); ld8(gp + R, gj); ld8(gp + 2 * R, gf); ld8(gp + 3 * R, go);
+      ld8(p.cbuf + (size_t)t * BR + ridx, cp);
+      ld8(p.cbuf + (size_t)(t + 1) * BR + ridx, cn);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dh[i] = 0.f;
+      if (p.dout) {
+        float d8[8];
+        ld8(p.dout + (size_t)t * BR + ridx, d8);
+        if (p.dscale) {
+          float s8[8];
+          ld8(p.dscale + (size_t)t * BR + ridx, s8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dh[i] = d8[i] * s8[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dh[i] = d8[i];
+        }
+      }
+      mbar_wait(bar_tfull, (uint32_t)s & 1u);
+      tc_fence_after();
+      float v[32];
+      {
+        float vx[32];
+        tmem_ld32(tacc, v);
+        tmem_ld32(tacc + BN, vx);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += vx[i];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty);
+      // send the 8 columns each peer owns; slot index of this CTA in a peer's buffer: kq - (kq > d)
+      const uint32_t par = (uint32_t)(s & 1) * (XBUF * 4);
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        if (d == kq) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dh[i] += v[8 * d + i];
+        } else {
+          const int slot = kq - (kq > d ? 1 : 0);
+          const uint32_t a = xremote[d] + par + (uint32_t)((slot * 128 + r) * 32);
+          st_cluster_f4(a, v[8 * d], v[8 * d + 1], v[8 * d + 2], v[8 * d + 3]);
+          st_cluster_f4(a + 16, v[8 * d + 4], v[8 * d + 5], v[8 * d + 6], v[8 * d + 7]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+          if (d != kq) mbar_arrive_release_cluster(xbar_remote[d]);
+      }
+      mbar_wait_cluster(bar_x, (uint32_t)s & 1u);
+      {
+        const float* xb = reinterpret_cast<const float*>(smem + off_x) + (s & 1) * XBUF;
+#pragma unroll
+        for (int sl = 0; sl < 3; ++sl) {
+          const float4 a = *reinterpret_cast<const float4*>(xb + (sl * 128 + r) * 8);
+          const float4 c = *reinterpret_cast<const float4*>(xb + (sl * 128 + r) * 8 + 4);
+          dh[0] += a.x; dh[1] += a.y; dh[2] += a.z; dh[3] += a.w; dh[4] += c.x; dh[5] += c.y; dh[6] += c.z; dh[7] += c.w;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float tcn = tanh_fast(cn[i]);
+        const float dcc = dc[i] + dh[i] * go[i] * (1.f - tcn * tcn);
+        const float di = dcc * gj[i] * gi[i] * (1.f - gi[i]);
+        const float dj = dcc * gi[i] * (1.f - gj[i] * gj[i]);
+        const float df = dcc * cp[i] * gf[i] * (1.f - gf[i]);
+        const float d_o = dh[i] * tcn * go[i] * (1.f - go[i]);
+        gi[i] = di; gj[i] = dj; go[i] = d_o;
+        dc[i] = dcc * gf[i];
+        gf[i] = df;
+      }
+      if (row_ok) {
+        // dG_t split first: it gates the next step of the whole slab
+        const size_t so = ((size_t)((s + 1) & 1) * B + b) * 4 * R + unit;
+        uint2 h0, l0, h1, l1;
+        split_bf16x4(gi[0], gi[1], gi[2], gi[3], h0, l0); split_bf16x4(gi[4], gi[5], gi[6], gi[7], h1, l1);
+        *reinterpret_cast<uint4*>(p.gs1 + so) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+        *reinterpret_cast<uint4*>(p.gs2 + so) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+        split_bf16x4(gj[0], gj[1], gj[2], gj[3], h0, l0); split_bf16x4(gj[4], gj[5], gj[6], gj[7], h1, l1);
+        *reinterpret_cast<uint4*>(p.gs1 + so + R) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+        *reinterpret_cast<uint4*>(p.gs2 + so + R) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+        split_bf16x4(gf[0], gf[1], gf[2], gf[3], h0, l0); split_bf16x4(gf[4], gf[5], gf[6], gf[7], h1, l1);
+        *reinterpret_cast<uint4*>(p.gs1 + so + 2 * R) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+        *reinterpret_cast<uint4*>(p.gs2 + so + 2 * R) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+        split_bf16x4(go[0], go[1], go[2], go[3], h0, l0); split_bf16x4(go[4], go[5], go[6], go[7], h1, l1);
+        *reinterpret_cast<uint4*>(p.gs1 + so + 3 * R) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+        *reinterpret_cast<uint4*>(p.gs2 + so + 3 * R) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 4 && lane == 0)
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.flags + m_blk), "r"(1u) : "memory");
+      if (row_ok) {
+        st8(gp, gi); st8(gp + R, gj); st8(gp + 2 * R, gf); st8(gp + 3 * R, go);
+      }
+    }
+    if (row_ok) st8(p.dc + ridx, dc);
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                          // nobody leaves while a peer may still write into its shared memory
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+static size_t bwd_smem(int R, int* stages) {
+  const size_t resident = (size_t)2 * (R / 32) * (kBU * 64) + 2 * XBUF * 4;
+  long long room = (long long)224 * 1024 - (long long)resident;
+  int st = (int)(room / A_STAGE);
+  if (st > kMaxStages) st = kMaxStages;
+  if (st > R / 32) st = R / 32;
+  *stages = st;
+  return resident + (size_t)st * A_STAGE + 1024;
+}
+
+static int bwd_max_clusters(size_t smem) {
+  static int cached = -1;
+  static size_t cached_smem = 0;
+  if (cached >= 0 && cached_smem == smem) return cached;
+  cudaFuncSetAttribute(lstm_res_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(kSplit * 64);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kSplit; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, reinterpret_cast<const void*>(lstm_res_bwd_kernel), &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  cached = n; cached_smem = smem;
+  return n;
+}
+
+}  // namespace res
+}  // namespace mnn
+
+// CTAs of the weight-resident BPTT kernel for this shape under `sms` SMs (0: shape not taken)
+int mnn_lstm_res_bwd_ctas(int n_steps, int B, int R, int sms) {
+  static const char* env = getenv("MNN_LSTM_RES_BWD");   // "0": never
+  if ((env && env[0] == '0') || n_steps < 2 || R % 32 != 0 || B > 512) return 0;
+  int stages = 0;
+  const size_t smem = res::bwd_smem(R, &stages);
+  if (stages < 4) return 0;
+  const int clusters = ((B + tc::BM - 1) / tc::BM) * (R / res::kBU);
+  if (clusters * res::kSplit > sms || clusters > res::bwd_max_clusters(smem)) return 0;
+  return clusters * res::kSplit;
+}
+
+// gs: 32 B R bytes + 256 (split dG double buffer); steps t = t_top .. t_top - n_steps + 1, gates slot t_top + 1 holds
+// dG of the step after, dc the carried cell gradient
+int mnn_lstm_res_bwd(float* gates, const float* wh, const float* cbuf, const float* dout, const float* dscale, float* dc,
+                     int t_top, int n_steps, int B, int R, void* gs, unsigned int* flags, cudaStream_t stream) {
+  res::BParams p{};
+  p.gates = gates; p.cbuf = cbuf; p.dout = dout; p.dscale = dscale; p.dc = dc; p.wh = wh;
+  p.gs1 = reinterpret_cast<__nv_bfloat16*>(gs);
+  p.gs2 = p.gs1 + (size_t)2 * B * 4 * R;
+  p.B = B; p.R = R; p.t_top = t_top; p.n_steps = n_steps;
+  p.slabs = (B + tc::BM - 1) / tc::BM; p.blocks = R / res::kBU; p.kb_local = R / 32;
+  const size_t smem = res::bwd_smem(R, &p.stages);
+  p.flags = flags;
+  CUtensorMap m1, m2;
+  int rc = mnn_tc_make_map_bf16(p.gs1, 4LL * R, 4LL * R, 2LL * B, tc::BM, &m1);
+  if (rc) return rc;
+  rc = mnn_tc_make_map_bf16(p.gs2, 4LL * R, 4LL * R, 2LL * B, tc::BM, &m2);
+  if (rc) return rc;
+  cudaMemsetAsync(flags, 0, (size_t)p.slabs * sizeof(unsigned int), stream);
+  const size_t n4 = (size_t)B * R;   // B * 4R / 4
+  res::split_rows_kernel<<<(unsigned)((n4 + 255) / 256 < 296 ? (n4 + 255) / 256 : 296), 256, 0, stream>>>(
+      gates + (size_t)(t_top + 1) * B * 4 * R, p.gs1, p.gs2, n4);
+  rc = mnn_check_launch("lstm_res split_dG");
+  if (rc) return rc;
+  cudaFuncSetAttribute(res::lstm_res_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.slabs * p.blocks * res::kSplit);
+  cfg.blockDim = dim3(res::kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = res::kSplit; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 2;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, res::lstm_res_bwd_kernel, m1, m2, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    mnn_set_error(cudaGetErrorString(e));
+    return (int)e;
+  }
+  return mnn_check_launch("lstm_seq_bwd(resident)");
 }

@@ -20,6 +20,9 @@
 // lstm_res.cu: weight-resident persistent forward kernel for small per-GPU batches
 int mnn_lstm_res_ctas(int T, int B, int R, int sms);
 size_t mnn_lstm_res_workspace_bytes(int B, int R);
+int mnn_lstm_res_bwd_ctas(int n_steps, int B, int R, int sms);
+int mnn_lstm_res_bwd(float* gates, const float* wh, const float* cbuf, const float* dout, const float* dscale, float* dc,
+                     int t_top, int n_steps, int B, int R, void* gs, unsigned int* flags, cudaStream_t stream);
 int mnn_lstm_res_fwd(float* gates, const float* wh, float* hbuf, float* cbuf, float* out, float* dscale, const float* u,
                      float keep, unsigned long long seed, int T, int B, int R, void* hs, unsigned int* flags, int sms,
                      cudaStream_t stream);
@@ -1406,6 +1409,7 @@ extern "C" int mnn_lstm_seq_fwd_ctas(int T, int B, int R) {
 extern "C" int mnn_lstm_seq_bwd_ctas(int T, int B, int R) {
   if (!mnn_lstm_tc_supported(B, R)) return 0;
   const int sms = mnn_tc_num_sms();
+  if (const int n = mnn_lstm_res_bwd_ctas(T - 1, B, R, res_sms())) return n;
   if (use_pair_bwd(B, R, T, 1)) {
     const int need = (B / (2 * BM)) * (R / 256);
     int clusters = pair_bwd_clusters();
@@ -1530,6 +1534,11 @@ extern "C" int mnn_lstm_seq_bwd_tc_chunk(float* gates, const float* wh, const fl
   }
   const int t_top = has_next ? T - 1 : T - 2;
 
+  if (persistent && mnn_lstm_res_bwd_ctas(t_top + 1, B, R, res_sms())) {
+    uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+    return mnn_lstm_res_bwd(gates, wh, cbuf, dout, dscale, dc_work, t_top, t_top + 1, B, R, w8 + res_region_offset(B, R),
+                            reinterpret_cast<unsigned int*>(w8 + whp_region_bytes(R)), stream);
+  }
   if (use_pair_bwd(B, R, T, persistent)) {
     uint8_t* cnt = reinterpret_cast<uint8_t*>(ws) + whp_region_bytes(R);
     float* dh_acc = reinterpret_cast<float*>(cnt + kCounterBytes);

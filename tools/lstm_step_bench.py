@@ -16,6 +16,7 @@ gates0 = torch.randn(T, B, 4 * R, device='cuda', generator=g)
 wh = torch.randn(R, 4 * R, device='cuda', generator=g) * 0.05
 hbuf, cbuf = torch.zeros(T + 1, B, R, device='cuda'), torch.zeros(T + 1, B, R, device='cuda')
 out, dscale = torch.empty(T, B, R, device='cuda'), torch.empty(T, B, R, device='cuda')
+ops.set_sm_budget(int(os.environ.get('SMB', 0)))
 res = []
 for it in range(4):
     gates = gates0.clone()
@@ -26,5 +27,20 @@ for it in range(4):
     e1.record()
     torch.cuda.synchronize()
     res.append(e0.elapsed_time(e1))
-print(f'B={B} R={R} T={T} MNN_LSTM_RES={os.environ.get("MNN_LSTM_RES", "1")}: {min(res):.3f} ms = {min(res) / T * 1e3:.2f} us/step; '
+dout = torch.randn(T, B, R, device='cuda', generator=g)
+dh_work, dc_work = torch.empty(B, R, device='cuda'), torch.empty(B, R, device='cuda')
+resb = []
+gact = gates.clone()
+for it in range(4):
+    gb = gact.clone()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ops.lstm_seq_bwd(gb, wh, cbuf, dout, dscale, dh_work, dc_work, mode='tc', persistent=True)
+    e1.record()
+    torch.cuda.synchronize()
+    resb.append(e0.elapsed_time(e1))
+print(f'  bwd: {min(resb):.3f} ms = {min(resb) / T * 1e3:.2f} us/step; checksum {float(gb.double().sum()):.5f} '
+      f'{float(gb.double().abs().sum()):.3f} RES_BWD={os.environ.get("MNN_LSTM_RES_BWD", "1")}', flush=True)
+print(f'B={B} R={R} T={T} MNN_LSTM_RES={os.environ.get("MNN_LSTM_RES", "1")} SMB={os.environ.get("SMB", 0)}: {min(res):.3f} ms = {min(res) / T * 1e3:.2f} us/step; '
       f'checksum {float(hbuf[T].double().sum()):.6f} {float(out.double().sum()):.6f}', flush=True)
