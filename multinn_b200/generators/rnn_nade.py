@@ -186,6 +186,8 @@ class RnnNade(RnnEstimator):
         ready.record(main)                   # zeroed gradient buffers, staged inputs
         bulk.wait_event(ready)
         last = [None]
+        C = rnn.WAVEFRONT_CHUNK
+        dout_ready = {}                      # chunk -> events after which dout of that chunk is final (bulk stream)
 
         def hook(t0, t1, done, outs_top, budget, is_last):
             r0, r1 = t0 * B, t1 * B
@@ -204,16 +206,26 @@ class RnnNade(RnnEstimator):
                     ops.colsum(dfc[r0:r1], self._fc_bias.grad, accumulate=True)
                 finally:
                     ops.set_sm_budget(0)
-                if is_last or rnn.TRACE is not None:
-                    last[0] = rnn._event(f'fwd hook steps {t0}..{t1}')
-                    last[0].record(bulk)
+                ev = rnn._event(f'fwd hook steps {t0}..{t1}')
+                ev.record(bulk)
+                for c in range(t0 // C, (t1 + C - 1) // C):
+                    dout_ready.setdefault(c, []).append(ev)
+                if is_last:
+                    last[0] = ev
 
         outs, rnn_state = rnn.forward_sequence(inputs.contiguous(), keep=keep, u=u_drop, seed=seed, chunk_hook=hook)
         self._outs = outs
         self._state_from_fc(fc, rnn_state)
-        main.wait_event(last[0])
-        ops.sum_into(nll, ws['loss'], scale=gscale)
-        dx = rnn.backward_sequence(dout.view(T, B, -1), need_dx=need_dx, pipelined=True)
+        if rnn.PIPE_DESCENDING and rnn.use_pipeline(T, B):
+            # BPTT of a chunk waits for that chunk's dout only; the hooks still in flight run beside it on the bulk stream,
+            # and backward_sequence ends with main waiting for the bulk stream
+            dx = rnn.backward_sequence(dout.view(T, B, -1), need_dx=need_dx, pipelined=True, dout_ready=dout_ready)
+            main.wait_event(last[0])
+            ops.sum_into(nll, ws['loss'], scale=gscale)
+        else:
+            main.wait_event(last[0])
+            ops.sum_into(nll, ws['loss'], scale=gscale)
+            dx = rnn.backward_sequence(dout.view(T, B, -1), need_dx=need_dx, pipelined=True)
         return ws['loss'], nll, dx
 
     # -------------------------------------------------------------- generation
