@@ -20,8 +20,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    'C5': dict(B=2048, T=256, name='composer-lstm-multinade [2048,256,84,5] (BASELINE configs[4])'),
-    'C2': dict(B=256, T=128, name='composer-lstm-multinade [256,128,84,5] (BASELINE configs[1])'),
+    'C5': dict(B=2048, T=256, mode='composer', name='composer-lstm-multinade [2048,256,84,5] (BASELINE configs[4])'),
+    'C2': dict(B=256, T=128, mode='composer', name='composer-lstm-multinade [256,128,84,5] (BASELINE configs[1])'),
+    # the other BASELINE configs: parity-test cases (tools/config_check.py), timed here on request with the same contract line
+    'C1': dict(B=64, T=64, mode='jamming', name='jamming pass + lstm-nade [64,64,84,5] (BASELINE configs[0])',
+               kw=dict(encoder='Pass', generator='NADE')),
+    'C3': dict(B=512, T=128, mode='joint', name='joint dbn + lstm-rbm k=10 [512,128,84,5] (BASELINE configs[2])',
+               kw=dict(encoder='DBN', encoder_hidden=[168, 84], generator='RBM')),
+    'C4': dict(B=1024, T=256, mode='feedback-rnn',
+               name='feedback-rnn dbn + lstm-nade [1024,256,84,5] (BASELINE configs[3])',
+               kw=dict(encoder='DBN', encoder_hidden=[168, 84], generator='NADE', num_hidden_rnn=(256, 256),
+                       feedback=[256, 128])),
 }
 D, M, H, RNN = 84, 5, 256, (512, 256)
 # algorithmic forward flops per time-step (one (b,t) row, all 5 tracks); fwd+bwd = 3x by the 1:2 convention
@@ -43,9 +52,21 @@ FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # CUDA-core FMA peak of a 
 
 def profiled_traffic(kernel):
     """dram bytes per launch of `kernel` from the committed ncu --set full capture (profiles/*traffic.json), or None."""
-    p = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
-    if os.path.exists(p):
-        return json.load(open(p)).get(kernel)
+    for name in ('r2_traffic.json', 'r1_traffic.json'):
+        p = os.path.join(ROOT, 'profiles', name)
+        if os.path.exists(p):
+            return json.load(open(p)).get(kernel)
+    return None
+
+
+def profiled_step_traffic():
+    """Sum of dram bytes over every kernel of one training step from the same capture (C5 shapes), with its source."""
+    for name in ('r2_traffic.json', 'r1_traffic.json'):
+        p = os.path.join(ROOT, 'profiles', name)
+        if os.path.exists(p):
+            d = json.load(open(p))
+            tot = sum(v.get('dram_bytes_per_step', 0.0) for v in d.get('detail', {}).values())
+            return {'dram_bytes_per_step': tot, 'source': 'profiles/' + name}
     return None
 
 
@@ -124,29 +145,90 @@ def cpu_port_run(B, T, steps, warmup, threads=None):
     return B * T / float(np.mean(times)), cores, loss, float(np.mean(times))
 
 
+def config_of(wl, world):
+    """The `config` object of the JSON line: identical for both arms (the reference arm times a bounded SAMPLE of this
+    workload, described in its cpu_baseline.sample)."""
+    return {'workload': wl['name'], 'global_batch': wl['B'], 'time_steps': wl['T'], 'per_gpu_batch': wl['B'] // world,
+            'keep_prob': 0.9, 'parallelism': f'dp{world}', 'input_dtype': 'uint8 piano-rolls',
+            'l2_policy': 'per-step working set (~20 GB of activations at C5) exceeds the 126 MB L2'}
+
+
+def cpu_jamming_epoch(n_songs=64, T=64, batch=32, threads=None):
+    """BASELINE configs[0] on the host cores: Jamming (5 independent LSTM-NADE generators, one joint clip + Adam,
+    multinn_jamming.py:235-243) on synthetic [64,64,84,5] piano-rolls, ONE epoch with the reference's default batch of 32
+    (default_config.yaml:33) after one untimed warm-up step. Returns (time-steps/s, cores, seconds per epoch, loss)."""
+    import torch
+    from oracle import np_oracle as O
+    from oracle import torch_ref as R
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    plist = [R.to_torch(O.init_rnn_nade_params(D, D, H, RNN, seed=23 + m), torch.float32, requires_grad=True)
+             for m in range(M)]
+    leaves = [p for pl in plist for p in R.flat_params(pl)]
+    opt = R.TFAdam(leaves, lr=0.01)
+    X = torch.from_numpy(O.synthetic_pianoroll(n_songs, T, D, M, seed=23))
+    rng = np.random.default_rng(0)
+
+    def step(x):
+        u = [[torch.from_numpy(rng.random((T, x.shape[0], r), dtype=np.float32)) for r in RNN] for _ in range(M)]
+        loss, _ = R.jamming_loss(x, plist, keep=0.9, u_drop=u)
+        grads = torch.autograd.grad(loss, leaves)
+        opt.step(grads)
+        return float(loss.detach())
+
+    step(X[:batch])
+    t0 = time.perf_counter()
+    loss = None
+    for i in range(0, n_songs, batch):
+        loss = step(X[i:i + batch])
+    sec = time.perf_counter() - t0
+    return n_songs * T / sec, cores, sec, loss
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
-    sB, sT = args.cpu_batch, wl['T']
+    base = {'impl': 'reference', 'unit': 'time-steps/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': config_of(wl, max(1, args.gpus)), 'gpu_launches': 0}
+    if wl['mode'] == 'jamming':
+        v, cores, sec, loss = cpu_jamming_epoch(wl['B'], wl['T'])
+        sample = (f'the whole config: 1 epoch = {wl["B"]} songs x {wl["T"]} steps in batches of 32 ({sec:.2f} s), torch-CPU '
+                  'fp32 restatement of the TF1 graph, keep_prob 0.9')
+        print(json.dumps(dict(base, metric='train time-steps/sec (Jamming LSTM-NADE)', value=v, ms_per_step=sec * 1e3 / 2,
+                              cpu_baseline={'value': v, 'unit': 'time-steps/s', 'cores': cores, 'kind': 'port',
+                                            'sample': sample},
+                              e2e={'value': v, 'unit': 'time-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                              final_loss=loss)))
+        return
+    if wl['mode'] != 'composer':
+        print(json.dumps({'impl': 'reference', 'unavailable': f'no CPU restatement of a whole {wl["mode"]} training step '
+                                                              '(oracle/ holds its pieces; the headline workload is C5)'}))
+        return
+    sT = wl['T']
     steps = max(1, args.steps)
-    # bounded sample: keep the whole run within a few minutes whatever --steps asks for. Calibrated on 32 rows (8 rows
-    # would under-use the cores and shrink the sample - and with it the reference's throughput - more than needed)
-    v0, _, _, _ = cpu_port_run(min(32, sB), sT, 1, 0)
-    cap = int(args.cpu_seconds * v0 / (steps * sT)) // 8 * 8
+    # the slice batch of the bounded sample is picked by a sweep (the 84 x 5 stored [N,H] autograd tensors make the port
+    # memory-bound and batch-sensitive): one step at 32 / 64 / 128 rows, the fastest in time-steps/s is timed
+    sweep = {}
+    for sB in (32, 64, 128):
+        if sB > args.cpu_batch:
+            break
+        sweep[sB] = cpu_port_run(sB, sT, 1, 0)[0]
+        if sB * sT / sweep[sB] * (steps + 1) > args.cpu_seconds:       # the next size would not fit the time bound
+            break
+    sB = max(sweep, key=sweep.get)
+    cap = int(args.cpu_seconds * sweep[sB] / ((steps + 1) * sT)) // 8 * 8
     sB = max(8, min(sB, cap))
     v, cores, loss, sec = cpu_port_run(sB, sT, steps, min(args.warmup, 1))
-    sample = (f'[{sB},{sT},84,5] slice of the workload per step ({sec:.2f} s/step), torch-CPU fp32 op-for-op '
-              f'restatement of the TF1 graph (TF 1.13.1 not installable), keep_prob 0.9')
-    print(json.dumps({
-        'impl': 'reference', 'metric': 'train time-steps/sec (Composer LSTM-MultiNADE)', 'value': v,
-        'unit': 'time-steps/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
-        'data': 'synthetic', 'config': {'workload': wl['name'], 'global_batch': wl['B'], 'time_steps': wl['T']},
-        'cpu_baseline': {'value': v, 'unit': 'time-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
-        'e2e': {'value': v, 'unit': 'time-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'gpu_launches': 0, 'final_loss': loss}))
+    sample = (f'[{sB},{sT},84,5] slice of the workload per step ({sec:.2f} s/step; slice batch picked by a sweep: '
+              + ', '.join(f'{k} rows {x:.0f} ts/s' for k, x in sweep.items())
+              + '), torch-CPU fp32 op-for-op restatement of the TF1 graph (TF 1.13.1 not installable), keep_prob 0.9')
+    print(json.dumps(dict(base, metric='train time-steps/sec (Composer LSTM-MultiNADE)', value=v, ms_per_step=sec * 1e3,
+                          cpu_baseline={'value': v, 'unit': 'time-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+                          e2e={'value': v, 'unit': 'time-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                          final_loss=loss)))
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -169,7 +251,8 @@ def run_gpu(args):
     B, T = wl['B'], wl['T']
     assert B % world == 0
     Bl = B // world
-    model = MultINN(default_config(), default_params(mode='composer', keep_prob=0.9), 'composer')
+    composer = wl['mode'] == 'composer'
+    model = MultINN(default_config(), default_params(mode=wl['mode'], keep_prob=0.9, **wl.get('kw', {})), wl['mode'])
     step = model.train_generators('adam', 0.01)
 
     # synthetic Bernoulli(0.05) piano-rolls, two alternating host batches in pinned memory
@@ -231,28 +314,53 @@ def run_gpu(args):
     ms_e2e = timed(e2e_step, args.steps)
 
     # ---- per-phase device times of one more step (CUDA events on the launching stream) -> roofline
-    phases = profile_phases(model, xdev[0], args)
+    phases = profile_phases(model, xdev[0], args) if composer else {}
+    # ---- XU (MUFU) pipe peak, measured here: MEASURED_PEAKS.json has no figure for the pipe that bounds the NADE sigmoids
+    xu = None
+    if rank == 0:
+        from multinn_b200 import ops as _ops
+        try:
+            xu = {k: _ops.probe_mufu(k) for k in ('ex2', 'rcp', 'sigmoid')}
+        except Exception as e:          # noqa: BLE001 - a diagnostic must not cost the bench line
+            xu = {'error': repr(e)[:200]}
 
-    # ---- autoregressive sampling (BASELINE configs[4]: 512 steps from a 32-step intro); a 64-step sample is timed
+    # ---- autoregressive sampling (BASELINE configs[4]: ALL 512 steps from a 32-step intro, sample.py). Random-init weights
+    # draw ~50 % dense frames (worst case for the segment-form sampler); trained models draw ~5 % (the data's density):
+    # emulated by shifting the decoder-bias columns of the Dense layer by -3 for a second timing
     sampling = None
-    if not args.no_sampling:
+    if not args.no_sampling and composer:
+        S = 512
         intro = xdev[0][:, :32].contiguous()
         model.generate(intro, 4, seed=1)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        model.generate(intro, 64, seed=2)
-        e1.record()
-        torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) / 64 * 1e3
-        sampling = {'batch_per_gpu': Bl, 'intro_steps': 32, 'timed_steps': 64, 'us_per_generated_step': us,
-                    'generated_time_steps_per_s': world * Bl / (us * 1e-6),
-                    'note': 'random-init weights sample ~50 % dense frames: the worst case for the segment-form sampler'}
+        gen = model._model.generators[0]
+
+        def time_generate(seed):
+            n0 = _lib.lib.mnn_launch_count()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = model.generate(intro, S, seed=seed)
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) / S * 1e3
+            return {'us_per_generated_step': us, 'generated_time_steps_per_s': world * Bl / (us * 1e-6),
+                    'sample_density': float(out.mean()), 'launches_per_step': (_lib.lib.mnn_launch_count() - n0) / S}
+        dense_run = time_generate(2)
+        bias = gen._fc_bias.data
+        saved = bias.clone()
+        bias[M * H:] -= 3.0
+        sparse_run = time_generate(3)
+        bias.copy_(saved)
+        sampling = {'batch_per_gpu': Bl, 'intro_steps': 32, 'timed_steps': S, 'random_init': dense_run,
+                    'decoder_bias_minus_3': sparse_run,
+                    'us_per_generated_step': sparse_run['us_per_generated_step'],
+                    'generated_time_steps_per_s': sparse_run['generated_time_steps_per_s'],
+                    'note': 'headline = the ~5 % dense regime of trained models; random_init = ~50 % dense worst case'}
 
     # ---- size-independent property at the FULL bench size (after every timed region; never fatal): a sequence's per-row
     # NLL does not depend on what else is in the batch, although B = 2048 runs the pair kernels and B = 8 the 1-CTA ones
     fullsize = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and composer:
         try:
             sub = 8
             full = model.evaluate(xdev[0])['nll'][:sub * T].clone()
@@ -267,7 +375,7 @@ def run_gpu(args):
     # ---- RBM Gibbs chain of config C3's generator (84 x 256, k = 10): fused one-launch kernel vs the GEMM + half-step
     # path at generation and training row counts (tools/gibbs_bench.py; after every timed region; never fatal)
     gibbs = None
-    if rank == 0 and world == 1 and not args.no_sampling:
+    if rank == 0 and world == 1 and not args.no_sampling and composer:
         try:
             import importlib.util
             spec = importlib.util.spec_from_file_location('gibbs_bench', os.path.join(ROOT, 'tools', 'gibbs_bench.py'))
@@ -287,46 +395,65 @@ def run_gpu(args):
         gemm_ms = phases.get('gemm_ms', 0.0)
         gemm_tf = GEMM_TC_FLOPS_STEP * n_rows / (gemm_ms * 1e-3) / 1e12 if gemm_ms else 0.0
         n_gemm = max(1, phases.get('gemm_launches', 1))
+        metric = {'composer': 'train time-steps/sec (Composer LSTM-MultiNADE)',
+                  'jamming': 'train time-steps/sec (Jamming LSTM-NADE)',
+                  'joint': 'train time-steps/sec (Joint DBN + LSTM-RBM, CD-k k=10)',
+                  'feedback-rnn': 'train time-steps/sec (Feedback-RNN DBN + LSTM-NADE)'}[wl['mode']]
+        table = kernel_table(phases, n_rows, pk, xu) if composer else []
+        top = next((r for r in table if r['kernel'].startswith('nade_bwd')), None)
+        step_traffic = profiled_step_traffic()
+        if composer:
+            roofline = {
+                'bound': 'tensor',
+                'kernel': 'mnn::tc::gemm_tc2_kernel / gemm_tc_kernel (tcgen05 tf32 + bf16 cross terms, cta_group::2 pair tiles: '
+                          'input projections, Dense, data- and weight-gradient GEMMs; largest kernel CLASS of the step)',
+                'achieved': gemm_tf, 'peak': pk['tf_sust'], 'unit': 'TFLOP/s', 'frac': gemm_tf / pk['tf_sust'],
+                'traffic': profiled_traffic('gemm_tc'), 'peak_source': pk['src'] + ' (cuBLAS bf16, sustained)',
+                'launches_per_step': n_gemm, 'avg_launch_ms': gemm_ms / n_gemm,
+                'algorithmic_flops_per_step': GEMM_TC_FLOPS_STEP * n_rows,
+                'note': 'fp32-accurate path: every algorithmic MAC costs one tf32 MMA (half the bf16 rate) plus two bf16 '
+                        'cross-term MMAs (2 tf32 products with a binary A), so the ceiling against the bf16 denominator is 1/4',
+                # the single largest KERNEL of the step is the SIMT NADE backward: reported beside the class above
+                'top_kernel': top,
+                # HBM bytes of the whole step: profiled (ncu --set full, C5 shapes) against SURVEY 8(d)'s algorithmic figure
+                'step_traffic': {'profiled': step_traffic, 'algorithmic_bytes_per_step': 55_000 * n_rows,
+                                 'note': 'SURVEY 8(d): ~55 KB per time-step'},
+                'phases_ms': phases}
+        else:
+            # the other BASELINE configs share the kernels profiled on C5; their line carries the step time only
+            roofline = {'bound': 'tensor', 'kernel': 'same kernel classes as C5 (gemm_tc2 / lstm_tc / nade / rbm_gibbs); not '
+                                                     'broken down for this workload', 'achieved': None, 'peak': pk['tf_sust'],
+                        'unit': 'TFLOP/s', 'frac': None, 'traffic': None}
         out = {
-            'metric': 'train time-steps/sec (Composer LSTM-MultiNADE)', 'value': tps, 'unit': 'time-steps/s',
+            'metric': metric, 'value': tps, 'unit': 'time-steps/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': wl['name'], 'global_batch': B, 'time_steps': T, 'per_gpu_batch': Bl,
-                       'keep_prob': 0.9, 'parallelism': f'dp{world}', 'input_dtype': 'uint8 piano-rolls',
-                       'l2_policy': 'per-step working set (~20 GB of activations at C5) exceeds the 126 MB L2'},
+            'config': config_of(wl, world),
             'e2e': {'value': B * T / (ms_e2e * 1e-3), 'unit': 'time-steps/s', 'ms_per_step': ms_e2e,
                     'h2d_bytes_per_step': hosts[0].numel() * hosts[0].element_size(), 'd2h_bytes_per_step': 4},
             'gpu_launches': int(launches),
             'clocks': clk,
-            'roofline': {'bound': 'tensor', 'kernel': 'mnn::tc::gemm_tc2_kernel / gemm_tc_kernel (tcgen05 tf32 + bf16 cross terms, '
-                                                      'cta_group::2 pair tiles: input projections, Dense, data- and '
-                                                      'weight-gradient GEMMs; largest kernel class of the step)',
-                         'achieved': gemm_tf, 'peak': pk['tf_sust'], 'unit': 'TFLOP/s', 'frac': gemm_tf / pk['tf_sust'],
-                         'traffic': profiled_traffic('gemm_tc'), 'peak_source': pk['src'] + ' (cuBLAS bf16, sustained)',
-                         'launches_per_step': n_gemm, 'avg_launch_ms': gemm_ms / n_gemm,
-                         'algorithmic_flops_per_step': GEMM_TC_FLOPS_STEP * n_rows,
-                         'note': 'fp32-accurate path: every algorithmic MAC costs one tf32 MMA (half the bf16 rate) plus two bf16 '
-                                 'cross-term MMAs (2 tf32 products with a binary A), so the ceiling against the bf16 '
-                                 'denominator is 1/4',
-                         'phases_ms': phases},
-            'kernels': kernel_table(phases, n_rows, pk),
+            'roofline': roofline,
+            'kernels': table,
+            'xu_peak': xu,
             'sampling': sampling,
             'final_loss': final_loss,
             'fullsize_check': fullsize,
             'rbm_gibbs_chain_84x256_k10': gibbs,
         }
-        if world == 1 and not args.no_cpu:
-            v, cores, _, sec = cpu_port_run(args.cpu_batch, T, 3, 1)
+        if world == 1 and not args.no_cpu and composer:
+            v, cores, _, sec = cpu_port_run(min(args.cpu_batch, 64), T, 3, 1)
             out['cpu_baseline'] = {'value': v, 'unit': 'time-steps/s', 'cores': cores, 'kind': 'port',
-                                   'sample': f'[{args.cpu_batch},{T},84,5] slice, 1 warm-up + 3 timed steps '
+                                   'sample': f'[{min(args.cpu_batch, 64)},{T},84,5] slice, 1 warm-up + 3 timed steps '
                                              f'({sec:.2f} s/step), torch-CPU fp32 restatement of the TF1 graph'}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
-def kernel_table(ph, n_rows, pk):
-    """Per-kernel-class roofline fractions of one training step (per-GPU rows), from the CUDA-event phase times."""
+def kernel_table(ph, n_rows, pk, xu=None):
+    """Per-kernel-class roofline fractions of one training step (per-GPU rows), from the CUDA-event phase times.
+    xu: measured MUFU rates (ops.probe_mufu) -> the sigmoid-throughput rows of the NADE kernels."""
     def row(name, ms, bound, work, peak, unit, note=''):
         if not ms:
             return None
@@ -345,6 +472,14 @@ def kernel_table(ph, n_rows, pk):
             FP32_PEAK_TFLOPS, 'TFLOP/s', 'SIMT: useful flops vs the CUDA-core fp32 peak'),
         row('nade_fwd HBM', ph.get('nade_fwd_ms'), 'hbm', n_rows * (1700 * 4 + M * D * 4 + 80 + 20) / 1e9, pk['hbm'], 'GB/s',
             'reads fc, writes d b_dec + nll'),
+        # segment form: (1 + set bits among dims 0..D-2) * H sigmoids per (row, track): 5.15 * 256 * 5 at 5 % density; the
+        # backward recomputes them. Peak = the measured rate of the kernels' own sigmoid (ex2 + rcp) on the XU pipe
+        (row('nade_fwd XU', ph.get('nade_fwd_ms'), 'xu', n_rows * 5.15 * H * M / 1e9, xu['sigmoid'] / 2 / 1e9, 'Gsigmoid/s',
+             'sigmoids of the segment form vs the measured MUFU rate')
+         if xu and 'sigmoid' in xu else None),
+        (row('nade_bwd XU', ph.get('nade_bwd_ms'), 'xu', n_rows * 5.15 * H * M / 1e9, xu['sigmoid'] / 2 / 1e9, 'Gsigmoid/s',
+             'recomputed sigmoids vs the measured MUFU rate')
+         if xu and 'sigmoid' in xu else None),
         row('pack (input staging)', ph.get('pack_ms'), 'hbm', n_rows * (420 + 1680 + 80) / 1e9, pk['hbm'], 'GB/s'),
         row('colsum (bias grads)', ph.get('colsum_ms'), 'hbm', n_rows * (2048 + 1024 + 1700) * 4 / 1e9, pk['hbm'], 'GB/s'),
     ]

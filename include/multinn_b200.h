@@ -188,6 +188,12 @@ int mnn_axpy(float* y, const float* x, float alpha, size_t n, mnn_stream_t strea
 int mnn_clip_sgd(float* p, const float* g, size_t n, const float* sqnorm, float grad_scale, float clip_norm,
                  float lr, mnn_stream_t stream);
 
+/* Roofline probe (no reference counterpart): `iters` rounds of 8 independent MUFU chains per thread -- kind 0:
+ * ex2.approx, 1: rcp.approx, 2: the kernels' sigmoid (ex2 + rcp + 2 FMA-pipe ops). MUFU instructions executed =
+ * blocks * threads * iters * 8 (x2 for kind 2); bench.py times it with CUDA events to put an XU-pipe peak beside the HBM and
+ * tensor peaks of MEASURED_PEAKS.json. out: >= blocks floats. */
+int mnn_probe_mufu(float* out, int blocks, int threads, int iters, int kind, mnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,7 @@ SIGNATURES = {
     "mnn_scale_rows": [_p, _ll, _i, _p, _ll, _i, _p],
     "mnn_axpy": [_p, _p, _f, _sz, _p],
     "mnn_clip_sgd": [_p, _p, _sz, _p, _f, _f, _f, _p],
+    "mnn_probe_mufu": [_p, _i, _i, _i, _i, _p],
 }
 _RESTYPES = {"mnn_last_error_string": C.c_char_p, "mnn_launch_count": C.c_ulonglong, "mnn_reduce_workspace_bytes": C.c_size_t,
              "mnn_colsum_workspace_bytes": C.c_size_t, "mnn_lstm_workspace_bytes": C.c_size_t,

@@ -45,3 +45,32 @@ extern "C" int mnn_set_time_base(long long t_base) {
   g_row_map.t_base = t_base;
   return MNN_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ roofline probes
+// MUFU (XU pipe) peak: the NADE kernels are bounded by sigmoids = ex2.approx + rcp.approx, and MEASURED_PEAKS.json has no
+// figure for that pipe (SURVEY 7 asks for one). Each thread runs `iters` rounds of 8 independent ex2.approx chains
+// (kind 0), rcp.approx chains (kind 1) or full sigmoid_mufu chains (kind 2); out[block] keeps the compiler honest.
+// ops = grid * block * iters * 8 MUFU instructions (x2 for kind 2).
+__global__ void mufu_probe_kernel(float* out, int iters, int kind, float seed) {
+  float x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = seed + 0.001f * (threadIdx.x + 32 * i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (kind == 0) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
+      else if (kind == 1) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
+      else x[i] = mnn::sigmoid_mufu(x[i]);
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x[i];
+  if (s == 123.456f) out[blockIdx.x] = s;
+}
+extern "C" int mnn_probe_mufu(float* out, int blocks, int threads, int iters, int kind, cudaStream_t stream) {
+  MNN_REQUIRE(out && blocks > 0 && threads > 0 && threads <= 1024 && iters > 0 && kind >= 0 && kind <= 2, MNN_ERR_ARG,
+              "probe_mufu: bad argument");
+  mufu_probe_kernel<<<blocks, threads, 0, stream>>>(out, iters, kind, 0.25f);
+  return mnn_check_launch("probe_mufu");
+}

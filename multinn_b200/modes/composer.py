@@ -28,29 +28,26 @@ class MultINNComposer(MultINNCore):
                                        keep_prob=self.keep_prob, arena=self._arena, name='generator')
         return [self._generator]
 
-    def _require_pass(self):
-        if self.encoder_type != 'Pass':
-            raise NotImplementedError('Composer with DBN encoders: use feedback/joint modes or Pass encoders')
-
-    def _forward_backward(self, x, keep, u_drop, seed, lengths=None, loss_scale=1.0, **extra):
-        self._require_pass()
+    def _forward_backward(self, x, keep, u_drop, seed, lengths=None, loss_scale=1.0, u_enc=None, **extra):
         B, T, D, M = x.shape
-        st = self._stage_inputs(x, stacked=True, bits=True)
+        # per-track encodings (PassEncoder: the piano-rolls themselves; DBNEncoder: sampled codes,
+        # core/multi_encoder_nn.py:98-115) stacked with feature e*M + m (multinn_composer.py:73-80)
+        _, stack, bits = self._encode_tracks(x, u_enc, seed)
         # inputs = slots 0..T-1 ([0, x_0..x_{T-2}]), targets = slots 1..T (multinn_composer.py:82-86)
-        loss, nll, _ = self._generator.forward_backward(st['xin'][:T], st['bits'], keep=keep, u_drop=u_drop, seed=seed,
+        loss, nll, _ = self._generator.forward_backward(stack[:T], bits, keep=keep, u_drop=u_drop, seed=seed,
                                                         lengths=lengths, loss_scale=loss_scale)
         self._last_nll = (nll, T, B)
         return loss
 
-    def evaluate(self, x, lengths=None, cond_probs=False):
+    def evaluate(self, x, lengths=None, cond_probs=False, u_enc=None, seed=0):
         """is_train=False forward: per-row NLL[N,M] (rows n = b*T + t), `batch/loss` = mean over tracks of the
         per-track means (metrics/statistical.py:34, rnn_multinade.py:200-203). With variable `lengths` the rows
         t >= lengths[b] are removed (utils/sequences.py:29-37): `nll` then holds the valid rows only, b-major."""
-        self._require_pass()
         x = self._check_x(x, lengths)
         B, T, D, M = x.shape
-        st = self._stage_inputs(x, stacked=True, bits=True)
-        nll, cp = self._generator.log_prob(st['xin'][:T], st['bits'], cond_probs=cond_probs, lengths=lengths)
+        _, stack, bits = self._encode_tracks(x, u_enc, seed)
+        nll, cp = self._generator.log_prob(stack[:T], bits, cond_probs=cond_probs, lengths=lengths)
+        D = self._num_dims_generator
         keep_rows = self.valid_rows(lengths, T, B, x.device)
         out = {'nll': self.rows_to_reference_order(nll, T, B)}
         if cp is not None:
@@ -61,11 +58,11 @@ class MultINNComposer(MultINNCore):
         self._metrics.update(out)
         return out
 
-    def generate(self, x, num_steps, u=None, seed=0):
-        """multinn_composer.py:114-151. x[B,Ti,D,M] intro -> samples[B,num_steps,D,M]; u[num_steps,M,B,D]."""
-        self._require_pass()
+    def generate(self, x, num_steps, u=None, seed=0, u_enc=None, u_dec=None):
+        """multinn_composer.py:114-151. x[B,Ti,D,M] intro -> samples[B,num_steps,D,M]; u[num_steps,M,B,E]. DBN encoders:
+        the intro is encoded per track (u_enc), the generated codes are decoded per track (u_dec, :140-150)."""
         x = self._check_x(x, None)
         B, T, D, M = x.shape
-        st = self._stage_inputs(x, stacked=True)
-        samples = self._generator.generate(st['xin'], num_steps, u=u, seed=seed)     # whole padded intro
-        return samples.view(B, num_steps, D, M)
+        _, stack, _ = self._encode_tracks(x, u_enc, seed)
+        samples = self._generator.generate(stack, num_steps, u=u, seed=seed)     # whole padded intro
+        return self._decode_tracks(samples.view(B, num_steps, self._num_dims_generator, M), u_dec, seed)

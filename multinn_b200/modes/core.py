@@ -120,6 +120,40 @@ class MultINNCore(Model, abc.ABC):
                            st['bits'] if bits else None)
         return st
 
+    def _encode_tracks(self, x, u_enc=None, seed=0):
+        """core/multi_encoder_nn.py:66-115: zero-pad, unstack, encode every track with its own encoder (PassEncoder:
+        identity; DBNEncoder: SAMPLED last-layer codes, stop_gradient unless tune_encoder). Returns
+        (xe[M][(T+1),B,E] per-track encodings, stack[(T+1),B,E*M] with feature e*M + m as multinn_composer.py:73-80 /
+        multinn_feedback.py:67-73 stack them, bits[M,T*B,4] target masks of xe[m][1:])."""
+        B, T, D, M = x.shape
+        if self.encoder_type == 'Pass':
+            st = self._stage_inputs(x, stacked=True, per_track=True, bits=True)
+            return [st['xtr'][m] for m in range(M)], st['xin'], st['bits']
+        st = self._stage_inputs(x, per_track=True)
+        xe = []
+        for m, enc in enumerate(self._encoders):
+            _, h = enc.encode(st['xtr'][m].view((T + 1) * B, D), u=None if u_enc is None else u_enc[m], seed=seed + 31 * m)
+            xe.append(h.view(T + 1, B, -1))
+        stack = torch.stack(xe, dim=3).reshape(T + 1, B, -1)
+        bits = torch.empty(M, T * B, 4, dtype=torch.int32, device=x.device)
+        for m in range(M):
+            ops.pack_rows(xe[m][1:].reshape(T * B, -1), bits[m])
+        return xe, stack, bits
+
+    def _decode_tracks(self, samples_h, u_dec=None, seed=0):
+        """Per-track `encoder.decode` of generated codes samples_h[B,S,E,M] -> music[B,S,D,M] (multinn_composer.py:140-150,
+        multinn_jamming.py:125-132, multinn_feedback.py:166-172); identity for Pass encoders."""
+        B, S, E, M = samples_h.shape
+        if self.encoder_type == 'Pass':
+            return samples_h
+        music = torch.empty(B, S, self.num_dims, M, device=samples_h.device)
+        with ops.row_map_scaled(S):                        # decode rows are b-major (b*S + s)
+            for m, enc in enumerate(self._encoders):
+                h_m = samples_h[..., m].reshape(B * S, E).contiguous()      # the track slice is a strided view
+                _, v = enc.decode(h_m, u=None if u_dec is None else u_dec[m], seed=seed + 977 * m)
+                music[..., m] = v.view(B, S, self.num_dims)
+        return music
+
     @staticmethod
     def rows_to_reference_order(t, T, B):
         """[..., T*B] time-major rows -> [B*T, ...] in the reference's flatten order n = b*T + t

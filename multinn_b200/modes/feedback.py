@@ -48,22 +48,8 @@ class MultINNFeedback(MultINNCore):
 
     # ------------------------------------------------------------------ encodings
     def _encode(self, x, u_enc=None, seed=0):
-        """Per-track encodings xe[M][(T+1),B,E] of the zero-padded inputs and their stack [(T+1),B,E*M] (feature
-        e*M + m, multinn_feedback.py:67-73), plus target bit masks [M,T*B,4] of xe[m][1:]."""
-        B, T, D, M = x.shape
-        if self.encoder_type == 'Pass':
-            st = self._stage_inputs(x, stacked=True, per_track=True, bits=True)
-            return [st['xtr'][m] for m in range(M)], st['xin'], st['bits']
-        st = self._stage_inputs(x, per_track=True)
-        xe = []
-        for m, enc in enumerate(self._encoders):
-            _, h = enc.encode(st['xtr'][m].view((T + 1) * B, D), u=None if u_enc is None else u_enc[m], seed=seed + 31 * m)
-            xe.append(h.view(T + 1, B, -1))
-        stack = torch.stack(xe, dim=3).reshape(T + 1, B, -1)
-        bits = torch.empty(M, T * B, 4, dtype=torch.int32, device=x.device)
-        for m in range(M):
-            ops.pack_rows(xe[m][1:].reshape(T * B, -1), bits[m])
-        return xe, stack, bits
+        """Per-track encodings, their stack (feature e*M + m, multinn_feedback.py:67-73) and target bit masks."""
+        return self._encode_tracks(x, u_enc, seed)
 
     def _apply_feedback(self, stack, keep=1.0, u_fb=None, seed=0, save=True):
         """multinn_feedback.py:99-118: Dense feedback over every (padded) step. stack[(T+1),B,E*M] -> [(T+1),B,F]."""
@@ -143,11 +129,5 @@ class MultINNFeedback(MultINNCore):
             states = [gen.single_step(torch.cat([cur[:, :, m], x_fb], dim=1), states[m])
                       for m, gen in enumerate(self._generators)]
             prev = cur
-        music = torch.empty(B, num_steps, D, M, device=x.device)
-        with ops.row_map_scaled(num_steps):            # decode rows are b-major (b*S + s)
-            for m, enc in enumerate(self._encoders):
-                h_m = samples_h[..., m].reshape(B * num_steps, E).contiguous()     # the track slice is a strided view
-                _, v = enc.decode(h_m, u=None if u_dec is None else u_dec[m],
-                                  seed=seed + 977 * m) if enc.stochastic else enc.decode(h_m)
-                music[..., m] = v.view(B, num_steps, D)
+        music = self._decode_tracks(samples_h, u_dec, seed)
         return music

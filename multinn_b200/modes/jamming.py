@@ -26,32 +26,26 @@ class MultINNJamming(MultINNCore):
                                 num_hidden_rnn=g['num_hidden_rnn'], keep_prob=self.keep_prob, track_name=t,
                                 arena=self._arena, name=f'generator/{t}') for t in self.tracks]
 
-    def _require_pass(self):
-        if self.encoder_type != 'Pass':
-            raise NotImplementedError('Jamming with DBN encoders is not wired yet')
-
-    def _forward_backward(self, x, keep, u_drop, seed, lengths=None, loss_scale=1.0, **extra):
-        self._require_pass()
+    def _forward_backward(self, x, keep, u_drop, seed, lengths=None, loss_scale=1.0, u_enc=None, **extra):
         B, T, D, M = x.shape
-        st = self._stage_inputs(x, per_track=True, bits=True)
+        xe, _, bits = self._encode_tracks(x, u_enc, seed)          # multinn_jamming.py:60-68 over the track encodings
         total = torch.zeros(1, device=x.device)
         nlls = []
         for m, gen in enumerate(self._generators):
-            loss, nll, _ = gen.forward_backward(st['xtr'][m, :T], st['bits'][m:m + 1], keep=keep,
+            loss, nll, _ = gen.forward_backward(xe[m][:T], bits[m:m + 1], keep=keep,
                                                 u_drop=None if u_drop is None else u_drop[m],
                                                 seed=seed + 104729 * m, loss_scale=loss_scale / M, lengths=lengths)
             total += loss
             nlls.append(nll)
         return total
 
-    def evaluate(self, x, lengths=None):
-        self._require_pass()
+    def evaluate(self, x, lengths=None, u_enc=None, seed=0):
         x = self._check_x(x, lengths)
         B, T, D, M = x.shape
-        st = self._stage_inputs(x, per_track=True, bits=True)
+        xe, _, bits = self._encode_tracks(x, u_enc, seed)
         nll = torch.empty(M, T * B, device=x.device)
         for m, gen in enumerate(self._generators):
-            n, _ = gen.log_prob(st['xtr'][m, :T], st['bits'][m:m + 1], lengths=lengths)
+            n, _ = gen.log_prob(xe[m][:T], bits[m:m + 1], lengths=lengths)
             nll[m] = n[0]
         out = {'nll': self.rows_to_reference_order(nll, T, B)}
         keep_rows = self.valid_rows(lengths, T, B, x.device)
@@ -61,14 +55,14 @@ class MultINNJamming(MultINNCore):
         self._metrics.update(out)
         return out
 
-    def generate(self, x, num_steps, u=None, seed=0):
-        """multinn_jamming.py:101-133: every track generated independently; u[num_steps,M,B,D]."""
-        self._require_pass()
+    def generate(self, x, num_steps, u=None, seed=0, u_enc=None, u_dec=None):
+        """multinn_jamming.py:101-133: every track generated independently over its encodings, then decoded;
+        u[num_steps,M,B,E]."""
         x = self._check_x(x, None)
         B, T, D, M = x.shape
-        st = self._stage_inputs(x, per_track=True)
-        out = torch.empty(B, num_steps, D, M, device=x.device)
+        xe, _, _ = self._encode_tracks(x, u_enc, seed)
+        out = torch.empty(B, num_steps, self._num_dims_generator, M, device=x.device)
         for m, gen in enumerate(self._generators):
-            s = gen.generate(st['xtr'][m], num_steps, u=None if u is None else u[:, m:m + 1], seed=seed + 104729 * m)
+            s = gen.generate(xe[m].contiguous(), num_steps, u=None if u is None else u[:, m:m + 1], seed=seed + 104729 * m)
             out[..., m] = s
-        return out
+        return self._decode_tracks(out, u_dec, seed)

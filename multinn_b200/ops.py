@@ -343,3 +343,19 @@ def axpy(y, x, alpha):
 def clip_sgd(p, g, sqnorm, lr, grad_scale=1.0, clip_norm=5.0):
     check(lib.mnn_clip_sgd(_ptr(p), _ptr(g), p.numel(), _ptr(sqnorm), float(grad_scale), float(clip_norm), float(lr),
                            _stream()), "clip_sgd")
+
+
+def probe_mufu(kind='ex2', blocks=None, threads=512, iters=4096):
+    """XU-pipe peak probe: returns MUFU instructions per second (per thread-lane ops/s) measured with CUDA events."""
+    k = {'ex2': 0, 'rcp': 1, 'sigmoid': 2}[kind]
+    blocks = blocks or 8 * num_sms()
+    out = torch.zeros(blocks, device='cuda')
+    check(lib.mnn_probe_mufu(_ptr(out), blocks, threads, 64, k, _stream()), "probe_mufu")
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(lib.mnn_probe_mufu(_ptr(out), blocks, threads, iters, k, _stream()), "probe_mufu")
+    e1.record()
+    torch.cuda.synchronize()
+    n = blocks * threads * iters * 8 * (2 if k == 2 else 1)
+    return n / (e0.elapsed_time(e1) * 1e-3)

@@ -417,6 +417,57 @@ def test_joint_rbm_fit_loop_monitors_generator_log_likelihood(tmp_path):
     assert all(np.isfinite(h['valid_log_likelihood']) and h['valid_log_likelihood'] > 0 for h in hist)
 
 
+# ----------------------------------------------------------------------------- Composer / Jamming over DBN encodings
+def _track_codes(x, esd, tracks, u_enc, B, T):
+    """Oracle: per-track DBN codes of the zero-padded inputs (core/multi_encoder_nn.py:66-115), [M][B,T+1,E]."""
+    codes = []
+    for m, t in enumerate(tracks):
+        rbms = [tuple(a.astype(f64) for a in r) for r in dbn_params(esd, f'encoder/{t}', 2)]
+        pad = np.concatenate([np.zeros((B, 1, 84)), x[..., m]], axis=1)                      # [B,T+1,D]
+        rows = pad.transpose(1, 0, 2).reshape((T + 1) * B, 84).astype(f64)                   # time-major like the device
+        _, h = O.dbn_forward(rows, rbms, [a.astype(f64) for a in u_enc[m]])
+        codes.append(h.reshape(T + 1, B, -1).transpose(1, 0, 2))
+    return codes
+
+
+@pytest.mark.parametrize('mode', ['composer', 'jamming'])
+def test_composer_and_jamming_over_dbn_encodings(mode):
+    """core/multi_encoder_nn.py:98-115: the generators of Composer / Jamming run over the per-track encoders' SAMPLED codes
+    (inputs codes[:, :-1], targets codes[:, 1:]); with the same uniforms the per-row NLL equals the oracle's on the same
+    codes, one training step runs, and generation decodes back to [B,S,84,5] binary piano-rolls."""
+    B, T = 4, 5
+    model = make(mode, encoder='DBN', encoder_hidden=[168, 84], generator='NADE', num_hidden=128, num_hidden_rnn=(48, 32))
+    core = model._model
+    rng = np.random.default_rng(41)
+    sd, esd = sd_np(core.arena), sd_np(core.encoder_arena)
+    x = O.synthetic_pianoroll(B, T, seed=15, density=0.1)
+    N1 = (T + 1) * B
+    u_enc = [[rng.random((N1, 168), dtype=np.float32), rng.random((N1, 84), dtype=np.float32)] for _ in range(5)]
+    out = model.evaluate(cu(x), u_enc=[[cu(a) for a in um] for um in u_enc])
+    codes = _track_codes(x, esd, core.tracks, u_enc, B, T)
+    if mode == 'composer':
+        stack = np.stack(codes, axis=3).reshape(B, T + 1, -1)                                # feature e*M + m
+        p = O.cast_params(dict(lstm=[(sd[f'generator/rnn/cell_{l}/kernel'], sd[f'generator/rnn/cell_{l}/bias'])
+                                     for l in range(2)],
+                               dense=(sd['generator/dense/kernel'], sd['generator/dense/bias']),
+                               nade=[(sd['generator/nade/w_enc'][m], sd['generator/nade/w_dec'][m]) for m in range(5)]), f64)
+        outs, _ = O.rnn_scan(stack[:, :-1], p['lstm'])
+        fc = O.dense(outs.reshape(B * T, -1), *p['dense'])
+        be, bd = O.split_biases_multi(fc, 5, 128, 84)
+        tgt = stack[:, 1:].reshape(B * T, 84, 5)
+        ref = np.stack([O.nade_log_prob(tgt[:, :, m], be[m], bd[m], *p['nade'][m])[0] for m in range(5)], 1)
+    else:
+        ref = np.stack([O.rnn_nade_forward(codes[m][:, :-1], codes[m][:, 1:],
+                                           O.cast_params(rnn_nade_params(sd, f'generator/{t}', 2), f64))['nll']
+                        for m, t in enumerate(core.tracks)], 1)
+    np.testing.assert_allclose(out['nll'].cpu().numpy(), ref, rtol=1e-4)
+    step = model.train_generators('adam', 0.01)
+    l0 = float(step(cu(x), u_enc=[[cu(a) for a in um] for um in u_enc]))
+    assert abs(l0 - ref.mean(0).mean()) < 1e-4 * ref.mean()
+    s = model.generate(cu(x), 3)
+    assert s.shape == (B, 3, 84, 5) and set(np.unique(s.cpu().numpy())) <= {0.0, 1.0}
+
+
 # ----------------------------------------------------------------------------- Feedback / Feedback-RNN (config C4)
 def _fb_case(mode, encoder):
     kw = dict(num_hidden=128, num_hidden_rnn=(48, 32), feedback=[40, 24])

@@ -88,6 +88,8 @@ def test_every_wrapper_matches_the_abi_signature(dry):
     ops.clip_sgd(f(100), f(100), f(1), 0.01)
     ops.scale_rows(f(N, 12), f(N))
     ops.axpy(f(100), f(100), -0.5)
+    check_probe = ops.lib.mnn_probe_mufu(None, 8, 128, 4, 0, 0)
+    assert check_probe == 0
     ops.set_nade_mode('simt')
     ops.set_nade_mode('tc')
     with ops.row_map(B, 4 * B, B):
