@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE ONLY (see oracle/__init__.py). PARITY UNPINNED.
+"""TEST INFRASTRUCTURE ONLY (see oracle/__init__.py: pinned by the reference's own modules run on tests/tf_stub).
 
 Restatement (i): NumPy literal-loop form of the reference hot path. Mirrors the TF1 graph
 op for op (D-loop for NADE, T-loop for the LSTM, k-loop for the Gibbs chain). Default dtype

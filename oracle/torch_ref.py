@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE ONLY (see oracle/__init__.py). PARITY UNPINNED.
+"""TEST INFRASTRUCTURE ONLY (see oracle/__init__.py: pinned by the reference's own modules run on tests/tf_stub).
 
 Restatement (ii): torch-CPU form with autograd, op for op like the TF1 graph (python-unrolled
 84-iteration NADE loop per track as in common/nade.py:199-226, per-step LSTM loop as in

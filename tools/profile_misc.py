@@ -60,6 +60,7 @@ for R in (512, 256):
     for _ in range(2):
         gg = gates.clone()
         ops.lstm_seq_fwd(gg, wh, hbuf, cbuf, out=o, dscale=ds, keep=0.9, seed=1, mode='tc', persistent=True)
-        ops.lstm_seq_bwd(gg, wh, cbuf, dout, ds, dh, dc, mode='tc', persistent=True)
+        if os.environ.get('MISC_SKIP_BWD') != '1':     # ncu cannot replay the cluster + cooperative BPTT kernel (r2o: error 9)
+            ops.lstm_seq_bwd(gg, wh, cbuf, dout, ds, dh, dc, mode='tc', persistent=True)
 torch.cuda.synchronize()
 print('profile_misc ok')
