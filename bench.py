@@ -269,12 +269,16 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(fn, n):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t_host = time.perf_counter()
         for i in range(n):
             fn(i)
+        host_ms[0] = (time.perf_counter() - t_host) * 1e3 / n      # host time to ENQUEUE a step (no sync inside fn)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')
@@ -305,6 +309,7 @@ def run_gpu(args):
         clocks.start()
     n0 = _lib.lib.mnn_launch_count()
     ms = timed(resident, args.steps)
+    host_enqueue_ms = host_ms[0]
     launches = (_lib.lib.mnn_launch_count() - n0)
     clk = clocks.stop() if rank == 0 else None
     final_loss = float(losses[-1])
@@ -434,6 +439,7 @@ def run_gpu(args):
             'e2e': {'value': B * T / (ms_e2e * 1e-3), 'unit': 'time-steps/s', 'ms_per_step': ms_e2e,
                     'h2d_bytes_per_step': hosts[0].numel() * hosts[0].element_size(), 'd2h_bytes_per_step': 4},
             'gpu_launches': int(launches),
+            'host_enqueue_ms_per_step': host_enqueue_ms,
             'clocks': clk,
             'roofline': roofline,
             'kernels': table,

@@ -9,6 +9,7 @@ set of eager methods on device tensors:
 Inputs are staged once per call by the K0 kernel (zero-pad, unstack/stack, shift, target bit masks).
 """
 import abc
+import os
 
 import torch
 
@@ -119,6 +120,30 @@ class MultINNCore(Model, abc.ABC):
         ops.pack_pianoroll(x, st['xin'] if stacked else None, st['xtr'] if per_track else None,
                            st['bits'] if bits else None)
         return st
+
+    # The per-track generators of Jamming / Feedback(-RNN) are independent between the encode and the feedback backward
+    # (multinn_jamming.py:60-68, multinn_feedback.py:86-94 build M separate sub-graphs that TF may run concurrently): each
+    # runs on its own stream. At the data-parallel shard sizes a generator's recurrences are latency chains on 16-64 SMs,
+    # so five of them side by side cost little more than one (C4 on 8 GPUs: 51 -> see DESIGN.md section 10).
+    TRACK_STREAMS = os.environ.get('MNN_TRACK_STREAMS', '1') != '0'
+
+    def _per_track(self, fn):
+        """[fn(m, generator) for every generator], each call on its own stream between two joins with the current one."""
+        gens = self._generators
+        if not self.TRACK_STREAMS or len(gens) < 2 or not torch.cuda.is_available():
+            return [fn(m, g) for m, g in enumerate(gens)]
+        main = torch.cuda.current_stream()
+        streams = self.__dict__.setdefault('_track_streams', [torch.cuda.Stream() for _ in gens])
+        start = torch.cuda.Event()
+        start.record(main)
+        out = []
+        for m, (g, st) in enumerate(zip(gens, streams)):
+            with torch.cuda.stream(st):
+                st.wait_event(start)
+                out.append(fn(m, g))
+        for st in streams:
+            main.wait_stream(st)
+        return out
 
     def _encode_tracks(self, x, u_enc=None, seed=0):
         """core/multi_encoder_nn.py:66-115: zero-pad, unstack, encode every track with its own encoder (PassEncoder:

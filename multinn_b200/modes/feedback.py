@@ -70,13 +70,12 @@ class MultINNFeedback(MultINNCore):
         fb = self._apply_feedback(stack, keep=keep, u_fb=u_fb, seed=seed + 17)
         E, F = self._num_dims_generator, fb.shape[2]
         dfb = torch.zeros(T + 1, B, F, device=x.device)
-        total = torch.zeros(1, device=x.device)
-        for m, gen in enumerate(self._generators):
+        def one(m, gen):
             inp = torch.cat([xe[m][:T], fb[:T]], dim=2)                       # multinn_feedback.py:86-88
-            loss, nll, dx = gen.forward_backward(inp, bits[m:m + 1], keep=keep,
-                                                 u_drop=None if u_drop is None else u_drop[m],
-                                                 seed=seed + 104729 * m, loss_scale=loss_scale / M, need_dx=True,
-                                                 lengths=lengths)
+            return gen.forward_backward(inp, bits[m:m + 1], keep=keep, u_drop=None if u_drop is None else u_drop[m],
+                                        seed=seed + 104729 * m, loss_scale=loss_scale / M, need_dx=True, lengths=lengths)
+        total = torch.zeros(1, device=x.device)
+        for loss, _, dx in self._per_track(one):
             total += loss
             dfb[:T] += dx[:, :, E:]
         self._feedback_backward(dfb)

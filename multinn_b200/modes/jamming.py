@@ -29,14 +29,12 @@ class MultINNJamming(MultINNCore):
     def _forward_backward(self, x, keep, u_drop, seed, lengths=None, loss_scale=1.0, u_enc=None, **extra):
         B, T, D, M = x.shape
         xe, _, bits = self._encode_tracks(x, u_enc, seed)          # multinn_jamming.py:60-68 over the track encodings
+        def one(m, gen):
+            return gen.forward_backward(xe[m][:T], bits[m:m + 1], keep=keep, u_drop=None if u_drop is None else u_drop[m],
+                                        seed=seed + 104729 * m, loss_scale=loss_scale / M, lengths=lengths)
         total = torch.zeros(1, device=x.device)
-        nlls = []
-        for m, gen in enumerate(self._generators):
-            loss, nll, _ = gen.forward_backward(xe[m][:T], bits[m:m + 1], keep=keep,
-                                                u_drop=None if u_drop is None else u_drop[m],
-                                                seed=seed + 104729 * m, loss_scale=loss_scale / M, lengths=lengths)
+        for loss, _, _ in self._per_track(one):
             total += loss
-            nlls.append(nll)
         return total
 
     def evaluate(self, x, lengths=None, u_enc=None, seed=0):
