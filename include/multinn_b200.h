@@ -147,6 +147,25 @@ int mnn_nade_sample(const float* fc, long long ld, int enc_col0, int dec_col0, c
                     unsigned long long offset, float* out, long long out_ld, int out_dim_stride, int out_track_stride,
                     float* nll, int N, int M, int D, int H, mnn_stream_t stream);
 
+/* K6 fused -- the whole generation scan of generators/rnn_estimator.py:271-323 (`generate`: per step sample_single =
+ * M x NADE.sample, then single_step = MultiRNNCell + Dense output layer, rnn_nade.py:253-277) for num_steps steps in ONE
+ * cooperative launch; B <= 128 (sample.py's batches: num_songs x intros). The grid's CTAs split into sampler / LSTM
+ * layer / Dense groups that keep their weights in shared memory for the whole call and hand the state over through
+ * counters in `ws` (gen_fused.cu). State after the intro scan comes in, state after the last step goes out: c_l, h_l
+ * [B, r_l] per layer (1 or 2 layers; layer 1 pointers NULL for one), fc[B, ldfc] = the Dense output (NADE biases,
+ * columns [M*H b_enc | M*D b_dec]). Layer-0 input = the sampled frame (num_inputs == M*D, feature d*M + m). u[S, M, B, D]
+ * uniforms or NULL (+ use_philox: counter ((global row * M + m) * D + i, offset0 + step), key seed; neither: p >= .5).
+ * out[b*out_ld + s*out_step + d*M + m] in {0,1}. ws >= mnn_generate_fused_workspace_bytes(...) (0: shape not taken).
+ * Arithmetic: bf16-pair operands (16 mantissa bits) on tcgen05, fp32 accumulation; the multi-launch path
+ * (mnn_nade_sample + mnn_gemm_tc + mnn_lstm_cell_fwd per step) stays the fp32-accurate one. */
+size_t mnn_generate_fused_workspace_bytes(int num_layers, int num_inputs, int r0, int r1, int B, int M, int D, int H);
+int mnn_generate_fused(int num_layers, int num_inputs, const float* kern0, const float* bias0, float* c0, float* h0, int r0,
+                       const float* kern1, const float* bias1, float* c1, float* h1, int r1, const float* dense_kernel,
+                       const float* dense_bias, const float* w_enc, const float* w_dec, float* fc, long long ldfc,
+                       const float* u, int use_philox, unsigned long long seed, unsigned long long offset0, float* out,
+                       long long out_ld, long long out_step, int B, int S, int M, int D, int H, void* ws,
+                       mnn_stream_t stream);
+
 /* K7 -- RBM half-steps: p = sigmoid(pre + bias), s = float(u < p). common/rbm.py:337-387, used by forward
  * (:148-167), reconstruct (:169-190), the Gibbs chain (:192-231), DBN (common/dbn.py:136-180) and the sigmoid
  * Dense feedback module (common/dnn.py:97-116). ld_bias == 0 broadcasts one bias row. */

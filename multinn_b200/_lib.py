@@ -56,6 +56,9 @@ SIGNATURES = {
     "mnn_set_nade_mode": [_i],
     "mnn_nade_logprob_bwd": [_p, _p, _ll, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _ll, _p],
     "mnn_nade_sample": [_p, _ll, _i, _i, _p, _p, _p, _i, _u64, _u64, _p, _ll, _i, _i, _p, _i, _i, _i, _i, _p],
+    "mnn_generate_fused_workspace_bytes": [_i, _i, _i, _i, _i, _i, _i, _i],
+    "mnn_generate_fused": [_i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _ll, _p, _i, _u64, _u64, _p,
+                           _ll, _ll, _i, _i, _i, _i, _i, _p, _p],
     "mnn_bias_sigmoid_sample": [_p, _ll, _p, _ll, _p, _ll, _i, _u64, _u64, _p, _ll, _p, _ll, _i, _i, _p],
     "mnn_rbm_gibbs_smem_bytes": [_i, _i],
     "mnn_rbm_gibbs": [_p, _ll, _p, _p, _ll, _p, _ll, _p, _p, _i, _u64, _u64, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _p],
@@ -72,7 +75,7 @@ SIGNATURES = {
 }
 _RESTYPES = {"mnn_last_error_string": C.c_char_p, "mnn_launch_count": C.c_ulonglong, "mnn_reduce_workspace_bytes": C.c_size_t,
              "mnn_colsum_workspace_bytes": C.c_size_t, "mnn_lstm_workspace_bytes": C.c_size_t,
-             "mnn_rbm_gibbs_smem_bytes": C.c_size_t}
+             "mnn_rbm_gibbs_smem_bytes": C.c_size_t, "mnn_generate_fused_workspace_bytes": C.c_size_t}
 
 for _name, _args in SIGNATURES.items():
     _fn = getattr(lib, _name, None)

@@ -229,6 +229,29 @@ class RnnNade(RnnEstimator):
         return ws['loss'], nll, dx
 
     # -------------------------------------------------------------- generation
+    def generate(self, x, num_steps, u=None, seed=0):
+        """rnn_estimator.py:271-323. The intro scan runs through the sequence kernels; the num_steps-step scan of
+        {sample_single, single_step} then runs as ONE launch of the persistent kernel `mnn_generate_fused` (samplers, LSTM
+        layers and the Dense layer as CTA groups with resident weights) when the batch fits one 128-row slab and the sampled
+        frame is the layer-0 input (Composer, Jamming, Joint-with-NADE; not the Feedback modes, whose generators take
+        [sample ; feedback]); otherwise, and in parity runs with supplied uniforms unless ops.GENERATE_MODE == 'fused', as the
+        per-step loop of the base class (8 launches per step, fp32-accurate)."""
+        M, D, H = self._num_tracks, self._num_dims, self._num_hidden[-1]
+        B = x.shape[1]
+        rnn = self._rnn
+        fits = ops.generate_fused_supported(rnn.num_layers, self._num_inputs, rnn.num_units, B, M, D, H)
+        mode = ops.GENERATE_MODE
+        if not fits or mode == 'steps' or (mode == 'auto' and u is not None):
+            return super().generate(x, num_steps, u=u, seed=seed)
+        state = self._get_state(x, lengths=None, last_outputs=True)
+        fc = self._fc_of(state).contiguous()
+        out = torch.empty(B, num_steps, M * D, device=x.device)
+        ops.generate_fused([k.data for k in rnn.kernels], [b.data for b in rnn.biases],
+                           [(s.c.contiguous(), s.h.contiguous()) for s in state.rnn_state], self._fc_kernel.data,
+                           self._fc_bias.data, self._bank.w_enc.data, self._bank.w_dec.data, fc, out,
+                           u=None if u is None else u.contiguous(), use_philox=True, seed=seed, offset0=0)
+        return out
+
     def single_step(self, inputs, initial_state):
         """rnn_nade.py:253-277: one RNN step + Dense -> new biases."""
         out, rnn_state = self._rnn.step(inputs, initial_state.rnn_state)

@@ -359,3 +359,43 @@ def probe_mufu(kind='ex2', blocks=None, threads=512, iters=4096):
     torch.cuda.synchronize()
     n = blocks * threads * iters * 8 * (2 if k == 2 else 1)
     return n / (e0.elapsed_time(e1) * 1e-3)
+
+
+# ----------------------------------------------------------------------------- fused generation (K6)
+# 'auto': the one-launch persistent kernel (csrc/gen_fused.cu) for Philox sampling when the shape fits (B <= 128, the
+# sampled frame is the layer-0 input), the fp32-accurate multi-launch loop when uniforms are supplied (parity runs) or
+# the shape does not fit; 'fused' / 'steps' force one or the other.
+GENERATE_MODE = 'auto'
+_gen_ws = {}
+
+
+def generate_fused_supported(num_layers, num_inputs, units, B, M, D, H):
+    r = list(units) + [0]
+    return num_layers in (1, 2) and num_inputs == M * D and int(
+        lib.mnn_generate_fused_workspace_bytes(num_layers, num_inputs, r[0], r[1], B, M, D, H)) > 0
+
+
+def generate_fused(kernels, biases, state, dense_kernel, dense_bias, w_enc, w_dec, fc, out, u=None, use_philox=True, seed=0,
+                   offset0=0):
+    """All S = out.shape[1] generation steps in one launch. state: [(c, h)] per layer (updated in place), fc[B, C] the
+    Dense output after the intro (updated to the one after the last step), out[B, S, M*D]."""
+    L = len(kernels)
+    B, S = out.shape[0], out.shape[1]
+    M, D, H = w_enc.shape
+    units = [k.shape[1] // 4 for k in kernels]
+    num_inputs = kernels[0].shape[0] - units[0]
+    r = units + [0]
+    need = int(lib.mnn_generate_fused_workspace_bytes(L, num_inputs, r[0], r[1], B, M, D, H))
+    if not need:
+        raise ValueError('generate_fused: shape not taken (B <= 128, 1-2 layers, num_inputs == M*D)')
+    key = (fc.device.index, torch.cuda.current_stream().cuda_stream, need)
+    ws = _gen_ws.get(key)
+    if ws is None:
+        ws = _gen_ws[key] = torch.empty(need, dtype=torch.uint8, device=fc.device)
+    assert out.is_contiguous() and fc.stride(1) == 1 and all(k.is_contiguous() for k in kernels)
+    c1, h1 = (state[1] if L > 1 else (None, None))
+    check(lib.mnn_generate_fused(L, num_inputs, _ptr(kernels[0]), _ptr(biases[0]), _ptr(state[0][0]), _ptr(state[0][1]),
+                                 units[0], _ptr(kernels[1]) if L > 1 else None, _ptr(biases[1]) if L > 1 else None,
+                                 _ptr(c1), _ptr(h1), r[1], _ptr(dense_kernel), _ptr(dense_bias), _ptr(w_enc), _ptr(w_dec),
+                                 _ptr(fc), fc.stride(0), _ptr(u), int(use_philox and u is None), seed, offset0, _ptr(out),
+                                 out.stride(0), out.stride(1), B, S, M, D, H, _ptr(ws), _stream()), "generate_fused")

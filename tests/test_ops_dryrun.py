@@ -88,6 +88,11 @@ def test_every_wrapper_matches_the_abi_signature(dry):
     ops.clip_sgd(f(100), f(100), f(1), 0.01)
     ops.scale_rows(f(N, 12), f(N))
     ops.axpy(f(100), f(100), -0.5)
+    Rg = (16, 8)
+    kern = [f(M * D + Rg[0], 4 * Rg[0]), f(Rg[0] + Rg[1], 4 * Rg[1])]
+    assert ops.generate_fused_supported(2, M * D, Rg, B, M, D, H)
+    ops.generate_fused(kern, [f(4 * Rg[0]), f(4 * Rg[1])], [(f(B, Rg[0]), f(B, Rg[0])), (f(B, Rg[1]), f(B, Rg[1]))],
+                       f(Rg[1], M * (H + D)), f(M * (H + D)), we, wd, f(B, M * (H + D)), f(B, 3, M * D), seed=5)
     check_probe = ops.lib.mnn_probe_mufu(None, 8, 128, 4, 0, 0)
     assert check_probe == 0
     ops.set_nade_mode('simt')
