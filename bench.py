@@ -341,6 +341,7 @@ def run_gpu(args):
         gen = model._model.generators[0]
 
         def time_generate(seed):
+            nonlocal intro
             n0 = _lib.lib.mnn_launch_count()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -349,7 +350,8 @@ def run_gpu(args):
             e1.record()
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) / S * 1e3
-            return {'us_per_generated_step': us, 'generated_time_steps_per_s': world * Bl / (us * 1e-6),
+            return {'batch': int(intro.shape[0]), 'us_per_generated_step': us,
+                    'generated_time_steps_per_s': world * intro.shape[0] / (us * 1e-6),
                     'sample_density': float(out.mean()), 'launches_per_step': (_lib.lib.mnn_launch_count() - n0) / S}
         sparse_run = time_generate(2)
         bias = gen._fc_bias.data
@@ -357,7 +359,22 @@ def run_gpu(args):
         bias[M * H:] += 3.0
         dense_run = time_generate(3)
         bias.copy_(saved)
+        # the batch sample.py really runs (default_config.yaml: num_songs 3 x (16 + 8) intros = 72 rows): the one-launch
+        # persistent kernel (mnn_generate_fused) against the per-step loop
+        from multinn_b200 import ops as _gops
+        small = {}
+        intro_small = xdev[0][:72, :32].contiguous()
+        saved_intro, saved_mode = intro, _gops.GENERATE_MODE
+        try:
+            intro = intro_small
+            for mode_name in ('fused', 'steps'):
+                _gops.GENERATE_MODE = mode_name
+                model.generate(intro, 4, seed=1)
+                small[mode_name] = time_generate(5)
+        finally:
+            intro, _gops.GENERATE_MODE = saved_intro, saved_mode
         sampling = {'batch_per_gpu': Bl, 'intro_steps': 32, 'timed_steps': S, 'as_trained': sparse_run,
+                    'batch_72_fused_one_launch': small.get('fused'), 'batch_72_step_loop': small.get('steps'),
                     'decoder_bias_plus_3': dense_run,
                     'us_per_generated_step': sparse_run['us_per_generated_step'],
                     'generated_time_steps_per_s': sparse_run['generated_time_steps_per_s'],
