@@ -50,3 +50,31 @@ class BaseMetrics:
                        f1_score=precision if precision > 0 else 0.0,                          # quirk Q5
                        true_f1=2 * precision * recall / (precision + recall) if precision + recall > 0 else 0.0)
         return out
+
+
+def global_reconstruction_metrics(targets, predictions, eps=1e-7):
+    """The reference's `metrics['global']` (core/multi_encoder_nn.py:117-152 -> encoders/pass_encoder.py:77-92 ->
+    statistical.py:6-47): per track, tf.losses.log_loss(targets, decoded predictions) summed over the dimensions is the
+    per-row 'log prob'; loss / log_likelihood are its row means, accuracy / precision / recall count elements; the
+    global value of each metric is the mean over the tracks (multinn_core.py:402-405). With Pass encoders the decoded
+    predictions are the generator's THRESHOLDED outputs (rnn_multinade.py:124-128), so every mismatch costs
+    -log(1e-7) = 16.1 and the number is a scaled Hamming distance, not a likelihood. targets, predictions: [M,N,D]
+    (track-major, any array type). Reporting code, float64 on the host."""
+    import numpy as np
+    to_np = lambda a: a.detach().cpu().numpy() if hasattr(a, 'detach') else np.asarray(a)
+    t, p = to_np(targets).astype(np.float64), to_np(predictions).astype(np.float64)
+    if t.shape != p.shape or t.ndim != 3:
+        raise ValueError(f'targets {t.shape} and predictions {p.shape} must both be [tracks, rows, dims]')
+    row = (-t * np.log(p + eps) - (1.0 - t) * np.log(1.0 - p + eps)).sum(2)            # losses_impl.log_loss
+    tb, pb = t > 0.5, p > 0.5
+    tp, fp, fn = (tb & pb).sum((1, 2)), (~tb & pb).sum((1, 2)), (tb & ~pb).sum((1, 2))
+    safe = lambda a, b: np.where(b > 0, a / np.maximum(b, 1), 0.0)
+    precision, recall = safe(tp, tp + fp), safe(tp, tp + fn)
+    loss = row.mean(1)
+    with np.errstate(over='ignore'):
+        perplexity = np.exp(row).mean(1)
+    per_track = dict(loss=loss, log_likelihood=loss, perplexity=perplexity, accuracy=(tb == pb).mean((1, 2)),
+                     precision=precision, recall=recall, f1_score=np.where(precision > 0, precision, 0.0))   # quirk Q5
+    out = {k: float(v.mean()) for k, v in per_track.items()}
+    out['tracks'] = {k: v.tolist() for k, v in per_track.items()}
+    return out

@@ -136,6 +136,18 @@ def get_default_graph():
 def reset_default_graph():
     del _scopes[:]
     _collections.clear()
+    _default_names.clear()
+
+
+_default_names = {}
+
+
+def unique_default_name(name):
+    """variable_scope(None, default_name=name): name, name_1, name_2, ... within the enclosing scope."""
+    key = _scoped(name)
+    n = _default_names.get(key, 0)
+    _default_names[key] = n + 1
+    return name if n == 0 else f'{name}_{n}'
 
 
 _collections = {}
@@ -367,7 +379,25 @@ def while_loop(cond, body, loop_vars, **kw):
     return vars_
 
 
+class _LazyScalar:
+    """tf.cond on the `is_train` placeholder whose branches are Python numbers (common/rnn.py:120, the dropout keep
+    probability): resolved when used, so one constructed model serves is_train = False and True."""
+
+    def __init__(self, pred, a, b):
+        self._pred, self._a, self._b = pred, a, b
+
+    def __float__(self):
+        return float(self._a if np.all(np.asarray(self._pred)) else self._b)
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(float(self), dtype=dtype or np.float64)
+
+
 def cond(pred, true_fn=None, false_fn=None, name=None):
+    if getattr(pred, 'name', '').split(':')[0].endswith('is_train'):
+        a, b = true_fn(), false_fn()
+        if isinstance(a, (int, float)) and isinstance(b, (int, float)):
+            return _LazyScalar(pred, a, b)
     return true_fn() if np.all(np.asarray(pred)) else false_fn()
 
 
@@ -476,3 +506,270 @@ class Session:
 
 
 __version__ = '1.13.1-numpy-stub'
+
+
+# ================================================================================================ graph-level pieces
+# (round 2, second step) enough of the graph-building API for the reference's MODE classes to run eagerly: placeholders
+# that hold fed values, the LSTM cell stack and the seq2seq decoder loop, tf.scan. With these,
+# tools/make_golden_ref.py builds `MultINN(config, params, 'composer' | 'jamming')` from the reference's own
+# multinn/models/multinn/*.py and generators/*.py: padding, unstacking / stacking of tracks, the input / target shift,
+# the flatten order, the Dense bias split and the loss come from the reference's code. The cell arithmetic below is
+# TF 1.13's LSTMBlockCell as documented: gates i, ci, f, o = split([x, h] . kernel + bias);
+# cs = tanh(ci) * sigmoid(i) + cs_prev * sigmoid(f + forget_bias); h = tanh(cs) * sigmoid(o); forget_bias = 0 for
+# CudnnCompatibleLSTMCell.
+class Dim(int):
+    value = property(lambda s: int(s))
+
+
+class _DimShape(TensorShape):
+    def __getitem__(self, i):
+        v = tuple.__getitem__(self, i)
+        return _DimShape(v) if isinstance(i, slice) else Dim(v)
+
+
+Tensor.shape = property(lambda self: _DimShape(np.ndarray.shape.__get__(self)))
+
+_feeds = {}
+
+
+def feed(**values):
+    """Values of the placeholders created from now on, by name ('x', 'lengths', 'is_train')."""
+    _feeds.update(values)
+
+
+def placeholder(dtype, shape=None, name=None):
+    if name not in _feeds:
+        raise KeyError(f'tf stub: no value fed for placeholder {name!r} (tf.feed(name=value) before building the graph)')
+    return _t(_feeds[name], name=name)
+
+
+_variables = []
+_Variable_plain = Variable
+
+
+def Variable(initial_value, dtype=None, name='Variable', trainable=True):   # noqa: F811 - registers the variable
+    v = _Variable_plain(initial_value, dtype, name, trainable)
+    _variables.append(v)
+    return v
+
+
+def local_variables():
+    return []
+
+
+def global_variables():
+    return list(_variables)
+
+
+def variables_initializer(var_list, name='init'):
+    return None
+
+
+LSTMStateTuple = __import__('collections').namedtuple('LSTMStateTuple', ('c', 'h'))
+
+
+class _LSTMBlockCell:
+    def __init__(self, num_units, forget_bias=0.0, name='cudnn_compatible_lstm_cell'):
+        self._num_units, self._forget_bias, self._name = num_units, forget_bias, name
+        self.kernel = self.bias = None
+        self._scope = None
+
+    state_size = property(lambda s: LSTMStateTuple(s._num_units, s._num_units))
+    output_size = property(lambda s: s._num_units)
+
+    def zero_state(self, batch_size, dtype=None):
+        z = lambda: _t(np.zeros((int(batch_size), self._num_units)))
+        return LSTMStateTuple(z(), z())
+
+    get_initial_state = lambda self, inputs=None, batch_size=None, dtype=None: self.zero_state(batch_size, dtype)
+
+    @property
+    def trainable_variables(self):
+        return [v for v in (self.kernel, self.bias) if v is not None]
+
+    variables = trainable_variables
+
+    def __call__(self, inputs, state, scope=None):
+        x, (cs_prev, h_prev) = np.asarray(inputs), state
+        if self.kernel is None:
+            with variable_scope(self._scope or self._name):
+                init = contrib.layers.xavier_initializer()          # the variable scope's default: glorot_uniform
+                self.kernel = Variable(init([x.shape[1] + self._num_units, 4 * self._num_units]), name='kernel')
+                self.bias = Variable(np.zeros(4 * self._num_units), name='bias')
+        xh = np.concatenate([x, np.asarray(h_prev)], axis=1)
+        g = xh @ np.asarray(self.kernel) + np.asarray(self.bias)
+        i, ci, f, o = np.split(g, 4, axis=1)
+        cs = np.tanh(ci) * _expit(i) + np.asarray(cs_prev) * _expit(f + self._forget_bias)
+        h = np.tanh(cs) * _expit(o)
+        return _t(h), LSTMStateTuple(_t(cs), _t(h))
+
+
+_dropout_uniforms = []
+
+
+def push_dropout_uniforms(arrays):
+    """Uniforms consumed by DropoutWrapper, one array per (step, layer) call in call order (tf.nn.dropout:
+    x / keep * floor(keep + u))."""
+    _dropout_uniforms.extend(np.asarray(a, dtype=np.float64) for a in arrays)
+
+
+dropout_log = []
+_drop_rng = [np.random.default_rng(0)]
+
+
+def seed_dropout(seed):
+    _drop_rng[0] = np.random.default_rng(seed)
+    del dropout_log[:]
+
+
+class _DropoutWrapper:
+    def __init__(self, cell, input_keep_prob=1.0, output_keep_prob=1.0, **kw):
+        self._cell, self._keep = cell, output_keep_prob
+
+    state_size = property(lambda s: s._cell.state_size)
+    output_size = property(lambda s: s._cell.output_size)
+    trainable_variables = property(lambda s: s._cell.trainable_variables)
+    variables = trainable_variables
+    zero_state = lambda self, batch_size, dtype=None: self._cell.zero_state(batch_size, dtype)
+
+    def __call__(self, inputs, state, scope=None):
+        out, new_state = self._cell(inputs, state)
+        keep = float(np.asarray(self._keep))
+        if keep < 1.0:
+            if _dropout_uniforms:
+                u = _dropout_uniforms.pop(0)
+            else:                                   # seeded draw, float32-representable, logged for the fixture
+                u = _drop_rng[0].random(np.asarray(out).shape, dtype=np.float32).astype(np.float64)
+            dropout_log.append(u)
+            out = _t(np.asarray(out) / keep * np.floor(keep + u))
+        return out, new_state
+
+
+class _MultiRNNCell:
+    def __init__(self, cells, state_is_tuple=True):
+        self._cells = list(cells)
+        for i, c in enumerate(self._cells):
+            inner = getattr(c, '_cell', c)
+            inner._scope = f'multi_rnn_cell/cell_{i}/{inner._name}'
+
+    state_size = property(lambda s: tuple(c.state_size for c in s._cells))
+    output_size = property(lambda s: s._cells[-1].output_size)
+
+    @property
+    def trainable_variables(self):
+        return [v for c in self._cells for v in c.trainable_variables]
+
+    variables = trainable_variables
+
+    def zero_state(self, batch_size, dtype=None):
+        return tuple(c.zero_state(batch_size, dtype) for c in self._cells)
+
+    get_initial_state = lambda self, inputs=None, batch_size=None, dtype=None: self.zero_state(batch_size, dtype)
+
+    def __call__(self, inputs, state, scope=None):
+        new, x = [], inputs
+        for c, s in zip(self._cells, state):
+            x, ns = c(x, s)
+            new.append(ns)
+        return x, tuple(new)
+
+
+class _TrainingHelper:
+    def __init__(self, inputs, sequence_length, time_major=False, name=None):
+        self.inputs, self.sequence_length = np.asarray(inputs), np.asarray(sequence_length)
+
+
+class _BasicDecoder:
+    def __init__(self, cell, helper, initial_state, output_layer=None):
+        self.cell, self.helper, self.initial_state, self.output_layer = cell, helper, initial_state, output_layer
+
+
+_DecoderOutput = __import__('collections').namedtuple('BasicDecoderOutput', ('rnn_output', 'sample_id'))
+
+
+def _dynamic_decode(decoder, output_time_major=False, impute_finished=False, maximum_iterations=None, **kw):
+    """tf.contrib.seq2seq.dynamic_decode with a TrainingHelper, impute_finished=False: the cell and the
+    output layer run on every step t < max(sequence_length) for EVERY row; outputs past a row's length are not zeroed and
+    its state keeps advancing. Returns (BasicDecoderOutput(rnn_output[B, T, C], sample_id), final_state, lengths)."""
+    h = decoder.helper
+    T = int(h.sequence_length.max())
+    state, outs = decoder.initial_state, []
+    for t in range(T):
+        out, state = decoder.cell(_t(h.inputs[:, t]), state)
+        if decoder.output_layer is not None:
+            out = decoder.output_layer(out)
+        outs.append(np.asarray(out))
+    rnn_output = _t(np.stack(outs, axis=1))
+    return _DecoderOutput(rnn_output, _t(np.argmax(np.asarray(rnn_output), -1))), state, _t(h.sequence_length)
+
+
+def scan(fn, elems, initializer=None, **kw):
+    """tf.scan over the leading axis; returns the stacked accumulator structure (tuples / namedtuples / lists of tensors)."""
+    import collections.abc as _abc
+    acc, outs = initializer, []
+    n = np.asarray(elems).shape[0]
+    for i in range(n):
+        acc = fn(acc, _t(np.asarray(elems)[i]))
+        outs.append(acc)
+
+    def stack_struct(items):
+        first = items[0]
+        if isinstance(first, tuple) and hasattr(first, '_fields'):
+            return type(first)(*(stack_struct([it[k] for it in items]) for k in range(len(first))))
+        if isinstance(first, (tuple, list)):
+            return type(first)(stack_struct([it[k] for it in items]) for k in range(len(first)))
+        if first is None:
+            return None
+        return _t(np.stack([np.asarray(it) for it in items]))
+    return stack_struct(outs)
+
+
+def clip_by_global_norm(t_list, clip_norm, use_norm=None, name=None):
+    gn = np.sqrt(sum(float((np.asarray(t) ** 2).sum()) for t in t_list))
+    return [_t(np.asarray(t) * clip_norm / max(gn, clip_norm)) for t in t_list], _t(gn)
+
+
+contrib.cudnn_rnn = types.SimpleNamespace(CudnnCompatibleLSTMCell=lambda num_units, reuse=None: _LSTMBlockCell(num_units, 0.0))
+contrib.rnn = types.SimpleNamespace(MultiRNNCell=_MultiRNNCell, LSTMStateTuple=LSTMStateTuple,
+                                    AttentionCellWrapper=_Anything('tf.contrib.rnn.AttentionCellWrapper'))
+contrib.seq2seq = types.SimpleNamespace(TrainingHelper=_TrainingHelper, BasicDecoder=_BasicDecoder,
+                                        dynamic_decode=_dynamic_decode)
+nn = types.SimpleNamespace(rnn_cell=types.SimpleNamespace(DropoutWrapper=_DropoutWrapper, MultiRNNCell=_MultiRNNCell,
+                                                          LSTMStateTuple=LSTMStateTuple),
+                           dynamic_rnn=_Anything('tf.nn.dynamic_rnn'), sigmoid=sigmoid)
+
+
+def _dynamic_rnn(cell, inputs, sequence_length=None, initial_state=None, dtype=None, **kw):
+    """tf.nn.dynamic_rnn, batch-major: for rows with t >= sequence_length the output is zero and the state is copied
+    through (frozen at the row's last valid step) -- unlike dynamic_decode(impute_finished=False) above."""
+    x = np.asarray(inputs)
+    B, T = x.shape[:2]
+    lengths = np.full(B, T) if sequence_length is None else np.asarray(sequence_length).astype(np.int64)
+    state = initial_state if initial_state is not None else cell.zero_state(B, dtype)
+    outs = []
+
+    def merge(new, old, live):
+        if isinstance(new, tuple) and hasattr(new, '_fields'):
+            return type(new)(*(merge(n, o, live) for n, o in zip(new, old)))
+        if isinstance(new, (tuple, list)):
+            return type(new)(merge(n, o, live) for n, o in zip(new, old))
+        return _t(np.where(live[:, None], np.asarray(new), np.asarray(old)))
+    for t in range(T):
+        out, new_state = cell(_t(x[:, t]), state)
+        live = t < lengths
+        outs.append(np.where(live[:, None], np.asarray(out), 0.0))
+        state = merge(new_state, state, live)
+    return _t(np.stack(outs, axis=1)), state
+
+
+nn.dynamic_rnn = _dynamic_rnn
+
+
+class _Layers:
+    @property
+    def Dense(self):
+        from tensorflow.python.layers.core import Dense
+        return Dense
+
+
+layers = _Layers()

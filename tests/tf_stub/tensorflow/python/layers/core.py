@@ -14,6 +14,9 @@ class Dense:
         self.kernel = self.bias = None
 
     def build(self, in_dim):
+        # tf.layers.Layer._set_scope: variable_scope(None, default_name='dense') -> 'dense', 'dense_1', ... unique
+        # within the enclosing scope, decided at the first call
+        self.name = tf.unique_default_name(self.name)
         with tf.variable_scope(self.name):
             self.kernel = tf.Variable(self._kinit([int(in_dim), self.units]), name='kernel')
             self.bias = tf.Variable(np.zeros(self.units), name='bias') if self.use_bias else None

@@ -219,6 +219,90 @@ def multinade_cases():
         log_likelihood=metrics['log_likelihood'], u=u, sample=sample, **w)
 
 
+def _reference_model(mode, x, lengths, is_train, H=128, R=(48, 32), feedback=(40, 24), keep_prob=1.0):
+    """MultINN(config, params, mode) from the reference's own models/multinn/*.py, built twice: the first build creates
+    the variables (lazily, inside the cells / Dense layers), which are then rounded to float32-representable values in
+    place; the second build recomputes the whole graph with them (the stub executes eagerly)."""
+    import yaml
+    from models.multinn.multinn import MultINN
+    with open(os.path.join(REF, 'configs', 'default_config.yaml')) as f:
+        config = yaml.safe_load(f)
+    with open(os.path.join(REF, 'configs', 'default_params.yaml')) as f:
+        params = yaml.safe_load(f)
+    config['training']['num_pixels'] = 1                       # D = 84, the shape BASELINE.json's configs use
+    params['generator'].update(num_hidden=H, num_hidden_rnn=list(R), feedback=list(feedback))
+    params['keep_prob'] = keep_prob
+    tf.reset_default_graph()
+    del tf._variables[:]
+    tf.feed(x=x, lengths=lengths, is_train=False)
+    model = MultINN(config, params, mode=mode, name='multinn')
+    for v in tf._variables:
+        v[...] = r32(A(v))
+    return model
+
+
+def _rebuild(model, x, lengths, is_train, seed):
+    """Re-runs the reference's build() on new placeholder values (the encoders / generators keep their variables)."""
+    core = model._model
+    core._x, core._lengths = tf.constant(x), tf.constant(A(lengths))
+    core._is_train[...] = is_train                             # in place: tf.cond(is_train, ...) holds this placeholder
+    for e in core.encoders:                                    # PassEncoder keeps references to the inputs it was built on
+        e._is_built = False
+    tf.seed_dropout(seed)
+    n_vars = len(tf._variables)
+    core.build(mode='eval')
+    assert len(tf._variables) == n_vars, 'the rebuild must reuse the variables'
+    gens = core.generators
+    out = dict(loss=A([g.metrics['batch/loss'] for g in gens]),
+               predictions=np.stack([A(p) for g in gens for p in (g.forward() if isinstance(g.forward(), list) else [g.forward()])]),
+               global_loss=core.metrics['loss'], global_accuracy=core.metrics['accuracy'],
+               global_precision=core.metrics['precision'], global_recall=core.metrics['recall'])
+    for i, u in enumerate(tf.dropout_log):
+        out[f'drop{i}'] = u
+    out['n_drop'] = len(tf.dropout_log)
+    return out
+
+
+def mode_cases():
+    """The MODE classes (models/multinn/multinn_{composer,jamming,feedback,feedback_rnn}.py + core/) built by the
+    reference's own code: input padding and per-track unstack (core/multi_encoder_nn.py:66-76), stack / shift
+    (multinn_composer.py:73-87, multinn_jamming.py:60-68, multinn_feedback.py:67-94), the LSTM stack under
+    dynamic_decode / dynamic_rnn, Dense, bias split, NADE loop, flatten with ragged lengths, per-track and global
+    metrics, dropout placement (is_train=True) and generate() with injected sampler uniforms."""
+    modes = {}
+    rng = _R32(77)
+    B, T, D, M, S = 3, 5, 84, 5, 3
+    x = (rng.random((B, T, D, M)) < 0.12).astype(np.float64)
+    full, ragged = A([T] * B), A([T, 2, 4])
+    for mode in ('composer', 'jamming', 'feedback', 'feedback-rnn'):
+        model = _reference_model(mode, x, full, False, keep_prob=0.8)
+        key = mode.replace('-', '_')
+        for v in tf._variables:
+            modes[f'{key}/var/{v.name[:-2]}'] = A(v)
+        for case, lengths, is_train in (('eval', full, False), ('ragged', ragged, False), ('train', ragged, True)):
+            for k, val in _rebuild(model, x, lengths, is_train, seed=5).items():
+                modes[f'{key}/{case}/{k}'] = A(val)
+        # generation: intro = the first 3 steps (multinn_composer.py:114-151 and siblings), uniforms u[S, M, D, B]
+        _rebuild(model, x[:, :3], A([3] * B), False, seed=5)
+        u = rng.random((S, M, D, B))
+        # draw order of the reference: Jamming runs each track's whole generate() in turn (multinn_jamming.py:117-125),
+        # the other modes sample all tracks inside one step; u[s, m, i] is always (step, track, dimension)
+        order = [(s, m) for m in range(M) for s in range(S)] if mode == 'jamming' else \
+                [(s, m) for s in range(S) for m in range(M)]
+        tfp.push_uniforms([u[s, m, i][:, None] for s, m in order for i in range(D)])
+        music = model.generate(S)
+        assert tfp.pending() == 0
+        modes[f'{key}/generate/u'] = u
+        modes[f'{key}/generate/music'] = A(music)
+    modes['x'] = x
+    modes['ragged'] = ragged
+    path = os.path.join(ROOT, 'tests', 'golden', 'ref_modes.npz')
+    modes = {k: (v.astype(np.float32) if '/var/' in k or '/drop' in k or k.endswith('/u') else
+                 v.astype(np.uint8) if k.endswith(('/predictions', '/music')) or k == 'x' else v) for k, v in modes.items()}
+    np.savez_compressed(path, **modes)
+    print(f'{path}: {len(modes)} arrays, {os.path.getsize(path) / 1024:.0f} KiB')
+
+
 if __name__ == '__main__':
     tf.set_random_seed(20261018)
     nade_cases()
@@ -229,3 +313,4 @@ if __name__ == '__main__':
     path = os.path.join(ROOT, 'tests', 'golden', 'ref_primitives.npz')
     np.savez_compressed(path, **out)
     print(f'{path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.0f} KiB')
+    mode_cases()
