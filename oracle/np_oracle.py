@@ -216,22 +216,31 @@ def composer_generate(x_intro, params, num_steps, u):
     B, Ti, D, M = x_intro.shape
     stack = x_intro.reshape(B, Ti, D * M)
     pad = np.concatenate([np.zeros((B, 1, D * M), x_intro.dtype), stack], axis=1)
-    outs, state = rnn_scan(pad, params['lstm'])
+    return multinade_generate(pad, params, num_steps, u).reshape(B, num_steps, D, M)
+
+
+def multinade_generate(intro, params, num_steps, u):
+    """RnnEstimator.generate for an RNN-MultiNADE over given (already padded / encoded) intro features
+    intro[B,T1,E*M], feature e*M + m (generators/rnn_estimator.py:271-323, rnn_multinade.py:292-317).
+    u[S,M,B,E] or None. Returns samples[B,S,E*M]."""
+    B = intro.shape[0]
+    M = len(params['nade'])
+    E, H = params['nade'][0][0].shape
+    outs, state = rnn_scan(intro, params['lstm'])
     K, b = params['dense']
-    H = params['nade'][0][0].shape[1]
     fc = dense(outs[:, -1], K, b)                                   # last_outputs=True, rnn_nade.py:223
     samples = []
     for s in range(num_steps):
-        be, bd = split_biases_multi(fc, M, H, D)
+        be, bd = split_biases_multi(fc, M, H, E)
         vs = []
         for m in range(M):
             v, _ = nade_sample(be[m], bd[m], *params['nade'][m], u=None if u is None else u[s, m])
             vs.append(v)
-        samp = np.stack(vs, axis=2).reshape(B, D * M)               # rnn_multinade.py:314-315
+        samp = np.stack(vs, axis=2).reshape(B, E * M)               # rnn_multinade.py:314-315
         samples.append(samp)
         o, state = multi_rnn_step(samp, state, params['lstm'])      # rnn_nade.py:267
         fc = dense(o, K, b)
-    return np.stack(samples, axis=1).reshape(B, num_steps, D, M)
+    return np.stack(samples, axis=1)
 
 
 # ----------------------------------------------------------------------------- RBM / DBN

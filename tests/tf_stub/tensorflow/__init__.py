@@ -477,7 +477,15 @@ class Summary:
     pass
 
 
-summary = types.SimpleNamespace(merge=lambda inputs, **k: None, histogram=lambda *a, **k: None,
+class _MergedSummary(dict):
+    """tf.summary.merge's result. Real TF returns a string tensor; multinn_core.py:242 then does
+    `self._summaries['weights'] = ...`, which works when `_summaries` is the dict `_combine_track_metrics` builds
+    (per-track modes) and raises TypeError when it is a merged tensor (Joint mode, multinn_joint.py:177-186 -- the
+    reference's Joint build() cannot finish at HEAD). The stand-in accepts the assignment so that the Joint graph's
+    numerics can still be recorded; summaries carry no numbers here."""
+
+
+summary = types.SimpleNamespace(merge=lambda inputs, **k: _MergedSummary(), histogram=lambda *a, **k: None,
                                 scalar=lambda *a, **k: None, FileWriter=_Anything('tf.summary.FileWriter'))
 
 

@@ -20,6 +20,17 @@ def push_uniforms(arrays):
     _queue.extend(np.asarray(a, dtype=np.float64) for a in arrays)
 
 
+_auto = [None]
+auto_log = []          # the uniform arrays drawn by the seeded fallback, in call order (float32-representable)
+
+
+def auto_uniforms(seed):
+    """When the injected queue is empty, draw from a seeded generator instead of raising, and log the arrays (for graphs
+    whose draw order is discovered by running them). seed=None switches the fallback off."""
+    _auto[0] = None if seed is None else np.random.default_rng(seed)
+    del auto_log[:]
+
+
 def pending():
     return len(_queue)
 
@@ -36,9 +47,13 @@ class _Bernoulli:
         self.probs = np.asarray(probs, dtype=np.float64) if probs is not None else _expit(np.asarray(logits, dtype=np.float64))
 
     def sample(self, sample_shape=(), seed=None, name='sample'):
-        if not _queue:
+        if not _queue and _auto[0] is not None:
+            u = _auto[0].random(self.probs.shape, dtype=np.float32).astype(np.float64)
+            auto_log.append(u)
+        elif not _queue:
             raise RuntimeError('tfp stub: Bernoulli.sample() called with no injected uniforms left (push_uniforms)')
-        u = _queue.popleft()
+        else:
+            u = _queue.popleft()
         if u.shape != self.probs.shape:
             raise ValueError(f'tfp stub: injected uniforms have shape {u.shape}, the distribution {self.probs.shape}')
         consumed.append(u.shape)

@@ -303,6 +303,74 @@ def mode_cases():
     print(f'{path}: {len(modes)} arrays, {os.path.getsize(path) / 1024:.0f} KiB')
 
 
+def dbn_mode_cases():
+    """Composer / Jamming / Joint over DBN encoders with RNN-NADE generators, from the reference's own classes
+    (encoders/dbn_encoder.py, common/dbn.py, multinn_joint.py + the files of mode_cases): the per-track (Joint: stacked)
+    zero-padded inputs are encoded to SAMPLED codes, the generators model the codes, generated codes are decoded.
+    Every Bernoulli draw comes from the stub's seeded fallback and is logged IN CALL ORDER (`draw{i}`), which is how the
+    draw order of the reference's graph is discovered rather than assumed:
+      build():    per encoder [encode layer 0, layer 1, reconstruct layer 1, layer 0]  (encoder.build, rows b*(T+1) + t),
+                  then per encoder the decode of the generator's predictions [layer 1, layer 0]  (rows n = b*T + t)
+      generate(): S x M x E sampler draws [B,1] (Jamming: track-major), then per encoder the decode [layer 1, layer 0]
+                  (rows b*S + s); the intro encodings are the ones build() sampled.
+    The RNN-RBM generator is not covered: the reference's RnnRBM cannot be constructed (`_init_estimator` reads `self.k`
+    before `self._k` is assigned, rnn_rbm.py:41-52) and its sampling call passes k=None into tf.constant (rnn_rbm.py:295 ->
+    common/rbm.py:223); Joint build() itself only finishes because the stub's merged summary accepts item assignment
+    (multinn_core.py:242 on multinn_joint.py:177-186's merged summary raises TypeError under real TF)."""
+    import yaml
+    from models.multinn.multinn import MultINN
+    with open(os.path.join(REF, 'configs', 'default_config.yaml')) as f:
+        config = yaml.safe_load(f)
+    with open(os.path.join(REF, 'configs', 'default_params.yaml')) as f:
+        params = yaml.safe_load(f)
+    config['training']['num_pixels'] = 1
+    params['generator'].update(type='NADE', num_hidden=128, num_hidden_rnn=[48, 32])
+    params['encoder'].update(type='DBN', num_hidden=[96, 84])
+    params['keep_prob'] = 1.0
+    rng = _R32(91)
+    B, T, D, M, S = 3, 4, 84, 5, 2
+    x = (rng.random((B, T, D, M)) < 0.12).astype(np.float64)
+    res = {'x': x.astype(np.uint8)}
+    for mode in ('composer', 'jamming', 'joint'):
+        tf.reset_default_graph()
+        del tf._variables[:]
+        tf.feed(x=x, lengths=A([T] * B), is_train=False)
+        tfp.auto_uniforms(7)
+        model = MultINN(config, params, mode=mode, name='multinn')     # first build: creates the lazy variables
+        for v in tf._variables:
+            v[...] = r32(A(v))
+        core = model._model
+        for e in core.encoders:
+            e._is_built = False
+        tfp.auto_uniforms(11)
+        n_vars = len(tf._variables)
+        core.build(mode='eval')
+        assert len(tf._variables) == n_vars
+        for v in tf._variables:
+            res[f'{mode}/var/{v.name[:-2]}'] = A(v).astype(np.float32)
+        res[f'{mode}/eval/loss'] = A([g.metrics['batch/loss'] for g in core.generators])
+        res[f'{mode}/eval/global_loss'] = A(core.metrics['batch/loss'])
+        for i, u in enumerate(tfp.auto_log):
+            res[f'{mode}/eval/draw{i}'] = u.astype(np.float32)
+        res[f'{mode}/eval/n_draw'] = A(len(tfp.auto_log))
+        n0 = len(tfp.auto_log)
+        music = model.generate(S)
+        draws = tfp.auto_log[n0:]
+        E = 84
+        n_s = S * M * E if mode != 'joint' else S * E
+        sampler = [u for u in draws if u.shape == (B, 1)]          # Jamming interleaves: per track [S*E sampler, 2 decode]
+        decode = [u for u in draws if u.shape != (B, 1)]
+        assert len(sampler) == n_s and len(decode) == 2 * len(core.encoders)
+        res[f'{mode}/generate/sampler_draws'] = np.concatenate(sampler, axis=1).T.astype(np.float32)   # [n_s, B] in call order
+        for i, u in enumerate(decode):
+            res[f'{mode}/generate/decode_draw{i}'] = u.astype(np.float32)
+        res[f'{mode}/generate/music'] = A(music).astype(np.uint8)
+    tfp.auto_uniforms(None)
+    path = os.path.join(ROOT, 'tests', 'golden', 'ref_dbn_modes.npz')
+    np.savez_compressed(path, **res)
+    print(f'{path}: {len(res)} arrays, {os.path.getsize(path) / 1024:.0f} KiB')
+
+
 if __name__ == '__main__':
     tf.set_random_seed(20261018)
     nade_cases()
@@ -314,3 +382,4 @@ if __name__ == '__main__':
     np.savez_compressed(path, **out)
     print(f'{path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.0f} KiB')
     mode_cases()
+    dbn_mode_cases()
