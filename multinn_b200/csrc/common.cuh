@@ -72,6 +72,41 @@ __device__ __forceinline__ float tanh_fast(float x) {
   const float big = fmaf(-2.0f, __fdividef(1.0f, 1.0f + __expf(2.0f * x)), 1.0f);
   return fabsf(x) < 0.04f ? poly : big;
 }
+// One LSTM cell from the four gate pre-activations with 5 MUFU.EX2 + 2 MUFU.RCP instead of 5 + 5. The XU pipe retires
+// rcp.approx at a third of the ex2.approx rate (mnn_probe_mufu: 5.4 against 15.8 per clock per SM), and the cell epilogue
+// of the recurrence kernels is XU-bound, so the four gate reciprocals share ONE rcp (Montgomery's trick:
+// 1/a = b*c*d * rcp(a*b*c*d)); the exponentials are clamped to 1e9 so that the product of four denominators stays finite
+// (a gate below 1e-9 comes out as 1e-9: absolute error < 1e-9). tanh keeps the odd polynomial near 0 (tanh_fast).
+// c' = tanh(j) * sig(i) + c * sig(f);  h' = tanh(c') * sig(o)   (common/rnn.py:124)
+__device__ __forceinline__ float ex2_clamped(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+  return fminf(e, 1.0e9f);
+}
+__device__ __forceinline__ float tanh_from_rcp(float x, float r) {   // r = 1 / (1 + e^{-2x})
+  const float x2 = x * x;
+  const float poly = x * fmaf(x2, fmaf(x2, 0.13333333f, -0.33333334f), 1.0f);
+  return fabsf(x) < 0.04f ? poly : fmaf(2.0f, r, -1.0f);
+}
+__device__ __forceinline__ void lstm_cell_xu(float pi, float pj, float pf, float po, float cprev, float& gi, float& gj,
+                                             float& gf, float& go, float& c, float& h) {
+  const float di = 1.0f + ex2_clamped(pi * -1.4426950408889634f);
+  const float dj = 1.0f + ex2_clamped(pj * -2.8853900817779268f);
+  const float df = 1.0f + ex2_clamped(pf * -1.4426950408889634f);
+  const float dO = 1.0f + ex2_clamped(po * -1.4426950408889634f);
+  const float pij = di * dj, pfo = df * dO;
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(pij * pfo));
+  const float rij = r * pfo, rfo = r * pij;          // 1 / (di dj), 1 / (df do)
+  gi = rij * dj;
+  gj = tanh_from_rcp(pj, rij * di);
+  gf = rfo * dO;
+  go = rfo * df;
+  c = fmaf(gj, gi, cprev * gf);
+  float rc;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(1.0f + ex2_clamped(c * -2.8853900817779268f)));
+  h = tanh_from_rcp(c, rc) * go;
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Packed fp32x2 FMA (Blackwell FFMA2): d = a*b + c on both halves.

@@ -249,11 +249,10 @@ lstm_res_fwd_kernel(const __grid_constant__ CUtensorMap map_h1, const __grid_con
       float hv[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float gi = sigmoid_fast(pre[0][i]), gj = tanh_fast(pre[1][i]);
-        const float gf = sigmoid_fast(pre[2][i]), go = sigmoid_fast(pre[3][i]);
+        float gi, gj, gf, go, cn;
+        lstm_cell_xu(pre[0][i], pre[1][i], pre[2][i], pre[3][i], cst[i], gi, gj, gf, go, cn, hv[i]);
         pre[0][i] = gi; pre[1][i] = gj; pre[2][i] = gf; pre[3][i] = go;
-        cst[i] = gj * gi + cst[i] * gf;
-        hv[i] = tanh_fast(cst[i]) * go;
+        cst[i] = cn;
       }
       if (row_ok) {
         // h_t first: it gates the next step of the whole slab

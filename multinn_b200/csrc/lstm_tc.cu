@@ -306,11 +306,9 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               float cv[8], hv[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float gi = sigmoid_fast(pre[0][i]), gj = tanh_fast(pre[1][i]);
-                const float gf = sigmoid_fast(pre[2][i]), go = sigmoid_fast(pre[3][i]);
+                float gi, gj, gf, go;
+                lstm_cell_xu(pre[0][i], pre[1][i], pre[2][i], pre[3][i], cp[i], gi, gj, gf, go, cv[i], hv[i]);
                 pre[0][i] = gi; pre[1][i] = gj; pre[2][i] = gf; pre[3][i] = go;
-                cv[i] = gj * gi + cp[i] * gf;
-                hv[i] = tanh_fast(cv[i]) * go;
               }
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
@@ -556,11 +554,9 @@ lstm_tc2_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       float cv[8], hv[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float gi = sigmoid_mufu(pre[0][i]), gj = tanh_mufu(pre[1][i]);
-        const float gf = sigmoid_mufu(pre[2][i]), go = sigmoid_mufu(pre[3][i]);
+        float gi, gj, gf, go;
+        lstm_cell_xu(pre[0][i], pre[1][i], pre[2][i], pre[3][i], cp[i], gi, gj, gf, go, cv[i], hv[i]);
         pre[0][i] = gi; pre[1][i] = gj; pre[2][i] = gf; pre[3][i] = go;
-        cv[i] = gj * gi + cp[i] * gf;
-        hv[i] = tanh_mufu(cv[i]) * go;
       }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {

@@ -7,6 +7,8 @@
 // h_i = sigmoid(a_i) is piecewise constant over i ("segments"); sigmoids are evaluated once per
 // segment, the decode dots l_i = b_dec_i + h_i . w_dec[i] for every i. Results are identical to
 // evaluating every i; only the transcendental count drops from D*H to (1 + popcount(v)) * H per row.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "multinn_b200.h"
 
@@ -247,7 +249,11 @@ struct BwdCfg {
   static constexpr size_t SMEM = kFloats * sizeof(float) + 2 * R * 8 * sizeof(uint32_t);  // + shifted masks (5 words, padded to 8)
 };
 
-template <int H, int D>
+// V = 0: the walk enters an unrolled run through a jump table and breaks out at the next boundary (round 1).
+// V = 1: straight-line walk over the group's DG dims with one warp-uniform boundary test per dim (no BRX dispatch, no
+//        run loop), and the (group, unit-half) -> warp map chosen so that every SM sub-partition holds one light and one
+//        heavy group (the prefix rebuild costs group g about (g + 1) / 4 of the row's set bits).
+template <int H, int D, int V>
 __global__ void __launch_bounds__(H, 1) nade_bwd_kernel(NadeArgs p) {
   using C_ = BwdCfg<H, D>;
   constexpr int G = C_::G, DG = C_::DG, DGP = C_::DGP, KQ = C_::KQ, R = C_::R;
@@ -265,7 +271,13 @@ __global__ void __launch_bounds__(H, 1) nade_bwd_kernel(NadeArgs p) {
   const int cta = blockIdx.x / p.M;
   const int nctas = (gridDim.x - m + p.M - 1) / p.M;
   const int tid = threadIdx.x;
-  const int kq = tid % KQ, ig = tid / KQ;          // a warp shares ig (KQ is a multiple of 32)
+  int kq = tid % KQ, ig = tid / KQ;                // a warp shares ig (KQ is a multiple of 32)
+  if constexpr (V == 1 && H == 256) {
+    // warps 0..7 sit on sub-partitions w % 4: pair groups (0,3) on SMSP 0 / 2 and (1,2) on SMSP 1 / 3
+    const int w = tid >> 5;
+    ig = (w & 4) ? 3 - (w & 1) : (w & 1);
+    kq = ((w >> 1) & 1) * 32 + (tid & 31);
+  }
   const int k0 = 4 * kq, lo = ig * DG;
   const float* gwe = p.w_enc + (size_t)m * D * H;
   const float* gwd = p.w_dec + (size_t)m * D * H;
@@ -387,6 +399,46 @@ __global__ void __launch_bounds__(H, 1) nade_bwd_kernel(NadeArgs p) {
       uint32_t rm = bm0 | bm1;
       const float* dl0 = db + (r * G + ig) * DGP;
       const float* dl1 = db + ((r + 1) * G + ig) * DGP;
+      auto boundary = [&](int s) {   // the set target bit j = lo + s - 1 ends the segment below local dim s
+        const int j = lo + s - 1;
+        if (bm0 & (1u << s)) {      // block-uniform within the warp (a warp shares ig and the row)
+          flush_seg(S0, dh0, h0);
+          dh0 = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4* ae = reinterpret_cast<float4*>(acce_s + (size_t)j * H + k0);
+          float4 acc = *ae;
+          add4(acc, S0);
+          *ae = acc;
+          sub4(a0, *reinterpret_cast<const float4*>(wenc_s + (size_t)j * H + k0));
+          h0 = sigmoid_mufu4(a0);
+        }
+        if (bm1 & (1u << s)) {
+          flush_seg(S1, dh1, h1);
+          dh1 = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4* ae = reinterpret_cast<float4*>(acce_s + (size_t)j * H + k0);
+          float4 acc = *ae;
+          add4(acc, S1);
+          *ae = acc;
+          sub4(a1, *reinterpret_cast<const float4*>(wenc_s + (size_t)j * H + k0));
+          h1 = sigmoid_mufu4(a1);
+        }
+      };
+      if constexpr (V == 1) {
+        float4 q0, q1;
+#pragma unroll
+        for (int I = DG - 1; I >= 0; --I) {
+          if ((I & 3) == 3 || I == DG - 1) {
+            q0 = *reinterpret_cast<const float4*>(dl0 + (I & ~3));
+            q1 = *reinterpret_cast<const float4*>(dl1 + (I & ~3));
+          }
+          const float d0 = (I & 3) == 3 ? q0.w : ((I & 3) == 2 ? q0.z : ((I & 3) == 1 ? q0.y : q0.x));
+          const float d1 = (I & 3) == 3 ? q1.w : ((I & 3) == 2 ? q1.z : ((I & 3) == 1 ? q1.y : q1.x));
+          fma4(dh0, d0, wd[I]);
+          fma4(dh1, d1, wd[I]);
+          fma4(aw[I], d0, h0);
+          fma4(aw[I], d1, h1);
+          if (I > 0 && (rm & (1u << I))) boundary(I);
+        }
+      } else {
       int i = DG - 1;
 #pragma unroll 1
       for (;;) {
@@ -421,28 +473,9 @@ __global__ void __launch_bounds__(H, 1) nade_bwd_kernel(NadeArgs p) {
 #undef MNN_BWD_STEP4
 #undef MNN_BWD_STEP
         if (s == 0) break;
-        const int j = lo + s - 1;   // the set target bit that ends the segment
-        if (bm0 & (1u << s)) {      // block-uniform within the warp (a warp shares ig and the row)
-          flush_seg(S0, dh0, h0);
-          dh0 = make_float4(0.f, 0.f, 0.f, 0.f);
-          float4* ae = reinterpret_cast<float4*>(acce_s + (size_t)j * H + k0);
-          float4 acc = *ae;
-          add4(acc, S0);
-          *ae = acc;
-          sub4(a0, *reinterpret_cast<const float4*>(wenc_s + (size_t)j * H + k0));
-          h0 = sigmoid_mufu4(a0);
-        }
-        if (bm1 & (1u << s)) {
-          flush_seg(S1, dh1, h1);
-          dh1 = make_float4(0.f, 0.f, 0.f, 0.f);
-          float4* ae = reinterpret_cast<float4*>(acce_s + (size_t)j * H + k0);
-          float4 acc = *ae;
-          add4(acc, S1);
-          *ae = acc;
-          sub4(a1, *reinterpret_cast<const float4*>(wenc_s + (size_t)j * H + k0));
-          h1 = sigmoid_mufu4(a1);
-        }
+        boundary(s);
         i = s - 1;
+      }
       }
       flush_seg(S0, dh0, h0);
       flush_seg(S1, dh1, h1);
@@ -661,16 +694,26 @@ extern "C" int mnn_nade_logprob_fwd(const uint32_t* bits, const float* fc, long 
   return mnn_check_launch("nade_logprob_fwd");
 }
 
-template <int H, int D>
-static int launch_bwd(const NadeArgs& a, cudaStream_t stream) {
+static int nade_bwd_variant() {   // MNN_NADE_BWD_V=0 selects the round-1 jump-table walk (A/B runs)
+  static const int v = [] { const char* e = getenv("MNN_NADE_BWD_V"); return e ? atoi(e) : 1; }();
+  return v;
+}
+
+template <int H, int D, int V>
+static int launch_bwd_v(const NadeArgs& a, cudaStream_t stream) {
   const size_t smem = BwdCfg<H, D>::SMEM;
-  cudaFuncSetAttribute(nade_bwd_kernel<H, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(nade_bwd_kernel<H, D, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int grid = num_sms();
   const int need = a.M * ((a.N + kBwdRows - 1) / kBwdRows);
   if (grid > need) grid = need;
   if (grid < a.M) grid = a.M;
-  nade_bwd_kernel<H, D><<<grid, H, smem, stream>>>(a);
+  nade_bwd_kernel<H, D, V><<<grid, H, smem, stream>>>(a);
   return mnn_check_launch("nade_logprob_bwd");
+}
+
+template <int H, int D>
+static int launch_bwd(const NadeArgs& a, cudaStream_t stream) {
+  return nade_bwd_variant() == 0 ? launch_bwd_v<H, D, 0>(a, stream) : launch_bwd_v<H, D, 1>(a, stream);
 }
 
 extern "C" int mnn_nade_logprob_bwd(const uint32_t* bits, const float* fc, long long ld, int enc_col0, int dec_col0,
