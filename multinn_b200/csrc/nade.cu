@@ -239,10 +239,29 @@ __device__ __forceinline__ void flush_seg(float4& S, const float4& dh, const flo
   S.z = fmaf(dh.z * h.z, 1.f - h.z, S.z); S.w = fmaf(dh.w * h.w, 1.f - h.w, S.w);
 }
 
+// packed (FADD2 / FMUL2 / FFMA2) forms of the three helpers: same roundings, half the issue slots
+__device__ __forceinline__ void add4p(float4& a, const float4& b) {
+  const float2 lo = fadd2(make_float2(a.x, a.y), make_float2(b.x, b.y));
+  const float2 hi = fadd2(make_float2(a.z, a.w), make_float2(b.z, b.w));
+  a = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ void sub4p(float4& a, const float4& b) {
+  const float2 lo = fsub2(make_float2(a.x, a.y), make_float2(b.x, b.y));
+  const float2 hi = fsub2(make_float2(a.z, a.w), make_float2(b.z, b.w));
+  a = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ void flush_segp(float4& S, const float4& dh, const float4& h) {
+  const float2 one = make_float2(1.f, 1.f);
+  const float2 hl = make_float2(h.x, h.y), hh = make_float2(h.z, h.w);
+  const float2 lo = ffma2(fmul2(make_float2(dh.x, dh.y), hl), fsub2(one, hl), make_float2(S.x, S.y));
+  const float2 hi = ffma2(fmul2(make_float2(dh.z, dh.w), hh), fsub2(one, hh), make_float2(S.z, S.w));
+  S = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
 template <int H, int D>
 struct BwdCfg {
   static constexpr int G = kBwdGroups, DG = D / G, DGP = (DG + 3) / 4 * 4, KQ = H / 4, R = kBwdRows;
-  static constexpr size_t kFloats = (size_t)2 * D * H      // wenc_s, acce_s
+  static constexpr size_t kFloats = (size_t)2 * D * H + H  // wenc_s (+ one all-zero row), acce_s
                                     + 2 * R * H            // a_s double buffer
                                     + 2 * R * G * DGP      // dl_s double buffer (per-group padded slices)
                                     + R * G * H;           // tot_s
@@ -250,18 +269,30 @@ struct BwdCfg {
 };
 
 // V = 0: the walk enters an unrolled run through a jump table and breaks out at the next boundary (round 1).
+// V = 3: V = 2 walking each group's dims UPWARDS. The walk needs the pre-activation prefix a at its first dim: top-down
+//        that is every set bit below the group's TOP (group g re-adds about (g + 1) / 4 of the row's bits, 2.5 / 4 on
+//        average, and the profile shows this rebuild as the largest single item, 21 % of the stall samples); bottom-up
+//        it is the bits below the group's BOTTOM (g / 4 of them, 1.5 / 4 on average, none for group 0). The suffix sums
+//        dW_enc[j] += sum_{i > j} gA_i become "row total from this group upwards minus the running prefix inside the
+//        group": the walk subtracts the running prefix at each set bit, the fix-up pass adds sum_{g' >= g} total(g').
+// V = 2: V = 1 with the float4 add / sub / segment-flush helpers on FADD2 / FMUL2 / FFMA2 (same roundings).
 // V = 1: straight-line walk over the group's DG dims with one warp-uniform boundary test per dim (no BRX dispatch, no
 //        run loop), and the (group, unit-half) -> warp map chosen so that every SM sub-partition holds one light and one
 //        heavy group (the prefix rebuild costs group g about (g + 1) / 4 of the row's set bits).
 template <int H, int D, int V>
 __global__ void __launch_bounds__(H, 1) nade_bwd_kernel(NadeArgs p) {
   using C_ = BwdCfg<H, D>;
+  constexpr bool PK = (V >= 2);
+  constexpr bool UP = (V == 3);   // walk the group's dims upwards (see the V = 3 note above the kernel)
+  auto ADD4 = [](float4& x, const float4& y) { if constexpr (PK) add4p(x, y); else add4(x, y); };
+  auto SUB4 = [](float4& x, const float4& y) { if constexpr (PK) sub4p(x, y); else sub4(x, y); };
+  auto FLUSH = [](float4& S, const float4& dh, const float4& h) { if constexpr (PK) flush_segp(S, dh, h); else flush_seg(S, dh, h); };
   constexpr int G = C_::G, DG = C_::DG, DGP = C_::DGP, KQ = C_::KQ, R = C_::R;
   static_assert(D % G == 0 && DG <= 31, "num_dims must be a multiple of 4 and at most 124");
   static_assert(KQ * G == H, "one thread per (hidden-unit quad, dim group)");
   extern __shared__ __align__(16) float smem[];
-  float* wenc_s = smem;                            // [D][H]
-  float* acce_s = wenc_s + (size_t)D * H;          // [D][H]
+  float* wenc_s = smem;                            // [D + 1][H], row D = 0
+  float* acce_s = wenc_s + (size_t)(D + 1) * H;    // [D][H]
   float* a_s = acce_s + (size_t)D * H;             // [2][R][H]
   float* dl_s = a_s + 2 * R * H;                   // [2][R][G][DGP]
   float* tot_s = dl_s + 2 * R * G * DGP;           // [R][G][H]
@@ -272,7 +303,7 @@ __global__ void __launch_bounds__(H, 1) nade_bwd_kernel(NadeArgs p) {
   const int nctas = (gridDim.x - m + p.M - 1) / p.M;
   const int tid = threadIdx.x;
   int kq = tid % KQ, ig = tid / KQ;                // a warp shares ig (KQ is a multiple of 32)
-  if constexpr (V == 1 && H == 256) {
+  if constexpr (V >= 1 && H == 256) {
     // warps 0..7 sit on sub-partitions w % 4: pair groups (0,3) on SMSP 0 / 2 and (1,2) on SMSP 1 / 3
     const int w = tid >> 5;
     ig = (w & 4) ? 3 - (w & 1) : (w & 1);
@@ -292,6 +323,7 @@ __global__ void __launch_bounds__(H, 1) nade_bwd_kernel(NadeArgs p) {
     reinterpret_cast<float4*>(wenc_s)[c] = __ldg(reinterpret_cast<const float4*>(gwe) + c);
     reinterpret_cast<float4*>(acce_s)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  for (int c = tid; c < H / 4; c += H) reinterpret_cast<float4*>(wenc_s + (size_t)D * H)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
   const uint32_t* bits = p.bits + (size_t)m * p.tstride * kNW;
   const int enc_col = p.enc_col0 + m * H, dec_col = p.dec_col0 + m * D;
   const int nbatches = (p.N + R - 1) / R;
@@ -370,9 +402,10 @@ __global__ void __launch_bounds__(H, 1) nade_bwd_kernel(NadeArgs p) {
       const uint32_t* sm1 = mb + (r + 1) * 8;
       float4 a0 = *reinterpret_cast<const float4*>(ab + r * H + k0);
       float4 a1 = *reinterpret_cast<const float4*>(ab + (r + 1) * H + k0);
-      // forward prefix up to the group's top dim hi = lo + DG - 1: all set target bits j < hi, i.e. shifted bits 1..hi
+      // forward prefix up to the walk's first dim: top-down hi = lo + DG - 1, bottom-up hi = lo: all set target bits
+      // j < hi, i.e. shifted bits 1..hi
       {
-        const int hi = lo + DG - 1;
+        const int hi = UP ? lo : lo + DG - 1;
 #pragma unroll
         for (int w = 0; w < kNW; ++w) {
           if (w * 32 > hi) break;    // warp-uniform
@@ -381,14 +414,14 @@ __global__ void __launch_bounds__(H, 1) nade_bwd_kernel(NadeArgs p) {
           uint32_t x0 = sm0[w] & keep, x1 = sm1[w] & keep;
           if (w == 0) { x0 &= ~1u; x1 &= ~1u; }
           while (x0) {
-            const int j = w * 32 + __ffs(x0) - 2;   // shifted bit s <-> target bit s - 1
+            const int j = w * 32 + __ffs(x0) - 2;
             x0 &= x0 - 1;
-            add4(a0, *reinterpret_cast<const float4*>(wenc_s + (size_t)j * H + k0));
+            ADD4(a0, *reinterpret_cast<const float4*>(wenc_s + (size_t)j * H + k0));
           }
           while (x1) {
             const int j = w * 32 + __ffs(x1) - 2;
             x1 &= x1 - 1;
-            add4(a1, *reinterpret_cast<const float4*>(wenc_s + (size_t)j * H + k0));
+            ADD4(a1, *reinterpret_cast<const float4*>(wenc_s + (size_t)j * H + k0));
           }
         }
       }
@@ -402,27 +435,75 @@ __global__ void __launch_bounds__(H, 1) nade_bwd_kernel(NadeArgs p) {
       auto boundary = [&](int s) {   // the set target bit j = lo + s - 1 ends the segment below local dim s
         const int j = lo + s - 1;
         if (bm0 & (1u << s)) {      // block-uniform within the warp (a warp shares ig and the row)
-          flush_seg(S0, dh0, h0);
+          FLUSH(S0, dh0, h0);
           dh0 = make_float4(0.f, 0.f, 0.f, 0.f);
           float4* ae = reinterpret_cast<float4*>(acce_s + (size_t)j * H + k0);
           float4 acc = *ae;
-          add4(acc, S0);
+          ADD4(acc, S0);
           *ae = acc;
-          sub4(a0, *reinterpret_cast<const float4*>(wenc_s + (size_t)j * H + k0));
+          SUB4(a0, *reinterpret_cast<const float4*>(wenc_s + (size_t)j * H + k0));
           h0 = sigmoid_mufu4(a0);
         }
         if (bm1 & (1u << s)) {
-          flush_seg(S1, dh1, h1);
+          FLUSH(S1, dh1, h1);
           dh1 = make_float4(0.f, 0.f, 0.f, 0.f);
           float4* ae = reinterpret_cast<float4*>(acce_s + (size_t)j * H + k0);
           float4 acc = *ae;
-          add4(acc, S1);
+          ADD4(acc, S1);
           *ae = acc;
-          sub4(a1, *reinterpret_cast<const float4*>(wenc_s + (size_t)j * H + k0));
+          SUB4(a1, *reinterpret_cast<const float4*>(wenc_s + (size_t)j * H + k0));
           h1 = sigmoid_mufu4(a1);
         }
       };
-      if constexpr (V == 1) {
+      if constexpr (UP) {
+        // unshifted group bits: bit q = v_{lo+q}; a set bit ends the segment ABOVE local dim q
+        const int l1 = lo + 1;
+        const uint32_t um0 = __funnelshift_r(sm0[l1 >> 5], sm0[(l1 >> 5) + 1], l1 & 31) & ((1u << DG) - 1u);
+        const uint32_t um1 = __funnelshift_r(sm1[l1 >> 5], sm1[(l1 >> 5) + 1], l1 & 31) & ((1u << DG) - 1u);
+        const uint32_t um = um0 | um1;
+        auto boundary_up = [&](int s, bool last) {   // after local dim s = target bit j = lo + s
+          const int j = lo + s;
+          if (um0 & (1u << s)) {
+            FLUSH(S0, dh0, h0);                      // S0 = running prefix of gA over the group's dims <= j
+            dh0 = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4* ae = reinterpret_cast<float4*>(acce_s + (size_t)j * H + k0);
+            float4 acc = *ae;
+            SUB4(acc, S0);
+            *ae = acc;
+            if (!last) {
+              ADD4(a0, *reinterpret_cast<const float4*>(wenc_s + (size_t)j * H + k0));
+              h0 = sigmoid_mufu4(a0);
+            }
+          }
+          if (um1 & (1u << s)) {
+            FLUSH(S1, dh1, h1);
+            dh1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4* ae = reinterpret_cast<float4*>(acce_s + (size_t)j * H + k0);
+            float4 acc = *ae;
+            SUB4(acc, S1);
+            *ae = acc;
+            if (!last) {
+              ADD4(a1, *reinterpret_cast<const float4*>(wenc_s + (size_t)j * H + k0));
+              h1 = sigmoid_mufu4(a1);
+            }
+          }
+        };
+        float4 q0, q1;
+#pragma unroll
+        for (int I = 0; I < DG; ++I) {
+          if ((I & 3) == 0) {
+            q0 = *reinterpret_cast<const float4*>(dl0 + I);
+            q1 = *reinterpret_cast<const float4*>(dl1 + I);
+          }
+          const float d0 = (I & 3) == 3 ? q0.w : ((I & 3) == 2 ? q0.z : ((I & 3) == 1 ? q0.y : q0.x));
+          const float d1 = (I & 3) == 3 ? q1.w : ((I & 3) == 2 ? q1.z : ((I & 3) == 1 ? q1.y : q1.x));
+          fma4(dh0, d0, wd[I]);
+          fma4(dh1, d1, wd[I]);
+          fma4(aw[I], d0, h0);
+          fma4(aw[I], d1, h1);
+          if (um & (1u << I)) boundary_up(I, I == DG - 1);
+        }
+      } else if constexpr (V >= 1) {
         float4 q0, q1;
 #pragma unroll
         for (int I = DG - 1; I >= 0; --I) {
@@ -477,15 +558,15 @@ __global__ void __launch_bounds__(H, 1) nade_bwd_kernel(NadeArgs p) {
         i = s - 1;
       }
       }
-      flush_seg(S0, dh0, h0);
-      flush_seg(S1, dh1, h1);
+      FLUSH(S0, dh0, h0);
+      FLUSH(S1, dh1, h1);
       *reinterpret_cast<float4*>(tot_s + ((size_t)r * G + ig) * H + k0) = S0;
       *reinterpret_cast<float4*>(tot_s + ((size_t)(r + 1) * G + ig) * H + k0) = S1;
     }
     __syncthreads();   // group totals of the batch are complete
 
     // fix-up: suffix sums that cross group borders, then d b_enc
-    if (ig < G - 1) {
+    if (UP || ig < G - 1) {
 #pragma unroll 1
       for (int r = 0; r < R; ++r) {
         // set target bits j in [lo, lo + DG): shifted bits lo+1 .. lo+DG
@@ -494,13 +575,14 @@ __global__ void __launch_bounds__(H, 1) nade_bwd_kernel(NadeArgs p) {
         uint32_t x = __funnelshift_r(sm5[l1 >> 5], sm5[(l1 >> 5) + 1], l1 & 31) & ((1u << DG) - 1u);
         if (!x) continue;
         float4 higher = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int g = ig + 1; g < G; ++g) add4(higher, *reinterpret_cast<const float4*>(tot_s + ((size_t)r * G + g) * H + k0));
+        for (int g = UP ? ig : ig + 1; g < G; ++g)   // bottom-up: own total included (the walk subtracted the running prefix)
+          ADD4(higher, *reinterpret_cast<const float4*>(tot_s + ((size_t)r * G + g) * H + k0));
         while (x) {
           const int j = lo + __ffs(x) - 1;
           x &= x - 1;
           float4* ae = reinterpret_cast<float4*>(acce_s + (size_t)j * H + k0);
           float4 acc = *ae;
-          add4(acc, higher);
+          ADD4(acc, higher);
           *ae = acc;
         }
       }
@@ -510,7 +592,7 @@ __global__ void __launch_bounds__(H, 1) nade_bwd_kernel(NadeArgs p) {
       if (row < p.N) {
         float4 t = *reinterpret_cast<const float4*>(tot_s + ((size_t)r * G) * H + k0);
 #pragma unroll
-        for (int g = 1; g < G; ++g) add4(t, *reinterpret_cast<const float4*>(tot_s + ((size_t)r * G + g) * H + k0));
+        for (int g = 1; g < G; ++g) ADD4(t, *reinterpret_cast<const float4*>(tot_s + ((size_t)r * G + g) * H + k0));
         *reinterpret_cast<float4*>(p.dfc + (size_t)row * p.ld + enc_col + k0) = t;
       }
     }
@@ -694,8 +776,8 @@ extern "C" int mnn_nade_logprob_fwd(const uint32_t* bits, const float* fc, long 
   return mnn_check_launch("nade_logprob_fwd");
 }
 
-static int nade_bwd_variant() {   // MNN_NADE_BWD_V=0 selects the round-1 jump-table walk (A/B runs)
-  static const int v = [] { const char* e = getenv("MNN_NADE_BWD_V"); return e ? atoi(e) : 1; }();
+static int nade_bwd_variant() {   // MNN_NADE_BWD_V: 0 = round-1 jump-table walk, 1 = straight-line walk, 2 = 1 + packed helpers, 3 (default) = 2 walking upwards
+  static const int v = [] { const char* e = getenv("MNN_NADE_BWD_V"); return e ? atoi(e) : 3; }();
   return v;
 }
 
@@ -713,7 +795,12 @@ static int launch_bwd_v(const NadeArgs& a, cudaStream_t stream) {
 
 template <int H, int D>
 static int launch_bwd(const NadeArgs& a, cudaStream_t stream) {
-  return nade_bwd_variant() == 0 ? launch_bwd_v<H, D, 0>(a, stream) : launch_bwd_v<H, D, 1>(a, stream);
+  switch (nade_bwd_variant()) {
+    case 0: return launch_bwd_v<H, D, 0>(a, stream);
+    case 1: return launch_bwd_v<H, D, 1>(a, stream);
+    case 2: return launch_bwd_v<H, D, 2>(a, stream);
+    default: return launch_bwd_v<H, D, 3>(a, stream);
+  }
 }
 
 extern "C" int mnn_nade_logprob_bwd(const uint32_t* bits, const float* fc, long long ld, int enc_col0, int dec_col0,
