@@ -32,7 +32,7 @@ class MultINNComposer(MultINNCore):
         B, T, D, M = x.shape
         # per-track encodings (PassEncoder: the piano-rolls themselves; DBNEncoder: sampled codes,
         # core/multi_encoder_nn.py:98-115) stacked with feature e*M + m (multinn_composer.py:73-80)
-        _, stack, bits = self._encode_tracks(x, u_enc, seed)
+        _, stack, bits = self._encode_tracks(x, u_enc, seed, need_tracks=False)
         # inputs = slots 0..T-1 ([0, x_0..x_{T-2}]), targets = slots 1..T (multinn_composer.py:82-86)
         loss, nll, _ = self._generator.forward_backward(stack[:T], bits, keep=keep, u_drop=u_drop, seed=seed,
                                                         lengths=lengths, loss_scale=loss_scale)
@@ -45,7 +45,7 @@ class MultINNComposer(MultINNCore):
         t >= lengths[b] are removed (utils/sequences.py:29-37): `nll` then holds the valid rows only, b-major."""
         x = self._check_x(x, lengths)
         B, T, D, M = x.shape
-        _, stack, bits = self._encode_tracks(x, u_enc, seed)
+        _, stack, bits = self._encode_tracks(x, u_enc, seed, need_tracks=False)
         nll, cp = self._generator.log_prob(stack[:T], bits, cond_probs=cond_probs, lengths=lengths)
         D = self._num_dims_generator
         keep_rows = self.valid_rows(lengths, T, B, x.device)
@@ -63,6 +63,6 @@ class MultINNComposer(MultINNCore):
         the intro is encoded per track (u_enc), the generated codes are decoded per track (u_dec, :140-150)."""
         x = self._check_x(x, None)
         B, T, D, M = x.shape
-        _, stack, _ = self._encode_tracks(x, u_enc, seed)
+        _, stack, _ = self._encode_tracks(x, u_enc, seed, need_tracks=False)
         samples = self._generator.generate(stack, num_steps, u=u, seed=seed)     # whole padded intro
         return self._decode_tracks(samples.view(B, num_steps, self._num_dims_generator, M), u_dec, seed)

@@ -145,15 +145,16 @@ class MultINNCore(Model, abc.ABC):
             main.wait_stream(st)
         return out
 
-    def _encode_tracks(self, x, u_enc=None, seed=0):
+    def _encode_tracks(self, x, u_enc=None, seed=0, need_tracks=True, need_stack=True):
         """core/multi_encoder_nn.py:66-115: zero-pad, unstack, encode every track with its own encoder (PassEncoder:
         identity; DBNEncoder: SAMPLED last-layer codes, stop_gradient unless tune_encoder). Returns
         (xe[M][(T+1),B,E] per-track encodings, stack[(T+1),B,E*M] with feature e*M + m as multinn_composer.py:73-80 /
         multinn_feedback.py:67-73 stack them, bits[M,T*B,4] target masks of xe[m][1:])."""
         B, T, D, M = x.shape
-        if self.encoder_type == 'Pass':
-            st = self._stage_inputs(x, stacked=True, per_track=True, bits=True)
-            return [st['xtr'][m] for m in range(M)], st['xin'], st['bits']
+        if self.encoder_type == 'Pass':   # identity: stage only the layouts the mode reads (each is a full pass over HBM)
+            st = self._stage_inputs(x, stacked=need_stack, per_track=need_tracks, bits=True)
+            return ([st['xtr'][m] for m in range(M)] if need_tracks else None, st['xin'] if need_stack else None,
+                    st['bits'])
         st = self._stage_inputs(x, per_track=True)
         xe = []
         for m, enc in enumerate(self._encoders):

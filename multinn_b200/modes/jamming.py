@@ -28,7 +28,7 @@ class MultINNJamming(MultINNCore):
 
     def _forward_backward(self, x, keep, u_drop, seed, lengths=None, loss_scale=1.0, u_enc=None, **extra):
         B, T, D, M = x.shape
-        xe, _, bits = self._encode_tracks(x, u_enc, seed)          # multinn_jamming.py:60-68 over the track encodings
+        xe, _, bits = self._encode_tracks(x, u_enc, seed, need_stack=False)          # multinn_jamming.py:60-68 over the track encodings
         def one(m, gen):
             return gen.forward_backward(xe[m][:T], bits[m:m + 1], keep=keep, u_drop=None if u_drop is None else u_drop[m],
                                         seed=seed + 104729 * m, loss_scale=loss_scale / M, lengths=lengths)
@@ -40,7 +40,7 @@ class MultINNJamming(MultINNCore):
     def evaluate(self, x, lengths=None, u_enc=None, seed=0):
         x = self._check_x(x, lengths)
         B, T, D, M = x.shape
-        xe, _, bits = self._encode_tracks(x, u_enc, seed)
+        xe, _, bits = self._encode_tracks(x, u_enc, seed, need_stack=False)
         nll = torch.empty(M, T * B, device=x.device)
         for m, gen in enumerate(self._generators):
             n, _ = gen.log_prob(xe[m][:T], bits[m:m + 1], lengths=lengths)
@@ -58,7 +58,7 @@ class MultINNJamming(MultINNCore):
         u[num_steps,M,B,E]."""
         x = self._check_x(x, None)
         B, T, D, M = x.shape
-        xe, _, _ = self._encode_tracks(x, u_enc, seed)
+        xe, _, _ = self._encode_tracks(x, u_enc, seed, need_stack=False)
         out = torch.empty(B, num_steps, self._num_dims_generator, M, device=x.device)
         for m, gen in enumerate(self._generators):
             s = gen.generate(xe[m].contiguous(), num_steps, u=None if u is None else u[:, m:m + 1], seed=seed + 104729 * m)
