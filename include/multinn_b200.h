@@ -64,6 +64,16 @@ int mnn_gemm_tc(const float* A, long long lda, int transA, const float* B, long 
  * per-GPU batches) instead of queueing CTAs behind them. Host-side, thread-local; no reference counterpart. */
 int mnn_set_sm_budget(int sms);
 
+/* Operand split of this thread's following mnn_gemm_tc launches on the CTA-pair kernel (host-side, thread-local; no
+ * reference counterpart -- the reference's tf.matmul is plain fp32):
+ *   0 (default)  "2.5 products": tf32(A).tf32(B) + bf16(A).bf16(B - tf32(B)) + bf16(A - tf32(A)).bf16(B), about 2^-20
+ *                per product; what evaluate(), generation and every parity test of a single GEMM use
+ *   1            bf16 PAIRS x = x1 + x2: A1.B1 + A1.B2 + A2.B1, all kind::f16 MMAs, about 2^-17 per product, 9 % faster
+ *                (half the operand bytes of the main product). The training step (modes/core.py step()) selects it:
+ *                loss and gradients stay inside the 1e-4 parity bar (tests/test_gpu_model.py trajectories and gradients
+ *                run through it). The environment variable MNN_GEMM_BF16X (0 / 1 / 2) overrides both. */
+int mnn_set_gemm_split(int mode);
+
 /* Data-parallel noise keying (no reference counterpart: the reference is single-device; SURVEY 8(e) asks that results
  * do not depend on the GPU count). Every entry point that can draw Philox noise (dropout in mnn_lstm_*_fwd*, the
  * Bernoulli draws of mnn_bias_sigmoid_sample, mnn_rbm_gibbs, mnn_nade_sample, mnn_sample_steps) keys the counter by the

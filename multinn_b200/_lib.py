@@ -36,6 +36,7 @@ SIGNATURES = {
     "mnn_pack_rows": [_p, _ll, _i, _p, _i, _i, _p],
     "mnn_gemm_f32": [_p, _ll, _i, _p, _ll, _i, _p, _ll, _p, _f, _f, _i, _i, _i, _p],
     "mnn_set_sm_budget": [_i],
+    "mnn_set_gemm_split": [_i],
     "mnn_set_row_map": [_ll, _ll, _ll],
     "mnn_set_time_base": [_ll],
     "mnn_gemm_tc_supported": [_p, _ll, _p, _ll],

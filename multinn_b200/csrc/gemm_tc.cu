@@ -298,12 +298,13 @@ template <bool A_MN, bool B_MN>
 __device__ __forceinline__ void convert_stage(uint8_t* base, int t, const Params& p) {
   using C_ = Cfg2;
   if (p.bf16x) {
+    const bool pair = p.bf16x == 2;
     if (p.share_conv) {
-      convert_bf16_tiles<A_MN, 256>(base, base + C_::A_BYTES, t, p.n_products == 3);
-      convert_bf16_tiles<B_MN, 256>(base + 2 * C_::A_BYTES, base + 2 * C_::A_BYTES + C_::B_BYTES, t, true);
+      convert_bf16_tiles<A_MN, 256>(base, base + C_::A_BYTES, t, p.n_products == 3, pair);
+      convert_bf16_tiles<B_MN, 256>(base + 2 * C_::A_BYTES, base + 2 * C_::A_BYTES + C_::B_BYTES, t, true, pair);
     } else {
-      convert_bf16_tiles<A_MN, 128>(base, base + C_::A_BYTES, t, p.n_products == 3);
-      convert_bf16_tiles<B_MN, 128>(base + 2 * C_::A_BYTES, base + 2 * C_::A_BYTES + C_::B_BYTES, t, true);
+      convert_bf16_tiles<A_MN, 128>(base, base + C_::A_BYTES, t, p.n_products == 3, pair);
+      convert_bf16_tiles<B_MN, 128>(base + 2 * C_::A_BYTES, base + 2 * C_::A_BYTES + C_::B_BYTES, t, true, pair);
     }
   } else {
     const float4* a_raw = reinterpret_cast<const float4*>(base);
@@ -439,11 +440,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 umma_bf16_2cta(tmem_x, dal, dbh, idesc16, 1u);
               }
             }
+            if (p.bf16x == 2) {
+              // all-bf16 pair scheme: the main product too is a kind::f16 MMA, A1.B1 (twice the tf32 rate, half the
+              // operand bytes); [hi | lo] = the bf16 pair x1 + x2
 #pragma unroll
-            for (int j = 0; j < BK / 8; ++j) {
-              const uint64_t da = smem_desc(a_raw + j * a_kstep, a_lbo, a_sbo, a_lay);
-              const uint64_t db = smem_desc(b_raw + j * b_kstep, b_lbo, b_sbo, b_lay);
-              umma_tf32_2cta(tmem_d, da, db, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
+              for (int j = 0; j < BK / 16; ++j) {
+                const uint64_t dah = smem_desc(a_lo + j * a16_kstep, a16_lbo, a16_sbo, a16_lay);
+                const uint64_t dbh = smem_desc(b_lo + j * b16_kstep, b16_lbo, b16_sbo, b16_lay);
+                umma_bf16_2cta(tmem_d, dah, dbh, idesc16, (kb > kb0 || j > 0) ? 1u : 0u);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < BK / 8; ++j) {
+                const uint64_t da = smem_desc(a_raw + j * a_kstep, a_lbo, a_sbo, a_lay);
+                const uint64_t db = smem_desc(b_raw + j * b_kstep, b_lbo, b_sbo, b_lay);
+                umma_tf32_2cta(tmem_d, da, db, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
+              }
             }
             umma_commit_2cta(bar_empty + 8 * stage);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -731,6 +743,7 @@ static int device_sms() {
 // SM budget of the calling thread's persistent GEMM grids (mnn_set_sm_budget): lets a GEMM run beside co-resident
 // persistent recurrence kernels of other streams instead of queueing CTAs behind them
 static thread_local int g_sm_budget = 0;
+static thread_local int g_gemm_split = 0;   // mnn_set_gemm_split: 0 = 2.5-product scheme, 1 = bf16 pairs (pair kernel only)
 static int num_sms() {
   const int n = device_sms();
   return (g_sm_budget > 0 && g_sm_budget < n) ? g_sm_budget : n;
@@ -821,6 +834,12 @@ extern "C" int mnn_set_sm_budget(int sms) {
   return MNN_OK;
 }
 
+extern "C" int mnn_set_gemm_split(int mode) {
+  MNN_REQUIRE(mode == 0 || mode == 1, MNN_ERR_ARG, "set_gemm_split: mode must be 0 (2.5 products) or 1 (bf16 pairs)");
+  mnn::tc::g_gemm_split = mode;
+  return MNN_OK;
+}
+
 extern "C" int mnn_gemm_tc_supported(const float* A, long long lda, const float* B, long long ldb) {
   return ((lda & 3) == 0) && ((ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
          ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
@@ -882,7 +901,8 @@ extern "C" int mnn_gemm_tc(const float* A, long long lda, int transA, const floa
     // cross terms as bf16 MMAs ("2.5 products"): on for general A; with a binary A (2 tf32 products) the extra bf16(A)
     // tile makes the converter warps the bottleneck (measured 3.15 -> 3.33 ms). MNN_GEMM_BF16X=0 / 1 forces it off / on.
     static const char* bf16x_env = getenv("MNN_GEMM_BF16X");
-    p.bf16x = bf16x_env ? (bf16x_env[0] == '1' ? 1 : 0) : (p.n_products == 3 ? 1 : 0);
+    p.bf16x = bf16x_env ? (bf16x_env[0] == '2' ? 2 : (bf16x_env[0] == '1' ? 1 : 0))
+                        : (g_gemm_split == 1 ? 2 : (p.n_products == 3 ? 1 : 0));
     static const char* share_env = getenv("MNN_GEMM_SHARE_KB");   // k-blocks per tile from which the epilogue warps convert too
     static const int share_kb = share_env ? atoi(share_env) : 8;
     // only with the bf16 tiles: in the tf32 path with a binary A just B is converted and the extra arrivals cost more

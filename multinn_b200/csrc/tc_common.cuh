@@ -196,8 +196,10 @@ __device__ __forceinline__ float tf32_residual(float x) { return x - __uint_as_f
 // layout of the same major-ness: K-major source (SWIZZLE_128B rows of 32 floats) -> K-major SWIZZLE_64B (64-byte rows,
 // 8-row atoms of 512 B); MN-major source (four {32 mn x 32 k} boxes, SWIZZLE_128B with 32-byte atoms) -> MN-major
 // SWIZZLE_128B (atoms of 64 mn x 8 k, k-groups 1 KB apart, the two 64-mn blocks 4 KB apart).
+// pair = true: the lo tile holds bf16(x - bf16(x)) instead, i.e. [hi | lo] is the bf16 PAIR x1 + x2 of the all-bf16
+// 3-product scheme (A1.B1 + A1.B2 + A2.B1, ~2^-17 relative; gemm_tc.cu bf16x = 2).
 template <bool MN, int NT>
-__device__ __forceinline__ void convert_bf16_tiles(const uint8_t* raw, uint8_t* dst, int t, bool want_lo) {
+__device__ __forceinline__ void convert_bf16_tiles(const uint8_t* raw, uint8_t* dst, int t, bool want_lo, bool pair = false) {
   static_assert(NT == 128 || NT == 256, "offsets below are hoisted for 128 or 256 converter threads");
   const float4* src = reinterpret_cast<const float4*>(raw) + t;
   // piece i = t + NT n. All index arithmetic that depends on t is done once; n is a compile-time constant.
@@ -224,10 +226,17 @@ __device__ __forceinline__ void convert_bf16_tiles(const uint8_t* raw, uint8_t* 
     if (!MN) off = off_even + (uint32_t)n * (NT * 8u);                         // NT / 8 rows = NT / 64 atoms of 512 B
     else if (NT == 128) off = (((n >> 1) & 1) ? off_odd : off_even) + (uint32_t)((n >> 2) * 4096 + (n & 1) * 2048);
     else off = ((n & 1) ? off_odd : off_even) + (uint32_t)((n >> 1) * 4096);
-    *reinterpret_cast<uint2*>(dst + off) = pack_bf16x4(x.x, x.y, x.z, x.w);
-    if (want_lo)
-      *reinterpret_cast<uint2*>(dst + BM * BK * 2 + off) =
-          pack_bf16x4(tf32_residual(x.x), tf32_residual(x.y), tf32_residual(x.z), tf32_residual(x.w));
+    const uint2 hi = pack_bf16x4(x.x, x.y, x.z, x.w);
+    *reinterpret_cast<uint2*>(dst + off) = hi;
+    if (want_lo) {
+      if (pair)
+        *reinterpret_cast<uint2*>(dst + BM * BK * 2 + off) =
+            pack_bf16x4(x.x - __uint_as_float(hi.x << 16), x.y - __uint_as_float(hi.x & 0xffff0000u),
+                        x.z - __uint_as_float(hi.y << 16), x.w - __uint_as_float(hi.y & 0xffff0000u));
+      else
+        *reinterpret_cast<uint2*>(dst + BM * BK * 2 + off) =
+            pack_bf16x4(tf32_residual(x.x), tf32_residual(x.y), tf32_residual(x.z), tf32_residual(x.w));
+    }
   }
 }
 
