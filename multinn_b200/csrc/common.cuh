@@ -107,6 +107,16 @@ __device__ __forceinline__ void lstm_cell_xu(float pi, float pj, float pf, float
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(1.0f + ex2_clamped(c * -2.8853900817779268f)));
   h = tanh_from_rcp(c, rc) * go;
 }
+// Four sigmoids with 4 MUFU.EX2 + ONE MUFU.RCP (see lstm_cell_xu: rcp.approx retires at a third of the ex2 rate).
+__device__ __forceinline__ float4 sigmoid4_xu(float4 a) {
+  const float dx = 1.0f + ex2_clamped(a.x * -1.4426950408889634f), dy = 1.0f + ex2_clamped(a.y * -1.4426950408889634f);
+  const float dz = 1.0f + ex2_clamped(a.z * -1.4426950408889634f), dw = 1.0f + ex2_clamped(a.w * -1.4426950408889634f);
+  const float pxy = dx * dy, pzw = dz * dw;
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(pxy * pzw));
+  const float rxy = r * pzw, rzw = r * pxy;
+  return make_float4(rxy * dy, rxy * dx, rzw * dw, rzw * dz);
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Packed fp32x2 FMA (Blackwell FFMA2): d = a*b + c on both halves.

@@ -723,10 +723,17 @@ lstm_tc2_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 umma_bf16_2cta(tmem_x, smem_desc(a_lo + A_BYTES / 2 + j * 32, 16, 512, 4), smem_desc(b_lo + j * 32, 16, 512, 4),
                                idesc16, 1u);
               }
+              if (p.bf16x == 2) {   // bf16 pairs: the main product too on kind::f16 (gemm_tc.cu, mnn_set_gemm_split)
+#pragma unroll
+                for (int j = 0; j < BK / 16; ++j)
+                  umma_bf16_2cta(tmem_d, smem_desc(a_lo + j * 32, 16, 512, 4), smem_desc(b_lo + j * 32, 16, 512, 4), idesc16,
+                                 (kb > 0 || j > 0) ? 1u : 0u);
+              } else {
 #pragma unroll
               for (int j = 0; j < BK / 8; ++j)
                 umma_tf32_2cta(tmem_d, smem_desc(a_raw + j * 32, 16, 1024, 2), smem_desc(b_raw + j * 32, 16, 1024, 2), idesc,
                                (kb > 0 || j > 0) ? 1u : 0u);
+              }
             } else {
 #pragma unroll
             for (int j = 0; j < BK / 8; ++j) {
@@ -767,8 +774,8 @@ lstm_tc2_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           const float4* b_raw = reinterpret_cast<const float4*>(base + 2 * A_BYTES);
           float4* b_lo = reinterpret_cast<float4*>(base + 2 * A_BYTES + B_BYTES);
           if (p.bf16x) {
-            convert_bf16_tiles<false, 128>(base, base + A_BYTES, tc, true);
-            convert_bf16_tiles<false, 128>(base + 2 * A_BYTES, base + 2 * A_BYTES + B_BYTES, tc, true);
+            convert_bf16_tiles<false, 128>(base, base + A_BYTES, tc, true, p.bf16x == 2);
+            convert_bf16_tiles<false, 128>(base + 2 * A_BYTES, base + 2 * A_BYTES + B_BYTES, tc, true, p.bf16x == 2);
           } else {
 #pragma unroll 4
             for (int i = tc; i < A_BYTES / 16; i += 128) a_lo[i] = tf32_lo4(a_raw[i]);
@@ -954,10 +961,17 @@ lstm_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               umma_bf16_2cta(tmem_x, smem_desc(a_lo + A_BYTES / 2 + j * 32, 16, 512, 4), smem_desc(b_lo + j * 32, 16, 512, 4),
                              idesc16, 1u);
             }
+            if (p.bf16x == 2) {   // bf16 pairs: the main product too on kind::f16
+#pragma unroll
+              for (int j = 0; j < BK / 16; ++j)
+                umma_bf16_2cta(tmem_d, smem_desc(a_lo + j * 32, 16, 512, 4), smem_desc(b_lo + j * 32, 16, 512, 4), idesc16,
+                               (kb > kb0 || j > 0) ? 1u : 0u);
+            } else {
 #pragma unroll
             for (int j = 0; j < BK / 8; ++j)
               umma_tf32_2cta(tmem_d, smem_desc(a_raw + j * 32, 16, 1024, 2), smem_desc(b_raw + j * 32, 16, 1024, 2), idesc,
                              (kb > kb0 || j > 0) ? 1u : 0u);
+            }
           } else {
 #pragma unroll
           for (int j = 0; j < BK / 8; ++j) {
@@ -1014,8 +1028,8 @@ lstm_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const float4* b_raw = reinterpret_cast<const float4*>(base + 2 * A_BYTES);
             float4* b_lo = reinterpret_cast<float4*>(base + 2 * A_BYTES + B_BYTES);
             if (p.bf16x) {
-              convert_bf16_tiles<false, 128>(base, base + A_BYTES, tc, true);
-              convert_bf16_tiles<false, 128>(base + 2 * A_BYTES, base + 2 * A_BYTES + B_BYTES, tc, true);
+              convert_bf16_tiles<false, 128>(base, base + A_BYTES, tc, true, p.bf16x == 2);
+              convert_bf16_tiles<false, 128>(base + 2 * A_BYTES, base + 2 * A_BYTES + B_BYTES, tc, true, p.bf16x == 2);
             } else {
 #pragma unroll 4
               for (int i = tc; i < A_BYTES / 16; i += 128) a_lo[i] = tf32_lo4(a_raw[i]);
@@ -1443,8 +1457,8 @@ extern "C" int mnn_lstm_seq_fwd_tc(float* gates, const float* wh, float* hbuf, f
     p.gates = gates; p.hbuf = hbuf; p.cbuf = cbuf; p.out = out; p.dscale = dscale; p.u = u; p.keep = keep; p.seed = seed; p.rmap = current_row_map();
     p.T = T; p.B = B; p.R = R; p.t0 = 0; p.t1 = T;
     p.slabs = (B + 2 * BM - 1) / (2 * BM); p.blocks = blocks; p.kb_total = (R + BK - 1) / BK; p.flags = flags;
-    static const char* bf16x_env = getenv("MNN_LSTM_BF16X");   // "0": 3xTF32
-    p.bf16x = (bf16x_env && bf16x_env[0] == '0') ? 0 : 1;
+    static const char* bf16x_env = getenv("MNN_LSTM_BF16X");   // "0": 3xTF32, "1": 2.5 products, "2": bf16 pairs
+    p.bf16x = bf16x_env ? (bf16x_env[0] == '0' ? 0 : (bf16x_env[0] == '2' ? 2 : 1)) : 1;
     CUtensorMap ma, mb;
     rc = mnn_tc_make_map(hbuf, R, R, (long long)(T + 1) * B, BM, false, &ma);
     if (rc) return rc;
@@ -1550,8 +1564,8 @@ extern "C" int mnn_lstm_seq_bwd_tc_chunk(float* gates, const float* wh, const fl
     if (splits < 1) splits = 1;
     q.kb_per_split = (kb_total + splits - 1) / splits;
     q.splits = (kb_total + q.kb_per_split - 1) / q.kb_per_split;
-    static const char* bf16x_env = getenv("MNN_LSTM_BF16X");   // "0": 3xTF32 in phase A
-    q.bf16x = (bf16x_env && bf16x_env[0] == '0') ? 0 : 1;
+    static const char* bf16x_env = getenv("MNN_LSTM_BF16X");   // "0": 3xTF32 in phase A, "1": 2.5 products, "2": bf16 pairs
+    q.bf16x = bf16x_env ? (bf16x_env[0] == '0' ? 0 : (bf16x_env[0] == '2' ? 2 : 1)) : 1;
     q.cntA = reinterpret_cast<unsigned int*>(cnt + 1024);
     q.cntB = reinterpret_cast<unsigned int*>(cnt + 2048);
     cudaMemsetAsync(cnt + 1024, 0, 2048, stream);

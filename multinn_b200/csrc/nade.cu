@@ -51,6 +51,10 @@ __device__ __forceinline__ uint32_t pick_word(const uint32_t (&w)[kNW], int idx)
 // K4 forward. One warp = kFwdRows rows of one track; lane owns H/32 hidden units (float4 chunks at
 // k = c*128 + lane*4). Eight output dims at a time: 32 partial dots per lane are reduce-scattered
 // over the warp so lane L ends with l(row L>>3, dim 8c + (L&7)) and does that element's sigmoid/BCE.
+__device__ __forceinline__ float4 sigmoid_fwd4(float4 a) {
+  return make_float4(sigmoid_mufu(a.x), sigmoid_mufu(a.y), sigmoid_mufu(a.z), sigmoid_mufu(a.w));
+}
+
 template <int NCH>
 __global__ void __launch_bounds__(kFwdThreads, 1) nade_fwd_kernel(NadeArgs p) {
   constexpr int H = NCH * 128;
@@ -98,8 +102,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) nade_fwd_kernel(NadeArgs p) {
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         a[r][c] = __ldg(reinterpret_cast<const float4*>(be + c * 128 + lane * 4));
-        h[r][c] = make_float4(sigmoid_mufu(a[r][c].x), sigmoid_mufu(a[r][c].y),
-                              sigmoid_mufu(a[r][c].z), sigmoid_mufu(a[r][c].w));
+        h[r][c] = sigmoid_fwd4(a[r][c]);
       }
     }
     const int erow = row0 + er;
@@ -136,8 +139,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) nade_fwd_kernel(NadeArgs p) {
               for (int c = 0; c < NCH; ++c) {
                 const float4 w = *reinterpret_cast<const float4*>(we + c * 128 + lane * 4);
                 a[r][c].x += w.x; a[r][c].y += w.y; a[r][c].z += w.z; a[r][c].w += w.w;
-                h[r][c] = make_float4(sigmoid_mufu(a[r][c].x), sigmoid_mufu(a[r][c].y),
-                                      sigmoid_mufu(a[r][c].z), sigmoid_mufu(a[r][c].w));
+                h[r][c] = sigmoid_fwd4(a[r][c]);
               }
             }
           }
@@ -221,6 +223,8 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src));
 }
+// (one shared reciprocal for the four, sigmoid4_xu, was measured and rejected here: 18.4 -> 18.9 ms backward, 7.4 -> 13.0 ms
+// forward -- these kernels are latency-, not XU-bound, and the product / rcp / multiply chain is longer)
 __device__ __forceinline__ float4 sigmoid_mufu4(float4 a) {
   return make_float4(sigmoid_mufu(a.x), sigmoid_mufu(a.y), sigmoid_mufu(a.z), sigmoid_mufu(a.w));
 }
