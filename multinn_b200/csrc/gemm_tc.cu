@@ -329,7 +329,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   using C_ = Cfg2;
   constexpr int STAGES = C_::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[3 * STAGES + 2];
+  __shared__ __align__(8) uint64_t bars[3 * STAGES + 4];
   __shared__ uint32_t tmem_base_s;
 
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -341,8 +341,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const uint32_t bar_full = smem_u32(&bars[0]);              // [STAGES] local TMA completion
   const uint32_t bar_conv = smem_u32(&bars[STAGES]);         // [STAGES] leader: 2 x 128 converter arrivals
   const uint32_t bar_empty = smem_u32(&bars[2 * STAGES]);    // [STAGES] multicast MMA commit
-  const uint32_t bar_tfull = smem_u32(&bars[3 * STAGES]);    // multicast MMA commit
-  const uint32_t bar_tempty = smem_u32(&bars[3 * STAGES + 1]);  // leader: 2 x 128 epilogue arrivals
+  const uint32_t bar_tfull = smem_u32(&bars[3 * STAGES]);    // [2] multicast MMA commit, one per accumulator buffer
+  const uint32_t bar_tempty = smem_u32(&bars[3 * STAGES + 2]);  // [2] leader: 2 x 128 epilogue arrivals
+  // bf16-pair split (bf16x == 2): all three products go into ONE accumulator, so the 512 TMEM columns hold two of them
+  // and the epilogue of tile i overlaps the mainloop of tile i + 1; the other splits keep main + aux, single buffered
+  const bool acc2 = p.bf16x == 2;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -350,8 +353,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       mbar_init(bar_conv + 8 * s, 2 * ((p.share_conv ? 2 : 1) * kConvThreads / 32));   // one elected arrive per converter warp
       mbar_init(bar_empty + 8 * s, 1);
     }
-    mbar_init(bar_tfull, 1);
-    mbar_init(bar_tempty, 2 * (kEpiThreads / 32));        // one elected arrive per epilogue warp
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 2 * (kEpiThreads / 32));        // one elected arrive per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -408,8 +413,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const uint32_t a_lay = A_MN ? 1 : 2, b_lay = B_MN ? 1 : 2;
       const uint32_t a_kstep = A_MN ? 1024 : 32, b_kstep = B_MN ? 1024 : 32;
       int stage = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      const uint32_t tmem_d = tmem_base, tmem_x = tmem_base + BN2;
+      uint32_t phase = 0;
+      int tile_no = 0;
       // bf16 cross-term tiles (convert_bf16_tiles): [hi | lo] of 8 KB each in the operand's "lo" region
       const uint32_t idesc16 = idesc_bf16(BN2, A_MN, B_MN, 2 * BM);
       const uint32_t a16_lbo = A_MN ? 4096 : 16, b16_lbo = B_MN ? 4096 : 16;
@@ -419,7 +424,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       for (int w = cluster_id; w < n_items; w += n_clusters) {
         const int split = w / (p.tiles_n * p.tiles_m);
         const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        mbar_wait(bar_tempty, acc_phase ^ 1);
+        const int abuf = acc2 ? (tile_no & 1) : 0, use_no = acc2 ? (tile_no >> 1) : tile_no;
+        const uint32_t tmem_d = tmem_base + (uint32_t)(abuf * BN2), tmem_x = acc2 ? tmem_d : tmem_base + BN2;
+        mbar_wait(bar_tempty + 8 * abuf, (uint32_t)((use_no & 1) ^ 1));
         tc_fence_after();
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_conv + 8 * stage, phase);   // both CTAs: TMA landed and lo tiles written
@@ -442,12 +449,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
             if (p.bf16x == 2) {
               // all-bf16 pair scheme: the main product too is a kind::f16 MMA, A1.B1 (twice the tf32 rate, half the
-              // operand bytes); [hi | lo] = the bf16 pair x1 + x2
+              // operand bytes); [hi | lo] = the bf16 pair x1 + x2. tmem_x == tmem_d here: the cross terms above opened
+              // the accumulator, so the main product always accumulates
 #pragma unroll
               for (int j = 0; j < BK / 16; ++j) {
                 const uint64_t dah = smem_desc(a_lo + j * a16_kstep, a16_lbo, a16_sbo, a16_lay);
                 const uint64_t dbh = smem_desc(b_lo + j * b16_kstep, b16_lbo, b16_sbo, b16_lay);
-                umma_bf16_2cta(tmem_d, dah, dbh, idesc16, (kb > kb0 || j > 0) ? 1u : 0u);
+                umma_bf16_2cta(tmem_d, dah, dbh, idesc16, 1u);
               }
             } else {
 #pragma unroll
@@ -477,8 +485,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           umma_commit_2cta(bar_empty + 8 * stage);   // both CTAs may refill this stage
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2cta(bar_tfull);                 // both CTAs' accumulator halves complete
-        acc_phase ^= 1;
+        umma_commit_2cta(bar_tfull + 8 * abuf);      // both CTAs' accumulator halves complete
+        ++tile_no;
       }
     }
   } else if (warp >= 8) {
@@ -501,7 +509,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue: this CTA's 128 rows x 256 columns
     const int q = warp - 4;
-    uint32_t acc_phase = 0;
+    int tile_no = 0;
     int store_no = 0;
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
     const uint32_t tempty_leader = mapa_cluster(bar_tempty, 0);
@@ -523,7 +531,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           if (++cstage == STAGES) { cstage = 0; cphase ^= 1; }
         }
       }
-      mbar_wait(bar_tfull, acc_phase);
+      const int abuf = acc2 ? (tile_no & 1) : 0, use_no = acc2 ? (tile_no >> 1) : tile_no;
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * BN2);
+      mbar_wait(bar_tfull + 8 * abuf, (uint32_t)(use_no & 1));
       tc_fence_after();
       const bool add_bias = p.bias != nullptr && (!p.atomic || split == 0);
       if (p.tma_store) {
@@ -536,8 +546,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           const int col0 = n0 + c * 32;
           if (col0 >= p.N) break;   // warp-uniform
           float v[32], vx[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN2 + c * 32), vx);
+          tmem_ld32(tacc + (uint32_t)(c * 32), v);
+          if (acc2) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) vx[i] = 0.f;
+          } else {
+            tmem_ld32(tacc + (uint32_t)(BN2 + c * 32), vx);
+          }
           float bv = 0.f;
           if (p.bias != nullptr && col0 + lane < p.N) bv = __ldg(p.bias + col0 + lane);
 #pragma unroll
@@ -563,8 +578,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int col0 = n0 + c * 32;
         if (col0 >= p.N) break;   // warp-uniform
         float v[32], vx[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN2 + c * 32), vx);
+        tmem_ld32(tacc + (uint32_t)(c * 32), v);
+        if (acc2) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) vx[i] = 0.f;
+        } else {
+          tmem_ld32(tacc + (uint32_t)(BN2 + c * 32), vx);
+        }
         if (row < p.M) {
           float* dst = p.C + (size_t)row * p.ldc + col0;
           const bool full = col0 + 32 <= p.N;
@@ -599,8 +619,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(tempty_leader);
-      acc_phase ^= 1;
+      if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * abuf);
+      ++tile_no;
     }
     if (threadIdx.x == 4 * 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }

@@ -72,3 +72,32 @@ def test_gemm_tc_matches_f32_kernel_on_views():
     ops.gemm(big[:, 420:], W[420:], C1, beta=1.0, mode='tc')
     ops.gemm(big[:, 420:], W[420:], C2, beta=1.0, mode='f32')
     assert float((C1 - C2).abs().max()) < 6e-4
+
+
+def _run_pair(M, N, K, ta, tb, **kw):
+    """The same check under the bf16-pair operand split (mnn_set_gemm_split(1), what the training step selects). Returns
+    max |error| / sqrt(K) divided by its allowance: 6e-5 for the split itself (~2^-17 per product: the worst element of a
+    K-term dot of unit normals sits near 4 sigma * 2^-17, a factor 2 of slack) plus _run's 4e-6 per 64 K-steps for the
+    accumulator's per-instruction truncation."""
+    from multinn_b200 import ops
+    with ops.gemm_split('pair'):
+        e = _run(M, N, K, ta, tb, **kw)
+    steps = 1.0 + min(K, 4096) / 64.0
+    return e * steps / (6e-5 + 4e-6 * steps)
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 1), (0, 0), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (300, 200, 100), (1000, 1700, 256), (2048, 2048, 512), (700, 520, 932)])
+def test_gemm_tc_pair_split(M, N, K, ta, tb):
+    """bf16 pairs x = x1 + x2 (16 mantissa bits): A1.B1 + A1.B2 + A2.B1 into ONE double-buffered TMEM accumulator."""
+    assert _run_pair(M, N, K, ta, tb) < 1.0
+
+
+def test_gemm_tc_pair_split_epilogues_and_split_k():
+    assert _run_pair(512, 340, 256, 0, 0, bias=True) < 1.0
+    assert _run_pair(512, 340, 256, 0, 1, beta=1.0) < 1.0
+    assert _run_pair(420, 2048, 16384, 1, 0) < 1.0
+    assert _run_pair(256, 1700, 8192, 1, 0, beta=1.0) < 1.0
+    assert _run_pair(512, 2048, 420, 0, 0, a_exact=True, bias=True) < 1.0
+    # many tiles per cluster: both accumulator buffers are reused several times
+    assert _run_pair(8192, 2048, 96, 0, 0, bias=True) < 1.0
