@@ -74,6 +74,20 @@ int mnn_set_sm_budget(int sms);
  *                run through it). The environment variable MNN_GEMM_BF16X (0 / 1 / 2) overrides both. */
 int mnn_set_gemm_split(int mode);
 
+/* Weights as bf16 pairs, split once per training step instead of once per output tile: mnn_split_bf16_pair writes
+ * W[rows, cols] (row stride ld floats) as two bf16 planes [rows][ld_elems] (hi = bf16(w), then lo = bf16(w - hi); ld_elems
+ * a multiple of 8, pad columns zero) into dst (2 * rows * ld_elems * 2 bytes, 16-byte aligned). mnn_gemm_tc_bpair is
+ * mnn_gemm_tc with B given as such planes (Bpair, row stride ldb_elems; the planes' logical shape is [K, N] for
+ * transB == 0 and [N, K] otherwise): TMA drops the planes straight into the operand tiles of the bf16-pair split, so the
+ * B half of the in-kernel conversion and its shared-memory traffic disappear. CTA-pair kernel only (M >= 256, N > 128,
+ * K >= 64: MNN_ERR_UNSUPPORTED otherwise); used for the input-projection, Dense and data-gradient GEMMs of the
+ * training step (common/rnn.py, generators/rnn_nade.py here; tf.matmul in common/rnn.py:124, rnn_nade.py:54-57,212). */
+int mnn_split_bf16_pair(const float* src, long long ld, int rows, int cols, void* dst, long long ld_elems,
+                        mnn_stream_t stream);
+int mnn_gemm_tc_bpair(const float* A, long long lda, int transA, const void* Bpair, long long ldb_elems, int transB,
+                      float* C, long long ldc, const float* bias, float alpha, float beta, int M, int N, int K, int a_exact,
+                      mnn_stream_t stream);
+
 /* Data-parallel noise keying (no reference counterpart: the reference is single-device; SURVEY 8(e) asks that results
  * do not depend on the GPU count). Every entry point that can draw Philox noise (dropout in mnn_lstm_*_fwd*, the
  * Bernoulli draws of mnn_bias_sigmoid_sample, mnn_rbm_gibbs, mnn_nade_sample, mnn_sample_steps) keys the counter by the

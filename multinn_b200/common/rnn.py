@@ -220,7 +220,7 @@ class RNN:
         hook = chunk_hook if (chunk_hook is not None and self.use_fwd_pipeline(T, B)) else None
         rows0 = (self.WAVEFRONT_CHUNK if hook is not None else T) * B
         ops.gemm(x.view(T * B, I)[:rows0], self.kernels[0].data[:I], ws[0]['gates'].view(T * B, 4 * r0)[:rows0],
-                 bias=self.biases[0].data, a_exact=self._binary_inputs)
+                 bias=self.biases[0].data, a_exact=self._binary_inputs, b_weight=True)
         if self._use_wavefront(T, B):
             self._forward_wavefront(ws, outs, T, B, keep, u, seed, dropout, hook, x)
         else:
@@ -230,7 +230,8 @@ class RNN:
                 kern = self.kernels[l].data
                 i_l = self.in_dims()[l]
                 if l > 0:
-                    ops.gemm(outs[l - 1].view(T * B, i_l), kern[:i_l], w['gates'].view(T * B, 4 * r), bias=self.biases[l].data)
+                    ops.gemm(outs[l - 1].view(T * B, i_l), kern[:i_l], w['gates'].view(T * B, 4 * r), bias=self.biases[l].data,
+                             b_weight=True)
                 if tail and l == self.num_layers - 1:
                     self._forward_top_chunked(w, kern[i_l:], outs, T, B, keep, u, seed, dropout, chunk_hook)
                     continue
@@ -303,7 +304,7 @@ class RNN:
                     for c in range(1, nch):
                         ops.gemm(x[c * C:(c + 1) * C].view(C * B, I), self.kernels[0].data[:I],
                                  ws[0]['gates'][c * C:(c + 1) * C].view(C * B, 4 * r0), bias=self.biases[0].data,
-                                 a_exact=self._binary_inputs)
+                                 a_exact=self._binary_inputs, b_weight=True)
                         proj[c] = self._event(f'fwd L0 projection chunk {c}')
                         proj[c].record(bulk)
                 finally:
@@ -324,7 +325,7 @@ class RNN:
                         ops.set_sm_budget(self.WAVEFRONT_GEMM_SMS)
                         try:
                             ops.gemm(outs[l - 1][t0:t1].reshape(C * B, i_l), kern[:i_l],
-                                     w['gates'][t0:t1].view(C * B, 4 * r), bias=self.biases[l].data)
+                                     w['gates'][t0:t1].view(C * B, 4 * r), bias=self.biases[l].data, b_weight=True)
                         finally:
                             ops.set_sm_budget(0)
                     ops.set_sm_budget(budgets[min(l, len(budgets) - 1)])   # wavefront mode: co-resident configurations
@@ -378,7 +379,8 @@ class RNN:
                 ops.lstm_seq_bwd(w['gates'], kern.data[i_l:], w['cbuf'], d, w['dscale'] if dropout else None,
                                  w['dh_work'], w['dc_work'])
                 if l > 0 or need_dx:
-                    ops.gemm(w['gates'].view(T * B, -1), kern.data[:i_l], w['d_in'].view(T * B, i_l), transB=True)   # dx = dG Wx^T
+                    ops.gemm(w['gates'].view(T * B, -1), kern.data[:i_l], w['d_in'].view(T * B, i_l), transB=True,
+                             b_weight=True)   # dx = dG Wx^T
                     d = w['d_in']
         # weight gradients: batched GEMMs over all T*B rows
         side = self.aux_stream(x.device) if (self.COLSUM_SIDE_STREAM and x.is_cuda) else None
@@ -456,7 +458,7 @@ class RNN:
                         if (l > 0 or need_dx) and aux is None:
                             ops.set_sm_budget(self.WAVEFRONT_GEMM_SMS)
                             ops.gemm(w['gates'][t0:t1].view(C * B, 4 * r), kern.data[:i_l],
-                                     w['d_in'][t0:t1].view(C * B, i_l), transB=True)
+                                     w['d_in'][t0:t1].view(C * B, i_l), transB=True, b_weight=True)
                     finally:
                         ops.set_sm_budget(0)
                     if (l > 0 or need_dx) and aux is not None:
@@ -471,7 +473,7 @@ class RNN:
                         ops.set_sm_budget(self.PIPE_AUX_SMS)
                         try:
                             ops.gemm(w['gates'][t0:t1].view(C * B, 4 * r), kern.data[:i_l],
-                                     w['d_in'][t0:t1].view(C * B, i_l), transB=True)
+                                     w['d_in'][t0:t1].view(C * B, i_l), transB=True, b_weight=True)
                         finally:
                             ops.set_sm_budget(0)
                         done[l][c].record(aux)

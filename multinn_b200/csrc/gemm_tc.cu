@@ -14,6 +14,7 @@
 //   warps 4-7   epilogue: tcgen05.ld 32x32b -> registers -> alpha*acc + bias + beta*C -> global (or red.add for split-K)
 // Operands may be K-major (row-major [rows,K]) or MN-major (row-major [K,rows]); all four combinations are
 // expressed through the UMMA instruction descriptor's a_major/b_major bits, so no transposed copies exist.
+#include <cuda_bf16.h>
 #include <cuda.h>
 
 #include <cstdlib>
@@ -42,6 +43,8 @@ struct Params {
   int tma_store;   // pair kernel: C tiles leave through shared memory + TMA (needs beta == 0, no split-K, aligned C)
   int bf16x;       // pair kernel: cross terms hi.lo + lo.hi as bf16 MMAs (kind::f16, twice the tf32 rate)
   int share_conv;  // pair kernel, long K loops: the epilogue warps convert too (256 converter threads per CTA)
+  int b_pre;       // pair kernel, bf16x == 2: B arrives as bf16 pair planes (mnn_split_bf16_pair); TMA drops them straight into
+                   // the [hi | lo] tiles: no raw B stage, no B conversion (a third less shared-memory traffic per stage)
 };
 
 template <int BN>
@@ -301,10 +304,10 @@ __device__ __forceinline__ void convert_stage(uint8_t* base, int t, const Params
     const bool pair = p.bf16x == 2;
     if (p.share_conv) {
       convert_bf16_tiles<A_MN, 256>(base, base + C_::A_BYTES, t, p.n_products == 3, pair);
-      convert_bf16_tiles<B_MN, 256>(base + 2 * C_::A_BYTES, base + 2 * C_::A_BYTES + C_::B_BYTES, t, true, pair);
+      if (!p.b_pre) convert_bf16_tiles<B_MN, 256>(base + 2 * C_::A_BYTES, base + 2 * C_::A_BYTES + C_::B_BYTES, t, true, pair);
     } else {
       convert_bf16_tiles<A_MN, 128>(base, base + C_::A_BYTES, t, p.n_products == 3, pair);
-      convert_bf16_tiles<B_MN, 128>(base + 2 * C_::A_BYTES, base + 2 * C_::A_BYTES + C_::B_BYTES, t, true, pair);
+      if (!p.b_pre) convert_bf16_tiles<B_MN, 128>(base + 2 * C_::A_BYTES, base + 2 * C_::A_BYTES + C_::B_BYTES, t, true, pair);
     }
   } else {
     const float4* a_raw = reinterpret_cast<const float4*>(base);
@@ -325,7 +328,7 @@ __device__ __forceinline__ void convert_stage(uint8_t* base, int t, const Params
 template <bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                const __grid_constant__ CUtensorMap map_c, const Params p) {
+                const __grid_constant__ CUtensorMap map_b2, const __grid_constant__ CUtensorMap map_c, const Params p) {
   using C_ = Cfg2;
   constexpr int STAGES = C_::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -394,7 +397,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
             for (int c = 0; c < BM / 32; ++c) tma_load_2d(a_dst + c * (BK * 128), &map_a, full, m0 + 32 * c, k0);
           }
-          if (!B_MN) {
+          if (p.b_pre) {
+            // pre-split B: bf16 planes (map_b: hi, map_b2: lo) land in the [hi | lo] tiles of the "lo" region in the UMMA
+            // layout the converter would have written: K-major SWIZZLE_64B box {32 k, 128 rows}; MN-major SWIZZLE_128B
+            // boxes {64 n, 32 k}, the two 64-n blocks 4 KB apart. Same byte count as the raw fp32 tile.
+            const uint32_t bh = b_dst + C_::B_BYTES, bl = bh + C_::B_BYTES / 2;
+            if (!B_MN) {
+              tma_load_2d(bh, &map_b, full, k0, n0);
+              tma_load_2d(bl, &map_b2, full, k0, n0);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                tma_load_2d(bh + c * 4096, &map_b, full, n0 + 64 * c, k0);
+                tma_load_2d(bl + c * 4096, &map_b2, full, n0 + 64 * c, k0);
+              }
+            }
+          } else if (!B_MN) {
             tma_load_2d(b_dst, &map_b, full, k0, n0);
           } else {
 #pragma unroll
@@ -750,6 +768,25 @@ static int make_map_bf16(const void* ptr, long long ld_elems, long long inner, l
   return MNN_OK;
 }
 
+// 2-D bf16 tensor map over a row-major matrix [outer = k][inner = mn], box {64 mn, 32 k}, SWIZZLE_128B: a box lands as the
+// UMMA canonical MN-major SWIZZLE_128B block of 64 mn x 32 k (128-byte rows = 64 mn, 8-row atoms of 1 KB = the k-groups)
+static int make_map_bf16_mn(const void* ptr, long long ld_elems, long long inner, long long outer, CUtensorMap* out) {
+  EncodeTiledFn enc = get_encode();
+  MNN_REQUIRE(enc != nullptr, MNN_ERR_UNSUPPORTED, "tensor map: cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 2};
+  const cuuint32_t box[2] = {64u, 32u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mnn_set_error("tensor map (bf16, MN-major): cuTensorMapEncodeTiled failed");
+    return MNN_ERR_ARG;
+  }
+  return MNN_OK;
+}
+
 static int device_sms() {
   static int n = 0;
   if (!n) {
@@ -798,7 +835,8 @@ static int num_clusters2(const void* fn) {
 }
 
 template <bool A_MN, bool B_MN>
-static int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const Params& p, cudaStream_t stream) {
+static int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const CUtensorMap& mc, const Params& p,
+                   cudaStream_t stream) {
   static int max_clusters = 0;
   if (!max_clusters) {
     cudaFuncSetAttribute(gemm_tc2_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2::SMEM);
@@ -807,16 +845,16 @@ static int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorM
   const int items = p.tiles_m * p.tiles_n * p.splits;
   int clusters = items < max_clusters ? items : max_clusters;
   if (clusters > num_sms() / 2) clusters = num_sms() / 2 > 0 ? num_sms() / 2 : 1;
-  gemm_tc2_kernel<A_MN, B_MN><<<2 * clusters, kThreads, Cfg2::SMEM, stream>>>(ma, mb, mc, p);
+  gemm_tc2_kernel<A_MN, B_MN><<<2 * clusters, kThreads, Cfg2::SMEM, stream>>>(ma, mb, mb2, mc, p);
   return mnn_check_launch("gemm_tc2");
 }
 
-static int dispatch_major2(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc,
-                           const Params& p, cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch2<false, false>(ma, mb, mc, p, s);
-  if (!a_mn && b_mn) return launch2<false, true>(ma, mb, mc, p, s);
-  if (a_mn && !b_mn) return launch2<true, false>(ma, mb, mc, p, s);
-  return launch2<true, true>(ma, mb, mc, p, s);
+static int dispatch_major2(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2,
+                           const CUtensorMap& mc, const Params& p, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch2<false, false>(ma, mb, mb2, mc, p, s);
+  if (!a_mn && b_mn) return launch2<false, true>(ma, mb, mb2, mc, p, s);
+  if (a_mn && !b_mn) return launch2<true, false>(ma, mb, mb2, mc, p, s);
+  return launch2<true, true>(ma, mb, mb2, mc, p, s);
 }
 
 template <int BN>
@@ -865,14 +903,11 @@ extern "C" int mnn_gemm_tc_supported(const float* A, long long lda, const float*
          ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
 }
 
-extern "C" int mnn_gemm_tc(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
-                           long long ldc, const float* bias, float alpha, float beta, int M, int N, int K, int a_exact,
-                           cudaStream_t stream) {
+// bpair != nullptr: B is given as bf16 pair planes (mnn_split_bf16_pair) with row stride ldb ELEMENTS; B itself is unused
+static int gemm_tc_impl(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+                        long long ldc, const float* bias, float alpha, float beta, int M, int N, int K, int a_exact,
+                        const void* bpair, cudaStream_t stream) {
   using namespace mnn::tc;
-  MNN_REQUIRE(A && B && C, MNN_ERR_ARG, "gemm_tc: null pointer");
-  MNN_REQUIRE(M > 0 && N > 0 && K > 0, MNN_ERR_ARG, "gemm_tc: non-positive size");
-  MNN_REQUIRE(mnn_gemm_tc_supported(A, lda, B, ldb), MNN_ERR_UNSUPPORTED,
-              "gemm_tc: TMA needs 16-byte aligned operand pointers and row strides that are multiples of 4 floats");
   const bool a_mn = transA != 0;   // A stored [K,M]: M contiguous
   const bool b_mn = transB == 0;   // B stored [K,N]: N contiguous
   static const bool force_1cta = getenv("MNN_GEMM_1CTA") != nullptr;
@@ -880,6 +915,8 @@ extern "C" int mnn_gemm_tc(const float* A, long long lda, int transA, const floa
   static const int pair_kmin = kmin_env ? atoi(kmin_env) : 64;
   // 256x256 tiles on CTA pairs; with the TMA-store epilogue they win down to K = 256 (Dense forward: 2.28 vs 3.67 ms)
   const bool pair = !force_1cta && M >= 256 && N > 128 && K >= pair_kmin;
+  MNN_REQUIRE(!bpair || pair, MNN_ERR_UNSUPPORTED,
+              "gemm_tc_bpair: a pre-split B needs the CTA-pair kernel (M >= 256, N > 128, K >= 64)");
   const int BN = pair ? BN2 : (N > 64 ? 128 : 64);
   const int TM = pair ? 2 * BM : BM;
   const int units = pair ? num_sms() / 2 : num_sms();
@@ -913,8 +950,23 @@ extern "C" int mnn_gemm_tc(const float* A, long long lda, int transA, const floa
   if (!a_mn) rc = make_map(A, lda, K, M, BM, false, &ma);    // [M rows][K]   box {32 k, 128 rows}
   else rc = make_map(A, lda, M, K, BK, true, &ma);           // [K rows][M]   box {32 m, 32 k}
   if (rc) return rc;
-  if (!b_mn) rc = make_map(B, ldb, K, N, box_n, false, &mb); // [N rows][K]   box {32 k, BN (or BN/2 per CTA) rows}
-  else rc = make_map(B, ldb, N, K, BK, true, &mb);           // [K rows][N]   box {32 n, 32 k}
+  CUtensorMap mb2;
+  if (bpair) {
+    // planes: hi at bpair, lo right behind it; [N rows][K] (K-major) or [K rows][N] (MN-major), row stride ldb elements
+    const long long rows_b = b_mn ? K : N;
+    const char* lo = static_cast<const char*>(bpair) + (size_t)rows_b * ldb * 2;
+    if (!b_mn) {
+      rc = make_map_bf16(bpair, ldb, K, N, box_n, &mb);
+      if (!rc) rc = make_map_bf16(lo, ldb, K, N, box_n, &mb2);
+    } else {
+      rc = make_map_bf16_mn(bpair, ldb, N, K, &mb);
+      if (!rc) rc = make_map_bf16_mn(lo, ldb, N, K, &mb2);
+    }
+  } else {
+    if (!b_mn) rc = make_map(B, ldb, K, N, box_n, false, &mb); // [N rows][K]   box {32 k, BN (or BN/2 per CTA) rows}
+    else rc = make_map(B, ldb, N, K, BK, true, &mb);           // [K rows][N]   box {32 n, 32 k}
+    mb2 = mb;
+  }
   if (rc) return rc;
 
   if (pair) {
@@ -927,6 +979,7 @@ extern "C" int mnn_gemm_tc(const float* A, long long lda, int transA, const floa
     static const int share_kb = share_env ? atoi(share_env) : 8;
     // only with the bf16 tiles: in the tf32 path with a binary A just B is converted and the extra arrivals cost more
     // than the shared work saves (dW1x 3.16 -> 3.71 ms)
+    if (bpair) { p.bf16x = 2; p.b_pre = 1; }   // the pre-split planes ARE the bf16 pair
     p.share_conv = (p.bf16x && share_kb > 0 && p.kb_per_split >= share_kb) ? 1 : 0;
     CUtensorMap mc = ma;
     p.tma_store = (!p.atomic && beta == 0.f && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
@@ -934,8 +987,56 @@ extern "C" int mnn_gemm_tc(const float* A, long long lda, int transA, const floa
       rc = make_map(C, ldc, N, M, BM, false, &mc);             // [M rows][N]   box {32 n, 128 rows}
       if (rc) return rc;
     }
-    return dispatch_major2(a_mn, b_mn, ma, mb, mc, p, stream);
+    return dispatch_major2(a_mn, b_mn, ma, mb, mb2, mc, p, stream);
   }
   if (BN == 128) return dispatch_major<128>(a_mn, b_mn, ma, mb, p, stream);
   return dispatch_major<64>(a_mn, b_mn, ma, mb, p, stream);
+}
+
+extern "C" int mnn_gemm_tc(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+                           long long ldc, const float* bias, float alpha, float beta, int M, int N, int K, int a_exact,
+                           cudaStream_t stream) {
+  MNN_REQUIRE(A && B && C, MNN_ERR_ARG, "gemm_tc: null pointer");
+  MNN_REQUIRE(M > 0 && N > 0 && K > 0, MNN_ERR_ARG, "gemm_tc: non-positive size");
+  MNN_REQUIRE(mnn_gemm_tc_supported(A, lda, B, ldb), MNN_ERR_UNSUPPORTED,
+              "gemm_tc: TMA needs 16-byte aligned operand pointers and row strides that are multiples of 4 floats");
+  return gemm_tc_impl(A, lda, transA, B, ldb, transB, C, ldc, bias, alpha, beta, M, N, K, a_exact, nullptr, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ pre-split weights
+namespace mnn {
+__global__ void split_bf16_pair_kernel(const float* __restrict__ src, long long ld, int rows, int cols, uint16_t* __restrict__ dst,
+                                       long long ldp) {
+  const long long n = (long long)rows * ldp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ldp), c = (int)(i - (long long)r * ldp);
+    const float x = c < cols ? __ldg(src + (size_t)r * ld + c) : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+    dst[i] = __bfloat16_as_ushort(hi);
+    dst[n + i] = __bfloat16_as_ushort(lo);
+  }
+}
+}  // namespace mnn
+
+extern "C" int mnn_split_bf16_pair(const float* src, long long ld, int rows, int cols, void* dst, long long ld_elems,
+                                   cudaStream_t stream) {
+  MNN_REQUIRE(src && dst && rows > 0 && cols > 0, MNN_ERR_ARG, "split_bf16_pair: bad argument");
+  MNN_REQUIRE(ld >= cols && ld_elems >= cols && (ld_elems & 7) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+              MNN_ERR_ARG, "split_bf16_pair: ld_elems must cover cols and be a multiple of 8, dst 16-byte aligned");
+  const long long n = (long long)rows * ld_elems;
+  const int blocks = (int)((n + 255) / 256 < 2048 ? (n + 255) / 256 : 2048);
+  mnn::split_bf16_pair_kernel<<<blocks, 256, 0, stream>>>(src, ld, rows, cols, static_cast<uint16_t*>(dst), ld_elems);
+  return mnn_check_launch("split_bf16_pair");
+}
+
+extern "C" int mnn_gemm_tc_bpair(const float* A, long long lda, int transA, const void* Bpair, long long ldb_elems, int transB,
+                                 float* C, long long ldc, const float* bias, float alpha, float beta, int M, int N, int K,
+                                 int a_exact, cudaStream_t stream) {
+  MNN_REQUIRE(A && Bpair && C, MNN_ERR_ARG, "gemm_tc_bpair: null pointer");
+  MNN_REQUIRE(M > 0 && N > 0 && K > 0, MNN_ERR_ARG, "gemm_tc_bpair: non-positive size");
+  MNN_REQUIRE((lda & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (ldb_elems & 7) == 0 &&
+                  (reinterpret_cast<uintptr_t>(Bpair) & 15) == 0,
+              MNN_ERR_UNSUPPORTED, "gemm_tc_bpair: TMA needs 16-byte aligned operands and row strides");
+  return gemm_tc_impl(A, lda, transA, nullptr, ldb_elems, transB, C, ldc, bias, alpha, beta, M, N, K, a_exact, Bpair, stream);
 }

@@ -100,7 +100,7 @@ class RnnNade(RnnEstimator):
         else:
             ws = self._workspace(T * B, inputs.device, training)
             fc = ws['fc']
-            ops.gemm(outs.reshape(T * B, -1), self._fc_kernel.data, fc, bias=self._fc_bias.data)
+            ops.gemm(outs.reshape(T * B, -1), self._fc_kernel.data, fc, bias=self._fc_bias.data, b_weight=True)
         self._outs = outs
         return self._state_from_fc(fc, rnn_state)
 
@@ -164,7 +164,7 @@ class RnnNade(RnnEstimator):
         outs = self._outs.reshape(N, -1)
         ops.gemm(outs, ws['dfc'], self._fc_kernel.grad, transA=True)
         ops.colsum(ws['dfc'], self._fc_bias.grad)
-        ops.gemm(ws['dfc'], self._fc_kernel.data, ws['dout'], transB=True)
+        ops.gemm(ws['dfc'], self._fc_kernel.data, ws['dout'], transB=True, b_weight=True)
         dx = self._rnn.backward_sequence(ws['dout'].view(T, B, -1), need_dx=need_dx)
         return ws['loss'], ws['nll'], dx
 
@@ -196,12 +196,12 @@ class RnnNade(RnnEstimator):
                 bulk.wait_event(done)
                 ops.set_sm_budget(budget)
                 try:
-                    ops.gemm(oc, self._fc_kernel.data, fc[r0:r1], bias=self._fc_bias.data)
+                    ops.gemm(oc, self._fc_kernel.data, fc[r0:r1], bias=self._fc_bias.data, b_weight=True)
                     ops.nade_logprob_fwd(bits[:, r0:r1], fc[r0:r1], self.enc_col0, self.dec_col0, self._bank.w_enc.data,
                                          self._bank.w_dec.data, nll[:, r0:r1], dfc=dfc[r0:r1], gscale=gscale)
                     ops.nade_logprob_bwd(bits[:, r0:r1], fc[r0:r1], self.enc_col0, self.dec_col0, self._bank.w_enc.data,
                                          self._bank.w_dec.data, dfc[r0:r1], self._bank.w_enc.grad, self._bank.w_dec.grad)
-                    ops.gemm(dfc[r0:r1], self._fc_kernel.data, dout[r0:r1], transB=True)
+                    ops.gemm(dfc[r0:r1], self._fc_kernel.data, dout[r0:r1], transB=True, b_weight=True)
                     ops.gemm(oc, dfc[r0:r1], self._fc_kernel.grad, transA=True, beta=1.0)
                     ops.colsum(dfc[r0:r1], self._fc_bias.grad, accumulate=True)
                 finally:

@@ -2,6 +2,7 @@
 memory, the current CUDA stream and torch.distributed. Every op launches on torch's current stream.
 """
 import contextlib
+import os
 
 import torch
 
@@ -45,15 +46,41 @@ def pack_rows(v, bits, D=None, dim_stride=1):
     check(lib.mnn_pack_rows(_ptr(v), ld, dim_stride, _ptr(bits), N, D, _stream()), "pack_rows")
 
 
-def gemm(A, B, C, transA=False, transB=False, bias=None, alpha=1.0, beta=0.0, a_exact=False, mode=None):
+_gemm_split = '2.5'
+_pair_cache = {}          # weights pre-split to bf16 pairs, valid inside one gemm_split('pair') block (= one training step)
+PRESPLIT_WEIGHTS = os.environ.get('MNN_PRESPLIT_WEIGHTS', '1') != '0'
+
+
+def split_bf16_pair(W):
+    """bf16 pair planes [2, rows, ld] (int16 storage) of a row-major fp32 matrix view; ld = cols rounded up to 8."""
+    rows, cols = W.shape
+    ldp = (cols + 7) // 8 * 8
+    out = torch.empty(2, rows, ldp, dtype=torch.int16, device=W.device)
+    check(lib.mnn_split_bf16_pair(_ptr(W), _rowstride(W), rows, cols, out.data_ptr(), ldp, _stream()), "split_bf16_pair")
+    return out
+
+
+def gemm(A, B, C, transA=False, transB=False, bias=None, alpha=1.0, beta=0.0, a_exact=False, mode=None, b_weight=False):
     """C[M,N] = alpha * op(A) op(B) + beta * C (+ bias). A, B, C are row-major 2-D views (row stride free).
     mode 'tc': tcgen05 3xTF32 (fp32-accurate) kernel; 'f32': CUDA-core fp32 kernel (also used when an operand is
-    not TMA-addressable). a_exact: A holds only tf32-exact values (binary inputs) -> 2 products instead of 3."""
+    not TMA-addressable). a_exact: A holds only tf32-exact values (binary inputs) -> 2 products instead of 3.
+    b_weight: B is a weight matrix that does not change inside the enclosing gemm_split('pair') block: it is split to
+    bf16 pairs once per block (cached by view) and handed to the kernel pre-split."""
     M, N = C.shape
     K = A.shape[0] if transA else A.shape[1]
     assert (A.shape[1] if transA else A.shape[0]) == M
     assert (B.shape[1] if transB else B.shape[0]) == K and (B.shape[0] if transB else B.shape[1]) == N
     mode = mode or GEMM_MODE
+    if (b_weight and PRESPLIT_WEIGHTS and _gemm_split == 'pair' and mode == 'tc' and M >= 256 and N > 128 and K >= 64
+            and _rowstride(A) % 4 == 0 and A.data_ptr() % 16 == 0):
+        key = (B.data_ptr(), tuple(B.shape), B.stride(0), torch.cuda.current_stream().cuda_stream)
+        pair = _pair_cache.get(key)
+        if pair is None:
+            pair = _pair_cache[key] = split_bf16_pair(B)
+        check(lib.mnn_gemm_tc_bpair(_ptr(A), _rowstride(A), int(transA), pair.data_ptr(), pair.shape[2], int(transB),
+                                    _ptr(C), _rowstride(C), _ptr(bias), float(alpha), float(beta), M, N, K, int(a_exact),
+                                    _stream()), "gemm_tc_bpair")
+        return
     if mode == 'tc' and lib.mnn_gemm_tc_supported(_ptr(A), _rowstride(A), _ptr(B), _rowstride(B)):
         check(lib.mnn_gemm_tc(_ptr(A), _rowstride(A), int(transA), _ptr(B), _rowstride(B), int(transB), _ptr(C),
                               _rowstride(C), _ptr(bias), float(alpha), float(beta), M, N, K, int(a_exact), _stream()),
@@ -71,11 +98,16 @@ def set_gemm_split(mode):
 
 @contextlib.contextmanager
 def gemm_split(mode):
+    global _gemm_split
     set_gemm_split(mode)
+    _gemm_split = mode
+    _pair_cache.clear()
     try:
         yield
     finally:
         set_gemm_split('2.5')
+        _gemm_split = '2.5'
+        _pair_cache.clear()
 
 
 def set_sm_budget(sms):

@@ -101,3 +101,32 @@ def test_gemm_tc_pair_split_epilogues_and_split_k():
     assert _run_pair(512, 2048, 420, 0, 0, a_exact=True, bias=True) < 1.0
     # many tiles per cluster: both accumulator buffers are reused several times
     assert _run_pair(8192, 2048, 96, 0, 0, bias=True) < 1.0
+
+
+@pytest.mark.parametrize("tb", [0, 1])
+@pytest.mark.parametrize("M,N,K,a_exact", [(512, 2048, 420, True), (1024, 1024, 512, False), (768, 1700, 256, False),
+                                           (512, 256, 1700, False), (2048, 512, 1024, False), (300, 200, 100, False)])
+def test_gemm_tc_presplit_weights(M, N, K, a_exact, tb):
+    """B handed over as bf16 pair planes (mnn_split_bf16_pair + mnn_gemm_tc_bpair; TMA writes the operand tiles directly,
+    K-major and MN-major): same result as the in-kernel split of the same pair mode (bit for bit without split-K) and within the pair bound
+    of the fp64 product. Ragged N (1700: plane stride padded to 1704) and K (420, 100) included."""
+    from multinn_b200 import ops
+    rng = np.random.default_rng(M + N + K)
+    A = ((rng.random((M, K)) < 0.2) if a_exact else rng.standard_normal((M, K))).astype(np.float32)
+    B = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    Ad, Bd, bd = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), torch.from_numpy(bias).cuda()
+    C1, C2 = torch.empty(M, N, device='cuda'), torch.empty(M, N, device='cuda')
+    with ops.gemm_split('pair'):
+        ops.gemm(Ad, Bd, C1, transB=bool(tb), bias=bd, a_exact=a_exact)
+        ops.gemm(Ad, Bd, C2, transB=bool(tb), bias=bd, a_exact=a_exact, b_weight=True)
+        used = len(ops._pair_cache)
+    assert used == (1 if (M >= 256 and N > 128 and K >= 64) else 0)
+    torch.cuda.synchronize()
+    if K < 1024:
+        assert torch.equal(C1, C2)
+    else:       # split-K: partial sums are red.add-ed in arrival order, two runs differ in the last bit
+        assert float((C1 - C2).abs().max()) < 2e-4
+    ref = A.astype(np.float64) @ (B.T if tb else B).astype(np.float64) + bias
+    scale = np.sqrt(0.2 * K) if a_exact else np.sqrt(K)
+    assert float(np.abs(C2.cpu().numpy() - ref).max() / scale) < 6e-5 + 4e-6 * (1 + K / 64)

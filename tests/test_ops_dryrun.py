@@ -62,6 +62,7 @@ def test_every_wrapper_matches_the_abi_signature(dry):
     ops.set_sm_budget(32)
     with ops.gemm_split('pair'):
         ops.gemm(f(4, 8), f(8, 12), f(4, 12))
+        ops.gemm(f(256, 64), f(64, 136), f(256, 136), b_weight=True)       # pre-split weight -> mnn_gemm_tc_bpair
     assert ops.lstm_seq_ctas(T, B, R, 64) == 8 and ops.lstm_seq_ctas(T, B, R, 64, backward=True) == 8
     ops.colsum(f(N, 12), f(12), accumulate=True)
     ops.lstm_cell_fwd(f(B, 4 * R), f(B, R), f(B, R), f(B, R), out=f(B, R), dscale=f(B, R), u=f(B, R), keep=0.9, seed=3)

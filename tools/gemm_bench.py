@@ -22,6 +22,10 @@ SHAPES = [  # name, M, N, K, transA, transB, a_exact
 
 def main():
     only = sys.argv[1:] or ['tc', 'f32']
+    pre = os.environ.get('GB_PRE') == '1'      # pair split with the weight operand pre-split (training-step path)
+    if os.environ.get('GB_PAIR') == '1' or pre:
+        ops.set_gemm_split('pair')
+        ops._gemm_split = 'pair'
     pick = os.environ.get('GB_ONLY')
     for name, M, Nn, K, ta, tb, ex in SHAPES:
         if pick and not any(t in name for t in pick.split(',')):
@@ -35,12 +39,12 @@ def main():
                 continue
             reps = 3 if M * Nn * K > 1e11 else 20
             for _ in range(2):
-                ops.gemm(A, B, C, transA=bool(ta), transB=bool(tb), a_exact=bool(ex), mode=mode)
+                ops.gemm(A, B, C, transA=bool(ta), transB=bool(tb), a_exact=bool(ex), mode=mode, b_weight=pre and not ta)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(reps):
-                ops.gemm(A, B, C, transA=bool(ta), transB=bool(tb), a_exact=bool(ex), mode=mode)
+                ops.gemm(A, B, C, transA=bool(ta), transB=bool(tb), a_exact=bool(ex), mode=mode, b_weight=pre and not ta)
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / reps
