@@ -429,14 +429,15 @@ def run_gpu(args):
         if composer:
             roofline = {
                 'bound': 'tensor',
-                'kernel': 'mnn::tc::gemm_tc2_kernel / gemm_tc_kernel (tcgen05 tf32 + bf16 cross terms, cta_group::2 pair tiles: '
+                'kernel': 'mnn::tc::gemm_tc2_kernel / gemm_tc_kernel (tcgen05 kind::f16 on bf16 operand pairs, cta_group::2 pair tiles: '
                           'input projections, Dense, data- and weight-gradient GEMMs; largest kernel CLASS of the step)',
                 'achieved': gemm_tf, 'peak': pk['tf_sust'], 'unit': 'TFLOP/s', 'frac': gemm_tf / pk['tf_sust'],
                 'traffic': profiled_traffic('gemm_tc'), 'peak_source': pk['src'] + ' (cuBLAS bf16, sustained)',
                 'launches_per_step': n_gemm, 'avg_launch_ms': gemm_ms / n_gemm,
                 'algorithmic_flops_per_step': GEMM_TC_FLOPS_STEP * n_rows,
-                'note': 'fp32-accurate path: every algorithmic MAC costs one tf32 MMA (half the bf16 rate) plus two bf16 '
-                        'cross-term MMAs (2 tf32 products with a binary A), so the ceiling against the bf16 denominator is 1/4',
+                'note': 'training-step GEMMs split every fp32 operand into a bf16 pair x1 + x2 and issue A1.B1 + A1.B2 + A2.B1 '
+                        '(3 bf16 MMAs per algorithmic MAC, 2 with a binary A; ~2^-17 per product), so the ceiling against '
+                        'the bf16 denominator is 1/3; measured bound: shared-memory bandwidth of the in-kernel split',
                 # the single largest KERNEL of the step is the SIMT NADE backward: reported beside the class above
                 'top_kernel': top,
                 # HBM bytes of the whole step: profiled (ncu --set full, C5 shapes) against SURVEY 8(d)'s algorithmic figure
@@ -487,7 +488,7 @@ def kernel_table(ph, n_rows, pk, xu=None):
                 'frac': ach / peak, 'note': note}
     rec_ms = ph.get('recur_fwd_ms', 0) + ph.get('recur_bwd_ms', 0)
     rows = [
-        row('gemm_tc2 / gemm_tc (tf32 + bf16 cross terms)', ph.get('gemm_ms'), 'tensor', GEMM_TC_FLOPS_STEP * n_rows / 1e12, pk['tf_sust'],
+        row('gemm_tc2 / gemm_tc (bf16 operand pairs)', ph.get('gemm_ms'), 'tensor', GEMM_TC_FLOPS_STEP * n_rows / 1e12, pk['tf_sust'],
             'TFLOP/s', 'algorithmic flops; x2-3 tf32 MMAs each'),
         row('lstm_tc2_fwd + lstm_tc3_bwd (pair recurrence)', rec_ms, 'tensor', 2 * RECUR_FLOPS_FWD * n_rows / 1e12,
             pk['tf_sust'], 'TFLOP/s', 'h.Wh and dG.Wh^T; latency chain per time step, see DESIGN.md'),
