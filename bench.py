@@ -52,7 +52,7 @@ FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # CUDA-core FMA peak of a 
 
 def profiled_traffic(kernel):
     """dram bytes per launch of `kernel` from the committed ncu --set full capture (profiles/*traffic.json), or None."""
-    for name in ('r2_traffic.json', 'r1_traffic.json'):
+    for name in ('r2_final_traffic.json', 'r2_traffic.json', 'r1_traffic.json'):
         p = os.path.join(ROOT, 'profiles', name)
         if os.path.exists(p):
             return json.load(open(p)).get(kernel)
@@ -61,7 +61,7 @@ def profiled_traffic(kernel):
 
 def profiled_step_traffic():
     """Sum of dram bytes over every kernel of one training step from the same capture (C5 shapes), with its source."""
-    for name in ('r2_traffic.json', 'r1_traffic.json'):
+    for name in ('r2_final_traffic.json', 'r2_traffic.json', 'r1_traffic.json'):
         p = os.path.join(ROOT, 'profiles', name)
         if os.path.exists(p):
             d = json.load(open(p))
