@@ -88,6 +88,18 @@ int mnn_gemm_tc_bpair(const float* A, long long lda, int transA, const void* Bpa
                       float* C, long long ldc, const float* bias, float alpha, float beta, int M, int N, int K, int a_exact,
                       mnn_stream_t stream);
 
+/* Binary A operands as an exact bf16 plane (a piano-roll bit is exact in bf16): mnn_pack_stacked_bf16 writes the stacked,
+ * zero-padded input rows of core/multi_encoder_nn.py:66-76 + multinn_composer.py:73-80 -- xin16[(t + 1) * B + b][i] =
+ * x[b][t][i], i = d * M + m, slot t = 0 and the pad columns zero, row stride ld16 elements (multiple of 8) -- from the
+ * [B, T, I] piano-roll batch (float32, or uint8 when x_is_u8). mnn_gemm_tc_abf16 is mnn_gemm_tc with A given as such a
+ * plane (row stride lda_elems; [M, K] for transA == 0, [K, M] otherwise) and B either fp32 (Bpair == NULL) or pre-split
+ * (Bpair, ldb_elems as in mnn_gemm_tc_bpair): no raw A stage and no A conversion in the kernel, half the A bytes from
+ * HBM. CTA-pair kernel only. Used for the layer-0 input projection and the x-rows weight gradient of the training step. */
+int mnn_pack_stacked_bf16(const void* x, int x_is_u8, void* xin16, long long ld16, int B, int T, int I, mnn_stream_t stream);
+int mnn_gemm_tc_abf16(const void* A16, long long lda_elems, int transA, const float* B, long long ldb, const void* Bpair,
+                      long long ldb_elems, int transB, float* C, long long ldc, const float* bias, float alpha, float beta,
+                      int M, int N, int K, mnn_stream_t stream);
+
 /* Data-parallel noise keying (no reference counterpart: the reference is single-device; SURVEY 8(e) asks that results
  * do not depend on the GPU count). Every entry point that can draw Philox noise (dropout in mnn_lstm_*_fwd*, the
  * Bernoulli draws of mnn_bias_sigmoid_sample, mnn_rbm_gibbs, mnn_nade_sample, mnn_sample_steps) keys the counter by the

@@ -43,6 +43,8 @@ SIGNATURES = {
     "mnn_gemm_tc": [_p, _ll, _i, _p, _ll, _i, _p, _ll, _p, _f, _f, _i, _i, _i, _i, _p],
     "mnn_gemm_tc_bpair": [_p, _ll, _i, _p, _ll, _i, _p, _ll, _p, _f, _f, _i, _i, _i, _i, _p],
     "mnn_split_bf16_pair": [_p, _ll, _i, _i, _p, _ll, _p],
+    "mnn_pack_stacked_bf16": [_p, _i, _p, _ll, _i, _i, _i, _p],
+    "mnn_gemm_tc_abf16": [_p, _ll, _i, _p, _ll, _p, _ll, _i, _p, _ll, _p, _f, _f, _i, _i, _i, _p],
     "mnn_lstm_cell_fwd": [_p, _p, _p, _p, _p, _p, _p, _f, _u64, _u64, _i, _i, _p],
     "mnn_lstm_seq_fwd": [_p, _p, _p, _p, _p, _p, _p, _f, _u64, _i, _i, _i, _p],
     "mnn_lstm_seq_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],

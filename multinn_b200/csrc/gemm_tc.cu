@@ -43,6 +43,7 @@ struct Params {
   int tma_store;   // pair kernel: C tiles leave through shared memory + TMA (needs beta == 0, no split-K, aligned C)
   int bf16x;       // pair kernel: cross terms hi.lo + lo.hi as bf16 MMAs (kind::f16, twice the tf32 rate)
   int share_conv;  // pair kernel, long K loops: the epilogue warps convert too (256 converter threads per CTA)
+  int a_pre;       // pair kernel, bf16x == 2, binary A: A arrives as ONE exact bf16 plane (no raw A stage, no A conversion)
   int b_pre;       // pair kernel, bf16x == 2: B arrives as bf16 pair planes (mnn_split_bf16_pair); TMA drops them straight into
                    // the [hi | lo] tiles: no raw B stage, no B conversion (a third less shared-memory traffic per stage)
 };
@@ -303,10 +304,10 @@ __device__ __forceinline__ void convert_stage(uint8_t* base, int t, const Params
   if (p.bf16x) {
     const bool pair = p.bf16x == 2;
     if (p.share_conv) {
-      convert_bf16_tiles<A_MN, 256>(base, base + C_::A_BYTES, t, p.n_products == 3, pair);
+      if (!p.a_pre) convert_bf16_tiles<A_MN, 256>(base, base + C_::A_BYTES, t, p.n_products == 3, pair);
       if (!p.b_pre) convert_bf16_tiles<B_MN, 256>(base + 2 * C_::A_BYTES, base + 2 * C_::A_BYTES + C_::B_BYTES, t, true, pair);
     } else {
-      convert_bf16_tiles<A_MN, 128>(base, base + C_::A_BYTES, t, p.n_products == 3, pair);
+      if (!p.a_pre) convert_bf16_tiles<A_MN, 128>(base, base + C_::A_BYTES, t, p.n_products == 3, pair);
       if (!p.b_pre) convert_bf16_tiles<B_MN, 128>(base + 2 * C_::A_BYTES, base + 2 * C_::A_BYTES + C_::B_BYTES, t, true, pair);
     }
   } else {
@@ -387,11 +388,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t full = bar_full + 8 * stage;
-          mbar_expect_tx(full, C_::A_BYTES + C_::B_BYTES);
+          mbar_expect_tx(full, (p.a_pre ? C_::A_BYTES / 2 : C_::A_BYTES) + C_::B_BYTES);
           const uint32_t a_dst = smem0 + stage * C_::STAGE_BYTES;
           const uint32_t b_dst = a_dst + 2 * C_::A_BYTES;
           const int k0 = kb * BK;
-          if (!A_MN) {
+          if (p.a_pre) {
+            // exact bf16 A (binary piano-roll rows): one plane straight into the hi tile of the "lo" region
+            const uint32_t ah = a_dst + C_::A_BYTES;
+            if (!A_MN) {
+              tma_load_2d(ah, &map_a, full, k0, m0);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 2; ++c) tma_load_2d(ah + c * 4096, &map_a, full, m0 + 64 * c, k0);
+            }
+          } else if (!A_MN) {
             tma_load_2d(a_dst, &map_a, full, k0, m0);
           } else {
 #pragma unroll
@@ -904,9 +914,10 @@ extern "C" int mnn_gemm_tc_supported(const float* A, long long lda, const float*
 }
 
 // bpair != nullptr: B is given as bf16 pair planes (mnn_split_bf16_pair) with row stride ldb ELEMENTS; B itself is unused
+// a16 != nullptr: A is given as ONE exact bf16 plane (binary rows) with row stride lda ELEMENTS; A itself is unused
 static int gemm_tc_impl(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
                         long long ldc, const float* bias, float alpha, float beta, int M, int N, int K, int a_exact,
-                        const void* bpair, cudaStream_t stream) {
+                        const void* bpair, cudaStream_t stream, const void* a16 = nullptr) {
   using namespace mnn::tc;
   const bool a_mn = transA != 0;   // A stored [K,M]: M contiguous
   const bool b_mn = transB == 0;   // B stored [K,N]: N contiguous
@@ -915,8 +926,8 @@ static int gemm_tc_impl(const float* A, long long lda, int transA, const float* 
   static const int pair_kmin = kmin_env ? atoi(kmin_env) : 64;
   // 256x256 tiles on CTA pairs; with the TMA-store epilogue they win down to K = 256 (Dense forward: 2.28 vs 3.67 ms)
   const bool pair = !force_1cta && M >= 256 && N > 128 && K >= pair_kmin;
-  MNN_REQUIRE(!bpair || pair, MNN_ERR_UNSUPPORTED,
-              "gemm_tc_bpair: a pre-split B needs the CTA-pair kernel (M >= 256, N > 128, K >= 64)");
+  MNN_REQUIRE((!bpair && !a16) || pair, MNN_ERR_UNSUPPORTED,
+              "gemm_tc: pre-split operands need the CTA-pair kernel (M >= 256, N > 128, K >= 64)");
   const int BN = pair ? BN2 : (N > 64 ? 128 : 64);
   const int TM = pair ? 2 * BM : BM;
   const int units = pair ? num_sms() / 2 : num_sms();
@@ -947,7 +958,10 @@ static int gemm_tc_impl(const float* A, long long lda, int transA, const float* 
   CUtensorMap ma, mb;
   int rc;
   const int box_n = pair ? BN2 / 2 : BN;
-  if (!a_mn) rc = make_map(A, lda, K, M, BM, false, &ma);    // [M rows][K]   box {32 k, 128 rows}
+  if (a16) {
+    if (!a_mn) rc = make_map_bf16(a16, lda, K, M, BM, &ma);  // [M rows][K]   box {32 k, 128 rows}, SWIZZLE_64B
+    else rc = make_map_bf16_mn(a16, lda, M, K, &ma);         // [K rows][M]   box {64 m, 32 k}, SWIZZLE_128B
+  } else if (!a_mn) rc = make_map(A, lda, K, M, BM, false, &ma);    // [M rows][K]   box {32 k, 128 rows}
   else rc = make_map(A, lda, M, K, BK, true, &ma);           // [K rows][M]   box {32 m, 32 k}
   if (rc) return rc;
   CUtensorMap mb2;
@@ -980,6 +994,7 @@ static int gemm_tc_impl(const float* A, long long lda, int transA, const float* 
     // only with the bf16 tiles: in the tf32 path with a binary A just B is converted and the extra arrivals cost more
     // than the shared work saves (dW1x 3.16 -> 3.71 ms)
     if (bpair) { p.bf16x = 2; p.b_pre = 1; }   // the pre-split planes ARE the bf16 pair
+    if (a16) { p.bf16x = 2; p.a_pre = 1; p.n_products = 2; }
     p.share_conv = (p.bf16x && share_kb > 0 && p.kb_per_split >= share_kb) ? 1 : 0;
     CUtensorMap mc = ma;
     p.tma_store = (!p.atomic && beta == 0.f && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
@@ -1039,4 +1054,82 @@ extern "C" int mnn_gemm_tc_bpair(const float* A, long long lda, int transA, cons
                   (reinterpret_cast<uintptr_t>(Bpair) & 15) == 0,
               MNN_ERR_UNSUPPORTED, "gemm_tc_bpair: TMA needs 16-byte aligned operands and row strides");
   return gemm_tc_impl(A, lda, transA, nullptr, ldb_elems, transB, C, ldc, bias, alpha, beta, M, N, K, a_exact, Bpair, stream);
+}
+
+extern "C" int mnn_gemm_tc_abf16(const void* A16, long long lda_elems, int transA, const float* B, long long ldb,
+                                 const void* Bpair, long long ldb_elems, int transB, float* C, long long ldc,
+                                 const float* bias, float alpha, float beta, int M, int N, int K, cudaStream_t stream) {
+  MNN_REQUIRE(A16 && (B || Bpair) && C, MNN_ERR_ARG, "gemm_tc_abf16: null pointer");
+  MNN_REQUIRE(M > 0 && N > 0 && K > 0, MNN_ERR_ARG, "gemm_tc_abf16: non-positive size");
+  MNN_REQUIRE((lda_elems & 7) == 0 && (reinterpret_cast<uintptr_t>(A16) & 15) == 0, MNN_ERR_UNSUPPORTED,
+              "gemm_tc_abf16: the bf16 A plane needs a 16-byte aligned pointer and a row stride that is a multiple of 8");
+  if (Bpair) {
+    MNN_REQUIRE((ldb_elems & 7) == 0 && (reinterpret_cast<uintptr_t>(Bpair) & 15) == 0, MNN_ERR_UNSUPPORTED,
+                "gemm_tc_abf16: the B planes need a 16-byte aligned pointer and a row stride that is a multiple of 8");
+    return gemm_tc_impl(nullptr, lda_elems, transA, nullptr, ldb_elems, transB, C, ldc, bias, alpha, beta, M, N, K, 1, Bpair,
+                        stream, A16);
+  }
+  MNN_REQUIRE((ldb & 3) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0, MNN_ERR_UNSUPPORTED,
+              "gemm_tc_abf16: B needs a 16-byte aligned pointer and a row stride that is a multiple of 4 floats");
+  return gemm_tc_impl(nullptr, lda_elems, transA, B, ldb, transB, C, ldc, bias, alpha, beta, M, N, K, 1, nullptr, stream, A16);
+}
+
+// stacked piano-roll rows as an exact bf16 plane: xin16[(t + 1) * B + b][0 .. D*M) = x[b][t][.][.] (feature d*M + m is the
+// memory order of x), slot t = 0 and the pad columns zero -- the A operand of the layer-0 projection and weight-gradient
+// GEMMs of the training step (core/multi_encoder_nn.py:66-76 + multinn_composer.py:73-80)
+namespace mnn {
+__device__ __forceinline__ uint32_t bf16x2_of(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// one thread = 8 consecutive features of one row: a 16-byte store, 8 input bytes (uint8) or two float4 loads (I % 4 == 0
+// keeps them aligned; other I take the scalar tail path)
+template <typename TIn>
+__global__ void pack_stacked_bf16_kernel(const TIn* __restrict__ x, uint16_t* __restrict__ out, int ld16, int B, int T, int I) {
+  const int chunks = ld16 >> 3;
+  const long long n = (long long)(T + 1) * B * chunks;
+  const bool aligned = (I & 3) == 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(i / chunks), ch = (int)(i - (long long)row * chunks);
+    const int t1 = row / B, b = row - t1 * B, c0 = ch * 8;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (t1 > 0 && c0 < I) {
+      const TIn* src = x + ((size_t)b * T + (t1 - 1)) * I + c0;
+      if (aligned && c0 + 8 <= I) {
+        if (sizeof(TIn) == 1) {
+          const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(src)), w1 = __ldg(reinterpret_cast<const uint32_t*>(src) + 1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { v[j] = (float)((w0 >> (8 * j)) & 0xffu); v[4 + j] = (float)((w1 >> (8 * j)) & 0xffu); }
+        } else {
+          const float4 f0 = __ldg(reinterpret_cast<const float4*>(src)), f1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+          v[0] = f0.x; v[1] = f0.y; v[2] = f0.z; v[3] = f0.w; v[4] = f1.x; v[5] = f1.y; v[6] = f1.z; v[7] = f1.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c0 + j < I) v[j] = (float)src[j];
+      }
+    }
+    *reinterpret_cast<uint4*>(out + (size_t)row * ld16 + c0) =
+        make_uint4(bf16x2_of(v[0], v[1]), bf16x2_of(v[2], v[3]), bf16x2_of(v[4], v[5]), bf16x2_of(v[6], v[7]));
+  }
+}
+}  // namespace mnn
+
+extern "C" int mnn_pack_stacked_bf16(const void* x, int x_is_u8, void* xin16, long long ld16, int B, int T, int I,
+                                     cudaStream_t stream) {
+  MNN_REQUIRE(x && xin16 && B > 0 && T > 0 && I > 0, MNN_ERR_ARG, "pack_stacked_bf16: bad argument");
+  MNN_REQUIRE(ld16 >= I && (ld16 & 7) == 0 && (reinterpret_cast<uintptr_t>(xin16) & 15) == 0, MNN_ERR_ARG,
+              "pack_stacked_bf16: ld16 must cover the row and be a multiple of 8, xin16 16-byte aligned");
+  MNN_REQUIRE(ld16 < (1ll << 30) && (long long)(T + 1) * B < (1ll << 31), MNN_ERR_ARG, "pack_stacked_bf16: too many rows");
+  const long long n = (long long)(T + 1) * B * (ld16 / 8);
+  const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  if (x_is_u8)
+    mnn::pack_stacked_bf16_kernel<uint8_t><<<blocks, 256, 0, stream>>>(static_cast<const uint8_t*>(x), static_cast<uint16_t*>(xin16),
+                                                                     (int)ld16, B, T, I);
+  else
+    mnn::pack_stacked_bf16_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float*>(x), static_cast<uint16_t*>(xin16),
+                                                                   (int)ld16, B, T, I);
+  return mnn_check_launch("pack_stacked_bf16");
 }

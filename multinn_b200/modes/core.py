@@ -120,6 +120,13 @@ class MultINNCore(Model, abc.ABC):
             st['bits'] = torch.empty(M, T * B, 4, dtype=torch.int32, device=dev)
         ops.pack_pianoroll(x, st['xin'] if stacked else None, st['xtr'] if per_track else None,
                            st['bits'] if bits else None)
+        if stacked and ops.BF16_INPUT_TWIN and ops._gemm_split == 'pair':
+            # training step: the binary stacked rows once more as an exact bf16 plane -- the layer-0 projection and the
+            # x-rows weight-gradient GEMM read it through TMA without the in-kernel operand split (ops.gemm, a_exact)
+            if 'xin16' not in st:
+                st['xin16'] = torch.empty((T + 1) * B, (D * M + 7) // 8 * 8, dtype=torch.int16, device=dev)
+            ops.pack_stacked_bf16(x, st['xin16'])
+            ops.register_twin(st['xin'].view((T + 1) * B, D * M), st['xin16'])
         return st
 
     # The per-track generators of Jamming / Feedback(-RNN) are independent between the encode and the feedback backward

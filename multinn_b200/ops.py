@@ -60,6 +60,38 @@ def split_bf16_pair(W):
     return out
 
 
+_twins = []               # (fp32 base tensor, its exact bf16 plane [rows, ld16]) registered by the input staging
+BF16_INPUT_TWIN = os.environ.get('MNN_BF16_INPUT_TWIN', '1') != '0'
+
+
+def pack_stacked_bf16(x, out):
+    """x[B,T,D,M] (float32 / uint8 / bool) -> out[(T+1)*B, ld16] int16 storage of the exact bf16 stacked rows."""
+    B, T = x.shape[0], x.shape[1]
+    I = x.shape[2] * x.shape[3]
+    assert x.is_contiguous() and out.is_contiguous() and out.shape[0] == (T + 1) * B
+    check(lib.mnn_pack_stacked_bf16(_ptr(x), int(x.dtype != torch.float32), out.data_ptr(), out.shape[1], B, T, I, _stream()),
+          "pack_stacked_bf16")
+
+
+def register_twin(base, twin):
+    """`twin` holds the same rows as the fp32 matrix `base` [rows, cols] as exact bf16 (binary data): GEMMs of the training
+    step whose A operand is a row block of `base` (a_exact=True) read the twin instead. One registration per base."""
+    _twins[:] = [(b, t) for b, t in _twins if b.data_ptr() != base.data_ptr()]
+    _twins.append((base, twin))
+    del _twins[:-4]
+
+
+def _twin_of(A):
+    """(pointer, row stride in elements) of the bf16 rows matching the row-block view A of a registered base, or None."""
+    for base, twin in _twins:
+        off = A.data_ptr() - base.data_ptr()
+        row_bytes = base.stride(0) * 4
+        if 0 <= off < base.shape[0] * row_bytes and off % row_bytes == 0 and A.stride(0) == base.stride(0) \
+                and A.shape[1] == base.shape[1] and off // row_bytes + A.shape[0] <= base.shape[0]:
+            return twin.data_ptr() + (off // row_bytes) * twin.shape[1] * 2, twin.shape[1]
+    return None
+
+
 def gemm(A, B, C, transA=False, transB=False, bias=None, alpha=1.0, beta=0.0, a_exact=False, mode=None, b_weight=False):
     """C[M,N] = alpha * op(A) op(B) + beta * C (+ bias). A, B, C are row-major 2-D views (row stride free).
     mode 'tc': tcgen05 3xTF32 (fp32-accurate) kernel; 'f32': CUDA-core fp32 kernel (also used when an operand is
@@ -71,6 +103,24 @@ def gemm(A, B, C, transA=False, transB=False, bias=None, alpha=1.0, beta=0.0, a_
     assert (A.shape[1] if transA else A.shape[0]) == M
     assert (B.shape[1] if transB else B.shape[0]) == K and (B.shape[0] if transB else B.shape[1]) == N
     mode = mode or GEMM_MODE
+    pair_ok = _gemm_split == 'pair' and mode == 'tc' and M >= 256 and N > 128 and K >= 64
+    if a_exact and pair_ok and BF16_INPUT_TWIN and _twins:
+        tw = _twin_of(A)
+        if tw is not None:
+            bp = None
+            if b_weight and PRESPLIT_WEIGHTS:
+                key = (B.data_ptr(), tuple(B.shape), B.stride(0), torch.cuda.current_stream().cuda_stream)
+                bp = _pair_cache.get(key)
+                if bp is None:
+                    bp = _pair_cache[key] = split_bf16_pair(B)
+            elif _rowstride(B) % 4 or B.data_ptr() % 16:
+                tw = None
+            if tw is not None:
+                check(lib.mnn_gemm_tc_abf16(tw[0], tw[1], int(transA), _ptr(B), _rowstride(B),
+                                            None if bp is None else bp.data_ptr(), 0 if bp is None else bp.shape[2],
+                                            int(transB), _ptr(C), _rowstride(C), _ptr(bias), float(alpha), float(beta),
+                                            M, N, K, _stream()), "gemm_tc_abf16")
+                return
     if (b_weight and PRESPLIT_WEIGHTS and _gemm_split == 'pair' and mode == 'tc' and M >= 256 and N > 128 and K >= 64
             and _rowstride(A) % 4 == 0 and A.data_ptr() % 16 == 0):
         key = (B.data_ptr(), tuple(B.shape), B.stride(0), torch.cuda.current_stream().cuda_stream)
@@ -102,12 +152,14 @@ def gemm_split(mode):
     set_gemm_split(mode)
     _gemm_split = mode
     _pair_cache.clear()
+    del _twins[:]
     try:
         yield
     finally:
         set_gemm_split('2.5')
         _gemm_split = '2.5'
         _pair_cache.clear()
+        del _twins[:]
 
 
 def set_sm_budget(sms):

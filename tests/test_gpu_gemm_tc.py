@@ -130,3 +130,42 @@ def test_gemm_tc_presplit_weights(M, N, K, a_exact, tb):
     ref = A.astype(np.float64) @ (B.T if tb else B).astype(np.float64) + bias
     scale = np.sqrt(0.2 * K) if a_exact else np.sqrt(K)
     assert float(np.abs(C2.cpu().numpy() - ref).max() / scale) < 6e-5 + 4e-6 * (1 + K / 64)
+
+
+@pytest.mark.parametrize("use_bpair", [False, True])
+def test_gemm_tc_bf16_input_plane(use_bpair):
+    """Binary stacked piano-roll rows as an exact bf16 plane (mnn_pack_stacked_bf16) feeding mnn_gemm_tc_abf16 as the A
+    operand, K-major (layer-0 projection X.Wx over a row block) and MN-major (x-rows weight gradient X^T.dG): identical
+    to the pair split of the fp32 rows, which is exact for binary A."""
+    from multinn_b200 import ops
+    rng = np.random.default_rng(5)
+    Bb, T, D, Mt, N = 16, 63, 84, 5, 2048
+    I = D * Mt
+    x = (rng.random((Bb, T, D, Mt)) < 0.07).astype(np.float32)
+    xd = torch.from_numpy(x).cuda()
+    xin = torch.zeros((T + 1) * Bb, I, device='cuda')
+    ops.pack_pianoroll(xd, xin.view(T + 1, Bb, I))
+    twin = torch.empty((T + 1) * Bb, 424, dtype=torch.int16, device='cuda')
+    ops.pack_stacked_bf16(xd.to(torch.uint8), twin)
+    # the plane holds exactly the staged rows
+    back = (twin.view(torch.bfloat16).float())[:, :I]
+    assert torch.equal(back, xin) and float(twin[:, I:].abs().max()) == 0
+    W = torch.from_numpy(rng.standard_normal((I, N)).astype(np.float32)).cuda()
+    dG = torch.from_numpy(rng.standard_normal(((T + 1) * Bb, N)).astype(np.float32)).cuda()
+    bias = torch.from_numpy(rng.standard_normal(N).astype(np.float32)).cuda()
+    rows = slice(Bb, Bb + 768)                         # a row block that does not start at the base
+    C1, C2 = torch.empty(768, N, device='cuda'), torch.empty(768, N, device='cuda')
+    G1, G2 = torch.empty(I, N, device='cuda'), torch.empty(I, N, device='cuda')
+    with ops.gemm_split('pair'):
+        ops.gemm(xin[rows], W, C1, bias=bias, a_exact=True, b_weight=use_bpair)
+        ops.gemm(xin, dG, G1, transA=True, a_exact=True)
+        n0 = len(ops._twins)
+        ops.register_twin(xin, twin)
+        ops.gemm(xin[rows], W, C2, bias=bias, a_exact=True, b_weight=use_bpair)
+        ops.gemm(xin, dG, G2, transA=True, a_exact=True)
+        assert n0 == 0 and len(ops._twins) == 1
+    torch.cuda.synchronize()
+    assert torch.equal(C1, C2)
+    assert float((G1 - G2).abs().max()) < 2e-4 * float(G1.abs().max())          # split-K: arrival order of the partial sums
+    ref = x.reshape(Bb, T, I).transpose(1, 0, 2).reshape(T * Bb, I)[0:768].astype(np.float64) @ W.cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(C2.cpu().numpy(), ref + bias.cpu().numpy(), atol=6e-5 * np.sqrt(0.07 * I) * 3)

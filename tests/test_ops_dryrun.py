@@ -63,6 +63,12 @@ def test_every_wrapper_matches_the_abi_signature(dry):
     with ops.gemm_split('pair'):
         ops.gemm(f(4, 8), f(8, 12), f(4, 12))
         ops.gemm(f(256, 64), f(64, 136), f(256, 136), b_weight=True)       # pre-split weight -> mnn_gemm_tc_bpair
+        xb = f(2, 255, 16, 4)                                             # [B,T,D,M]: 512 stacked rows of 64 features
+        base, twin = f(512, 64), torch.zeros(512, 64, dtype=torch.int16)
+        ops.pack_stacked_bf16(xb, twin)
+        ops.register_twin(base, twin)
+        ops.gemm(base[256:], f(64, 136), f(256, 136), a_exact=True, b_weight=True)      # bf16 A plane -> mnn_gemm_tc_abf16
+        ops.gemm(base, f(512, 136), f(64, 136), transA=True, a_exact=True)              # (too small for the pair kernel)
     assert ops.lstm_seq_ctas(T, B, R, 64) == 8 and ops.lstm_seq_ctas(T, B, R, 64, backward=True) == 8
     ops.colsum(f(N, 12), f(12), accumulate=True)
     ops.lstm_cell_fwd(f(B, 4 * R), f(B, R), f(B, R), f(B, R), out=f(B, R), dscale=f(B, R), u=f(B, R), keep=0.9, seed=3)
