@@ -896,6 +896,7 @@ int mnn_tc_make_map_bf16(const void* ptr, long long ld_elems, long long inner, l
 int mnn_tc_num_sms() { return mnn::tc::device_sms(); }
 
 int mnn_tc_sm_budget() { return mnn::tc::g_sm_budget; }
+int mnn_tc_gemm_split() { return mnn::tc::g_gemm_split; }   // mnn_set_gemm_split of the calling thread
 
 extern "C" int mnn_set_sm_budget(int sms) {
   mnn::tc::g_sm_budget = sms > 0 ? sms : 0;

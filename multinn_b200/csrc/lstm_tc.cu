@@ -10,6 +10,7 @@
 // is Wh transposed and permuted so that the four gate columns of a unit block are adjacent (prepared once per call).
 // Backward work item (slab m, unit block n): accumulator[128 rows, BN units] = dG_{t+1}[slab] . Wh^T, then the cell
 // backward for step t writes dG_t in place of the saved gate activations.
+#include <cuda_bf16.h>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -26,6 +27,10 @@ int mnn_lstm_res_bwd(float* gates, const float* wh, const float* cbuf, const flo
 int mnn_lstm_res_fwd(float* gates, const float* wh, float* hbuf, float* cbuf, float* out, float* dscale, const float* u,
                      float keep, unsigned long long seed, int T, int B, int R, void* hs, unsigned int* flags, int sms,
                      cudaStream_t stream);
+
+int mnn_tc_make_map_bf16(const void* ptr, long long ld_elems, long long inner, long long outer, int box_outer,
+                         CUtensorMap* out);   // gemm_tc.cu: K-major bf16 tiles, SWIZZLE_64B
+int mnn_tc_gemm_split();                       // gemm_tc.cu: mnn_set_gemm_split of the calling thread (1 = bf16 pairs)
 
 namespace mnn {
 namespace tc {
@@ -61,6 +66,7 @@ struct LstmParams {
   unsigned int* flags;  // [slabs] completed-item counters (persistent launches), zeroed by the host
   unsigned long long* trace;  // debug (MNN_LSTM_TRACE): [cta][step][16] globaltimer stamps, or null
   int bf16x;            // pair forward kernel: cross terms as bf16 MMAs (2.5-product scheme, see gemm_tc.cu)
+  int b_pre;            // pair forward kernel, bf16x == 2: WhP^T arrives as bf16 pair planes (split once per launch, not per step)
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -455,7 +461,8 @@ constexpr size_t kPairSmem = 2 * 7 * (size_t)(BM * 128) + 1024;   // epilogue ti
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLThreads, 1)
 lstm_tc2_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_c,
+                    const __grid_constant__ CUtensorMap map_b2, const __grid_constant__ CUtensorMap map_g,
+                    const __grid_constant__ CUtensorMap map_c,
                     const __grid_constant__ CUtensorMap map_o, const LstmParams p) {
   constexpr int BNP = 4 * kL2UB;                       // 256 gate columns per item
   constexpr int A_BYTES = BM * BK * 4, B_BYTES = (BNP / 2) * BK * 4;
@@ -663,7 +670,12 @@ lstm_tc2_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             mbar_expect_tx(full, A_BYTES + B_BYTES);
             const uint32_t a_dst = smem0 + stage * STAGE_BYTES;
             tma_load_2d(a_dst, &map_a, full, kb * BK, row0);
-            tma_load_2d(a_dst + 2 * A_BYTES, &map_b, full, kb * BK, brow0);
+            if (p.b_pre) {   // bf16 planes straight into the [hi | lo] tiles of the "lo" region (same bytes as the raw tile)
+              tma_load_2d(a_dst + 2 * A_BYTES + B_BYTES, &map_b, full, kb * BK, brow0);
+              tma_load_2d(a_dst + 2 * A_BYTES + B_BYTES + B_BYTES / 2, &map_b2, full, kb * BK, brow0);
+            } else {
+              tma_load_2d(a_dst + 2 * A_BYTES, &map_b, full, kb * BK, brow0);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           MNN_TRACE(1);
@@ -775,7 +787,7 @@ lstm_tc2_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           float4* b_lo = reinterpret_cast<float4*>(base + 2 * A_BYTES + B_BYTES);
           if (p.bf16x) {
             convert_bf16_tiles<false, 128>(base, base + A_BYTES, tc, true, p.bf16x == 2);
-            convert_bf16_tiles<false, 128>(base + 2 * A_BYTES, base + 2 * A_BYTES + B_BYTES, tc, true, p.bf16x == 2);
+            if (!p.b_pre) convert_bf16_tiles<false, 128>(base + 2 * A_BYTES, base + 2 * A_BYTES + B_BYTES, tc, true, p.bf16x == 2);
           } else {
 #pragma unroll 4
             for (int i = tc; i < A_BYTES / 16; i += 128) a_lo[i] = tf32_lo4(a_raw[i]);
@@ -842,12 +854,14 @@ struct Lstm3Params {
   unsigned int* cntB;     // [slabs]
   unsigned long long* trace;   // debug (MNN_LSTM_TRACE)
   int bf16x;              // phase A: cross terms as bf16 MMAs (2.5-product scheme, see gemm_tc.cu)
+  int b_pre;              // phase A, bf16x == 2: Wh arrives as bf16 pair planes (split once per launch)
 };
 constexpr int kCellRows = 16, kCellUnits = 16, kCellTile = kCellRows * kCellUnits * 4;   // 1 KB tiles
 constexpr size_t kBwd3Smem = 3 * 64 * 1024 + 1024;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLThreads, 1)
 lstm_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_b2,
                     const __grid_constant__ CUtensorMap map_dhr, const __grid_constant__ CUtensorMap map_dh,
                     const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_c,
                     const __grid_constant__ CUtensorMap map_do, const __grid_constant__ CUtensorMap map_ds,
@@ -928,7 +942,12 @@ lstm_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           mbar_expect_tx(full, A_BYTES + B_BYTES);
           const uint32_t a_dst = smem0 + stage * STAGE_BYTES;
           tma_load_2d(a_dst, &map_a, full, kb * BK, row0);
-          tma_load_2d(a_dst + 2 * A_BYTES, &map_b, full, kb * BK, brow0);
+          if (p.b_pre) {
+            tma_load_2d(a_dst + 2 * A_BYTES + B_BYTES, &map_b, full, kb * BK, brow0);
+            tma_load_2d(a_dst + 2 * A_BYTES + B_BYTES + B_BYTES / 2, &map_b2, full, kb * BK, brow0);
+          } else {
+            tma_load_2d(a_dst + 2 * A_BYTES, &map_b, full, kb * BK, brow0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -1029,7 +1048,7 @@ lstm_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             float4* b_lo = reinterpret_cast<float4*>(base + 2 * A_BYTES + B_BYTES);
             if (p.bf16x) {
               convert_bf16_tiles<false, 128>(base, base + A_BYTES, tc, true, p.bf16x == 2);
-              convert_bf16_tiles<false, 128>(base + 2 * A_BYTES, base + 2 * A_BYTES + B_BYTES, tc, true, p.bf16x == 2);
+              if (!p.b_pre) convert_bf16_tiles<false, 128>(base + 2 * A_BYTES, base + 2 * A_BYTES + B_BYTES, tc, true, p.bf16x == 2);
             } else {
 #pragma unroll 4
               for (int i = tc; i < A_BYTES / 16; i += 128) a_lo[i] = tf32_lo4(a_raw[i]);
@@ -1205,6 +1224,21 @@ __global__ void lstm_prep_wh_kernel(const float* __restrict__ wh, float* __restr
     const int u = row % UB, g = (row / UB) & 3, n = row / (4 * UB);
     const int unit = n * UB + u;
     whp[idx] = unit < R ? __ldg(wh + (size_t)k * 4 * R + (size_t)g * R + unit) : 0.f;
+  }
+}
+
+// the same permutation written as bf16 pair planes [rows][R] (hi, then lo right behind it) for the pre-split operand path
+__global__ void lstm_prep_wh_pair_kernel(const float* __restrict__ wh, uint16_t* __restrict__ planes, int R, int UB, int blocks) {
+  const size_t total = (size_t)blocks * 4 * UB * R;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % R);
+    const int row = (int)(idx / R);
+    const int u = row % UB, g = (row / UB) & 3, n = row / (4 * UB);
+    const int unit = n * UB + u;
+    const float w = unit < R ? __ldg(wh + (size_t)k * 4 * R + (size_t)g * R + unit) : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    planes[idx] = __bfloat16_as_ushort(hi);
+    planes[total + idx] = __bfloat16_as_ushort(__float2bfloat16_rn(w - __bfloat162float(hi)));
   }
 }
 
@@ -1449,7 +1483,13 @@ extern "C" int mnn_lstm_seq_fwd_tc(float* gates, const float* wh, float* hbuf, f
   const int blocks = (R + UB - 1) / UB;
   float* whp = reinterpret_cast<float*>(ws);
   unsigned int* flags = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(ws) + whp_region_bytes(R));
-  lstm_prep_wh_kernel<<<296, 256, 0, stream>>>(wh, whp, R, UB, blocks);
+  // MNN_LSTM_BF16X: "0" 3xTF32, "1" 2.5 products, "2" bf16 pairs, "3" bf16 pairs with the weights pre-split once per launch
+  // (pair kernels only). Unset: "3" while the calling thread is in the training step's pair mode (mnn_set_gemm_split(1):
+  // 26.1 -> 22.2 us per step at B = 2048, R = 512), "1" otherwise (evaluate / generate keep ~2^-20 per product)
+  static const char* bf16x_env0 = getenv("MNN_LSTM_BF16X");
+  const bool wh_pre = pair && (bf16x_env0 ? bf16x_env0[0] == '3' : mnn_tc_gemm_split() == 1);
+  if (wh_pre) lstm_prep_wh_pair_kernel<<<296, 256, 0, stream>>>(wh, reinterpret_cast<uint16_t*>(ws), R, UB, blocks);
+  else lstm_prep_wh_kernel<<<296, 256, 0, stream>>>(wh, whp, R, UB, blocks);
   int rc = mnn_check_launch("lstm_prep_wh");
   if (rc) return rc;
   if (pair) {
@@ -1458,11 +1498,19 @@ extern "C" int mnn_lstm_seq_fwd_tc(float* gates, const float* wh, float* hbuf, f
     p.T = T; p.B = B; p.R = R; p.t0 = 0; p.t1 = T;
     p.slabs = (B + 2 * BM - 1) / (2 * BM); p.blocks = blocks; p.kb_total = (R + BK - 1) / BK; p.flags = flags;
     static const char* bf16x_env = getenv("MNN_LSTM_BF16X");   // "0": 3xTF32, "1": 2.5 products, "2": bf16 pairs
-    p.bf16x = bf16x_env ? (bf16x_env[0] == '0' ? 0 : (bf16x_env[0] == '2' ? 2 : 1)) : 1;
-    CUtensorMap ma, mb;
+    p.bf16x = bf16x_env ? (bf16x_env[0] == '0' ? 0 : (bf16x_env[0] >= '2' ? 2 : 1)) : (wh_pre ? 2 : 1);
+    p.b_pre = wh_pre ? 1 : 0;
+    CUtensorMap ma, mb, mb2;
     rc = mnn_tc_make_map(hbuf, R, R, (long long)(T + 1) * B, BM, false, &ma);
     if (rc) return rc;
-    rc = mnn_tc_make_map(whp, R, R, (long long)blocks * 4 * UB, BM, false, &mb);
+    if (wh_pre) {
+      const long long rows = (long long)blocks * 4 * UB;
+      rc = mnn_tc_make_map_bf16(ws, R, R, rows, BM, &mb);
+      if (!rc) rc = mnn_tc_make_map_bf16(reinterpret_cast<uint16_t*>(ws) + (size_t)rows * R, R, R, rows, BM, &mb2);
+    } else {
+      rc = mnn_tc_make_map(whp, R, R, (long long)blocks * 4 * UB, BM, false, &mb);
+      mb2 = mb;
+    }
     if (rc) return rc;
     CUtensorMap mg, mc, mo;
     rc = mnn_tc_make_map(gates, 4LL * R, 4LL * R, (long long)T * B, BM, false, &mg);
@@ -1488,7 +1536,7 @@ extern "C" int mnn_lstm_seq_fwd_tc(float* gates, const float* wh, float* hbuf, f
     at[0].id = cudaLaunchAttributeCooperative;
     at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_tc2_fwd_kernel, ma, mb, mg, mc, mo, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_tc2_fwd_kernel, ma, mb, mb2, mg, mc, mo, p);
     if (e != cudaSuccess) {
       mnn_set_error(cudaGetErrorString(e));
       return (int)e;
@@ -1564,16 +1612,26 @@ extern "C" int mnn_lstm_seq_bwd_tc_chunk(float* gates, const float* wh, const fl
     if (splits < 1) splits = 1;
     q.kb_per_split = (kb_total + splits - 1) / splits;
     q.splits = (kb_total + q.kb_per_split - 1) / q.kb_per_split;
-    static const char* bf16x_env = getenv("MNN_LSTM_BF16X");   // "0": 3xTF32 in phase A, "1": 2.5 products, "2": bf16 pairs
-    q.bf16x = bf16x_env ? (bf16x_env[0] == '0' ? 0 : (bf16x_env[0] == '2' ? 2 : 1)) : 1;
+    static const char* bf16x_env = getenv("MNN_LSTM_BF16X");   // see mnn_lstm_seq_fwd_tc
+    const bool wh_pre = bf16x_env ? bf16x_env[0] == '3' : mnn_tc_gemm_split() == 1;
+    q.bf16x = bf16x_env ? (bf16x_env[0] == '0' ? 0 : (bf16x_env[0] >= '2' ? 2 : 1)) : (wh_pre ? 2 : 1);
+    q.b_pre = wh_pre ? 1 : 0;
     q.cntA = reinterpret_cast<unsigned int*>(cnt + 1024);
     q.cntB = reinterpret_cast<unsigned int*>(cnt + 2048);
     cudaMemsetAsync(cnt + 1024, 0, 2048, stream);
     cudaMemsetAsync(dh_acc, 0, BR * sizeof(float), stream);
-    CUtensorMap ma, mb, mdhr, mdh, mg, mc, mdo, mds, mdc;
+    CUtensorMap ma, mb, mb2, mdhr, mdh, mg, mc, mdo, mds, mdc;
     const long long TB = (long long)T * B;
     if ((rc = mnn_tc_make_map(gates, 4LL * R, 4LL * R, TB + (has_next ? B : 0), BM, false, &ma))) return rc;
-    if ((rc = mnn_tc_make_map(wh, 4LL * R, 4LL * R, R, BM, false, &mb))) return rc;
+    if (wh_pre) {
+      // Wh [R][4R] as bf16 pair planes in the (otherwise unused) permuted-weights region at the head of the workspace
+      if ((rc = mnn_split_bf16_pair(wh, 4LL * R, R, 4 * R, ws, 4LL * R, stream))) return rc;
+      if ((rc = mnn_tc_make_map_bf16(ws, 4LL * R, 4LL * R, R, BM, &mb))) return rc;
+      if ((rc = mnn_tc_make_map_bf16(reinterpret_cast<uint16_t*>(ws) + (size_t)R * 4 * R, 4LL * R, 4LL * R, R, BM, &mb2))) return rc;
+    } else {
+      if ((rc = mnn_tc_make_map(wh, 4LL * R, 4LL * R, R, BM, false, &mb))) return rc;
+      mb2 = mb;
+    }
     if ((rc = mnn_tc_make_map(dh_acc, R, R, B, BM, false, &mdhr))) return rc;
     if ((rc = mnn_tc_make_map_plain(dh_acc, R, R, B, kCellUnits, kCellRows, &mdh))) return rc;
     if ((rc = mnn_tc_make_map_plain(gates, 4LL * R, 4LL * R, TB, kCellUnits, kCellRows, &mg))) return rc;
@@ -1596,7 +1654,7 @@ extern "C" int mnn_lstm_seq_bwd_tc_chunk(float* gates, const float* wh, const fl
       cudaMalloc(&q.trace, trace_n * sizeof(unsigned long long));
       cudaMemsetAsync(q.trace, 0, trace_n * sizeof(unsigned long long), stream);
     }
-    cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_tc3_bwd_kernel, ma, mb, mdhr, mdh, mg, mc, mdo, mds, mdc, q);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_tc3_bwd_kernel, ma, mb, mb2, mdhr, mdh, mg, mc, mdo, mds, mdc, q);
     if (e != cudaSuccess) {
       mnn_set_error(cudaGetErrorString(e));
       return (int)e;
