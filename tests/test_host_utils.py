@@ -279,3 +279,28 @@ def test_recurrence_schedule_dispatch_for_the_baseline_shards():
     assert not rnn.use_pipeline(T, 2048) and not rnn.use_fwd_pipeline(T, 2048) and rnn.use_any_pipeline(T, 2048)
     for t, b in ((48, 256), (40, 256), (250, 2048)):            # T < 2 chunks, or not a multiple of the 32-step chunk
         assert not rnn.use_any_pipeline(t, b), (t, b)
+
+
+def test_bf16_twin_lookup_matches_row_blocks_only():
+    """ops._twin_of: a GEMM operand is redirected to the registered bf16 plane only when it is a full-width row block of the
+    registered fp32 matrix (pointer arithmetic on views; no launch involved)."""
+    import torch
+    from multinn_b200 import ops
+    base = torch.zeros(12, 20)
+    twin = torch.zeros(12, 24, dtype=torch.int16)
+    other = torch.zeros(12, 20)
+    saved = list(ops._twins)
+    try:
+        del ops._twins[:]
+        assert ops._twin_of(base) is None
+        ops.register_twin(base, twin)
+        assert ops._twin_of(base) == (twin.data_ptr(), 24)
+        assert ops._twin_of(base[4:9]) == (twin.data_ptr() + 4 * 24 * 2, 24)
+        assert ops._twin_of(base[:, :12]) is None          # narrower rows
+        assert ops._twin_of(base[::2]) is None             # strided rows
+        assert ops._twin_of(other[4:9]) is None            # another matrix
+        assert ops._twin_of(base.view(24, 10)) is None     # different row structure
+        ops.register_twin(base, torch.zeros(12, 32, dtype=torch.int16))   # re-registration replaces
+        assert len(ops._twins) == 1 and ops._twin_of(base)[1] == 32
+    finally:
+        ops._twins[:] = saved
