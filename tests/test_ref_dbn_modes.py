@@ -198,3 +198,104 @@ def test_cuda_generate_through_dbn_matches_reference_code(mode):
         u_enc, u_dec = u_enc[0], u_dec[0]
     music = m.generate(_cu(X), S, u=u, u_enc=u_enc, u_dec=u_dec)
     np.testing.assert_array_equal(music.cpu().numpy().astype(np.uint8), Z[f'{mode}/generate/music'])
+
+
+# ----------------------------------------------------------------------------- Joint + RNN-RBM (BASELINE config C3)
+# tests/golden/ref_joint_rbm.npz: the reference's own Joint mode with its RNN-RBM generator, run with the two outside
+# stand-ins its HEAD needs to start at all (tools/make_golden_ref.py::joint_rbm_case).
+J = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_joint_rbm.npz'))
+JX = J['x'].astype(np.float64)
+JB, JT = JX.shape[:2]
+JK, JH, JS = int(J['k']), 64, J['generate/music'].shape[1]
+
+
+def _jvars():
+    return {k[4:]: J[k].astype(f64) for k in J.files if k.startswith('var/')}
+
+
+def _joint_oracle_params():
+    v = _jvars()
+    enc = [(v[f'multinn/dbn-encoder/all/dbn/rbm/{i}/W'], v[f'multinn/dbn-encoder/all/dbn/rbm/{i}/bh'],
+            v[f'multinn/dbn-encoder/all/dbn/rbm/{i}/bv']) for i in range(2)]
+    g = 'multinn/rnn-rbm'
+    lstm = [(v[f'{g}/{g}/all/multi_rnn_cell/cell_{i}/cudnn_compatible_lstm_cell/kernel'],
+             v[f'{g}/{g}/all/multi_rnn_cell/cell_{i}/cudnn_compatible_lstm_cell/bias']) for i in range(2)]
+    gen = dict(lstm=lstm, rbm=(v[f'{g}/all/rbm/W'], v[f'{g}/all/rbm/bh'], v[f'{g}/all/rbm/bv']),
+               Wuh=v[f'{g}/all/Wuh'], Wuv=v[f'{g}/all/Wuv'])
+    return enc, gen
+
+
+def _jdraw(section, i):
+    return J[f'{section}/draw{i}'].astype(f64)
+
+
+def _joint_codes(enc):
+    """Sampled codes [B,T+1,E] of the stacked zero-padded inputs from the build()'s first two draws (rows b*(T+1) + t)."""
+    pad = np.concatenate([np.zeros((JB, 1, D * M)), JX.reshape(JB, JT, D * M)], axis=1)
+    _, h = O.dbn_forward(pad.reshape(JB * (JT + 1), -1), enc, [_jdraw('eval', 0), _jdraw('eval', 1)])
+    return h.reshape(JB, JT + 1, -1)
+
+
+def test_oracle_joint_rnn_rbm_matches_reference_code():
+    """Free-energy cost, chain samples and the monitored log-likelihood of the teacher-forced pass (rnn_rbm.py:94-119),
+    then generation (multinn_joint.py:188-215), against the reference's own classes."""
+    enc, gen = _joint_oracle_params()
+    codes = _joint_codes(enc)
+    uh = np.stack([_jdraw('eval', 4 + 2 * i) for i in range(JK)])            # [k, N, H], rows n = b*T + t
+    uv = np.stack([_jdraw('eval', 5 + 2 * i) for i in range(JK)])
+    r = O.rnn_rbm_forward(codes[:, :-1], codes[:, 1:], gen, JK, uh, uv)
+    np.testing.assert_allclose(r['loss'], J['eval/loss'], rtol=1e-10)
+    np.testing.assert_array_equal(r['sample'], J['eval/sample'])
+    tgt = codes[:, 1:].reshape(JB * JT, -1)
+    ll = -(tgt * np.log(r['cond_p'] + 1e-7) + (1 - tgt) * np.log(1 - r['cond_p'] + 1e-7)).sum(1).mean()
+    np.testing.assert_allclose(ll, J['eval/log_likelihood'], rtol=1e-10)
+    # generation: per step k x [h, v] draws [B, .], then the decode (rows b*S + s); the intro codes are build()'s
+    us = [(np.stack([_jdraw('generate', s * 2 * JK + 2 * i) for i in range(JK)]),
+           np.stack([_jdraw('generate', s * 2 * JK + 2 * i + 1) for i in range(JK)])) for s in range(JS)]
+    u_dec = [_jdraw('generate', JS * 2 * JK), _jdraw('generate', JS * 2 * JK + 1)]
+    h = O.rnn_rbm_generate(codes, gen, JK, JS, us)
+    _, vis = O.dbn_reconstruct(h.reshape(JB * JS, -1), enc, u_dec)
+    np.testing.assert_array_equal(vis.reshape(JB, JS, D, M), J['generate/music'])
+
+
+def _joint_model(device='cuda'):
+    from multinn_b200.multinn import MultINN, default_config, default_params
+    from multinn_b200.utils.tf_import import load_tf_variables
+    m = MultINN(default_config(), default_params(mode='joint', encoder='DBN', encoder_hidden=list(ENC), generator='RBM',
+                                                 num_hidden=JH, num_hidden_rnn=RNN, keep_prob=1.0), 'joint', device=device)
+    core = m._model
+    core._generator._k = core._generator.rbm._k = JK
+    v = _jvars()
+    load_tf_variables(m, {k: a for k, a in v.items() if 'dbn-encoder' not in k}, strict=True)
+    load_tf_variables(m, {k: a for k, a in v.items() if 'dbn-encoder' in k}, which='encoders', strict=True)
+    return m
+
+
+def test_reference_named_rnn_rbm_variables_import_strictly():
+    m = _joint_model(device='cpu')
+    sd = {k: v.numpy() for k, v in m.arena.state_dict().items()}
+    _, gen = _joint_oracle_params()
+    np.testing.assert_array_equal(sd['generator/Wuv'], gen['Wuv'].astype(np.float32))
+    np.testing.assert_array_equal(sd['generator/rbm/bh'].reshape(-1), gen['rbm'][1].astype(np.float32).reshape(-1))
+    np.testing.assert_array_equal(sd['generator/rnn/cell_1/kernel'], gen['lstm'][1][0].astype(np.float32))
+
+
+@pytest.mark.gpu
+def test_cuda_joint_rnn_rbm_matches_reference_code():
+    """C3 through the public interface: evaluate() (free-energy cost, chain samples) and generate() with the reference's
+    logged draws -- cost within 1e-4, samples and generated music bit for bit."""
+    m = _joint_model()
+    tm = lambda a, steps: _cu(_time_major(a, steps))              # reference rows b*steps + t -> device rows t*B + b
+    u_enc = [tm(_jdraw('eval', 0), JT + 1), tm(_jdraw('eval', 1), JT + 1)]
+    uh = torch.stack([tm(_jdraw('eval', 4 + 2 * i), JT) for i in range(JK)])
+    uv = torch.stack([tm(_jdraw('eval', 5 + 2 * i), JT) for i in range(JK)])
+    out = m.evaluate(_cu(JX), u_enc=u_enc, u_gibbs=(uh, uv))
+    np.testing.assert_allclose(float(out['batch/loss']), float(J['eval/loss']), rtol=1e-4, atol=1e-4)
+    got = out['sample'].cpu().numpy().reshape(JT, JB, -1).transpose(1, 0, 2).reshape(JB * JT, -1)
+    np.testing.assert_array_equal(got.astype(np.uint8), J['eval/sample'])
+    np.testing.assert_allclose(float(out['log_likelihood']), float(J['eval/log_likelihood']), rtol=2e-4)
+    us = [(torch.stack([_cu(_jdraw('generate', s * 2 * JK + 2 * i)) for i in range(JK)]),
+           torch.stack([_cu(_jdraw('generate', s * 2 * JK + 2 * i + 1)) for i in range(JK)])) for s in range(JS)]
+    u_dec = [_cu(_jdraw('generate', JS * 2 * JK)), _cu(_jdraw('generate', JS * 2 * JK + 1))]
+    music = m.generate(_cu(JX), JS, u=us, u_enc=u_enc, u_dec=u_dec)
+    np.testing.assert_array_equal(music.cpu().numpy().astype(np.uint8), J['generate/music'])

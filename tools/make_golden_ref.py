@@ -371,6 +371,88 @@ def dbn_mode_cases():
     print(f'{path}: {len(res)} arrays, {os.path.getsize(path) / 1024:.0f} KiB')
 
 
+def joint_rbm_case():
+    """Joint mode with the RNN-RBM generator (BASELINE config C3: multinn_joint.py + generators/rnn_rbm.py + common/rbm.py +
+    encoders/dbn_encoder.py). The reference cannot run this at HEAD (`RnnRBM.__init__` reads `self.k`
+    before `self._k` exists; `sample_single` passes k=None into `tf.constant`), so TWO stand-ins for the evident intent are
+    applied from outside, the reference files stay untouched: the class attribute `RnnRBM._k` (what `self._k = k` would have
+    set before `_init_estimator` runs) and a wrapper that gives `RBM.sample` the RBM's own `_k` when called without `k` (its
+    docstring: "or None if the internal value of k should be used"). Everything else -- stacking and padding of the
+    inputs, DBN encoding to sampled codes, `dynamic_rnn` over the LSTM stack, `bh_t = bh + o.Wuh`, `bv_t = bv + o.Wuv`,
+    the Gibbs chain from the INPUT frame, the free-energy cost, generation and decoding -- is the reference's code.
+    Draws are logged in call order: build(): encode [2], reconstruct [2], chain k x [h, v], decode of the predictions [2];
+    generate(): per step k x [h, v], then the decode [2]."""
+    import functools
+    import yaml
+    from models.common.rbm import RBM as RefRBM
+    from models.generators.rnn_rbm import RnnRBM
+    from models.multinn.multinn import MultINN
+    K = 4
+    had_k = '_k' in RnnRBM.__dict__
+    orig_sample = RefRBM.sample
+
+    @functools.wraps(orig_sample)
+    def sample_with_own_k(self, v, bh=None, bv=None, k=None):
+        return orig_sample(self, v, bh, bv, self._k if k is None else k)
+
+    RnnRBM._k = K
+    RefRBM.sample = sample_with_own_k
+    try:
+        with open(os.path.join(REF, 'configs', 'default_config.yaml')) as f:
+            config = yaml.safe_load(f)
+        with open(os.path.join(REF, 'configs', 'default_params.yaml')) as f:
+            params = yaml.safe_load(f)
+        config['training']['num_pixels'] = 1
+        params['generator'].update(type='RBM', num_hidden=64, num_hidden_rnn=[48, 32])
+        params['encoder'].update(type='DBN', num_hidden=[96, 84])
+        params['keep_prob'] = 1.0
+        rng = _R32(97)
+        B, T, D, M, S = 3, 4, 84, 5, 2
+        x = (rng.random((B, T, D, M)) < 0.12).astype(np.float64)
+        res = {'x': x.astype(np.uint8), 'k': A(K)}
+        tf.reset_default_graph()
+        del tf._variables[:]
+        tf.feed(x=x, lengths=A([T] * B), is_train=False)
+        tfp.auto_uniforms(13)
+        model = MultINN(config, params, mode='joint', name='multinn')
+        rs = np.random.default_rng(5)
+        for v in tf._variables:
+            if v.name.endswith(('/bh:0', '/bv:0')) and 'rnn-rbm' in v.name:      # non-zero RBM biases (zeros at init)
+                v[...] = rs.standard_normal(v.shape) * 0.1
+            v[...] = r32(A(v))
+        core = model._model
+        for e in core.encoders:
+            e._is_built = False
+        tfp.auto_uniforms(17)
+        n_vars = len(tf._variables)
+        core.build(mode='eval')
+        assert len(tf._variables) == n_vars
+        for v in tf._variables:
+            res[f'var/{v.name[:-2]}'] = A(v).astype(np.float32)
+        gen = core.generators[0]
+        res['eval/loss'] = A(gen.metrics['batch/loss'])
+        res['eval/log_likelihood'] = A(gen.metrics['log_likelihood'])
+        res['eval/sample'] = A(gen.forward()).astype(np.uint8)
+        assert len(tfp.auto_log) == 4 + 2 * K + 2
+        for i, u in enumerate(tfp.auto_log):
+            res[f'eval/draw{i}'] = u.astype(np.float32)
+        n0 = len(tfp.auto_log)
+        music = model.generate(S)
+        draws = tfp.auto_log[n0:]
+        assert len(draws) == S * 2 * K + 2
+        for i, u in enumerate(draws):
+            res[f'generate/draw{i}'] = u.astype(np.float32)
+        res['generate/music'] = A(music).astype(np.uint8)
+    finally:
+        RefRBM.sample = orig_sample
+        if not had_k:
+            del RnnRBM._k
+        tfp.auto_uniforms(None)
+    path = os.path.join(ROOT, 'tests', 'golden', 'ref_joint_rbm.npz')
+    np.savez_compressed(path, **res)
+    print(f'{path}: {len(res)} arrays, {os.path.getsize(path) / 1024:.0f} KiB')
+
+
 if __name__ == '__main__':
     tf.set_random_seed(20261018)
     nade_cases()
@@ -383,3 +465,4 @@ if __name__ == '__main__':
     print(f'{path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.0f} KiB')
     mode_cases()
     dbn_mode_cases()
+    joint_rbm_case()
