@@ -14,10 +14,12 @@ import pytest
 import torch
 
 from oracle import np_oracle as O
+from oracle import torch_ref as R
 
 Z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_dbn_modes.npz'))
 TRACKS = ['Drums', 'Piano', 'Guitar', 'Bass', 'Strings']
-MODES = ['composer', 'jamming', 'joint']
+MODES = ['composer', 'jamming', 'joint', 'feedback', 'feedback_rnn']      # feedback_rnn + DBN + NADE = BASELINE config C4
+FEEDBACK = (40, 24)
 X = Z['x'].astype(np.float64)
 B, T, D, M = X.shape
 E, H, RNN, ENC = 84, 128, (48, 32), (96, 84)
@@ -59,6 +61,21 @@ def generator_params(mode):
     return out
 
 
+def feedback_params(mode):
+    v = variables(mode)
+    if mode == 'feedback':
+        return [(v[f'multinn/feedback/dense{s}/kernel'], v[f'multinn/feedback/dense{s}/bias']) for s in ('', '_1')]
+    return lstm_layers(v, 'multinn/feedback')
+
+
+def _tt(a):
+    if isinstance(a, (list, tuple)):
+        return type(a)(_tt(b) for b in a)
+    if isinstance(a, dict):
+        return {k: _tt(b) for k, b in a.items()}
+    return torch.tensor(np.ascontiguousarray(a), dtype=torch.float64)
+
+
 def encoder_inputs(mode):
     """Zero-padded encoder inputs [B,T+1,Dv]: per track (core/multi_encoder_nn.py:66-76) or stacked with feature
     d*M + m (multinn_joint.py:76-89)."""
@@ -93,6 +110,9 @@ def oracle_loss(mode):
         tgt = stack[:, 1:].reshape(B * T, E, M)
         nll = np.stack([O.nade_log_prob(tgt[:, :, m], be[m], bd[m], *p['nade'][m])[0] for m in range(M)], 1)
         return np.array([nll.mean(0).mean()])
+    if mode in ('feedback', 'feedback_rnn'):
+        _, nll = R.feedback_loss(_tt(codes), _tt(p), _tt(feedback_params(mode)), 'dense' if mode == 'feedback' else 'rnn')
+        return nll.mean(0).numpy()
     return np.array([O.rnn_nade_forward(c[:, :-1], c[:, 1:], q)['loss'] for c, q in zip(codes, p)])
 
 
@@ -100,7 +120,7 @@ def sampler_uniforms(mode):
     """The [n,B] sampler draws in call order -> u[S,G,B,E] with G generators' tracks: Composer draws step-major then
     track then dimension; Jamming runs each track's whole generation in turn; Joint has one track of E codes."""
     d = Z[f'{mode}/generate/sampler_draws'].astype(f64)
-    if mode == 'composer':
+    if mode in ('composer', 'feedback', 'feedback_rnn'):
         return d.reshape(S, M, E, B).transpose(0, 1, 3, 2)
     if mode == 'jamming':
         return d.reshape(M, S, E, B).transpose(1, 0, 3, 2)
@@ -118,6 +138,9 @@ def oracle_music(mode):
     codes, p, u = oracle_codes(mode), generator_params(mode), sampler_uniforms(mode)
     if mode == 'composer':
         h = O.multinade_generate(np.stack(codes, axis=3).reshape(B, T + 1, -1), p, S, u).reshape(B, S, E, M)
+        h = [h[..., m] for m in range(M)]
+    elif mode in ('feedback', 'feedback_rnn'):
+        h = O.feedback_generate(codes, p, feedback_params(mode), 'dense' if mode == 'feedback' else 'rnn', S, u)
         h = [h[..., m] for m in range(M)]
     else:
         h = [O.multinade_generate(c, dict(lstm=q['lstm'], dense=q['dense'], nade=[q['nade']]), S, u[:, g:g + 1])
@@ -141,7 +164,7 @@ def test_oracle_generate_through_dbn_matches_reference_code(mode):
 
 def test_draw_counts():
     """4 build draws per encoder + 2 per encoder for decoding the predictions; generation: S*tracks*E sampler draws."""
-    for mode, n_enc in (('composer', 5), ('jamming', 5), ('joint', 1)):
+    for mode, n_enc in (('composer', 5), ('jamming', 5), ('joint', 1), ('feedback', 5), ('feedback_rnn', 5)):
         assert int(Z[f'{mode}/eval/n_draw']) == 6 * n_enc
         assert Z[f'{mode}/generate/sampler_draws'].shape == (S * E * (1 if mode == 'joint' else M), B)
 
@@ -150,8 +173,10 @@ def test_draw_counts():
 def _model(mode, device='cuda'):
     from multinn_b200.multinn import MultINN, default_config, default_params
     from multinn_b200.utils.tf_import import load_tf_variables
-    m = MultINN(default_config(), default_params(mode=mode, encoder='DBN', encoder_hidden=list(ENC), generator='NADE',
-                                                 num_hidden=H, num_hidden_rnn=RNN, keep_prob=1.0), mode, device=device)
+    name = mode.replace('_', '-')
+    kw = {'feedback': list(FEEDBACK)} if mode.startswith('feedback') else {}
+    m = MultINN(default_config(), default_params(mode=name, encoder='DBN', encoder_hidden=list(ENC), generator='NADE',
+                                                 num_hidden=H, num_hidden_rnn=RNN, keep_prob=1.0, **kw), name, device=device)
     v = variables(mode)
     load_tf_variables(m, {k: a for k, a in v.items() if 'dbn-encoder' not in k}, strict=True)
     load_tf_variables(m, {k: a for k, a in v.items() if 'dbn-encoder' in k}, which='encoders', strict=True)

@@ -324,14 +324,15 @@ def dbn_mode_cases():
     with open(os.path.join(REF, 'configs', 'default_params.yaml')) as f:
         params = yaml.safe_load(f)
     config['training']['num_pixels'] = 1
-    params['generator'].update(type='NADE', num_hidden=128, num_hidden_rnn=[48, 32])
+    params['generator'].update(type='NADE', num_hidden=128, num_hidden_rnn=[48, 32], feedback=[40, 24])
     params['encoder'].update(type='DBN', num_hidden=[96, 84])
     params['keep_prob'] = 1.0
     rng = _R32(91)
     B, T, D, M, S = 3, 4, 84, 5, 2
     x = (rng.random((B, T, D, M)) < 0.12).astype(np.float64)
     res = {'x': x.astype(np.uint8)}
-    for mode in ('composer', 'jamming', 'joint'):
+    for mode in ('composer', 'jamming', 'joint', 'feedback', 'feedback-rnn'):     # feedback-rnn + DBN + NADE = config C4
+        key = mode.replace('-', '_')
         tf.reset_default_graph()
         del tf._variables[:]
         tf.feed(x=x, lengths=A([T] * B), is_train=False)
@@ -347,12 +348,12 @@ def dbn_mode_cases():
         core.build(mode='eval')
         assert len(tf._variables) == n_vars
         for v in tf._variables:
-            res[f'{mode}/var/{v.name[:-2]}'] = A(v).astype(np.float32)
-        res[f'{mode}/eval/loss'] = A([g.metrics['batch/loss'] for g in core.generators])
-        res[f'{mode}/eval/global_loss'] = A(core.metrics['batch/loss'])
+            res[f'{key}/var/{v.name[:-2]}'] = A(v).astype(np.float32)
+        res[f'{key}/eval/loss'] = A([g.metrics['batch/loss'] for g in core.generators])
+        res[f'{key}/eval/global_loss'] = A(core.metrics['batch/loss'])
         for i, u in enumerate(tfp.auto_log):
-            res[f'{mode}/eval/draw{i}'] = u.astype(np.float32)
-        res[f'{mode}/eval/n_draw'] = A(len(tfp.auto_log))
+            res[f'{key}/eval/draw{i}'] = u.astype(np.float32)
+        res[f'{key}/eval/n_draw'] = A(len(tfp.auto_log))
         n0 = len(tfp.auto_log)
         music = model.generate(S)
         draws = tfp.auto_log[n0:]
@@ -361,10 +362,10 @@ def dbn_mode_cases():
         sampler = [u for u in draws if u.shape == (B, 1)]          # Jamming interleaves: per track [S*E sampler, 2 decode]
         decode = [u for u in draws if u.shape != (B, 1)]
         assert len(sampler) == n_s and len(decode) == 2 * len(core.encoders)
-        res[f'{mode}/generate/sampler_draws'] = np.concatenate(sampler, axis=1).T.astype(np.float32)   # [n_s, B] in call order
+        res[f'{key}/generate/sampler_draws'] = np.concatenate(sampler, axis=1).T.astype(np.float32)   # [n_s, B] in call order
         for i, u in enumerate(decode):
-            res[f'{mode}/generate/decode_draw{i}'] = u.astype(np.float32)
-        res[f'{mode}/generate/music'] = A(music).astype(np.uint8)
+            res[f'{key}/generate/decode_draw{i}'] = u.astype(np.float32)
+        res[f'{key}/generate/music'] = A(music).astype(np.uint8)
     tfp.auto_uniforms(None)
     path = os.path.join(ROOT, 'tests', 'golden', 'ref_dbn_modes.npz')
     np.savez_compressed(path, **res)
