@@ -304,3 +304,38 @@ def test_bf16_twin_lookup_matches_row_blocks_only():
         assert len(ops._twins) == 1 and ops._twin_of(base)[1] == 32
     finally:
         ops._twins[:] = saved
+
+
+def test_bookkeeping_classes_behave_like_the_reference_ones():
+    """tests/golden/ref_host.json was recorded from the reference's own TrainingStats / LossAccumulator
+    (tools/make_golden_host.py); the rewritten classes must show the same counters, printed line and pickled tuple."""
+    import json
+    import os
+    import pickle
+    import tempfile
+    from multinn_b200.utils.training import LossAccumulator, TrainingStats
+    with open(os.path.join(os.path.dirname(__file__), 'golden', 'ref_host.json')) as f:
+        ref = json.load(f)
+    acc = LossAccumulator()
+    for x, want in zip(ref['losses'], ref['accumulator']):
+        acc.update(float(x))
+        assert repr(float(acc.loss())) == want['loss'] and acc.num_bad() == want['num_bad']
+        assert acc.ratio_bad() == want['ratio_bad'] and str(acc) == want['line']
+    acc.clear()
+    assert repr(float(acc.loss())) == ref['cleared']['loss'] and acc.num_bad() == ref['cleared']['num_bad']
+    st = TrainingStats()
+    for op, want in zip(ref['stats_script'], ref['stats_states']):
+        if isinstance(op, list):
+            getattr(st, op[0])(*op[1:])
+        else:
+            getattr(st, op)()
+        assert [st.steps, st.epoch, st.run, st.metric_best, st.idle_epochs] == want
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, 'stats.pkl')
+        st.save(path)
+        with open(path, 'rb') as f:
+            assert list(pickle.load(f)) == ref['pickled']
+        st2 = TrainingStats(steps=9, epoch=9, run=9, metric_best=0.0)
+        st2.new_idle_epoch()
+        st2.load(path)
+        assert [st2.steps, st2.epoch, st2.run, st2.metric_best, st2.idle_epochs] == ref['loaded']
