@@ -339,3 +339,30 @@ def test_bookkeeping_classes_behave_like_the_reference_ones():
         st2.new_idle_epoch()
         st2.load(path)
         assert [st2.steps, st2.epoch, st2.run, st2.metric_best, st2.idle_epochs] == ref['loaded']
+
+
+def test_data_helpers_behave_like_the_reference_ones(tmp_path):
+    """tests/golden/ref_host_data.npz was recorded from the reference's own utils/data.py (tools/make_golden_host.py) on a
+    small synthetic dataset: split, pixel padding + folding, lengths file, sampling inputs, MIDI padding."""
+    import os
+    import numpy as np
+    from multinn_b200.utils import data as D
+    ref = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_host_data.npz'))
+    np.save(tmp_path / 'songs.npy', ref['songs'])
+    np.save(tmp_path / 'lengths.npy', ref['lengths'])
+    cfg = dict(filename=str(tmp_path / 'songs'), source='npy', sequence_lengths=None, instruments=['a', 'b', 'c', 'd', 'e'],
+               split=dict(num_train=7, num_valid=3, num_test=2), pitch_range=dict(lowest=24, highest=30))
+    for name, step, with_len in (('s1', 1, False), ('s3', 3, False), ('s2len', 2, True)):
+        cfg['sequence_lengths'] = str(tmp_path / 'lengths.npy') if with_len else None
+        (xt, lt), (xv, lv), (xs, ls) = D.load_data(cfg, step_size=step)
+        for k, got in (('xt', xt), ('lt', lt), ('xv', xv), ('lv', lv), ('xs', xs), ('ls', ls)):
+            np.testing.assert_array_equal(got, ref[f'{name}/{k}'], err_msg=f'{name}/{k}')
+    cfg['sequence_lengths'] = None
+    (xt, _), (xv, _), _ = D.load_data(cfg, step_size=1)
+    samp = dict(intro_beats=2, intro_ids=dict(train=dict(start=1, end=5), valid=dict(start=0, end=2)),
+                save_ids=dict(train=[0, 2], valid=[1]), num_save=3)
+    intro, save_ids, labels = D.prepare_sampling_inputs(xt, xv, samp, beat_size=2)
+    np.testing.assert_array_equal(intro, ref['samp/intro'])
+    np.testing.assert_array_equal(save_ids, ref['samp/save_ids'])
+    assert list(labels) == [str(x) for x in ref['samp/labels']]
+    np.testing.assert_array_equal(D.pad_to_midi(xt[:2].astype(np.float32), cfg), ref['midi/pad'])
