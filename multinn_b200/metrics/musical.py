@@ -202,5 +202,6 @@ def metric_summary(bar_music, tracks):
                 out[f'{scope}/{name}'] = float(ops[name][i])
     for i in range(1, len(tracks)):
         for j in range(i + 1, len(tracks)):
-            out[f'sample_scores/inter-track/TD/{tracks[i]}-{tracks[j]}'] = float(ops['TD'][i - 1][j - 1])
+            pair = f'{tracks[i]}-{tracks[j]}'          # scope TD/<a>-<b> AND a scalar of the same name (musical_tf.py:222-225)
+            out[f'sample_scores/inter-track/TD/{pair}/{pair}'] = float(ops['TD'][i - 1][j - 1])
     return out

@@ -87,7 +87,7 @@ def test_metric_summary_layout():
     assert len(s) == 2 * 5 + 1 + 3 * 4 + 6
     assert 'sample_scores/intra-track/Drums/DP' in s and 'sample_scores/intra-track/Drums/QN' not in s
     assert s['sample_scores/intra-track/Piano/QN'] == float(GOLD['sparse48/QN'][1])
-    assert s['sample_scores/inter-track/TD/Piano-Bass'] == pytest.approx(float(GOLD['sparse48/TD'][1][3]), rel=1e-12)
+    assert s['sample_scores/inter-track/TD/Piano-Bass/Piano-Bass'] == pytest.approx(float(GOLD['sparse48/TD'][1][3]), rel=1e-12)
 
 
 @pytest.mark.skipif(not os.path.exists(gen.REF), reason='the reference checkout is not present on this machine')
@@ -131,3 +131,22 @@ def test_metric_invariants_on_random_rolls():
         assert np.all(MM.empty_bar_rate(silent) == 1) and np.all(np.isnan(MM.qualified_note_rate(silent)))
 
     check()
+
+
+@pytest.mark.parametrize('name', ['sparse48', 'dense96', 'pitch20', 'silent_track'])
+def test_metric_summary_equals_the_reference_tf_module(name):
+    """tests/golden/musical_summary.json: tags and values recorded from the reference's `get_metric_summary_ops`
+    (metrics/musical_tf.py, run on the NumPy TF stand-in by tools/make_golden_musical.py::summary_cases)."""
+    import json
+    with open(os.path.join(os.path.dirname(__file__), 'golden', 'musical_summary.json')) as f:
+        ref = json.load(f)[name]
+    case = [c for c in gen.CASES if c[0] == name][0]
+    roll = gen.case_roll(*case)
+    with np.errstate(all='ignore'):
+        got = MM.metric_summary(roll.astype(np.float32), ['Drums', 'Piano', 'Guitar', 'Bass', 'Strings'])
+    assert sorted(got) == sorted(ref)
+    for tag, want in ref.items():
+        if want is None:
+            assert np.isnan(got[tag]), tag
+        else:
+            assert got[tag] == pytest.approx(want, rel=1e-6, abs=1e-9), tag      # the TF module computes EB / UP / PR in fp32

@@ -781,3 +781,42 @@ class _Layers:
 
 
 layers = _Layers()
+
+
+# ================================================================================================ metrics/musical_tf.py
+# (round 2, third step) the few extra ops `get_metric_summary_ops` uses; tf.summary.scalar records (scoped tag, value) so
+# that tools/make_golden_musical.py can pin the TensorBoard tags and values of the sample scores.
+def count_nonzero(x, axis=None, keepdims=False, dtype=None, name=None):
+    return _t(np.count_nonzero(np.asarray(x), axis=axis, keepdims=keepdims).astype(np.float64 if dtype is not None else np.int64))
+
+
+def reduce_any(x, axis=None, keepdims=False, name=None):
+    return _t(np.any(np.asarray(x), axis=axis, keepdims=keepdims))
+
+
+def reduce_all(x, axis=None, keepdims=False, name=None):
+    return _t(np.all(np.asarray(x), axis=axis, keepdims=keepdims))
+
+
+class _Eager:
+    def __init__(self, a):
+        self._a = np.asarray(a)
+
+    def numpy(self):
+        return self._a
+
+
+def py_function(func, inp, Tout, name=None):
+    return _t(np.asarray(func(*[_Eager(a) for a in inp]), dtype=np.float64))
+
+
+scalar_log = []
+
+
+def _summary_scalar(name, tensor, **kw):
+    scalar_log.append((_scoped(name), float(np.asarray(tensor))))
+    return None
+
+
+summary.scalar = _summary_scalar
+Summary = _Anything('tf.Summary')
