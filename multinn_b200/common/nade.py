@@ -17,6 +17,12 @@ class NADEBank:
     """Weights of M NADEs: w_enc[M,D,H] (reference per-NADE w_enc[D,1,H]) and w_dec[M,D,H] (w_dec[D,H,1])."""
 
     def __init__(self, arena, num_tracks, num_dims, num_hidden, name='nade'):
+        if num_dims > 128:
+            # fail at construction, not at the first launch: the kernels keep both weight matrices of a track in shared
+            # memory and the row masks in four words (DESIGN.md section 7). `training.num_pixels: 3` of the reference's shipped
+            # default config gives num_dims = 252: use `num_pixels: 1` (the BASELINE shapes) with this package
+            raise NotImplementedError(f'NADE kernels are built for num_dims <= 128 (and num_hidden 128 or 256); got '
+                                      f'num_dims={num_dims}')
         std = 1.0 / math.sqrt(num_dims)                       # nade.py:48-50
         self.num_tracks, self.num_dims, self.num_hidden = num_tracks, num_dims, num_hidden
         self.w_enc = arena.add(f'{name}/w_enc', (num_tracks, num_dims, num_hidden), truncated_normal(std))
